@@ -1,0 +1,807 @@
+/*
+ * dynfu_oracle.cpp -- CPU ORACLE (test infrastructure, never shipped, never on the product path).
+ *
+ * A dependency-free C++17 restatement of the arithmetic of swarth100/dynfu's per-frame hot path.
+ * Compile with -ffp-contract=off: the reference is plain x86-64 C++ (no FMA contraction), so every
+ * float operation below is rounded separately, in the reference's evaluation order.
+ *
+ * Citations are into /root/reference.  Quaternions are (w,x,y,z), Hamilton product.
+ *
+ * Built twice by oracle/Makefile:
+ *   oracle/libdynfu_oracle.so          kNN = brute force, key (dist2, idx)          [default checker]
+ *   oracle/_ref/libdynfu_oracle_nf.so  kNN = the reference's vendored nanoflann KD-tree
+ *                                      (-DORC_USE_NANOFLANN, header compiled where it lies)
+ */
+#include "dynfu_oracle.h"
+
+#include <algorithm>
+#include <cassert>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifdef ORC_USE_NANOFLANN
+#include <nanoflann.hpp> /* /root/reference/include/nanoflann/nanoflann.hpp, v0x123 */
+#endif
+
+namespace {
+
+constexpr int KNN = 8; /* include/dynfu/warp_field.hpp:27 */
+
+/* ------------------------------------------------------------------------------------------ */
+/* boost::math::quaternion<float> subset                                                       */
+
+struct Quat {
+    float w, x, y, z;
+};
+
+/* boost/math/quaternion.hpp operator*= : at = a*ar-b*br-c*cr-d*dr, ... evaluated left to right */
+inline Quat qmul(const Quat& p, const Quat& q) {
+    const float a = p.w, b = p.x, c = p.y, d = p.z;
+    const float ar = q.w, br = q.x, cr = q.y, dr = q.z;
+    Quat r;
+    r.w = a * ar - b * br - c * cr - d * dr;
+    r.x = a * br + b * ar + c * dr - d * cr;
+    r.y = a * cr - b * dr + c * ar + d * br;
+    r.z = a * dr + b * cr - c * br + d * ar;
+    return r;
+}
+inline Quat qadd(const Quat& p, const Quat& q) { return {p.w + q.w, p.x + q.x, p.y + q.y, p.z + q.z}; }
+inline Quat qsub(const Quat& p, const Quat& q) { return {p.w - q.w, p.x - q.x, p.y - q.y, p.z - q.z}; }
+inline Quat qscale(const Quat& p, float s) { return {p.w * s, p.x * s, p.y * s, p.z * s}; }
+inline Quat qdiv(const Quat& p, float s) { return {p.w / s, p.x / s, p.y / s, p.z / s}; }
+inline Quat qconj(const Quat& p) { return {p.w, -p.x, -p.y, -p.z}; }
+/* boost::math::norm(q) is the Cayley norm = SUM OF SQUARES (real(q*conj(q))) */
+inline float qnorm_boost(const Quat& p) { return p.w * p.w + p.x * p.x + p.y * p.y + p.z * p.z; }
+
+struct DQ {
+    Quat real, dual;
+};
+
+inline DQ load_dq(const float* a) { return {{a[0], a[1], a[2], a[3]}, {a[4], a[5], a[6], a[7]}}; }
+inline void store_dq(const DQ& d, float* o) {
+    o[0] = d.real.w; o[1] = d.real.x; o[2] = d.real.y; o[3] = d.real.z;
+    o[4] = d.dual.w; o[5] = d.dual.x; o[6] = d.dual.y; o[7] = d.dual.z;
+}
+
+/* dual_quaternion.hpp:31,42-45 : real = rot / norm(rot) [squared norm!], dual = ((0,t)*real)*0.5f */
+inline DQ dq_from_rot_trans(const Quat& rot, const float t[3]) {
+    DQ d;
+    d.real = qdiv(rot, qnorm_boost(rot));
+    d.dual = qscale(qmul(Quat{0.f, t[0], t[1], t[2]}, d.real), 0.5f);
+    return d;
+}
+
+/* dual_quaternion.hpp:48-67 : cos/sin of (T * 0.5) are evaluated in double, stored to T */
+inline DQ dq_from_euler(float yaw, float pitch, float roll, float x, float y, float z) {
+    float cy = (float) std::cos(yaw * 0.5);
+    float sy = (float) std::sin(yaw * 0.5);
+    float cr = (float) std::cos(roll * 0.5);
+    float sr = (float) std::sin(roll * 0.5);
+    float cp = (float) std::cos(pitch * 0.5);
+    float sp = (float) std::sin(pitch * 0.5);
+    float qw = cy * cr * cp + sy * sr * sp;
+    float qx = cy * sr * cp - sy * cr * sp;
+    float qy = cy * cr * sp + sy * sr * cp;
+    float qz = sy * cr * cp - cy * sr * sp;
+    float t[3] = {x, y, z};
+    return dq_from_rot_trans(Quat{qw, qx, qy, qz}, t);
+}
+
+/* dual_quaternion.hpp:127-129 */
+inline DQ dq_mul(const DQ& a, const DQ& b) {
+    return {qmul(a.real, b.real), qadd(qmul(a.real, b.dual), qmul(a.dual, b.real))};
+}
+
+/* dual_quaternion.hpp:139-144 : only the real part is normalised */
+inline bool dq_normalize(DQ& d) {
+    float magnitude = sqrtf(d.real.w * d.real.w + d.real.x * d.real.x + d.real.y * d.real.y + d.real.z * d.real.z);
+    bool ok = magnitude > 1.192092896e-07f;
+    d.real = qscale(d.real, 1.0f / magnitude);
+    return ok;
+}
+
+struct V3 {
+    float x, y, z;
+};
+inline V3 cross(const V3& a, const V3& b) { /* cv::Vec3f::cross */
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+inline V3 vadd(const V3& a, const V3& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 vsub(const V3& a, const V3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 vscale(float s, const V3& a) { return {a.x * s, a.y * s, a.z * s}; }
+
+/* dual_quaternion.hpp:204-215
+ *   vect + 2.f * rv.cross(rv.cross(vect) + rw * vect) + 2.f * (rw * dv - dw * rv + rv.cross(dv)) */
+inline V3 dq_transform_vertex(const DQ& d, const V3& v) {
+    V3 rv{d.real.x, d.real.y, d.real.z};
+    V3 dv{d.dual.x, d.dual.y, d.dual.z};
+    V3 a = vscale(2.f, cross(rv, vadd(cross(rv, v), vscale(d.real.w, v))));
+    V3 b = vscale(2.f, vadd(vsub(vscale(d.real.w, dv), vscale(d.dual.w, rv)), cross(rv, dv)));
+    return vadd(vadd(v, a), b);
+}
+/* rotation only: what a normal transform should be (not what the reference does) */
+inline V3 dq_rotate(const DQ& d, const V3& v) {
+    V3 rv{d.real.x, d.real.y, d.real.z};
+    V3 a = vscale(2.f, cross(rv, vadd(cross(rv, v), vscale(d.real.w, v))));
+    return vadd(v, a);
+}
+
+/* src/dynfu/utils/node.cpp:29-36 : float differences, pow/exp in double, result cast to float */
+inline float node_weight(const float* np, float dg_w, const float* p) {
+    double dx = (double) (np[0] - p[0]);
+    double dy = (double) (np[1] - p[1]);
+    double dz = (double) (np[2] - p[2]);
+    double distSq = dx * dx + dy * dy + dz * dz;
+    double w2 = (double) dg_w * (double) dg_w;
+    return (float) std::exp(-distSq / (2 * w2));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* kNN index                                                                                   */
+
+/* nanoflann L2_Simple_Adaptor::evalMetric (include/nanoflann/nanoflann.hpp:338-345) */
+inline float dist2(const float* q, const float* p) {
+    float r = 0.f;
+    for (int i = 0; i < 3; ++i) {
+        const float diff = q[i] - p[i];
+        r += diff * diff;
+    }
+    return r;
+}
+
+#ifdef ORC_USE_NANOFLANN
+/* adaptor with the interface of include/nanoflann/pointcloud.hpp:11-44 over a flat xyz array */
+struct FlatCloud {
+    const float* pts;
+    size_t n;
+    inline size_t kdtree_get_point_count() const { return n; }
+    inline float kdtree_get_pt(const size_t idx, int dim) const { return pts[idx * 3 + dim]; }
+    template <class BBOX>
+    bool kdtree_get_bbox(BBOX&) const { return false; }
+};
+typedef nanoflann::L2_Simple_Adaptor<float, FlatCloud> nf_adaptor;               /* warp_field.hpp:29 */
+typedef nanoflann::KDTreeSingleIndexAdaptor<nf_adaptor, FlatCloud, 3> nf_tree_t; /* warp_field.hpp:30 */
+#endif
+
+struct KnnIndex {
+    const float* nodes;
+    int N;
+#ifdef ORC_USE_NANOFLANN
+    FlatCloud cloud;
+    std::unique_ptr<nf_tree_t> tree;
+#endif
+    KnnIndex(const float* nodes_, int N_) : nodes(nodes_), N(N_) {
+#ifdef ORC_USE_NANOFLANN
+        cloud.pts = nodes;
+        cloud.n = (size_t) N;
+        /* warp_field.cpp:26-27 : leaf size 10 */
+        tree.reset(new nf_tree_t(3, cloud, nanoflann::KDTreeSingleIndexAdaptorParams(10)));
+        tree->buildIndex();
+#endif
+    }
+    /* returns n found (min(k,N)); ascending */
+    int query(const float* q, int k, int32_t* idx, float* d2) const {
+#ifdef ORC_USE_NANOFLANN
+        /* warp_field.cpp:111-122 */
+        size_t ret[16];
+        float dd[16];
+        int n = (int) tree->knnSearch(q, (size_t) k, ret, dd);
+        for (int i = 0; i < n; ++i) {
+            idx[i] = (int32_t) ret[i];
+            if (d2) d2[i] = dd[i];
+        }
+        return n;
+#else
+        float bd[17];
+        int32_t bi[17];
+        int cnt = 0;
+        for (int j = 0; j < N; ++j) {
+            float d = dist2(q, nodes + 3 * (size_t) j);
+            if (cnt == k && !(d < bd[k - 1])) continue; /* j ascending: equal dist keeps lower idx */
+            int i = cnt < k ? cnt : k - 1;
+            while (i > 0 && bd[i - 1] > d) {
+                bd[i] = bd[i - 1];
+                bi[i] = bi[i - 1];
+                --i;
+            }
+            bd[i] = d;
+            bi[i] = j;
+            if (cnt < k) ++cnt;
+        }
+        for (int i = 0; i < cnt; ++i) {
+            idx[i] = bi[i];
+            if (d2) d2[i] = bd[i];
+        }
+        return cnt;
+#endif
+    }
+};
+
+/* src/dynfu/warp_field.cpp:127-148 (REF_COMPOSE) and the north-star's true DQB (DQB_SUM) */
+inline DQ blend_point(const KnnIndex& index, const float* pos, const float* dq, const float* dg_w, const float* p,
+                      int blend_mode) {
+    int32_t nb[KNN];
+    int n = index.query(p, KNN, nb, nullptr);
+    if (blend_mode == ORC_BLEND_REF_COMPOSE) {
+        DQ sum = dq_from_euler(0.f, 0.f, 0.f, 0.f, 0.f, 0.f); /* warp_field.cpp:133 */
+        for (int k = 0; k < n; ++k) {
+            const int j = nb[k];
+            float w = node_weight(pos + 3 * (size_t) j, dg_w[j], p);
+            DQ node = load_dq(dq + 8 * (size_t) j);
+            DQ weighted{node.real, qscale(node.dual, w)}; /* dual_quaternion.hpp:120 : dual only */
+            /* dual_quaternion.hpp:131-135 : dual first with the OLD real, then real */
+            Quat nd = qadd(qmul(sum.real, weighted.dual), qmul(sum.dual, weighted.real));
+            sum.real = qmul(sum.real, weighted.real);
+            sum.dual = nd;
+        }
+        dq_normalize(sum);
+        return sum;
+    }
+    /* DQB_SUM: Q = sum_k w_k * sign_k * q_k ; both parts divided by |real| ; no support -> identity */
+    Quat ar{0.f, 0.f, 0.f, 0.f}, ad{0.f, 0.f, 0.f, 0.f};
+    Quat r0{1.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < n; ++k) {
+        const int j = nb[k];
+        float w = node_weight(pos + 3 * (size_t) j, dg_w[j], p);
+        DQ node = load_dq(dq + 8 * (size_t) j);
+        if (k == 0) r0 = node.real;
+        float dot = node.real.w * r0.w + node.real.x * r0.x + node.real.y * r0.y + node.real.z * r0.z;
+        float ws = dot < 0.f ? -w : w;
+        ar = qadd(ar, qscale(node.real, ws));
+        ad = qadd(ad, qscale(node.dual, ws));
+    }
+    float m2 = ar.w * ar.w + ar.x * ar.x + ar.y * ar.y + ar.z * ar.z;
+    if (!(m2 > 0.f)) return DQ{{1.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float inv = 1.0f / sqrtf(m2);
+    return DQ{qscale(ar, inv), qscale(ad, inv)};
+}
+
+inline float half2float(uint16_t h) {
+    _Float16 f;
+    std::memcpy(&f, &h, 2);
+    return (float) f;
+}
+inline uint16_t float2half(float v) {
+    _Float16 f = (_Float16) v; /* round to nearest even, like __float2half_rn */
+    uint16_t h;
+    std::memcpy(&h, &f, 2);
+    return h;
+}
+
+inline float tukey(float tukey_offset, float c, const float e[3]) {
+    /* opt_solver.cpp:204-212 : sqrt/pow promote to double */
+    double s = std::sqrt((double) (e[0] * e[0] + e[1] * e[1] + e[2] * e[2])) / tukey_offset;
+    if (s < c) return (float) std::pow(1.f - std::pow(s, 2) / std::pow((double) c, 2), 2);
+    return 0.f;
+}
+
+} /* namespace */
+
+/* ============================================================================================ */
+extern "C" {
+
+void orc_dq_from_rot_trans(const float rot[4], const float t[3], float out[8]) {
+    store_dq(dq_from_rot_trans(Quat{rot[0], rot[1], rot[2], rot[3]}, t), out);
+}
+void orc_dq_from_euler(float yaw, float pitch, float roll, float x, float y, float z, float out[8]) {
+    store_dq(dq_from_euler(yaw, pitch, roll, x, y, z), out);
+}
+/* dual_quaternion.hpp:70-86 */
+void orc_dq_from_rodrigues(const float rod[3], const float t[3], float out[8]) {
+    double nrm = std::sqrt((double) rod[0] * rod[0] + (double) rod[1] * rod[1] + (double) rod[2] * rod[2]);
+    double theta = 2 * std::atan(nrm);
+    double ith = 1.0 / theta;
+    float axis[3] = {(float) (rod[0] * ith), (float) (rod[1] * ith), (float) (rod[2] * ith)};
+    double an = std::sqrt((double) axis[0] * axis[0] + (double) axis[1] * axis[1] + (double) axis[2] * axis[2]);
+    double ian = 1.0 / an;
+    float axn[3] = {(float) (axis[0] * ian), (float) (axis[1] * ian), (float) (axis[2] * ian)};
+    double s = std::sin(0.5 * theta);
+    Quat rot{(float) std::cos(0.5 * theta), (float) (s * axn[0]), (float) (s * axn[1]), (float) (s * axn[2])};
+    rot = qdiv(rot, qnorm_boost(rot));
+    store_dq(dq_from_rot_trans(rot, t), out);
+}
+void orc_dq_add(const float a[8], const float b[8], float out[8]) { /* :99-101 */
+    DQ x = load_dq(a), y = load_dq(b);
+    store_dq(DQ{qadd(x.real, y.real), qadd(x.dual, y.dual)}, out);
+}
+void orc_dq_sub(const float a[8], const float b[8], float out[8]) { /* :109-111 */
+    DQ x = load_dq(a), y = load_dq(b);
+    store_dq(DQ{qsub(x.real, y.real), qsub(x.dual, y.dual)}, out);
+}
+void orc_dq_scale(const float a[8], float s, float out[8]) { /* :120-125 : dual only */
+    DQ x = load_dq(a);
+    store_dq(DQ{x.real, qscale(x.dual, s)}, out);
+}
+void orc_dq_mul(const float a[8], const float b[8], float out[8]) { store_dq(dq_mul(load_dq(a), load_dq(b)), out); }
+void orc_dq_conj(const float a[8], float out[8]) { /* :137 */
+    DQ x = load_dq(a);
+    store_dq(DQ{qconj(x.real), qconj(x.dual)}, out);
+}
+int orc_dq_normalize(const float a[8], float out[8]) {
+    DQ x = load_dq(a);
+    bool ok = dq_normalize(x);
+    store_dq(x, out);
+    return ok ? 0 : 1;
+}
+void orc_dq_get_translation(const float a[8], float t[3]) { /* :94-97 */
+    DQ x = load_dq(a);
+    Quat q = qmul(qscale(x.dual, 2.0f), qconj(x.real));
+    t[0] = q.x; t[1] = q.y; t[2] = q.z;
+}
+float orc_dq_get_roll(const float a[8]) { /* :148-161 */
+    DQ d = load_dq(a);
+    float sinr = (float) (+2.0 * (d.real.w * d.real.x + d.real.y * d.real.z));
+    float cosr = (float) (+1.0 - 2.0 * (d.real.x * d.real.x + d.real.y * d.real.y));
+    float roll = atan2f(sinr, cosr);
+    if (roll > M_PI) roll -= (float) M_PI_2;
+    return roll;
+}
+float orc_dq_get_pitch(const float a[8]) { /* :163-177 */
+    DQ d = load_dq(a);
+    float sinp = (float) (+2.0 * (d.real.w * d.real.y - d.real.z * d.real.x));
+    if (std::fabs(sinp) >= 1) return (float) std::copysign(M_PI / 2, (double) sinp);
+    return asinf(sinp);
+}
+float orc_dq_get_yaw(const float a[8]) { /* :179-192 */
+    DQ d = load_dq(a);
+    float siny = (float) (+2.0 * (d.real.w * d.real.z + d.real.x * d.real.y));
+    float cosy = (float) (+1.0 - 2.0 * (d.real.y * d.real.y + d.real.z * d.real.z));
+    float yaw = atan2f(siny, cosy);
+    if (yaw > M_PI) yaw -= (float) M_PI_2;
+    return yaw;
+}
+void orc_dq_get_rodrigues(const float a[8], float rod[3]) { /* :196-202 */
+    DQ d = load_dq(a);
+    double nrm = std::sqrt((double) d.real.x * d.real.x + (double) d.real.y * d.real.y + (double) d.real.z * d.real.z);
+    float theta = 2 * acosf(d.real.w);
+    double tn = std::tan(0.5 * theta);
+    float q[3] = {(float) (d.real.x * tn), (float) (d.real.y * tn), (float) (d.real.z * tn)};
+    double inv = 1.0 / nrm;
+    rod[0] = (float) (q[0] * inv); rod[1] = (float) (q[1] * inv); rod[2] = (float) (q[2] * inv);
+}
+void orc_dq_transform_vertex(const float a[8], const float v[3], float out[3]) {
+    V3 r = dq_transform_vertex(load_dq(a), V3{v[0], v[1], v[2]});
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+/* dual_quaternion.hpp:217-228 : the reference applies the vertex formula (translation included) */
+void orc_dq_transform_normal(const float a[8], const float n[3], int normal_mode, float out[3]) {
+    V3 r = normal_mode == ORC_NORMAL_REF ? dq_transform_vertex(load_dq(a), V3{n[0], n[1], n[2]})
+                                         : dq_rotate(load_dq(a), V3{n[0], n[1], n[2]});
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+int orc_dq_to_string(const float a[8], char* buf, int buflen) { /* :230-232 + boost operator<< */
+    return snprintf(buf, (size_t) buflen, "real: (%g,%g,%g,%g)\ndual: (%g,%g,%g,%g)\n", a[0], a[1], a[2], a[3], a[4],
+                    a[5], a[6], a[7]);
+}
+
+float orc_node_weight(const float node_pos[3], float dg_w, const float p[3]) { return node_weight(node_pos, dg_w, p); }
+
+long orc_knn(const float* nodes_xyz, int N, const float* q_xyz, long Q, int k, int32_t* idx_out,
+             float* dist2_out_or_null) {
+    if (k > 16) k = 16;
+    KnnIndex index(nodes_xyz, N);
+    long ties = 0;
+#pragma omp parallel for schedule(static) reduction(+ : ties)
+    for (long i = 0; i < Q; ++i) {
+        int32_t idx[17];
+        float d2[17];
+        int kk = std::min(k + 1, N);
+#ifdef ORC_USE_NANOFLANN
+        kk = std::min(k, N);
+#endif
+        int n = index.query(q_xyz + 3 * i, kk, idx, d2);
+        for (int j = 0; j + 1 < n; ++j)
+            if (d2[j] == d2[j + 1]) {
+                ++ties;
+                break;
+            }
+        for (int j = 0; j < k; ++j) {
+            idx_out[i * k + j] = j < n ? idx[j] : -1;
+            if (dist2_out_or_null) dist2_out_or_null[i * k + j] = j < n ? d2[j] : INFINITY;
+        }
+    }
+    return ties;
+}
+
+void orc_blend(const float* pos, const float* dq, const float* dg_w, int N, const float* p_xyz, long Q,
+               int blend_mode, float* dq_out) {
+    KnnIndex index(pos, N);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < Q; ++i) store_dq(blend_point(index, pos, dq, dg_w, p_xyz + 3 * i, blend_mode), dq_out + 8 * i);
+}
+
+/* src/dynfu/warp_field.cpp:150-171 */
+void orc_warp(const float* pos, const float* dq, const float* dg_w, int N, const float* v, const float* n_or_null,
+              long P, int blend_mode, int normal_mode, float* v_out, float* n_out_or_null) {
+    KnnIndex index(pos, N);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < P; ++i) {
+        DQ b = blend_point(index, pos, dq, dg_w, v + 3 * i, blend_mode);
+        V3 r = dq_transform_vertex(b, V3{v[3 * i], v[3 * i + 1], v[3 * i + 2]});
+        v_out[3 * i] = r.x; v_out[3 * i + 1] = r.y; v_out[3 * i + 2] = r.z;
+        if (n_or_null && n_out_or_null) {
+            V3 nn{n_or_null[3 * i], n_or_null[3 * i + 1], n_or_null[3 * i + 2]};
+            V3 rn = normal_mode == ORC_NORMAL_REF ? dq_transform_vertex(b, nn) : dq_rotate(b, nn);
+            n_out_or_null[3 * i] = rn.x; n_out_or_null[3 * i + 1] = rn.y; n_out_or_null[3 * i + 2] = rn.z;
+        }
+    }
+}
+
+/* src/kfusion/cuda/imgproc.cu:233-245 (called with finv = 1/f, :252) */
+void orc_compute_dists(const uint16_t* depth, size_t depth_pitch_bytes, uint16_t* dists, size_t dists_pitch_bytes,
+                       int rows, int cols, const float intr[4]) {
+    const float finvx = 1.f / intr[0], finvy = 1.f / intr[1], cx = intr[2], cy = intr[3];
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < rows; ++y) {
+        const uint16_t* drow = (const uint16_t*) ((const char*) depth + (size_t) y * depth_pitch_bytes);
+        uint16_t* orow = (uint16_t*) ((char*) dists + (size_t) y * dists_pitch_bytes);
+        for (int x = 0; x < cols; ++x) {
+            float xl = ((float) x - cx) * finvx;
+            float yl = ((float) y - cy) * finvy;
+            float lambda = sqrtf(xl * xl + yl * yl + 1);
+            orow[x] = float2half((float) drow[x] * lambda * 0.001f);
+        }
+    }
+}
+
+uint16_t orc_float2half(float f) { return float2half(f); }
+float orc_half2float(uint16_t h) { return half2float(h); }
+
+/* src/kfusion/cuda/tsdf_volume.cu:11-22 : pack_tsdf(0.f, 0) == 0x00000000 */
+void orc_tsdf_clear(uint32_t* vol, const int dims[3], int z0, int z1) {
+    size_t plane = (size_t) dims[0] * dims[1];
+    std::memset(vol + plane * (size_t) z0, 0, plane * (size_t) (z1 - z0) * sizeof(uint32_t));
+}
+
+/* src/kfusion/tsdf_volume.cpp:57-61 */
+float orc_trunc_dist(float requested, const float voxel[3]) {
+    float max_coeff = std::max(std::max(voxel[0], voxel[1]), voxel[2]);
+    return std::max(requested, 2.1f * max_coeff);
+}
+
+/*
+ * src/kfusion/cuda/tsdf_volume.cu:43-94 (TsdfIntegrator) + include/kfusion/cuda/device.hpp:40-45,59-67,
+ * with the warp of src/dynfu/warp_field.cpp:127-148 + dual_quaternion.hpp:204-215 inserted before vol2cam.
+ *
+ * CANONICAL ARITHMETIC: the reference kernel accumulates vc += zstep and uses __fdividef;
+ * neither is reproducible on a CPU nor invariant under z-slab sharding, and no reference test pins them.
+ * Here vc is computed directly per voxel with a fixed fmaf chain, IEEE division and sqrt.
+ */
+long orc_tsdf_integrate(uint32_t* vol, const int dims[3], const float voxel[3], float trunc, int max_weight,
+                        const float vol2cam[12], const float intr[4], const uint16_t* dists, size_t pitch_bytes,
+                        int rows, int cols, const float* pos, const float* dq, const float* dg_w, int N,
+                        int blend_mode, int z0, int z1, float* f32_out) {
+    std::unique_ptr<KnnIndex> index;
+    if (pos && N > 0) index.reset(new KnnIndex(pos, N));
+    const float* R = vol2cam;          /* row-major 3x3 */
+    const float* T = vol2cam + 9;      /* translation   */
+    const float fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
+    const float trunc_inv = 1.f / trunc; /* tsdf_volume.cu:106 */
+    const size_t plane = (size_t) dims[0] * dims[1];
+    long touched = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : touched)
+    for (int z = z0; z < z1; ++z)
+        for (int y = 0; y < dims[1]; ++y)
+            for (int x = 0; x < dims[0]; ++x) {
+                float p[3] = {(float) x * voxel[0], (float) y * voxel[1], (float) z * voxel[2]};
+                if (index) {
+                    DQ b = blend_point(*index, pos, dq, dg_w, p, blend_mode);
+                    V3 w = dq_transform_vertex(b, V3{p[0], p[1], p[2]});
+                    p[0] = w.x; p[1] = w.y; p[2] = w.z;
+                }
+                float vcx = fmaf(R[2], p[2], fmaf(R[1], p[1], fmaf(R[0], p[0], T[0])));
+                float vcy = fmaf(R[5], p[2], fmaf(R[4], p[1], fmaf(R[3], p[0], T[1])));
+                float vcz = fmaf(R[8], p[2], fmaf(R[7], p[1], fmaf(R[6], p[0], T[2])));
+                if (!(vcz > 0.f)) continue; /* tsdf_volume.cu:74 (vc.z <= 0) */
+                float u = fmaf(fx, vcx / vcz, cx); /* device.hpp:40-45 */
+                float v = fmaf(fy, vcy / vcz, cy);
+                if (!(u >= 0.f && v >= 0.f && u < (float) cols && v < (float) rows)) continue; /* :70 */
+                int ui = (int) u, vi = (int) v; /* point-filtered tex2D: texel floor(coo) */
+                uint16_t hd = *(const uint16_t*) ((const char*) dists + (size_t) vi * pitch_bytes + (size_t) ui * 2);
+                float Dp = half2float(hd);
+                if (Dp == 0.f) continue; /* :74 */
+                float sdf = Dp - sqrtf(fmaf(vcz, vcz, fmaf(vcy, vcy, vcx * vcx))); /* :77 */
+                if (sdf >= -trunc) {                                               /* :79 */
+                    float tsdf = fminf(1.f, sdf * trunc_inv);                      /* :80 */
+                    size_t vi_lin = (size_t) x + (size_t) y * dims[0] + plane * (size_t) z;
+                    uint32_t packed = vol[vi_lin];
+                    float tsdf_prev = half2float((uint16_t) (packed & 0xffffu)); /* ushort2.x = half bits */
+                    int weight_prev = (int) (packed >> 16);                      /* ushort2.y = weight    */
+                    float tsdf_new = fmaf(tsdf_prev, (float) weight_prev, tsdf) / (float) (weight_prev + 1); /* :86 */
+                    int weight_new = std::min(weight_prev + 1, max_weight);                                 /* :87 */
+                    vol[vi_lin] = (uint32_t) float2half(tsdf_new) | ((uint32_t) weight_new << 16);
+                    if (f32_out) {
+                        f32_out[2 * vi_lin] = tsdf_new;
+                        f32_out[2 * vi_lin + 1] = (float) weight_new;
+                    }
+                    ++touched;
+                }
+            }
+    return touched;
+}
+
+float orc_tukey(float tukey_offset, float c, const float err[3]) { return tukey(tukey_offset, c, err); }
+/* opt_solver.cpp:233-239 */
+float orc_huber(float k, float e) {
+    if (std::fabs(e) <= k) return 1.f;
+    return k / std::fabs(e);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Solver: energy.t restated as a sparse linear least-squares problem, double precision        */
+
+namespace {
+struct Problem {
+    int N;
+    long P;
+    std::vector<int32_t> nbr;   /* P*8  data graph, opt_solver.cpp:56-72  */
+    std::vector<double> w;      /* P*8  w(canon[v], n_k), energy.t:15-17,49-52 */
+    std::vector<int32_t> nnbr;  /* N*8  reg graph,  opt_solver.cpp:74-105 */
+    std::vector<double> d;      /* P*3  live - canon */
+    std::vector<double> theta;  /* P    tukey */
+    double wreg2;               /* w_reg^2 = lambda/(N*8), opt_solver.cpp:30 */
+    /* transposed data graph (node -> (point,k)) for a race-free, deterministic J^T product */
+    std::vector<long> tptr;
+    std::vector<long> tent;
+    /* transposed reg graph (node m -> nodes n that list m) */
+    std::vector<long> rptr;
+    std::vector<int32_t> rent;
+    const orc_solver_params* prm;
+};
+
+void build_problem(Problem& pb, const float* pos, const float* dg_w, int N, const float* canon, const float* live,
+                   long P, const orc_solver_params* prm) {
+    pb.N = N;
+    pb.P = P;
+    pb.prm = prm;
+    pb.nbr.assign((size_t) P * KNN, 0);
+    pb.w.assign((size_t) P * KNN, 0.0);
+    pb.nnbr.assign((size_t) N * KNN, 0);
+    pb.d.assign((size_t) P * 3, 0.0);
+    pb.theta.assign((size_t) P, 1.0);
+    pb.wreg2 = (double) prm->lambda / ((double) N * KNN);
+    KnnIndex index(pos, N);
+#pragma omp parallel for schedule(static)
+    for (long v = 0; v < P; ++v) {
+        int32_t nb[KNN];
+        int n = index.query(canon + 3 * v, KNN, nb, nullptr);
+        for (int k = 0; k < KNN; ++k) {
+            int j = k < n ? nb[k] : nb[0];
+            pb.nbr[v * KNN + k] = j;
+            pb.w[v * KNN + k] = k < n ? (double) node_weight(pos + 3 * (size_t) j, dg_w[j], canon + 3 * v) : 0.0;
+        }
+        for (int c = 0; c < 3; ++c) pb.d[v * 3 + c] = (double) live[v * 3 + c] - (double) canon[v * 3 + c];
+    }
+#pragma omp parallel for schedule(static)
+    for (int a = 0; a < N; ++a) {
+        int32_t nb[KNN];
+        int n = index.query(pos + 3 * (size_t) a, KNN, nb, nullptr);
+        for (int k = 0; k < KNN; ++k) pb.nnbr[(size_t) a * KNN + k] = k < n ? nb[k] : a;
+    }
+    /* transposes by counting sort */
+    pb.tptr.assign((size_t) N + 1, 0);
+    for (long e = 0; e < P * KNN; ++e) pb.tptr[pb.nbr[e] + 1]++;
+    for (int a = 0; a < N; ++a) pb.tptr[a + 1] += pb.tptr[a];
+    pb.tent.assign((size_t) P * KNN, 0);
+    {
+        std::vector<long> cur(pb.tptr.begin(), pb.tptr.end() - 1);
+        for (long e = 0; e < P * KNN; ++e) pb.tent[cur[pb.nbr[e]]++] = e;
+    }
+    pb.rptr.assign((size_t) N + 1, 0);
+    for (long e = 0; e < (long) N * KNN; ++e) pb.rptr[pb.nnbr[e] + 1]++;
+    for (int a = 0; a < N; ++a) pb.rptr[a + 1] += pb.rptr[a];
+    pb.rent.assign((size_t) N * KNN, 0);
+    {
+        std::vector<long> cur(pb.rptr.begin(), pb.rptr.end() - 1);
+        for (long e = 0; e < (long) N * KNN; ++e) pb.rent[cur[pb.nnbr[e]]++] = (int32_t) (e / KNN);
+    }
+}
+
+/* residual of energy.t:47-55 without the sqrt(tukey) factor: e_v = live - canon - sum_k w_k t[n_k] */
+inline void point_residual(const Problem& pb, const double* t, long v, double e[3]) {
+    double s[3] = {0, 0, 0};
+    for (int k = 0; k < KNN; ++k) {
+        const double wk = pb.w[v * KNN + k];
+        const double* tk = t + 3 * (size_t) pb.nbr[v * KNN + k];
+        s[0] += wk * tk[0]; s[1] += wk * tk[1]; s[2] += wk * tk[2];
+    }
+    for (int c = 0; c < 3; ++c) e[c] = pb.d[v * 3 + c] - s[c];
+}
+
+void update_tukey(Problem& pb, const double* t) {
+#pragma omp parallel for schedule(static)
+    for (long v = 0; v < pb.P; ++v) {
+        double e[3];
+        point_residual(pb, t, v, e);
+        float ef[3] = {(float) e[0], (float) e[1], (float) e[2]};
+        pb.theta[v] = (double) tukey(pb.prm->tukey_offset, pb.prm->psi_data, ef);
+    }
+}
+
+double energy(const Problem& pb, const double* t) {
+    double E = 0;
+#pragma omp parallel for schedule(static) reduction(+ : E)
+    for (long v = 0; v < pb.P; ++v) {
+        double e[3];
+        point_residual(pb, t, v, e);
+        E += pb.theta[v] * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    }
+    double Er = 0;
+    if (pb.wreg2 > 0) {
+#pragma omp parallel for schedule(static) reduction(+ : Er)
+        for (int a = 0; a < pb.N; ++a)
+            for (int k = 0; k < KNN; ++k) { /* energy.t:73-78 : w_reg * (t[v_i] - t[n]) */
+                int m = pb.nnbr[(size_t) a * KNN + k];
+                for (int c = 0; c < 3; ++c) {
+                    double df = t[3 * (size_t) m + c] - t[3 * (size_t) a + c];
+                    Er += pb.wreg2 * df * df;
+                }
+            }
+    }
+    return E + Er;
+}
+
+/* y = (W^T Theta W + wreg2 * L) x, x and y are N*3 */
+void apply_A(const Problem& pb, const double* x, double* y, std::vector<double>& s) {
+    s.resize((size_t) pb.P * 3);
+#pragma omp parallel for schedule(static)
+    for (long v = 0; v < pb.P; ++v) {
+        double a[3] = {0, 0, 0};
+        for (int k = 0; k < KNN; ++k) {
+            const double wk = pb.w[v * KNN + k];
+            const double* xk = x + 3 * (size_t) pb.nbr[v * KNN + k];
+            a[0] += wk * xk[0]; a[1] += wk * xk[1]; a[2] += wk * xk[2];
+        }
+        for (int c = 0; c < 3; ++c) s[v * 3 + c] = pb.theta[v] * a[c];
+    }
+#pragma omp parallel for schedule(static)
+    for (int a = 0; a < pb.N; ++a) {
+        double acc[3] = {0, 0, 0};
+        for (long q = pb.tptr[a]; q < pb.tptr[a + 1]; ++q) {
+            long e = pb.tent[q];
+            long v = e / KNN;
+            for (int c = 0; c < 3; ++c) acc[c] += pb.w[e] * s[v * 3 + c];
+        }
+        if (pb.wreg2 > 0) {
+            for (int k = 0; k < KNN; ++k) { /* edges (a -> m): d/dt_a of (t_m - t_a)^2 */
+                int m = pb.nnbr[(size_t) a * KNN + k];
+                for (int c = 0; c < 3; ++c) acc[c] += pb.wreg2 * (x[3 * (size_t) a + c] - x[3 * (size_t) m + c]);
+            }
+            for (long q = pb.rptr[a]; q < pb.rptr[a + 1]; ++q) { /* edges (n -> a) */
+                int n = pb.rent[q];
+                for (int c = 0; c < 3; ++c) acc[c] += pb.wreg2 * (x[3 * (size_t) a + c] - x[3 * (size_t) n + c]);
+            }
+        }
+        for (int c = 0; c < 3; ++c) y[3 * (size_t) a + c] = acc[c];
+    }
+}
+
+void diag_A(const Problem& pb, double* dg) {
+#pragma omp parallel for schedule(static)
+    for (int a = 0; a < pb.N; ++a) {
+        double acc = 0;
+        for (long q = pb.tptr[a]; q < pb.tptr[a + 1]; ++q) {
+            long e = pb.tent[q];
+            acc += pb.theta[e / KNN] * pb.w[e] * pb.w[e];
+        }
+        if (pb.wreg2 > 0) {
+            for (int k = 0; k < KNN; ++k)
+                if (pb.nnbr[(size_t) a * KNN + k] != a) acc += pb.wreg2;
+            for (long q = pb.rptr[a]; q < pb.rptr[a + 1]; ++q)
+                if (pb.rent[q] != a) acc += pb.wreg2;
+        }
+        dg[a] = acc;
+    }
+}
+
+double dot3(const double* a, const double* b, size_t n) {
+    double s = 0;
+    for (size_t i = 0; i < n; ++i) s += a[i] * b[i];
+    return s;
+}
+} /* namespace */
+
+int orc_solve(const float* pos, float* dq_inout, const float* dg_w, int N, const float* canon, const float* live,
+              long P, const orc_solver_params* prm, double* t_out, double* stats_out) {
+    if (N < KNN) return 1; /* precondition (reference UB at opt_solver.cpp:63-66) */
+    Problem pb;
+    build_problem(pb, pos, dg_w, N, canon, live, P, prm);
+    const size_t n3 = (size_t) N * 3;
+    std::vector<double> t(n3, 0.0) /* opt_solver.cpp:192-193 */, b(n3), r(n3), z(n3), p(n3), q(n3), dg((size_t) N), s, dl(n3);
+    update_tukey(pb, t.data());
+    double E0 = energy(pb, t.data());
+    double E = E0;
+    long pcg_total = 0, gn_total = 0;
+    double rz_ref = -1.0; /* scale of the first GN step's preconditioned residual: the stop reference */
+    for (int outer = 0; outer < prm->num_iter; ++outer) {
+        update_tukey(pb, t.data()); /* preNonlinearSolve, opt_solver.cpp:135-140 */
+        double E_outer = energy(pb, t.data());
+        for (int gn = 0; gn < prm->nonlinear_iter; ++gn) {
+            /* rhs = -J^T r = W^T Theta e(t) - reg * t  (A t includes both) */
+            apply_A(pb, t.data(), q.data(), s);
+            /* b0 = W^T Theta d */
+#pragma omp parallel for schedule(static)
+            for (int a = 0; a < N; ++a) {
+                double acc[3] = {0, 0, 0};
+                for (long qq = pb.tptr[a]; qq < pb.tptr[a + 1]; ++qq) {
+                    long e = pb.tent[qq];
+                    long v = e / KNN;
+                    for (int c = 0; c < 3; ++c) acc[c] += pb.w[e] * pb.theta[v] * pb.d[v * 3 + c];
+                }
+                for (int c = 0; c < 3; ++c) b[3 * (size_t) a + c] = acc[c] - q[3 * (size_t) a + c];
+            }
+            diag_A(pb, dg.data());
+            std::fill(dl.begin(), dl.end(), 0.0);
+            r = b;
+            for (int a = 0; a < N; ++a)
+                for (int c = 0; c < 3; ++c) z[3 * (size_t) a + c] = dg[a] > 0 ? r[3 * (size_t) a + c] / dg[a] : 0.0;
+            p = z;
+            double rz = dot3(r.data(), z.data(), n3);
+            if (rz_ref < 0) rz_ref = rz;
+            const double rz_stop = prm->pcg_tol * prm->pcg_tol * rz_ref;
+            for (int it = 0; it < prm->linear_iter && rz > 0; ++it) {
+                if (rz <= rz_stop) break; /* converged relative to the problem's initial scale */
+                apply_A(pb, p.data(), q.data(), s);
+                double pq = dot3(p.data(), q.data(), n3);
+                if (!(pq > 0)) break;
+                double alpha = rz / pq;
+                for (size_t i = 0; i < n3; ++i) {
+                    dl[i] += alpha * p[i];
+                    r[i] -= alpha * q[i];
+                }
+                for (int a = 0; a < N; ++a)
+                    for (int c = 0; c < 3; ++c) z[3 * (size_t) a + c] = dg[a] > 0 ? r[3 * (size_t) a + c] / dg[a] : 0.0;
+                double rz_new = dot3(r.data(), z.data(), n3);
+                double beta = rz_new / rz;
+                rz = rz_new;
+                for (size_t i = 0; i < n3; ++i) p[i] = z[i] + beta * p[i];
+                ++pcg_total;
+            }
+            for (size_t i = 0; i < n3; ++i) t[i] += dl[i];
+            ++gn_total;
+            double E_new = energy(pb, t.data());
+            bool conv = std::fabs(E - E_new) <= 1e-12 * std::max(E_new, 1e-300);
+            E = E_new;
+            if (prm->early_out && conv) break;
+        }
+        if (prm->early_out && std::fabs(E_outer - E) <= 1e-12 * std::max(E, 1e-300) && outer > 0) break;
+    }
+    for (size_t i = 0; i < n3; ++i) t_out[i] = t[i];
+    /* write back ONCE: opt_solver.cpp:270-285 + node.cpp:19-23 : dg_se3 := DQ(0,0,0,t) * dg_se3 */
+    for (int a = 0; a < N; ++a) {
+        DQ inc = dq_from_euler(0.f, 0.f, 0.f, (float) t[3 * (size_t) a], (float) t[3 * (size_t) a + 1],
+                               (float) t[3 * (size_t) a + 2]);
+        store_dq(dq_mul(inc, load_dq(dq_inout + 8 * (size_t) a)), dq_inout + 8 * (size_t) a);
+    }
+    if (stats_out) {
+        stats_out[0] = E0; stats_out[1] = E; stats_out[2] = (double) pcg_total; stats_out[3] = (double) gn_total;
+    }
+    return 0;
+}
+
+double orc_energy(const float* pos, const float* dg_w, int N, const float* canon, const float* live, long P,
+                  const orc_solver_params* prm, const double* t, const double* t_tukey) {
+    Problem pb;
+    build_problem(pb, pos, dg_w, N, canon, live, P, prm);
+    update_tukey(pb, t_tukey);
+    return energy(pb, t);
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+} /* extern "C" */

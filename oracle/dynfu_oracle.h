@@ -1,0 +1,127 @@
+/*
+ * dynfu_oracle.h -- C interface of the CPU ORACLE for the dynfu hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library.  The product
+ * (libdynfu_b200.so) never links, loads or calls anything in oracle/.
+ *
+ * Every function restates, on the CPU and with no third-party dependency, the arithmetic of
+ * a function of the reference swarth100/dynfu; the reference file:line each one follows is
+ * given next to its definition in dynfu_oracle.cpp.
+ *
+ * Parity status:
+ *   - dual-quaternion algebra : PINNED by the 23 golden cases of test/quaternion_test.cpp
+ *   - kNN                     : PINNED against the reference's vendored nanoflann
+ *                               (oracle/_ref/libdynfu_oracle_nf.so, compiled from the reference header)
+ *   - blend / warp            : PINNED through the DQ goldens + the OptTest post-conditions
+ *   - TSDF integrate          : parity UNPINNED -- the reference has no CPU integrator and no test
+ *                               of it; this is a restatement of its CUDA kernel in a defined
+ *                               IEEE arithmetic (see DESIGN.md "canonical arithmetic")
+ *   - solver                  : parity UNPINNED at the Opt boundary (Opt/Terra are not in the tree,
+ *                               Ceres is never linked); pinned only by the 8 OptTest post-conditions
+ */
+#ifndef DYNFU_ORACLE_H
+#define DYNFU_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* quaternions are (w,x,y,z); a dual quaternion is 8 floats: real wxyz then dual wxyz */
+
+enum { ORC_BLEND_REF_COMPOSE = 0, ORC_BLEND_DQB_SUM = 1 };
+enum { ORC_NORMAL_REF = 0, ORC_NORMAL_ROTATE_ONLY = 1 };
+
+/* ---- dual quaternion algebra (include/dynfu/utils/dual_quaternion.hpp) ---- */
+void orc_dq_from_rot_trans(const float rot[4], const float t[3], float out[8]);
+void orc_dq_from_euler(float yaw, float pitch, float roll, float x, float y, float z, float out[8]);
+void orc_dq_from_rodrigues(const float rod[3], const float t[3], float out[8]);
+void orc_dq_add(const float a[8], const float b[8], float out[8]);
+void orc_dq_sub(const float a[8], const float b[8], float out[8]);
+void orc_dq_scale(const float a[8], float s, float out[8]);
+void orc_dq_mul(const float a[8], const float b[8], float out[8]);
+void orc_dq_conj(const float a[8], float out[8]);
+int  orc_dq_normalize(const float a[8], float out[8]); /* returns 0 ok, 1 if |real| <= FLT_EPS */
+void orc_dq_get_translation(const float a[8], float t[3]);
+float orc_dq_get_roll(const float a[8]);
+float orc_dq_get_pitch(const float a[8]);
+float orc_dq_get_yaw(const float a[8]);
+void orc_dq_get_rodrigues(const float a[8], float rod[3]);
+void orc_dq_transform_vertex(const float a[8], const float v[3], float out[3]);
+void orc_dq_transform_normal(const float a[8], const float n[3], int normal_mode, float out[3]);
+/* writes "real: (w,x,y,z)\ndual: (w,x,y,z)\n" (operator<<); returns length */
+int  orc_dq_to_string(const float a[8], char* buf, int buflen);
+
+/* ---- node weight (src/dynfu/utils/node.cpp:29-36) ---- */
+float orc_node_weight(const float node_pos[3], float dg_w, const float p[3]);
+
+/* ---- kNN (src/dynfu/warp_field.cpp:111-122 + nanoflann metric) ----
+ * brute force, key (dist2, idx) lexicographic, ascending.  k <= 16.  Returns the number of
+ * queries whose (k+1) smallest distances contain a bit-equal pair (ties): must be 0 for the
+ * result to be comparable with nanoflann's visitation-order tie break. */
+long orc_knn(const float* nodes_xyz, int N, const float* q_xyz, long Q, int k,
+             int32_t* idx_out, float* dist2_out_or_null);
+
+/* ---- blend / warp (src/dynfu/warp_field.cpp:127-171) ---- */
+/* nodes: pos_xyz[N*3], dq[N*8], dg_w[N].  k is fixed at 8 (KNN, warp_field.hpp:27). */
+void orc_blend(const float* pos, const float* dq, const float* dg_w, int N,
+               const float* p_xyz, long Q, int blend_mode, float* dq_out);
+void orc_warp(const float* pos, const float* dq, const float* dg_w, int N,
+              const float* v, const float* n_or_null, long P, int blend_mode, int normal_mode,
+              float* v_out, float* n_out_or_null);
+
+/* ---- depth -> ray length (src/kfusion/cuda/imgproc.cu:233-245) ---- */
+void orc_compute_dists(const uint16_t* depth, size_t depth_pitch_bytes, uint16_t* dists,
+                       size_t dists_pitch_bytes, int rows, int cols, const float intr[4]);
+
+/* ---- half helpers (include/kfusion/cuda/device.hpp:59-67) ---- */
+uint16_t orc_float2half(float f);
+float    orc_half2float(uint16_t h);
+
+/* ---- TSDF (src/kfusion/cuda/tsdf_volume.cu:11-22, 43-94) ---- */
+void orc_tsdf_clear(uint32_t* vol, const int dims[3], int z0, int z1);
+/* nodes may be NULL (N=0) -> rigid.  Processes planes [z0,z1).  If f32_out (dims voxels of
+ * float2 {tsdf, weight}) is non-NULL the pre-rounding float result of touched voxels is also
+ * written there (untouched voxels are left as they were).  Returns #touched voxels. */
+long orc_tsdf_integrate(uint32_t* vol, const int dims[3], const float voxel[3], float trunc,
+                        int max_weight, const float vol2cam[12], const float intr[4],
+                        const uint16_t* dists, size_t pitch_bytes, int rows, int cols,
+                        const float* pos, const float* dq, const float* dg_w, int N,
+                        int blend_mode, int z0, int z1, float* f32_out_or_null);
+float orc_trunc_dist(float requested, const float voxel[3]); /* tsdf_volume.cpp:57-61 */
+
+/* ---- robust weights (src/dynfu/utils/opt_solver.cpp:204-212, 233-239) ---- */
+float orc_tukey(float tukey_offset, float c, const float err[3]);
+float orc_huber(float k, float e);
+
+/* ---- solver (opt_solver.cpp + energy.t; contract in DESIGN.md) ---- */
+typedef struct {
+    int   num_iter;        /* outer iterations (Tukey re-weighting)          */
+    int   nonlinear_iter;  /* GN steps per outer iteration                   */
+    int   linear_iter;     /* PCG steps per GN step                          */
+    float tukey_offset, psi_data, lambda, psi_reg;
+    double pcg_tol;        /* PCG stops when r.z <= tol^2 * (r.z of the first GN step); 0 = never */
+    int   early_out;       /* stop outer loop when relative energy change < 1e-12 */
+} orc_solver_params;
+
+/* Solves energy.t (translation-only point-to-point, un-normalised Gaussian weights) in double.
+ * t_out[N*3]: optimal translations (NOT yet composed onto the node DQs);
+ * dq_inout[N*8]: node DQs, updated ONCE as DQ(0,0,0,t) * dq (node.cpp:19-23).
+ * stats_out[4] = {initial energy, final energy, total PCG iterations, total GN steps}. */
+int orc_solve(const float* pos, float* dq_inout, const float* dg_w, int N,
+              const float* canon, const float* live, long P,
+              const orc_solver_params* prm, double* t_out, double* stats_out);
+/* energy of energy.t at translations t (double) with Tukey weights computed at t_tukey */
+double orc_energy(const float* pos, const float* dg_w, int N, const float* canon,
+                  const float* live, long P, const orc_solver_params* prm,
+                  const double* t, const double* t_tukey);
+
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
