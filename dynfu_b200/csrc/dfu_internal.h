@@ -1,0 +1,70 @@
+// Internal declarations shared by the translation units of libdynfu_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/dynfu_b200.h"
+
+// ---- error plumbing: status codes out, message kept per thread (no exceptions, no exit()) ----------
+void dfu_set_error(const char* fmt, ...);
+#define DFU_CUDA_OK(expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            dfu_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));  \
+            return DFU_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+#define DFU_REQUIRE(cond, code, msg)                               \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            dfu_set_error("%s: %s", __func__, msg);                \
+            return code;                                           \
+        }                                                          \
+    } while (0)
+#define DFU_LAUNCH_OK() DFU_CUDA_OK(cudaGetLastError())
+
+static inline cudaStream_t as_stream(dfu_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int div_up(long a, long b) { return (int) ((a + b - 1) / b); }
+
+// ---- the warp field handle ---------------------------------------------------------------------------
+// Node state in HBM (DESIGN.md "data layout"): three float4 arrays padded to a multiple of 32 entries.
+//   pos_w[i] = (dg_v.x, dg_v.y, dg_v.z, dg_w)   padding: (+inf,+inf,+inf,1)  -> never a neighbour
+//   real[i], dual[i]                             dg_se3 as two quaternions (w,x,y,z)
+struct BrickTable {            // per-volume-geometry acceleration data for the warped integrator
+    float2* bounds = nullptr;  // per 8x8x8 brick: (squared dist of brick centre to its 8th, and to its 1st node)
+    size_t capacity = 0;       // bricks allocated
+    int dims[3] = {0, 0, 0};
+    float voxel[3] = {0, 0, 0};
+    uint64_t node_epoch = 0;   // positions epoch the table was built for
+    bool valid = false;
+};
+
+struct dfu_warpfield {
+    int device = 0;
+    int N = 0;            // nodes
+    int Npad = 0;         // padded to 32
+    int capacity = 0;     // allocated entries
+    float epsilon = 0.f;
+    float4* pos_w = nullptr;
+    float4* real = nullptr;
+    float4* dual = nullptr;
+    // device flags/scalars: [0] = 1 if every node has real == (1,0,0,0) and dual.w == 0 (translation-only field),
+    //                       [1] = max dg_w as float bits
+    int* flags = nullptr;
+    float* staging = nullptr;  // device staging for *_host uploads (N*12 floats)
+    size_t staging_cap = 0;
+    uint64_t node_epoch = 0;   // bumped when positions change
+    BrickTable bricks;
+    bool initialised = false;
+};
+
+// kernels living in warpfield.cu that tsdf.cu / solver.cu launch
+int dfu_wf_refresh_flags(dfu_warpfield* wf, cudaStream_t st);
+int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float voxel[3], cudaStream_t st);
+int dfu_wf_build_data_graph(const dfu_warpfield* wf, const float* canon, const float* live, int P, int32_t* nbr,
+                            float* wts, float* dvec, cudaStream_t st);
+int dfu_wf_build_node_graph(const dfu_warpfield* wf, int32_t* nnbr, cudaStream_t st);

@@ -1,0 +1,328 @@
+// TSDF volume kernels: compute_dists, clear, rigid and WARPED projective integration.
+//
+// Replaces kfusion::device::{compute_dists, clear_volume, integrate}
+// (src/kfusion/cuda/imgproc.cu:233-254, src/kfusion/cuda/tsdf_volume.cu:11-34, 43-121) and inserts the
+// per-voxel warp Warpfield::calcDQB(p).transformVertex(p) (src/dynfu/warp_field.cpp:127-148,
+// include/dynfu/utils/dual_quaternion.hpp:204-215) in front of vol2cam.
+//
+// Layout in HBM: the reference's own ushort2{half tsdf, u16 weight} volume, x fastest.  One CTA owns a
+// 32x8x8-voxel tile = four 8x8x8 bricks.  Every thread owns quads of 4 x-consecutive voxels, so volume
+// traffic is 128-bit ld/st (streaming, evict-first) and a warp of the rigid pass covers whole 128-byte
+// lines.  A brick is "near" when some voxel of it may have a non-zero node weight; near bricks run the
+// exact per-voxel 8-NN + blend, all other bricks are provably un-warped and take the rigid path.
+#include "blend.cuh"
+#include "dfu_internal.h"
+
+using namespace dfu;
+
+namespace {
+
+struct IntegrateArgs {
+    uint32_t* vol;
+    int dx, dy, dz;
+    float vsx, vsy, vsz;
+    float trunc, trunc_inv;
+    int max_weight;
+    float R[9], T[3];
+    float fx, fy, cx, cy;
+    const uint16_t* dists;
+    size_t pitch;
+    int rows, cols;
+    int z0, z1, zt0;  // planes [z0,z1); zt0 = first tile plane (multiple of 8)
+    int ntx, nty;
+    // warp field (warped != 0)
+    int warped, blend_mode;
+    const float4 *pos_w, *real, *dual;
+    int N;
+    const int* flags;
+    const float2* bounds;
+    int bdx, bdy;
+};
+
+DFU_DEV uint4 ld_stream(const uint4* p) { return __ldcs(p); }
+DFU_DEV void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
+
+// TsdfIntegrator::operator() body for one voxel whose (warped) volume-frame position is (px,py,pz)
+// (src/kfusion/cuda/tsdf_volume.cu:66-80, Projector include/kfusion/cuda/device.hpp:40-45) in the canonical
+// arithmetic of DESIGN.md: direct fmaf chain for vc, IEEE division and sqrt.  Returns true and the
+// truncated sdf when the voxel is to be updated.
+DFU_DEV bool voxel_tsdf(const IntegrateArgs& a, float px, float py, float pz, float& tsdf) {
+    const float vcx = __fmaf_rn(a.R[2], pz, __fmaf_rn(a.R[1], py, __fmaf_rn(a.R[0], px, a.T[0])));
+    const float vcy = __fmaf_rn(a.R[5], pz, __fmaf_rn(a.R[4], py, __fmaf_rn(a.R[3], px, a.T[1])));
+    const float vcz = __fmaf_rn(a.R[8], pz, __fmaf_rn(a.R[7], py, __fmaf_rn(a.R[6], px, a.T[2])));
+    if (!(vcz > 0.f)) return false;  // tsdf_volume.cu:74 (vc.z <= 0)
+    const float u = __fmaf_rn(a.fx, __fdiv_rn(vcx, vcz), a.cx);
+    const float v = __fmaf_rn(a.fy, __fdiv_rn(vcy, vcz), a.cy);
+    if (!(u >= 0.f && v >= 0.f && u < (float) a.cols && v < (float) a.rows)) return false;  // :70
+    const int ui = (int) u, vi = (int) v;  // point-filtered tex2D: texel floor(coo)
+    const unsigned short hd =
+        __ldg(reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(a.dists) + (size_t) vi * a.pitch) + ui);
+    const float Dp = __half2float(__ushort_as_half(hd));
+    if (Dp == 0.f) return false;  // :74
+    const float sdf = fsub(Dp, __fsqrt_rn(__fmaf_rn(vcz, vcz, __fmaf_rn(vcy, vcy, fmul(vcx, vcx)))));  // :77
+    if (!(sdf >= -a.trunc)) return false;                                                           // :79
+    tsdf = fminf(1.f, fmul(sdf, a.trunc_inv));                                                      // :80
+    return true;
+}
+
+// running average (tsdf_volume.cu:83-90)
+DFU_DEV uint32_t voxel_update(const IntegrateArgs& a, uint32_t packed, float tsdf) {
+    int weight_prev;
+    const float tsdf_prev = unpack_tsdf(packed, weight_prev);
+    const float tsdf_new = __fdiv_rn(__fmaf_rn(tsdf_prev, (float) weight_prev, tsdf), (float) (weight_prev + 1));
+    const int weight_new = min(weight_prev + 1, a.max_weight);
+    return pack_tsdf(tsdf_new, weight_new);
+}
+
+DFU_DEV void quad_commit(const IntegrateArgs& a, size_t lin, const bool (&hit)[4], const float (&ts)[4]) {
+    if (!(hit[0] | hit[1] | hit[2] | hit[3])) return;  // untouched quads cost no volume traffic
+    uint4* p = reinterpret_cast<uint4*>(a.vol + lin);
+    uint4 v = ld_stream(p);
+    if (hit[0]) v.x = voxel_update(a, v.x, ts[0]);
+    if (hit[1]) v.y = voxel_update(a, v.y, ts[1]);
+    if (hit[2]) v.z = voxel_update(a, v.z, ts[2]);
+    if (hit[3]) v.w = voxel_update(a, v.w, ts[3]);
+    st_stream(p, v);
+}
+
+constexpr int CHUNK = 1024;          // nodes examined per candidate-compaction round
+constexpr int SEG = CHUNK / 4;       // per-warp segment of the candidate buffer (4 warps)
+
+struct IntegrateSmem {
+    float4 cand[CHUNK];  // (x, y, z, index bits) of the candidate nodes of the current chunk
+    int cnt[4];
+};
+
+__global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ IntegrateArgs a) {
+    __shared__ IntegrateSmem sm;
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int tile_x = bid % a.ntx;
+    bid /= a.ntx;
+    const int tile_y = bid % a.nty;
+    const int tile_z = bid / a.nty;
+    const int x0 = tile_x * 32, y0 = tile_y * 8, zt = a.zt0 + tile_z * 8;
+    const size_t plane = (size_t) a.dx * a.dy;
+
+    // ---- classify the four bricks of this tile ------------------------------------------------------
+    int near_mask = 0;
+    bool translation_only = false;
+    const float r_brick = 3.5f * sqrtf(a.vsx * a.vsx + a.vsy * a.vsy + a.vsz * a.vsz);  // brick half diagonal
+    const size_t brick0 = a.warped ? (size_t) (x0 / 8) + (size_t) a.bdx * ((y0 / 8) + (size_t) a.bdy * (zt / 8)) : 0;
+    if (a.warped) {
+        translation_only = a.flags[0] != 0;
+        const float maxw = __int_as_float(a.flags[1]);
+        // a weight is exactly 0 beyond sqrt(209)*dg_w (dfu_math.cuh node_weight); 1.001 covers rounding
+        const float r_active = 14.4569f * maxw * 1.001f + 1e-6f;
+        const bool all_near = (a.blend_mode == DFU_BLEND_REF_COMPOSE) && !translation_only;
+#pragma unroll
+        for (int sb = 0; sb < 4; ++sb) {
+            const float2 b = __ldg(&a.bounds[brick0 + sb]);
+            if (all_near || (sqrtf(b.y) - r_brick <= r_active)) near_mask |= 1 << sb;
+        }
+    }
+
+    // ---- rigid pass: every quad of a brick that is not near ------------------------------------------
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const int lin = it * 128 + tid;
+        const int qx = lin & 7, yy = (lin >> 3) & 7, zz = lin >> 6;
+        const int z = zt + zz;
+        if ((near_mask >> (qx >> 1)) & 1) continue;
+        if (z < a.z0 || z >= a.z1) continue;
+        const int x = x0 + qx * 4, y = y0 + yy;
+        const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
+        bool hit[4];
+        float ts[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) hit[v] = voxel_tsdf(a, fmul((float) (x + v), a.vsx), py, pz, ts[v]);
+        quad_commit(a, (size_t) x + (size_t) y * a.dx + plane * (size_t) z, hit, ts);
+    }
+    if (near_mask == 0) return;
+
+    // ---- near pass: exact per-voxel 8-NN over a culled candidate list, blend, integrate -----------------
+    const int warp = tid >> 5, lane = tid & 31;
+    const int qx2 = tid & 1, yy = (tid >> 1) & 7, zz = tid >> 4;
+#pragma unroll 1
+    for (int sb = 0; sb < 4; ++sb) {
+        if (!((near_mask >> sb) & 1)) continue;  // uniform over the CTA
+        // any node among the 8 nearest of ANY voxel of the brick lies within d8(centre) + 2r of the centre
+        float thr2;
+        {
+            const float th = (sqrtf(__ldg(&a.bounds[brick0 + sb]).x) + 2.f * r_brick) * 1.0001f + 1e-6f;
+            thr2 = th * th;
+        }
+        const int z = zt + zz;
+        const int x = x0 + sb * 8 + qx2 * 4, y = y0 + yy;
+        const float bcx = (x0 + sb * 8 + 3.5f) * a.vsx, bcy = (y0 + 3.5f) * a.vsy, bcz = (zt + 3.5f) * a.vsz;
+        const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
+        float px[4];
+        Top8 t[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            px[v] = fmul((float) (x + v), a.vsx);
+            top8_init(t[v]);
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < a.N; c0 += CHUNK) {
+            // each warp compacts its 256-node slice, in index order, into its own segment
+            int n = 0;
+#pragma unroll 1
+            for (int j = 0; j < SEG; j += 32) {
+                const int idx = c0 + warp * SEG + j + lane;
+                bool keep = false;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < a.N) {
+                    p = __ldg(&a.pos_w[idx]);
+                    const float ddx = p.x - bcx, ddy = p.y - bcy, ddz = p.z - bcz;
+                    keep = (ddx * ddx + ddy * ddy + ddz * ddz) <= thr2;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    p.w = __int_as_float(idx);
+                    sm.cand[warp * SEG + n + __popc(m & ((1u << lane) - 1u))] = p;
+                }
+                n += __popc(m);
+            }
+            if (lane == 0) sm.cnt[warp] = n;
+            __syncthreads();
+#pragma unroll 1
+            for (int sg = 0; sg < 4; ++sg) {
+                const int cn = sm.cnt[sg];
+                const float4* __restrict__ cl = sm.cand + sg * SEG;
+#pragma unroll 1
+                for (int j = 0; j < cn; ++j) {
+                    const float4 p = cl[j];  // warp-wide broadcast
+                    const int idx = __float_as_int(p.w);
+                    const float dy = fsub(py, p.y), dz = fsub(pz, p.z);
+                    const float dy2 = fmul(dy, dy), dz2 = fmul(dz, dz);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float dxv = fsub(px[v], p.x);
+                        const float d = fadd(fadd(fmul(dxv, dxv), dy2), dz2);  // nanoflann metric, bit exact
+                        if (d < t[v].d[DFU_KNN - 1]) top8_insert(t[v], d, idx);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (z < a.z0 || z >= a.z1) continue;
+        bool hit[4];
+        float ts[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            V3 w;
+            if (translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
+                w = warp_translation_only(t[v], px[v], py, pz, a.pos_w, a.dual);
+            } else {
+                const DQ b = blend(a.blend_mode, t[v], px[v], py, pz, a.pos_w, a.real, a.dual);
+                w = dq_transform_vertex(b, V3{px[v], py, pz});
+            }
+            hit[v] = voxel_tsdf(a, w.x, w.y, w.z, ts[v]);
+        }
+        quad_commit(a, (size_t) x + (size_t) y * a.dx + plane * (size_t) z, hit, ts);
+    }
+}
+
+// compute_dists_kernel (src/kfusion/cuda/imgproc.cu:233-245); the reference's guard uses || (:237, a
+// latent out-of-bounds access) -- the bounds check here is the intended &&.
+__global__ void compute_dists_kernel(const uint16_t* __restrict__ depth, size_t dpitch, uint16_t* __restrict__ dists,
+                                     size_t opitch, int rows, int cols, float finvx, float finvy, float cx, float cy) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < cols && y < rows) {
+        const float xl = fmul(fsub((float) x, cx), finvx);
+        const float yl = fmul(fsub((float) y, cy), finvy);
+        const float lambda = __fsqrt_rn(fadd(fadd(fmul(xl, xl), fmul(yl, yl)), 1.f));
+        const uint16_t d = *reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(depth) + (size_t) y * dpitch + 2 * (size_t) x);
+        *reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(dists) + (size_t) y * opitch + 2 * (size_t) x) =
+            __half_as_ushort(__float2half_rn(fmul(fmul((float) d, lambda), 0.001f)));
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int dfu_compute_dists(const uint16_t* depth, size_t depth_pitch_bytes, uint16_t* dists, size_t dists_pitch_bytes,
+                      int rows, int cols, const float intr_host[4], dfu_stream stream) {
+    DFU_REQUIRE(depth && dists && intr_host, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(rows > 0 && cols > 0, DFU_ERR_INVALID, "bad image size");
+    dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8));
+    compute_dists_kernel<<<grid, block, 0, as_stream(stream)>>>(depth, depth_pitch_bytes, dists, dists_pitch_bytes, rows,
+                                                                cols, 1.f / intr_host[0], 1.f / intr_host[1],
+                                                                intr_host[2], intr_host[3]);
+    DFU_LAUNCH_OK();
+    return DFU_OK;
+}
+
+float dfu_tsdf_trunc_dist(float requested, const float vs[3]) {
+    const float m = fmaxf(fmaxf(vs[0], vs[1]), vs[2]);
+    return fmaxf(requested, 2.1f * m);
+}
+
+int dfu_tsdf_clear(void* volume, const int dims[3], int z0, int z1, dfu_stream stream) {
+    DFU_REQUIRE(volume && dims, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(0 <= z0 && z0 <= z1 && z1 <= dims[2], DFU_ERR_INVALID, "bad z range");
+    const size_t plane = (size_t) dims[0] * dims[1];
+    // pack_tsdf(0.f, 0) == 0x00000000 (tsdf_volume.cu:20)
+    DFU_CUDA_OK(cudaMemsetAsync(reinterpret_cast<uint32_t*>(volume) + plane * (size_t) z0, 0,
+                                plane * (size_t) (z1 - z0) * sizeof(uint32_t), as_stream(stream)));
+    return DFU_OK;
+}
+
+int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float trunc_dist, int max_weight,
+                       const float vol2cam[12], const float intr[4], const uint16_t* dists, size_t pitch, int rows,
+                       int cols, dfu_warpfield* wf, int blend_mode, int z0, int z1, dfu_stream stream) {
+    DFU_REQUIRE(volume && dims && vs && vol2cam && intr && dists, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(dims[0] > 0 && dims[0] % 32 == 0, DFU_ERR_INVALID, "dims.x must be a positive multiple of 32");
+    DFU_REQUIRE(dims[1] > 0 && dims[1] % 8 == 0, DFU_ERR_INVALID, "dims.y must be a positive multiple of 8");
+    DFU_REQUIRE(0 <= z0 && z0 <= z1 && z1 <= dims[2], DFU_ERR_INVALID, "bad z range");
+    DFU_REQUIRE(max_weight >= 1 && max_weight <= 65535, DFU_ERR_INVALID, "max_weight out of the u16 range");
+    DFU_REQUIRE(((uintptr_t) volume & 15) == 0, DFU_ERR_INVALID, "volume must be 16-byte aligned");
+    DFU_REQUIRE(blend_mode == DFU_BLEND_REF_COMPOSE || blend_mode == DFU_BLEND_DQB_SUM, DFU_ERR_INVALID, "bad blend_mode");
+    if (z0 == z1) return DFU_OK;
+    cudaStream_t st = as_stream(stream);
+    IntegrateArgs a{};
+    a.vol = reinterpret_cast<uint32_t*>(volume);
+    a.dx = dims[0]; a.dy = dims[1]; a.dz = dims[2];
+    a.vsx = vs[0]; a.vsy = vs[1]; a.vsz = vs[2];
+    a.trunc = trunc_dist;
+    a.trunc_inv = 1.f / trunc_dist;  // tsdf_volume.cu:106
+    a.max_weight = max_weight;
+    for (int i = 0; i < 9; ++i) a.R[i] = vol2cam[i];
+    for (int i = 0; i < 3; ++i) a.T[i] = vol2cam[9 + i];
+    a.fx = intr[0]; a.fy = intr[1]; a.cx = intr[2]; a.cy = intr[3];
+    a.dists = dists;
+    a.pitch = pitch;
+    a.rows = rows;
+    a.cols = cols;
+    a.z0 = z0;
+    a.z1 = z1;
+    a.zt0 = z0 / 8 * 8;
+    a.ntx = dims[0] / 32;
+    a.nty = dims[1] / 8;
+    const int ntz = (z1 - a.zt0 + 7) / 8;
+    if (wf) {
+        DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
+        int rc = dfu_wf_build_brick_table(wf, dims, vs, st);
+        if (rc != DFU_OK) return rc;
+        a.warped = 1;
+        a.blend_mode = blend_mode;
+        a.pos_w = wf->pos_w;
+        a.real = wf->real;
+        a.dual = wf->dual;
+        a.N = wf->N;
+        a.flags = wf->flags;
+        a.bounds = wf->bricks.bounds;
+        a.bdx = dims[0] / 8;
+        a.bdy = dims[1] / 8;
+    }
+    const long nblocks = (long) a.ntx * a.nty * ntz;
+    DFU_REQUIRE(nblocks <= 0x7fffffffL, DFU_ERR_INVALID, "volume too large for one launch");
+    integrate_kernel<<<(unsigned) nblocks, 128, 0, st>>>(a);
+    DFU_LAUNCH_OK();
+    return DFU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,524 @@
+// Warp field on the device: node storage, exact 8-NN, blending, point warping.
+// Replaces class Warpfield (include/dynfu/warp_field.hpp:32-78, src/dynfu/warp_field.cpp), Node
+// (src/dynfu/utils/node.cpp) and the DualQuaternion arithmetic they call, for whole arrays of points.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "dfu_internal.h"
+#include "blend.cuh"
+#include "knn.cuh"
+
+using namespace dfu;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local char g_err[512] = "";
+void dfu_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* dfu_last_error(void) { return g_err; }
+extern "C" int dfu_version(void) { return DFU_VERSION; }
+
+extern "C" int dfu_device_check(int device) {
+    int n = 0;
+    DFU_CUDA_OK(cudaGetDeviceCount(&n));
+    DFU_REQUIRE(device >= 0 && device < n, DFU_ERR_CUDA, "no such CUDA device");
+    cudaDeviceProp p;
+    DFU_CUDA_OK(cudaGetDeviceProperties(&p, device));
+    DFU_REQUIRE(p.major == 10, DFU_ERR_CUDA, "device is not sm_100 (this library ships sm_100a code only)");
+    return DFU_OK;
+}
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+#define DFU_GUARD(dev)                                                     \
+    DeviceGuard _guard(dev);                                               \
+    if (!_guard.ok) {                                                      \
+        dfu_set_error("%s: cannot select CUDA device %d", __func__, dev);  \
+        return DFU_ERR_CUDA;                                               \
+    }
+
+// ---- node packing ------------------------------------------------------------------------------
+__global__ void pack_nodes_kernel(const float* __restrict__ pos, const float* __restrict__ dq,
+                                  const float* __restrict__ dgw, int N, int Npad, float4* __restrict__ pos_w,
+                                  float4* __restrict__ real, float4* __restrict__ dual) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Npad) return;
+    if (i < N) {
+        if (pos) pos_w[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dgw[i]);
+        if (dq) {
+            real[i] = make_float4(dq[8 * i], dq[8 * i + 1], dq[8 * i + 2], dq[8 * i + 3]);
+            dual[i] = make_float4(dq[8 * i + 4], dq[8 * i + 5], dq[8 * i + 6], dq[8 * i + 7]);
+        }
+    } else {
+        if (pos) pos_w[i] = make_float4(INFINITY, INFINITY, INFINITY, 1.f);
+        if (dq) {
+            real[i] = make_float4(1.f, 0.f, 0.f, 0.f);
+            dual[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+__global__ void unpack_nodes_kernel(const float4* __restrict__ pos_w, const float4* __restrict__ real,
+                                    const float4* __restrict__ dual, int N, float* __restrict__ pos,
+                                    float* __restrict__ dq, float* __restrict__ dgw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float4 p = pos_w[i];
+    if (pos) {
+        pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z;
+    }
+    if (dgw) dgw[i] = p.w;
+    if (dq) {
+        const float4 r = real[i], d = dual[i];
+        dq[8 * i] = r.x; dq[8 * i + 1] = r.y; dq[8 * i + 2] = r.z; dq[8 * i + 3] = r.w;
+        dq[8 * i + 4] = d.x; dq[8 * i + 5] = d.y; dq[8 * i + 6] = d.z; dq[8 * i + 7] = d.w;
+    }
+}
+
+// flags[0] = 1 iff every node is a pure translation: real == (1,0,0,0) and dual.w == 0 (the only state the
+// reference ever produces, src/dynfu/utils/opt_solver.cpp:280-281); flags[1] = max dg_w (float bits)
+__global__ void node_flags_kernel(const float4* __restrict__ pos_w, const float4* __restrict__ real,
+                                  const float4* __restrict__ dual, int N, int* __restrict__ flags) {
+    __shared__ int s_ok;
+    __shared__ unsigned s_maxw;
+    if (threadIdx.x == 0) {
+        s_ok = 1;
+        s_maxw = 0u;
+    }
+    __syncthreads();
+    int ok = 1;
+    float mw = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float4 r = real[i], d = dual[i];
+        ok &= (r.x == 1.f && r.y == 0.f && r.z == 0.f && r.w == 0.f && d.x == 0.f);
+        mw = fmaxf(mw, pos_w[i].w);
+    }
+    if (!ok) atomicAnd(&s_ok, 0);
+    atomicMax(&s_maxw, __float_as_uint(mw));  // dg_w > 0: uint order == float order
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        flags[0] = s_ok;
+        flags[1] = (int) s_maxw;
+    }
+}
+
+// dg_se3 := DQ(0,0,0,t) * dg_se3   (src/dynfu/utils/node.cpp:19-23, opt_solver.cpp:278-283)
+__global__ void update_translations_kernel(float4* __restrict__ real, float4* __restrict__ dual,
+                                           const float* __restrict__ t, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const DQ inc = dq_from_translation(t[3 * i], t[3 * i + 1], t[3 * i + 2]);
+    const DQ old{make_quat(real[i]), make_quat(dual[i])};
+    const DQ res = dq_mul(inc, old);
+    real[i] = to_float4(res.real);
+    dual[i] = to_float4(res.dual);
+}
+
+// ---- the per-point kernel: kNN, optionally followed by blend / warp -------------------------------
+enum { OP_KNN = 0, OP_BLEND = 1, OP_WARP = 2, OP_BOUNDS = 3, OP_GRAPH = 4, OP_NODEGRAPH = 5 };
+
+struct PointArgs {
+    const float4 *pos_w, *real, *dual;
+    int Npad;
+    const float* q;   // Q*3 query points (OP_BOUNDS: unused)
+    int Q;
+    int32_t* idx;     // OP_KNN
+    float* dist2;     // OP_KNN (may be null)
+    float* dq_out;    // OP_BLEND
+    const float* n_in;  // OP_WARP
+    float* v_out;
+    float* n_out;
+    int blend_mode, normal_mode;
+    // OP_GRAPH: data graph of the solver (idx = neighbours, wts = node weights, dvec = live - canon)
+    float* wts;
+    const float* live;
+    float* dvec;
+    // OP_BOUNDS: queries are the centres of the 8x8x8 bricks of a volume
+    float2* bounds;
+    int bdim[3];
+    float voxel[3];
+};
+
+template <int OP>
+__global__ void __launch_bounds__(256) points_kernel(const PointArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    KnnSmem& sm = *reinterpret_cast<KnnSmem*>(smem_raw);
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = q < a.Q;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        if (OP == OP_BOUNDS) {
+            const int bx = q % a.bdim[0], by = (q / a.bdim[0]) % a.bdim[1], bz = q / (a.bdim[0] * a.bdim[1]);
+            qx = (bx * 8 + 3.5f) * a.voxel[0];
+            qy = (by * 8 + 3.5f) * a.voxel[1];
+            qz = (bz * 8 + 3.5f) * a.voxel[2];
+        } else if (OP == OP_NODEGRAPH) {  // queries are the node positions themselves
+            const float4 p = a.pos_w[q];
+            qx = p.x; qy = p.y; qz = p.z;
+        } else {
+            qx = a.q[3 * (size_t) q];
+            qy = a.q[3 * (size_t) q + 1];
+            qz = a.q[3 * (size_t) q + 2];
+        }
+    }
+    Top8 t;
+    knn8_scan_block(sm, a.pos_w, a.Npad, qx, qy, qz, active, t);
+    if (!active) return;
+
+    if (OP == OP_GRAPH) {
+        // CombinedSolver::initializeDataGraph (src/dynfu/utils/opt_solver.cpp:56-72) + the per-edge weight of
+        // energy.t:15-17,49-52 + (live - canon) of energy.t:55
+        int32_t* o = a.idx + (size_t) q * DFU_KNN;
+        float* w = a.wts + (size_t) q * DFU_KNN;
+#pragma unroll
+        for (int k = 0; k < DFU_KNN; ++k) {
+            const int j = t.i[k];
+            o[k] = j;
+            const float4 nd = __ldg(&a.pos_w[j]);
+            w[k] = node_weight(nd.x, nd.y, nd.z, nd.w, qx, qy, qz, t.d[k]);
+        }
+        a.dvec[3 * (size_t) q] = a.live[3 * (size_t) q] - qx;
+        a.dvec[3 * (size_t) q + 1] = a.live[3 * (size_t) q + 1] - qy;
+        a.dvec[3 * (size_t) q + 2] = a.live[3 * (size_t) q + 2] - qz;
+    } else if (OP == OP_KNN || OP == OP_NODEGRAPH) {
+        int32_t* o = a.idx + (size_t) q * DFU_KNN;
+#pragma unroll
+        for (int k = 0; k < DFU_KNN; ++k) o[k] = t.i[k];
+        if (a.dist2) {
+            float* d = a.dist2 + (size_t) q * DFU_KNN;
+#pragma unroll
+            for (int k = 0; k < DFU_KNN; ++k) d[k] = t.d[k];
+        }
+    } else if (OP == OP_BOUNDS) {
+        a.bounds[q] = make_float2(t.d[DFU_KNN - 1], t.d[0]);
+    } else {
+        const DQ b = blend(a.blend_mode, t, qx, qy, qz, a.pos_w, a.real, a.dual);
+        if (OP == OP_BLEND) {
+            float* o = a.dq_out + (size_t) q * 8;
+            o[0] = b.real.w; o[1] = b.real.x; o[2] = b.real.y; o[3] = b.real.z;
+            o[4] = b.dual.w; o[5] = b.dual.x; o[6] = b.dual.y; o[7] = b.dual.z;
+        } else {
+            // Warpfield::warpToLive (src/dynfu/warp_field.cpp:150-171)
+            V3 nn{0.f, 0.f, 0.f};
+            if (a.n_in) nn = V3{a.n_in[3 * (size_t) q], a.n_in[3 * (size_t) q + 1], a.n_in[3 * (size_t) q + 2]};
+            const V3 r = dq_transform_vertex(b, V3{qx, qy, qz});
+            a.v_out[3 * (size_t) q] = r.x;
+            a.v_out[3 * (size_t) q + 1] = r.y;
+            a.v_out[3 * (size_t) q + 2] = r.z;
+            if (a.n_in && a.n_out) {
+                const V3 rn = a.normal_mode == DFU_NORMAL_REF ? dq_transform_vertex(b, nn) : dq_rotate(b, nn);
+                a.n_out[3 * (size_t) q] = rn.x;
+                a.n_out[3 * (size_t) q + 1] = rn.y;
+                a.n_out[3 * (size_t) q + 2] = rn.z;
+            }
+        }
+    }
+}
+
+template <int OP>
+int launch_points(const dfu_warpfield* wf, PointArgs& a, cudaStream_t st) {
+    a.pos_w = wf->pos_w;
+    a.real = wf->real;
+    a.dual = wf->dual;
+    a.Npad = wf->Npad;
+    if (a.Q == 0) return DFU_OK;
+    static bool attr_set = false;  // per template instantiation
+    if (!attr_set) {
+        DFU_CUDA_OK(cudaFuncSetAttribute(points_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) sizeof(KnnSmem)));
+        attr_set = true;
+    }
+    points_kernel<OP><<<div_up(a.Q, 256), 256, sizeof(KnnSmem), st>>>(a);
+    DFU_LAUNCH_OK();
+    return DFU_OK;
+}
+
+int ensure_capacity(dfu_warpfield* wf, int N) {
+    const int Npad = (N + 31) / 32 * 32;
+    if (Npad > wf->capacity) {
+        if (wf->pos_w) cudaFree(wf->pos_w);
+        if (wf->real) cudaFree(wf->real);
+        if (wf->dual) cudaFree(wf->dual);
+        wf->pos_w = wf->real = wf->dual = nullptr;
+        wf->capacity = 0;
+        DFU_CUDA_OK(cudaMalloc(&wf->pos_w, (size_t) Npad * sizeof(float4)));
+        DFU_CUDA_OK(cudaMalloc(&wf->real, (size_t) Npad * sizeof(float4)));
+        DFU_CUDA_OK(cudaMalloc(&wf->dual, (size_t) Npad * sizeof(float4)));
+        wf->capacity = Npad;
+    }
+    if (!wf->flags) DFU_CUDA_OK(cudaMalloc(&wf->flags, 4 * sizeof(int)));
+    wf->N = N;
+    wf->Npad = Npad;
+    return DFU_OK;
+}
+
+int ensure_staging(dfu_warpfield* wf, size_t floats) {
+    if (floats > wf->staging_cap) {
+        if (wf->staging) cudaFree(wf->staging);
+        wf->staging = nullptr;
+        wf->staging_cap = 0;
+        DFU_CUDA_OK(cudaMalloc(&wf->staging, floats * sizeof(float)));
+        wf->staging_cap = floats;
+    }
+    return DFU_OK;
+}
+
+}  // namespace
+
+int dfu_wf_refresh_flags(dfu_warpfield* wf, cudaStream_t st) {
+    node_flags_kernel<<<1, 256, 0, st>>>(wf->pos_w, wf->real, wf->dual, wf->N, wf->flags);
+    DFU_LAUNCH_OK();
+    return DFU_OK;
+}
+
+// Acceleration data for the warped integrator: for every 8x8x8 brick of the volume, the squared distance
+// from its centre to the 8th and to the 1st nearest node.  Depends only on node POSITIONS and the volume
+// geometry, so it is cached until either changes (the reference rebuilds its KD-tree at the same moments,
+// src/dynfu/warp_field.cpp:24-27,85-94).
+int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float voxel[3], cudaStream_t st) {
+    BrickTable& bt = wf->bricks;
+    const bool same = bt.valid && bt.node_epoch == wf->node_epoch && bt.dims[0] == dims[0] && bt.dims[1] == dims[1] &&
+                      bt.dims[2] == dims[2] && bt.voxel[0] == voxel[0] && bt.voxel[1] == voxel[1] &&
+                      bt.voxel[2] == voxel[2];
+    if (same) return DFU_OK;
+    const int bd[3] = {dims[0] / 8, dims[1] / 8, (dims[2] + 7) / 8};
+    const size_t nb = (size_t) bd[0] * bd[1] * bd[2];
+    if (nb > bt.capacity) {
+        if (bt.bounds) cudaFree(bt.bounds);
+        bt.bounds = nullptr;
+        bt.capacity = 0;
+        DFU_CUDA_OK(cudaMalloc(&bt.bounds, nb * sizeof(float2)));
+        bt.capacity = nb;
+    }
+    PointArgs a{};
+    a.Q = (int) nb;
+    a.bounds = bt.bounds;
+    for (int i = 0; i < 3; ++i) {
+        a.bdim[i] = bd[i];
+        a.voxel[i] = voxel[i];
+        bt.dims[i] = dims[i];
+        bt.voxel[i] = voxel[i];
+    }
+    int rc = launch_points<OP_BOUNDS>(wf, a, st);
+    if (rc != DFU_OK) return rc;
+    bt.node_epoch = wf->node_epoch;
+    bt.valid = true;
+    return DFU_OK;
+}
+
+// data graph + weights + (live - canon) for the solver; requires N >= 8
+int dfu_wf_build_data_graph(const dfu_warpfield* wf, const float* canon, const float* live, int P, int32_t* nbr,
+                            float* wts, float* dvec, cudaStream_t st) {
+    PointArgs a{};
+    a.q = canon;
+    a.Q = P;
+    a.idx = nbr;
+    a.wts = wts;
+    a.live = live;
+    a.dvec = dvec;
+    return launch_points<OP_GRAPH>(wf, a, st);
+}
+// regularisation graph: 8-NN of every node among the nodes (includes itself; opt_solver.cpp:74-105)
+int dfu_wf_build_node_graph(const dfu_warpfield* wf, int32_t* nnbr, cudaStream_t st) {
+    PointArgs a{};
+    a.Q = wf->N;
+    a.idx = nnbr;
+    return launch_points<OP_NODEGRAPH>(wf, a, st);
+}
+
+// ================================================================================================
+extern "C" {
+
+int dfu_warpfield_create(dfu_warpfield** out, int device) {
+    DFU_REQUIRE(out != nullptr, DFU_ERR_INVALID, "out is NULL");
+    int rc = dfu_device_check(device);
+    if (rc != DFU_OK) return rc;
+    *out = new dfu_warpfield();
+    (*out)->device = device;
+    return DFU_OK;
+}
+
+int dfu_warpfield_destroy(dfu_warpfield* wf) {
+    if (!wf) return DFU_OK;
+    DeviceGuard g(wf->device);
+    cudaFree(wf->pos_w);
+    cudaFree(wf->real);
+    cudaFree(wf->dual);
+    cudaFree(wf->flags);
+    cudaFree(wf->staging);
+    cudaFree(wf->bricks.bounds);
+    delete wf;
+    return DFU_OK;
+}
+
+int dfu_warpfield_init(dfu_warpfield* wf, float epsilon, const float* pos_xyz, const float* dq, const float* dg_w,
+                       int N, dfu_stream stream) {
+    DFU_REQUIRE(wf && pos_xyz && dq && dg_w, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(N >= 1, DFU_ERR_INVALID, "N must be >= 1");
+    DFU_GUARD(wf->device);
+    int rc = ensure_capacity(wf, N);
+    if (rc != DFU_OK) return rc;
+    wf->epsilon = epsilon;
+    cudaStream_t st = as_stream(stream);
+    pack_nodes_kernel<<<div_up(wf->Npad, 256), 256, 0, st>>>(pos_xyz, dq, dg_w, N, wf->Npad, wf->pos_w, wf->real,
+                                                             wf->dual);
+    DFU_LAUNCH_OK();
+    wf->node_epoch++;
+    wf->initialised = true;
+    return dfu_wf_refresh_flags(wf, st);
+}
+
+int dfu_warpfield_init_host(dfu_warpfield* wf, float epsilon, const float* pos_xyz_host, const float* dq_host,
+                            const float* dg_w_host, int N, dfu_stream stream) {
+    DFU_REQUIRE(wf && pos_xyz_host && dq_host && dg_w_host, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(N >= 1, DFU_ERR_INVALID, "N must be >= 1");
+    DFU_GUARD(wf->device);
+    int rc = ensure_staging(wf, (size_t) N * 12);
+    if (rc != DFU_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    float* s = wf->staging;
+    DFU_CUDA_OK(cudaMemcpyAsync(s, pos_xyz_host, (size_t) N * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    DFU_CUDA_OK(cudaMemcpyAsync(s + (size_t) N * 3, dq_host, (size_t) N * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+    DFU_CUDA_OK(cudaMemcpyAsync(s + (size_t) N * 11, dg_w_host, (size_t) N * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = dfu_warpfield_init(wf, epsilon, s, s + (size_t) N * 3, s + (size_t) N * 11, N, stream);
+    if (rc != DFU_OK) return rc;
+    DFU_CUDA_OK(cudaStreamSynchronize(st));  // host buffers may be reused on return
+    return DFU_OK;
+}
+
+int dfu_warpfield_num_nodes(const dfu_warpfield* wf, int* N_host) {
+    DFU_REQUIRE(wf && N_host, DFU_ERR_INVALID, "NULL argument");
+    *N_host = wf->N;
+    return DFU_OK;
+}
+
+int dfu_warpfield_get_nodes(const dfu_warpfield* wf, float* pos_xyz, float* dq, float* dg_w, dfu_stream stream) {
+    DFU_REQUIRE(wf, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
+    DFU_GUARD(wf->device);
+    unpack_nodes_kernel<<<div_up(wf->N, 256), 256, 0, as_stream(stream)>>>(wf->pos_w, wf->real, wf->dual, wf->N,
+                                                                           pos_xyz, dq, dg_w);
+    DFU_LAUNCH_OK();
+    return DFU_OK;
+}
+
+int dfu_warpfield_get_nodes_host(const dfu_warpfield* wf, float* pos_xyz_host, float* dq_host, float* dg_w_host,
+                                 dfu_stream stream) {
+    DFU_REQUIRE(wf, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
+    DFU_GUARD(wf->device);
+    dfu_warpfield* w = const_cast<dfu_warpfield*>(wf);
+    const size_t N = (size_t) wf->N;
+    int rc = ensure_staging(w, N * 12);
+    if (rc != DFU_OK) return rc;
+    float* s = w->staging;
+    rc = dfu_warpfield_get_nodes(wf, s, s + N * 3, s + N * 11, stream);
+    if (rc != DFU_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    if (pos_xyz_host) DFU_CUDA_OK(cudaMemcpyAsync(pos_xyz_host, s, N * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (dq_host) DFU_CUDA_OK(cudaMemcpyAsync(dq_host, s + N * 3, N * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (dg_w_host) DFU_CUDA_OK(cudaMemcpyAsync(dg_w_host, s + N * 11, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    DFU_CUDA_OK(cudaStreamSynchronize(st));
+    return DFU_OK;
+}
+
+int dfu_warpfield_set_transforms(dfu_warpfield* wf, const float* dq, dfu_stream stream) {
+    DFU_REQUIRE(wf && dq, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
+    DFU_GUARD(wf->device);
+    cudaStream_t st = as_stream(stream);
+    pack_nodes_kernel<<<div_up(wf->Npad, 256), 256, 0, st>>>(nullptr, dq, nullptr, wf->N, wf->Npad, wf->pos_w,
+                                                             wf->real, wf->dual);
+    DFU_LAUNCH_OK();
+    return dfu_wf_refresh_flags(wf, st);
+}
+
+int dfu_warpfield_set_transforms_host(dfu_warpfield* wf, const float* dq_host, dfu_stream stream) {
+    DFU_REQUIRE(wf && dq_host, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
+    DFU_GUARD(wf->device);
+    int rc = ensure_staging(wf, (size_t) wf->N * 12);
+    if (rc != DFU_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    DFU_CUDA_OK(cudaMemcpyAsync(wf->staging, dq_host, (size_t) wf->N * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = dfu_warpfield_set_transforms(wf, wf->staging, stream);
+    if (rc != DFU_OK) return rc;
+    DFU_CUDA_OK(cudaStreamSynchronize(st));
+    return DFU_OK;
+}
+
+int dfu_warpfield_update_translations(dfu_warpfield* wf, const float* t_xyz, dfu_stream stream) {
+    DFU_REQUIRE(wf && t_xyz, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
+    DFU_GUARD(wf->device);
+    cudaStream_t st = as_stream(stream);
+    update_translations_kernel<<<div_up(wf->N, 256), 256, 0, st>>>(wf->real, wf->dual, t_xyz, wf->N);
+    DFU_LAUNCH_OK();
+    return dfu_wf_refresh_flags(wf, st);
+}
+
+int dfu_warpfield_knn(const dfu_warpfield* wf, const float* q_xyz, int Q, int32_t* idx, float* dist2,
+                      dfu_stream stream) {
+    DFU_REQUIRE(wf && (Q == 0 || (q_xyz && idx)), DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(Q >= 0, DFU_ERR_INVALID, "negative Q");
+    DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
+    DFU_GUARD(wf->device);
+    PointArgs a{};
+    a.q = q_xyz;
+    a.Q = Q;
+    a.idx = idx;
+    a.dist2 = dist2;
+    return launch_points<OP_KNN>(wf, a, as_stream(stream));
+}
+
+int dfu_warpfield_blend(const dfu_warpfield* wf, const float* p_xyz, int Q, float* dq_out, int blend_mode,
+                        dfu_stream stream) {
+    DFU_REQUIRE(wf && (Q == 0 || (p_xyz && dq_out)), DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(Q >= 0, DFU_ERR_INVALID, "negative Q");
+    DFU_REQUIRE(blend_mode == DFU_BLEND_REF_COMPOSE || blend_mode == DFU_BLEND_DQB_SUM, DFU_ERR_INVALID, "bad blend_mode");
+    DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
+    DFU_GUARD(wf->device);
+    PointArgs a{};
+    a.q = p_xyz;
+    a.Q = Q;
+    a.dq_out = dq_out;
+    a.blend_mode = blend_mode;
+    return launch_points<OP_BLEND>(wf, a, as_stream(stream));
+}
+
+int dfu_warpfield_warp(const dfu_warpfield* wf, const float* v_xyz, const float* n_xyz, int P, float* v_out,
+                       float* n_out, int blend_mode, int normal_mode, dfu_stream stream) {
+    DFU_REQUIRE(wf && (P == 0 || (v_xyz && v_out)), DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(P >= 0, DFU_ERR_INVALID, "negative P");
+    DFU_REQUIRE(blend_mode == DFU_BLEND_REF_COMPOSE || blend_mode == DFU_BLEND_DQB_SUM, DFU_ERR_INVALID, "bad blend_mode");
+    DFU_REQUIRE(normal_mode == DFU_NORMAL_REF || normal_mode == DFU_NORMAL_ROTATE_ONLY, DFU_ERR_INVALID, "bad normal_mode");
+    DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
+    DFU_GUARD(wf->device);
+    PointArgs a{};
+    a.q = v_xyz;
+    a.Q = P;
+    a.n_in = n_xyz;
+    a.v_out = v_out;
+    a.n_out = n_out;
+    a.blend_mode = blend_mode;
+    a.normal_mode = normal_mode;
+    return launch_points<OP_WARP>(wf, a, as_stream(stream));
+}
+
+}  // extern "C"

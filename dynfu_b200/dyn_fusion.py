@@ -1,0 +1,114 @@
+"""DynFusion -- the per-frame operator of the hot path (kfusion::KinFu::operator() / DynFusion::operator(),
+src/kfusion/kinfu.cpp:140-234, src/dynfu/dyn_fusion.cpp:48-145), restricted to the steps SURVEY.md §8 puts in
+scope: computeDists -> warpToLive (kNN + DQB) -> CombinedSolver -> warped TSDF integration.
+
+Marching cubes, ICP and the 1-NN correspondence search are NOT on the path (§8f): canonical vertices and the
+live vertices paired with them are supplied by the caller, exactly like the reference's solver tests do."""
+from dataclasses import dataclass, field
+
+import torch
+
+from ._lib import BLEND_REF_COMPOSE
+from .solver import CombinedSolver, CombinedSolverParameters
+from .tsdf_volume import TsdfVolume, compute_dists
+from .warpfield import Warpfield
+
+
+@dataclass
+class KinFuParams:
+    """kfusion::KinFuParams::default_params (src/kfusion/kinfu.cpp:10-44), hot-path fields only."""
+    cols: int = 640
+    rows: int = 480
+    intr: tuple = (525.0, 525.0, 319.5, 239.5)
+    volume_dims: tuple = (512, 512, 512)
+    volume_size: tuple = (3.0, 3.0, 3.0)
+    volume_pose_t: tuple = (-1.5, -1.5, 0.5)  # Affine3f().translate(-size/2, -size/2, 0.5)
+    tsdf_trunc_dist: float = 0.04
+    tsdf_max_weight: int = 64
+
+
+@dataclass
+class DynFuParams:
+    """DynFuParams::defaultParams (src/dynfu/dyn_fusion.cpp:6-31)."""
+    kinfuParams: KinFuParams = field(default_factory=lambda: KinFuParams(volume_dims=(128, 128, 128)))
+    tukeyOffset: float = 4.652
+    lambda_: float = 200.0
+    psi_data: float = 0.01
+    psi_reg: float = 1e-4
+    L: int = 4
+    beta: int = 4
+    epsilon: float = 0.1
+    node_step: int = 128  # every 128th canonical vertex becomes a node (dyn_fusion.cpp:151)
+    solver: CombinedSolverParameters = field(default_factory=CombinedSolverParameters)
+    blend_mode: int = BLEND_REF_COMPOSE
+
+
+class DynFusion:
+    def __init__(self, params, device=None, z0=0, z1=None):
+        self.params = params
+        kp = params.kinfuParams
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.volume = TsdfVolume(kp.volume_dims, self.device, z0=z0, z1=z1, size=kp.volume_size)  # kinfu.cpp:49-54
+        self.volume.setTruncDist(kp.tsdf_trunc_dist)
+        self.volume.setMaxWeight(kp.tsdf_max_weight)
+        pose = torch.eye(4, dtype=torch.float64)
+        pose[:3, 3] = torch.tensor(kp.volume_pose_t, dtype=torch.float64)
+        self.volume.setPose(pose)
+        self.camera_pose = torch.eye(4, dtype=torch.float64)  # poses_.back(): ICP is skipped (dyn_fusion.cpp:100-105)
+        self.warpfield = None
+        self.solver = None
+        self.frame_counter = 0
+        self.canonicalVertices = None
+        self.canonicalNormals = None
+        self.canonicalWarpedToLive = None
+        self._depth_dev = torch.empty((kp.rows, kp.cols), dtype=torch.int16, device=self.device)
+        self._dists = torch.empty_like(self._depth_dev)
+        self.allreduce = None
+
+    # DynFusion::init (src/dynfu/dyn_fusion.cpp:147-168); explicit nodes may be given instead of the 128-stride pick
+    def init(self, canonicalVertices, canonicalNormals=None, nodes=None):
+        cv = torch.as_tensor(canonicalVertices, dtype=torch.float32).to(self.device).reshape(-1, 3).contiguous()
+        self.canonicalVertices = cv
+        self.canonicalNormals = None if canonicalNormals is None else torch.as_tensor(
+            canonicalNormals, dtype=torch.float32).to(self.device).reshape(-1, 3).contiguous()
+        if nodes is None:
+            pos = cv[::self.params.node_step].contiguous()
+            n = pos.shape[0]
+            dq = torch.zeros((n, 8), dtype=torch.float32, device=self.device)
+            dq[:, 0] = 1.0
+            w = torch.full((n,), 3 * self.params.epsilon, dtype=torch.float32, device=self.device)  # :156
+        else:
+            pos, dq, w = nodes
+        self.warpfield = Warpfield(self.device)
+        self.warpfield.init(self.params.epsilon, pos, dq, w)
+        self.solver = CombinedSolver(self.warpfield, self.params.solver, self.params.tukeyOffset, self.params.psi_data,
+                                     self.params.lambda_, self.params.psi_reg)  # dyn_fusion.cpp:193
+        if self.allreduce is not None:
+            self.solver.setAllReduce(self.allreduce)
+
+    def uploadDepth(self, depth_host):
+        """demo.cpp:90 depth_device_.upload(...): pinned uint16 [rows, cols] -> device."""
+        self._depth_dev.copy_(depth_host.view(torch.int16) if depth_host.dtype == torch.uint16 else depth_host,
+                              non_blocking=True)
+        return self._depth_dev
+
+    # DynFusion::warpCanonicalToLiveOpt (src/dynfu/dyn_fusion.cpp:182-210)
+    def warpCanonicalToLiveOpt(self, liveVertices):
+        self.canonicalWarpedToLive, _ = self.warpfield.warpToLive(self.canonicalVertices, None, self.params.blend_mode)
+        self.solver.initializeProblemInstance(self.canonicalWarpedToLive, liveVertices)
+        self.solver.solveAll()
+
+    # DynFusion::operator() (src/dynfu/dyn_fusion.cpp:48-145), hot-path steps
+    def __call__(self, depth_host, liveVertices=None):
+        kp = self.params.kinfuParams
+        depth = self.uploadDepth(depth_host)
+        compute_dists(depth, kp.intr, out=self._dists)  # :55
+        if self.frame_counter == 0 or self.warpfield is None:
+            self.volume.integrate(self._dists, self.camera_pose, kp.intr)  # :70 (rigid, canonical frame)
+        else:
+            if liveVertices is not None:
+                self.warpCanonicalToLiveOpt(liveVertices)  # :140
+            # non-rigid surface fusion (README.md:14-17 "future additions"): live depth into the canonical volume
+            self.volume.integrate(self._dists, self.camera_pose, kp.intr, self.warpfield, self.params.blend_mode)
+        self.frame_counter += 1
+        return True

@@ -1,0 +1,188 @@
+/*
+ * dynfu_b200.h -- C-ABI of the B200-native DynamicFusion hot path (libdynfu_b200.so, sm_100a).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point names
+ * the interface of the reference (swarth100/dynfu, paths relative to its root) that it replaces.
+ * INTEGRATION.md shows the reference-side binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns a dfu_status (0 = ok); nothing throws or exit()s across the boundary
+ *     (the reference prints and exit(0)s on CUDA errors, include/kfusion/safe_call.hpp:12-22);
+ *     dfu_last_error() gives the message of the calling thread's last failure;
+ *   - pointers are DEVICE pointers unless the parameter or function name ends in _host; small POD
+ *     parameter blocks (dims, voxel size, intrinsics, vol2cam, params structs) are read on the host
+ *     at call time, like the by-value POD views of include/kfusion/internal.hpp:36-55;
+ *   - every call takes a cudaStream_t (as void*), is asynchronous with respect to the host and adds
+ *     no hidden device synchronisation (the reference cudaDeviceSynchronize()s after integrate,
+ *     src/kfusion/cuda/tsdf_volume.cu:120); *_host variants synchronise the stream before returning;
+ *   - the caller owns every buffer; handles own only their internal scratch; the TSDF volume is
+ *     borrowed (it is the reference's own ushort2 blob, src/kfusion/tsdf_volume.cpp:32-38);
+ *   - quaternions are (w,x,y,z), Hamilton product; a dual quaternion is 8 floats, real then dual
+ *     (include/dynfu/utils/dual_quaternion.hpp); points/normals are packed xyz floats;
+ *   - k is fixed at 8 (KNN, include/dynfu/warp_field.hpp:27).
+ *
+ * There is NO CPU fallback anywhere behind this header: without a CUDA device every compute entry
+ * point fails with DFU_ERR_CUDA.
+ */
+#ifndef DYNFU_B200_H
+#define DYNFU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFU_KNN 8
+#define DFU_VERSION 100
+
+typedef enum {
+    DFU_OK = 0,
+    DFU_ERR_INVALID = 1,      /* bad argument (null pointer, bad size, unsupported dims)           */
+    DFU_ERR_CUDA = 2,         /* CUDA runtime error; message in dfu_last_error()                    */
+    DFU_ERR_PRECONDITION = 3, /* e.g. fewer than 8 nodes for the solver (reference UB,              */
+                              /* src/dynfu/utils/opt_solver.cpp:63-66)                              */
+    DFU_ERR_NOT_INIT = 4      /* handle used before init (nanoflann throws, nanoflann.hpp:1209)     */
+} dfu_status;
+
+/* how the 8 weighted node transforms are combined */
+typedef enum {
+    DFU_BLEND_REF_COMPOSE = 0, /* what Warpfield::calcDQB does (src/dynfu/warp_field.cpp:127-148):   */
+                               /* Q = prod_k (real_k, w_k*dual_k), nearest first, real normalised    */
+    DFU_BLEND_DQB_SUM = 1      /* true dual-quaternion blending: Q = sum_k w_k q_k / |real|          */
+} dfu_blend_mode;
+
+typedef enum {
+    DFU_NORMAL_REF = 0,        /* DualQuaternion::transformNormal (dual_quaternion.hpp:217-228):     */
+                               /* the vertex formula, translation included                           */
+    DFU_NORMAL_ROTATE_ONLY = 1
+} dfu_normal_mode;
+
+typedef struct dfu_warpfield dfu_warpfield; /* replaces class Warpfield (include/dynfu/warp_field.hpp:32-78) */
+typedef struct dfu_solver dfu_solver;       /* replaces class CombinedSolver (include/dynfu/utils/opt_solver.hpp:19-110) */
+typedef void* dfu_stream;                   /* cudaStream_t */
+
+int dfu_version(void);
+const char* dfu_last_error(void);
+/* 0 if a usable sm_100 device is visible, DFU_ERR_CUDA otherwise */
+int dfu_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Warp field  (replaces Warpfield + Node + the nanoflann KD-tree + DualQuaternion on the hot path)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Warpfield::Warpfield() (src/dynfu/warp_field.cpp:6) */
+int dfu_warpfield_create(dfu_warpfield** out, int device);
+int dfu_warpfield_destroy(dfu_warpfield* wf);
+
+/* Warpfield::init(epsilon, nodes) (src/dynfu/warp_field.cpp:10-28): stores the nodes and builds the
+ * search structure.  pos_xyz[N*3] = Node::dg_v, dq[N*8] = Node::dg_se3, dg_w[N] = Node::dg_w
+ * (include/dynfu/utils/node.hpp:55-58).  N >= 1. */
+int dfu_warpfield_init(dfu_warpfield* wf, float epsilon, const float* pos_xyz, const float* dq,
+                       const float* dg_w, int N, dfu_stream stream);
+int dfu_warpfield_init_host(dfu_warpfield* wf, float epsilon, const float* pos_xyz_host,
+                            const float* dq_host, const float* dg_w_host, int N, dfu_stream stream);
+
+/* Warpfield::getNodes() (src/dynfu/warp_field.cpp:32): any output pointer may be NULL */
+int dfu_warpfield_num_nodes(const dfu_warpfield* wf, int* N_host);
+int dfu_warpfield_get_nodes(const dfu_warpfield* wf, float* pos_xyz, float* dq, float* dg_w, dfu_stream stream);
+int dfu_warpfield_get_nodes_host(const dfu_warpfield* wf, float* pos_xyz_host, float* dq_host,
+                                 float* dg_w_host, dfu_stream stream);
+
+/* Node::setTransformation for all nodes (src/dynfu/utils/node.cpp:25) */
+int dfu_warpfield_set_transforms(dfu_warpfield* wf, const float* dq, dfu_stream stream);
+int dfu_warpfield_set_transforms_host(dfu_warpfield* wf, const float* dq_host, dfu_stream stream);
+/* Node::updateTransformation with DQ(0,0,0,t) for all nodes: dg_se3 := DQ(0,0,0,t_i) * dg_se3
+ * (src/dynfu/utils/node.cpp:19-23 as called from opt_solver.cpp:270-285).  t_xyz[N*3]. */
+int dfu_warpfield_update_translations(dfu_warpfield* wf, const float* t_xyz, dfu_stream stream);
+
+/* Warpfield::findNeighborsIndex(8, vertex) for Q query points (src/dynfu/warp_field.cpp:111-122).
+ * idx[Q*8] ascending by (squared distance, index); dist2 may be NULL.  Squared distances are the
+ * float ((dx*dx)+dy*dy)+dz*dz of nanoflann's L2_Simple_Adaptor (nanoflann.hpp:338-345), bit for bit.
+ * With fewer than 8 nodes the missing entries are -1 / +inf (the reference returns a shorter vector). */
+int dfu_warpfield_knn(const dfu_warpfield* wf, const float* q_xyz, int Q, int32_t* idx, float* dist2,
+                      dfu_stream stream);
+
+/* Warpfield::calcDQB(point) for Q points (src/dynfu/warp_field.cpp:127-148): dq_out[Q*8] */
+int dfu_warpfield_blend(const dfu_warpfield* wf, const float* p_xyz, int Q, float* dq_out, int blend_mode,
+                        dfu_stream stream);
+
+/* Warpfield::warpToLive(frame) (src/dynfu/warp_field.cpp:150-171): v_out[i] = calcDQB(v[i]).transformVertex(v[i]),
+ * n_out[i] = calcDQB(v[i]).transformNormal(n[i]).  n / n_out may both be NULL.  In-place is allowed. */
+int dfu_warpfield_warp(const dfu_warpfield* wf, const float* v_xyz, const float* n_xyz, int P, float* v_out,
+                       float* n_out, int blend_mode, int normal_mode, dfu_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * TSDF volume  (layout of kfusion::cuda::TsdfVolume: ushort2 {half tsdf bits, u16 weight} per voxel,
+ * idx = x + y*dims.x + z*dims.x*dims.y, include/kfusion/cuda/device.hpp:20-35,59-67)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* cuda::computeDists (src/kfusion/imgproc.cpp:38-41 -> src/kfusion/cuda/imgproc.cu:233-254):
+ * depth u16 millimetres -> ray length in metres as half bits.  intr_host = {fx, fy, cx, cy}. */
+int dfu_compute_dists(const uint16_t* depth, size_t depth_pitch_bytes, uint16_t* dists, size_t dists_pitch_bytes,
+                      int rows, int cols, const float intr_host[4], dfu_stream stream);
+
+/* TsdfVolume::setTruncDist clamp (src/kfusion/tsdf_volume.cpp:57-61) */
+float dfu_tsdf_trunc_dist(float requested, const float voxel_size_host[3]);
+
+/* TsdfVolume::clear (src/kfusion/tsdf_volume.cpp:74-80 -> tsdf_volume.cu:11-34), planes [z0,z1) */
+int dfu_tsdf_clear(void* volume, const int dims_host[3], int z0, int z1, dfu_stream stream);
+
+/* TsdfVolume::integrate (src/kfusion/tsdf_volume.cpp:82-93 -> tsdf_volume.cu:43-121), planes [z0,z1).
+ * vol2cam_host = 9 floats row-major R then 3 floats t (device::Aff3f, include/kfusion/internal.hpp:28-34)
+ * = camera_pose.inv() * volume_pose.  wf == NULL integrates rigidly, exactly like the reference; with a
+ * warp field every voxel position (volume-local metres, the frame of the nodes) is first moved by
+ * calcDQB(p).transformVertex(p).  dims.x % 32 == 0 (src/kfusion/kinfu.cpp:47) and dims.y % 8 == 0. */
+int dfu_tsdf_integrate(void* volume, const int dims_host[3], const float voxel_size_host[3], float trunc_dist,
+                       int max_weight, const float vol2cam_host[12], const float intr_host[4],
+                       const uint16_t* dists, size_t dists_pitch_bytes, int rows, int cols, dfu_warpfield* wf,
+                       int blend_mode, int z0, int z1, dfu_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Solver  (replaces CombinedSolver + Opt + energy.t)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+    int num_iter;       /* CombinedSolverParameters::numIter      : outer iterations (Tukey re-weighting) */
+    int nonlinear_iter; /* CombinedSolverParameters::nonLinearIter : Gauss-Newton steps per outer iteration */
+    int linear_iter;    /* CombinedSolverParameters::linearIter    : PCG steps per Gauss-Newton step        */
+    float tukey_offset; /* CombinedSolver ctor, src/dynfu/utils/opt_solver.cpp:3-13                        */
+    float psi_data;
+    float lambda;
+    float psi_reg;
+    float pcg_tol;      /* PCG stops when r.z <= tol^2 * (r.z of the first GN step); 0 = never             */
+    int early_out;      /* CombinedSolverParameters::earlyOut                                               */
+} dfu_solver_params;
+
+/* all-reduce hook for data-parallel solves: sums buf[count] floats over ranks, in place, on stream */
+typedef int (*dfu_allreduce_fn)(float* buf, size_t count, void* ctx, dfu_stream stream);
+
+/* CombinedSolver::CombinedSolver(warpfield, params, tukeyOffset, psi_data, lambda, psi_reg)
+ * (src/dynfu/utils/opt_solver.cpp:3-13).  The solver SHARES the warp field's nodes, as the
+ * reference's by-value Warpfield copy shares its shared_ptr<Node>s. */
+int dfu_solver_create(dfu_solver** out, dfu_warpfield* wf, const dfu_solver_params* params_host);
+int dfu_solver_destroy(dfu_solver* s);
+/* ranks hold disjoint point partitions; fn sums the per-node normal-equation buffers over ranks */
+int dfu_solver_set_allreduce(dfu_solver* s, dfu_allreduce_fn fn, void* ctx);
+
+/* CombinedSolver::initializeProblemInstance(canonicalFrame, liveFrame, affine)
+ * (src/dynfu/utils/opt_solver.cpp:15-54): uploads nothing (pointers are device), builds the kNN data
+ * graph (:56-72) and regularisation graph (:74-105), zeroes the unknowns (:192-193).
+ * normals and affine may be NULL (the reference's energy never reads them, energy.t:29,32). */
+int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* canon_n, const float* live_v,
+                            const float* live_n, int P, const float affine_host[12], dfu_stream stream);
+
+/* CombinedSolverBase::solveAll() [Opt, not in the reference tree]: runs the outer/GN/PCG loops on the
+ * device and composes the result onto the warp field's nodes ONCE (opt_solver.cpp:270-285). */
+int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream);
+
+/* results of the last solve_all: t_xyz[N*3] (device, may be NULL) and
+ * stats_host[4] = {initial energy, final energy, PCG iterations, GN steps} (synchronises the stream) */
+int dfu_solver_get_translations(const dfu_solver* s, float* t_xyz, dfu_stream stream);
+int dfu_solver_get_stats_host(const dfu_solver* s, double stats_host[4], dfu_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNFU_B200_H */

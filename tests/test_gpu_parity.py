@@ -1,0 +1,431 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Every test calls the CUDA path THROUGH THE C-ABI
+(dynfu_b200.* are thin ctypes wrappers) and checks it against the CPU oracle on the same seeded inputs.
+Bar: bit-exact for indices / squared distances / packed TSDF; float tolerances are written in each test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyoracle
+from tests import fixtures_opt as fx
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dfu():
+    import dynfu_b200
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return dynfu_b200
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dtype=dtype)
+
+
+def make_wf(dfu, pos, dq, dg_w, eps=0.0125):
+    wf = dfu.Warpfield()
+    wf.init(eps, dev(pos), dev(dq), dev(dg_w))
+    return wf
+
+
+def num_equal(a, b):
+    """bit-exact up to the sign of zero"""
+    return np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("n_nodes,n_q", [(4096, 20000), (1000, 777), (8, 33), (33, 1)])
+def test_knn_bit_exact(dfu, oracle, n_nodes, n_q):
+    rng = np.random.default_rng(synth.SEED + n_nodes)
+    pos, dq, dg_w, _ = synth.sphere_nodes(n_nodes, 0.0125)
+    q = (pos[rng.integers(0, n_nodes, n_q)] + rng.normal(0, 0.05, (n_q, 3))).astype(np.float32)
+    idx_o, d_o, ties = oracle.knn(pos, q, return_dist=True)
+    assert ties == 0  # otherwise nanoflann's order would be visitation dependent
+    wf = make_wf(dfu, pos, dq, dg_w)
+    idx_g, d_g = wf.findNeighborsIndex(8, dev(q), return_dist=True)
+    assert np.array_equal(idx_g.cpu().numpy(), idx_o)
+    assert np.array_equal(d_g.cpu().numpy(), d_o)
+
+
+def test_knn_matches_reference_nanoflann(dfu, oracle_nf):
+    """straight against the reference's own KD-tree code (oracle/_ref, prebuilt from the reference header)"""
+    rng = np.random.default_rng(5)
+    pos, dq, dg_w, _ = synth.sphere_nodes(4096, 0.0125)
+    q = (pos[rng.integers(0, 4096, 5000)] + rng.normal(0, 0.03, (5000, 3))).astype(np.float32)
+    idx_n, d_n, _ = oracle_nf.knn(pos, q, return_dist=True)
+    wf = make_wf(dfu, pos, dq, dg_w)
+    idx_g, d_g = wf.findNeighborsIndex(8, dev(q), return_dist=True)
+    assert np.array_equal(idx_g.cpu().numpy(), idx_n)
+    assert np.array_equal(d_g.cpu().numpy(), d_n)
+
+
+def test_knn_ties_by_distance_then_index(dfu, oracle):
+    """integer-lattice nodes of the reference's OptTest tie on purpose: key is (dist2, idx)"""
+    q = np.array([(0, 0.04, 0), (2, 2, 2), (10.5, 10.5, 10.5), (0, 0, 0)], np.float32)
+    idx_o, d_o, _ = oracle.knn(fx.ALL_NODES, q, return_dist=True)
+    wf = make_wf(dfu, fx.ALL_NODES, fx.identity_dq(18), np.full(18, 2.0, np.float32))
+    idx_g, d_g = wf.findNeighborsIndex(8, dev(q), return_dist=True)
+    assert np.array_equal(idx_g.cpu().numpy(), idx_o)
+    assert np.array_equal(d_g.cpu().numpy(), d_o)
+
+
+def test_knn_fewer_than_8_nodes_and_empty_query(dfu, oracle):
+    pos = fx.NODES_GROUP1[:5]
+    wf = make_wf(dfu, pos, fx.identity_dq(5), np.full(5, 2.0, np.float32))
+    q = np.array([(0.1, 0.2, 0.3)], np.float32)
+    idx_g, d_g = wf.findNeighborsIndex(8, dev(q), return_dist=True)
+    idx_o, d_o, _ = oracle.knn(pos, q, return_dist=True)
+    assert np.array_equal(idx_g.cpu().numpy(), idx_o)  # -1 padded, like the reference's shorter vector
+    assert np.array_equal(d_g.cpu().numpy(), d_o)
+    empty = wf.findNeighborsIndex(8, torch.empty((0, 3), device="cuda"))
+    assert empty.shape == (0, 8)
+    with pytest.raises(dfu.DfuError):
+        wf.findNeighborsIndex(4, dev(q))
+
+
+def test_uninitialised_warpfield_is_an_error(dfu):
+    wf = dfu.Warpfield()
+    with pytest.raises(dfu.DfuError) as e:  # nanoflann throws before buildIndex (nanoflann.hpp:1209)
+        wf.findNeighborsIndex(8, torch.zeros((1, 3), device="cuda"))
+    assert e.value.code == 4
+
+
+# ------------------------------------------------------------------------------------ blend and warp
+@pytest.mark.parametrize("rotations", [False, True])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_blend_and_warp_bit_exact(dfu, oracle, rotations, mode):
+    rng = np.random.default_rng(11)
+    pos, dq, dg_w, _ = synth.sphere_nodes(1024, 0.025, rotations=rotations)
+    pts = (pos[rng.integers(0, 1024, 3000)] + rng.normal(0, 0.03, (3000, 3))).astype(np.float32)
+    nrm = rng.normal(size=(3000, 3)).astype(np.float32)
+    synth.assert_no_knn_ties(oracle, pos, pts)
+    wf = make_wf(dfu, pos, dq, dg_w, 0.025)
+    b_g = wf.calcDQB(dev(pts), mode).cpu().numpy()
+    b_o = oracle.blend(pos, dq, dg_w, pts, mode)
+    assert num_equal(b_g, b_o), np.abs(b_g - b_o).max()
+    for nm in (0, 1):
+        v_g, n_g = wf.warpToLive(dev(pts), dev(nrm), mode, nm)
+        v_o, n_o = oracle.warp(pos, dq, dg_w, pts, nrm, mode, nm)
+        assert num_equal(v_g.cpu().numpy(), v_o)
+        assert num_equal(n_g.cpu().numpy(), n_o)
+
+
+def test_get_nodes_and_update_translations(dfu, oracle):
+    pos, dq, dg_w, _ = synth.sphere_nodes(300, 0.025, rotations=True)
+    wf = make_wf(dfu, pos, dq, dg_w)
+    p, d, w = wf.getNodes()
+    assert np.array_equal(p.cpu().numpy(), pos) and np.array_equal(d.cpu().numpy(), dq) and np.array_equal(w.cpu().numpy(), dg_w)
+    t = np.random.default_rng(2).normal(0, 0.01, (300, 3)).astype(np.float32)
+    wf.updateTranslations(dev(t))
+    exp = np.stack([oracle.dq_mul(oracle.dq_from_euler(0, 0, 0, *t[i]), dq[i]) for i in range(300)])
+    assert num_equal(wf.getNodes()[1].cpu().numpy(), exp)
+
+
+# ------------------------------------------------------------------------------------------ TSDF
+def test_compute_dists_bit_exact(dfu, oracle):
+    for (cols, rows) in [(640, 480), (1280, 720)]:
+        intr = synth.intr_for(cols, rows)
+        depth = synth.sphere_depth(rows, cols, intr)
+        d_o = oracle.compute_dists(depth, intr)
+        d_g = dfu.compute_dists(dev(depth.view(np.int16), torch.int16), intr).cpu().numpy().view(np.uint16)
+        assert np.array_equal(d_g, d_o)
+
+
+def _volume(dfu, dim, z0=0, z1=None):
+    vol = dfu.TsdfVolume((dim, dim, dim), z0=z0, z1=z1)
+    vol.setTruncDist(synth.TRUNC)
+    vol.setMaxWeight(synth.MAX_WEIGHT)
+    pose = np.eye(4)
+    pose[:3, 3] = synth.VOLUME_T
+    vol.setPose(pose)
+    return vol
+
+
+def _oracle_integrate(o, vol, dists, nodes=None, mode=0, **kw):
+    dim = vol.shape[0]
+    vs = synth.voxel_size(dim)
+    return o.tsdf_integrate(vol, vs, o.trunc_dist(synth.TRUNC, vs), synth.MAX_WEIGHT, synth.VOL2CAM, synth.INTR, dists,
+                            nodes=nodes, blend_mode=mode, **kw)
+
+
+@pytest.fixture(scope="module")
+def dists_np(oracle):
+    return oracle.compute_dists(synth.sphere_depth(), synth.INTR)
+
+
+def _mismatch(a, b):
+    return int(np.count_nonzero(a != b))
+
+
+def test_tsdf_rigid_bit_exact_two_frames(dfu, oracle, dists_np):
+    dim = 96
+    ref = np.zeros((dim,) * 3, np.uint32)
+    vol = _volume(dfu, dim)
+    assert vol.getTruncDist() == pytest.approx(oracle.trunc_dist(synth.TRUNC, synth.voxel_size(dim)))
+    d = dev(dists_np.view(np.int16), torch.int16)
+    for frame in range(2):
+        touched = _oracle_integrate(oracle, ref, dists_np)
+        vol.integrate(d, np.eye(4), synth.INTR)
+        got = vol.data.cpu().numpy().view(np.uint32)
+        assert touched > 0 and _mismatch(got, ref) == 0
+    assert (ref >> 16).max() == 2
+    vol.clear()
+    assert not vol.data.any()
+
+
+@pytest.mark.parametrize("mode,rotations", [(0, False), (0, True), (1, True), (1, False)])
+def test_tsdf_warped_bit_exact(dfu, oracle, dists_np, mode, rotations):
+    """warped integrate == oracle: translation-only fast path (0,False), the reference's compose quirk with
+    rotations (0,True), and true DQB (1,*).  Packed ushort2 compared bit for bit, two frames (weights 1 -> 2)."""
+    dim = 64
+    pos, dq, dg_w, _ = synth.sphere_nodes(512, 0.03, rotations=rotations)
+    wf = make_wf(dfu, pos, dq, dg_w, 0.03)
+    ref = np.zeros((dim,) * 3, np.uint32)
+    vol = _volume(dfu, dim)
+    d = dev(dists_np.view(np.int16), torch.int16)
+    for frame in range(2):
+        _oracle_integrate(oracle, ref, dists_np, nodes=(pos, dq, dg_w), mode=mode)
+        vol.integrate(d, np.eye(4), synth.INTR, wf, mode)
+        got = vol.data.cpu().numpy().view(np.uint32)
+        assert _mismatch(got, ref) == 0, "%d voxels differ" % _mismatch(got, ref)
+    rigid = np.zeros((dim,) * 3, np.uint32)
+    _oracle_integrate(oracle, rigid, dists_np)
+    _oracle_integrate(oracle, rigid, dists_np)
+    assert _mismatch(ref, rigid) > 100  # the warp moved the surface
+
+
+def test_tsdf_warped_c1_lite(dfu, oracle, dists_np):
+    """128^3, 1024 nodes, eps 0.025 (C1 at half resolution): bit-exact against the oracle"""
+    dim = 128
+    pos, dq, dg_w, _ = synth.sphere_nodes(1024, 0.025)
+    wf = make_wf(dfu, pos, dq, dg_w, 0.025)
+    ref = np.zeros((dim,) * 3, np.uint32)
+    _oracle_integrate(oracle, ref, dists_np, nodes=(pos, dq, dg_w))
+    vol = _volume(dfu, dim)
+    vol.integrate(dev(dists_np.view(np.int16), torch.int16), np.eye(4), synth.INTR, wf)
+    assert _mismatch(vol.data.cpu().numpy().view(np.uint32), ref) == 0
+
+
+def test_tsdf_properties_at_full_size(dfu, dists_np):
+    """512^3 / 4096 nodes (BASELINE configs[1]) through size-independent properties:
+    identity warp == rigid integrate; z-slab shards == full volume; translation-only fast path == general path."""
+    dim = 512
+    d = dev(dists_np.view(np.int16), torch.int16)
+    pos, dq, dg_w, _ = synth.sphere_nodes(4096, 0.0125)
+    rigid = _volume(dfu, dim)
+    rigid.integrate(d, np.eye(4), synth.INTR)
+    ident = _volume(dfu, dim)
+    ident.integrate(d, np.eye(4), synth.INTR, make_wf(dfu, pos, synth.identity_dq(4096), dg_w))
+    assert torch.equal(rigid.data, ident.data)
+    del ident
+    wf = make_wf(dfu, pos, dq, dg_w)
+    full = _volume(dfu, dim)
+    full.integrate(d, np.eye(4), synth.INTR, wf)
+    assert not torch.equal(full.data, rigid.data)
+    for g, (z0, z1) in enumerate([(0, 128), (128, 256), (256, 384), (384, 512), (100, 203)]):
+        slab = _volume(dfu, dim, z0, z1)
+        slab.integrate(d, np.eye(4), synth.INTR, wf)
+        assert torch.equal(slab.data, full.data[z0:z1]), "slab %d differs" % g
+    # general REF_COMPOSE path (forced by one node with a non-identity rotation far outside the volume)
+    pos2 = np.concatenate([pos, [[50.0, 50.0, 50.0]]]).astype(np.float32)
+    dq2 = np.concatenate([dq, synth.translations_to_dq(np.zeros((1, 3)), np.random.default_rng(1))])
+    wf2 = make_wf(dfu, pos2, dq2, np.concatenate([dg_w, [0.0375]]).astype(np.float32))
+    part = _volume(dfu, dim, 224, 288)
+    part.integrate(d, np.eye(4), synth.INTR, wf2)
+    assert torch.equal(part.data, full.data[224:288])
+
+
+def test_tsdf_bad_arguments(dfu, dists_np):
+    d = dev(dists_np.view(np.int16), torch.int16)
+    with pytest.raises(dfu.DfuError):  # dims.x % 32 (src/kfusion/kinfu.cpp:47)
+        dfu.TsdfVolume((48, 48, 48)).integrate(d, np.eye(4), synth.INTR)
+    vol = _volume(dfu, 64)
+    with pytest.raises(dfu.DfuError):
+        vol.integrate(d, np.eye(4), synth.INTR, dfu.Warpfield())  # warp field not initialised
+
+
+# ---------------------------------------------------------------------------------------- solver
+def _gpu_solve(dfu, nodes, dq, src, dst, lambda_=0.0, **kw):
+    wf = make_wf(dfu, nodes, dq, np.full(len(nodes), fx.DG_W, np.float32), fx.EPSILON_DYNFU)
+    prm = dfu.CombinedSolverParameters(numIter=fx.PARAMS["num_iter"], nonLinearIter=fx.PARAMS["nonlinear_iter"],
+                                       linearIter=fx.PARAMS["linear_iter"], useOpt=False, useOptLM=True, earlyOut=True, **kw)
+    s = dfu.CombinedSolver(wf, prm, fx.PARAMS["tukey_offset"], fx.PARAMS["psi_data"], lambda_, fx.PARAMS["psi_reg"])
+    s.initializeProblemInstance(dev(src), dev(dst))
+    s.solveAll()
+    return wf, s
+
+
+def _warp(wf, v):
+    return wf.warpToLive(dev(v))[0].cpu().numpy()
+
+
+@pytest.mark.parametrize("case", fx.SINGLE_SOLVE_CASES, ids=[c[0] for c in fx.SINGLE_SOLVE_CASES])
+def test_opt_single_solve(dfu, case):
+    """test/opt_optimisation_test.cpp:212-451: calcDQB(v).transformVertex(v) ~= target within 1e-3 (:94)"""
+    _, nodes, src, dst = case
+    wf, s = _gpu_solve(dfu, nodes, fx.identity_dq(len(nodes)), src, dst)
+    assert np.max(np.abs(_warp(wf, src) - dst)) <= fx.MAX_ERROR
+    st = s.getStats()
+    assert st["final_energy"] <= st["initial_energy"]
+
+
+def test_opt_warp_twice_thrice_reverse(dfu):
+    nodes = fx.NODES_GROUP1
+    # :454-527
+    wf, _ = _gpu_solve(dfu, nodes, fx.identity_dq(8), fx.WARP_SRC, fx.WARP_T1)
+    assert np.max(np.abs(_warp(wf, fx.WARP_SRC) - fx.WARP_T1)) <= fx.MAX_ERROR
+    w1 = _warp(wf, fx.WARP_SRC)
+    dq1 = wf.getNodes()[1].cpu().numpy()
+    wf2, _ = _gpu_solve(dfu, nodes, dq1, w1, fx.WARP_T2)
+    assert np.max(np.abs(_warp(wf2, fx.WARP_SRC) - fx.WARP_T2)) <= fx.MAX_ERROR
+    # :530-630
+    w2 = _warp(wf2, w1)
+    dq2 = wf2.getNodes()[1].cpu().numpy()
+    wf3, _ = _gpu_solve(dfu, nodes, dq2, w2, fx.WARP_T3)
+    assert np.max(np.abs(_warp(wf3, w1) - fx.WARP_T3)) <= fx.MAX_ERROR
+    # :632-698
+    wfr, _ = _gpu_solve(dfu, nodes, dq1, fx.WARP_T1, fx.WARP_SRC)
+    assert np.max(np.abs(_warp(wfr, fx.WARP_SRC) - fx.WARP_SRC)) <= fx.MAX_ERROR
+
+
+def test_solver_needs_8_nodes(dfu):
+    with pytest.raises(dfu.DfuError) as e:
+        _gpu_solve(dfu, fx.NODES_GROUP1[:5], fx.identity_dq(5), fx.WARP_SRC, fx.WARP_T1)
+    assert e.value.code == 3  # DFU_ERR_PRECONDITION
+
+
+def _wellposed(seed=3, N=1024, P=30000):
+    rng = np.random.default_rng(seed)
+    pos, _, dg_w, t_true = synth.sphere_nodes(N, 0.025)
+    canon = (pos[rng.integers(0, N, P)] + rng.normal(0, 0.01, (P, 3))).astype(np.float32)
+    return pos, dg_w, canon, t_true
+
+
+@pytest.mark.parametrize("lambda_", [200.0, 5.0])
+def test_solver_matches_oracle_energy_and_transforms(dfu, oracle, lambda_):
+    """Well-posed problem (P >> N, lambda > 0): converged energy and node translations within 1e-4 relative of
+    the double-precision oracle (the north-star's bar against 'Ceres'; see DESIGN.md on why the oracle stands in)."""
+    pos, dg_w, canon, t_true = _wellposed()
+    N = len(pos)
+    wtmp = oracle.warp(pos, synth.translations_to_dq(0.2 * t_true), dg_w, canon)  # displacement < tukey support
+    live = wtmp.astype(np.float32)
+    prm_o = pyoracle.default_params(num_iter=6, nonlinear_iter=2, linear_iter=400, lambda_=lambda_, pcg_tol=1e-10)
+    t_o, dq_o, st_o = oracle.solve(pos, synth.identity_dq(N), dg_w, canon, live, prm_o)
+    wf = make_wf(dfu, pos, synth.identity_dq(N), dg_w, 0.025)
+    prm = dfu.CombinedSolverParameters(numIter=6, nonLinearIter=2, linearIter=400, earlyOut=True, pcgTolerance=1e-7)
+    s = dfu.CombinedSolver(wf, prm, 4.652, 1e-2, lambda_, 1e-4)
+    s.initializeProblemInstance(dev(canon), dev(live))
+    s.solveAll()
+    st = s.getStats()
+    t_g = s.getTranslations().cpu().numpy().astype(np.float64)
+    assert abs(st["initial_energy"] - st_o[0]) <= 1e-4 * st_o[0]
+    assert abs(st["final_energy"] - st_o[1]) <= 1e-4 * st_o[1], (st, st_o)
+    scale = np.abs(t_o).max()
+    assert np.max(np.abs(t_g - t_o)) <= 1e-4 * scale, np.max(np.abs(t_g - t_o)) / scale
+    # the write-back composed DQ(0,0,0,t) onto the nodes exactly once
+    dq_g = wf.getNodes()[1].cpu().numpy()
+    assert np.max(np.abs(dq_g - dq_o)) <= 1e-4 * scale
+    assert np.all(dq_g[:, 0] == 1.0) and not dq_g[:, 1:5].any()
+
+
+def test_solver_fixed_iteration_mode_is_async_and_matches_oracle(dfu, oracle):
+    """bench configuration: 5 GN iterations x <= 10 PCG, no early out (no host sync inside solveAll)"""
+    pos, dg_w, canon, t_true = _wellposed(seed=9)
+    N = len(pos)
+    live = oracle.warp(pos, synth.translations_to_dq(0.2 * t_true), dg_w, canon)
+    prm_o = pyoracle.default_params(num_iter=5, nonlinear_iter=1, linear_iter=10, lambda_=200.0, pcg_tol=0.0, early_out=0)
+    t_o, _, st_o = oracle.solve(pos, synth.identity_dq(N), dg_w, canon, live, prm_o)
+    wf = make_wf(dfu, pos, synth.identity_dq(N), dg_w, 0.025)
+    prm = dfu.CombinedSolverParameters(numIter=5, nonLinearIter=1, linearIter=10, earlyOut=False, pcgTolerance=0.0)
+    s = dfu.CombinedSolver(wf, prm, 4.652, 1e-2, 200.0, 1e-4)
+    s.initializeProblemInstance(dev(canon), dev(live))
+    s.solveAll()
+    st = s.getStats()
+    assert st["pcg_iterations"] == 50 and st["gn_steps"] == 5
+    assert abs(st["final_energy"] - st_o[1]) <= 1e-4 * st_o[1], (st, st_o)
+    t_g = s.getTranslations().cpu().numpy()
+    assert np.max(np.abs(t_g - t_o)) <= 1e-4 * np.abs(t_o).max()
+
+
+def test_solver_allreduce_hook_two_partitions(dfu, oracle):
+    """data-parallel contract on one GPU: two solvers hold disjoint point partitions and exchange their
+    normal-equation buffers through the all-reduce hook; the result equals the single-partition solve."""
+    pos, dg_w, canon, t_true = _wellposed(seed=4, N=512, P=8000)
+    N = len(pos)
+    live = oracle.warp(pos, synth.translations_to_dq(0.2 * t_true), dg_w, canon)
+    prm = dfu.CombinedSolverParameters(numIter=3, nonLinearIter=1, linearIter=12, earlyOut=False, pcgTolerance=0.0)
+
+    def run(parts):
+        wfs, solvers, bufs = [], [], {}
+        for lo, hi in parts:
+            wf = make_wf(dfu, pos, synth.identity_dq(N), dg_w, 0.025)
+            s = dfu.CombinedSolver(wf, prm, 4.652, 1e-2, 200.0, 1e-4)
+            s.initializeProblemInstance(dev(canon[lo:hi]), dev(live[lo:hi]))
+            wfs.append(wf)
+            solvers.append(s)
+        return wfs, solvers
+
+    wfs, (s_full,) = run([(0, 8000)])
+    s_full.solveAll()
+    t_full = s_full.getTranslations().cpu().numpy()
+
+    # emulate 2 ranks in lock step with threads: the hook sums the two ranks' buffers
+    import threading
+    wfs2, solvers = run([(0, 3000), (3000, 8000)])
+    barrier = threading.Barrier(2)
+    shared = [None, None]
+
+    def make_hook(rank):
+        def hook(t):
+            torch.cuda.current_stream().synchronize()
+            shared[rank] = t.clone()
+            barrier.wait()
+            total = shared[0] + shared[1]
+            barrier.wait()
+            t.copy_(total)
+        return hook
+
+    for r, s in enumerate(solvers):
+        s.setAllReduce(make_hook(r))
+    ths = [threading.Thread(target=s.solveAll) for s in solvers]
+    [th.start() for th in ths]
+    [th.join() for th in ths]
+    t0 = solvers[0].getTranslations().cpu().numpy()
+    t1 = solvers[1].getTranslations().cpu().numpy()
+    assert np.array_equal(t0, t1)  # every rank computes bit-identical iterates after the all-reduce
+    assert np.max(np.abs(t0 - t_full)) <= 1e-5 * np.abs(t_full).max()
+
+
+# --------------------------------------------------------------------------------- frame operator
+def test_frame_operator_end_to_end(dfu, oracle):
+    """DynFusion()(depth): frame 0 rigid into the canonical volume, frame 1 = warp + solve + warped fusion;
+    checked step by step against the oracle."""
+    dim = 64
+    kp = dfu.KinFuParams(volume_dims=(dim, dim, dim))
+    prm = dfu.DynFuParams(kinfuParams=kp, epsilon=0.03, lambda_=200.0,
+                          solver=dfu.CombinedSolverParameters(numIter=5, nonLinearIter=1, linearIter=10, earlyOut=False,
+                                                              pcgTolerance=0.0))
+    depth = synth.sphere_depth()
+    pos, _, dg_w, t_true = synth.sphere_nodes(512, 0.03)
+    canon = synth.backproject(depth, synth.INTR, stride=4)
+    live = oracle.warp(pos, synth.translations_to_dq(0.2 * t_true), dg_w, canon)
+    df = dfu.DynFusion(prm)
+    df.init(dev(canon), None, nodes=(dev(pos), dev(synth.identity_dq(512)), dev(dg_w)))
+    dpin = torch.from_numpy(depth.view(np.int16)).pin_memory()
+    assert df(dpin) and df(dpin, dev(live))
+    torch.cuda.synchronize()
+    # oracle replay
+    dists = oracle.compute_dists(depth, synth.INTR)
+    ref = np.zeros((dim,) * 3, np.uint32)
+    _oracle_integrate(oracle, ref, dists)
+    prm_o = pyoracle.default_params(num_iter=5, nonlinear_iter=1, linear_iter=10, lambda_=200.0, pcg_tol=0.0, early_out=0)
+    t_o, dq_o, st_o = oracle.solve(pos, synth.identity_dq(512), dg_w, canon, live, prm_o)
+    st = df.solver.getStats()
+    assert abs(st["final_energy"] - st_o[1]) <= 1e-4 * st_o[1]
+    dq_g = df.warpfield.getNodes()[1].cpu().numpy()
+    assert np.max(np.abs(dq_g - dq_o)) <= 1e-4 * np.abs(t_o).max()
+    # the fused volume: replay the oracle integrator with the GPU's own solved transforms -> bit exact
+    _oracle_integrate(oracle, ref, dists, nodes=(pos, dq_g, dg_w))
+    assert _mismatch(df.volume.data.cpu().numpy().view(np.uint32), ref) == 0
