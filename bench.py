@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of DynamicFusion's per-frame hot path on B200 (BASELINE.json's metric).
+
+One step = one frame of the full per-frame loop of BASELINE configs[2] at the size of configs[1]:
+    compute_dists -> warpToLive of the canonical surface points (8-NN + DQB) -> data graph
+    -> 5 Gauss-Newton iterations x 10 PCG iterations (Tukey re-weighting each GN iteration)
+    -> write-back onto the nodes -> WARPED TSDF integration of the live depth into the 512^3 canonical volume
+on a synthetic bending cylinder (4096 nodes, ~76k surface points, 640x480 depth).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+N > 1 runs under torchrun (one rank per GPU, NCCL): the volume is sharded into z-slabs, the surface points are
+partitioned, the per-node normal-equation buffers are all-reduced ("strong" scaling: same frame, more GPUs).
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with the frame's inputs already resident in HBM;
+`e2e` = the same through the public API with HOST inputs (pinned depth + live points up, energy + node
+transforms down, every step).  `roofline` is for the dominant kernel (integrate_kernel) from CUDA events
+measured inside this run; `cpu_baseline` is the CPU oracle (restated reference path, kNN through the
+reference's own nanoflann when oracle/_ref is present) timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests import synth  # noqa: E402
+
+DIM = 512
+N_THETA, N_Y = 64, 64
+EPSILON = 0.0125
+KAPPA = 0.05
+GN_ITERS, PCG_ITERS = 5, 10
+LAMBDA = 200.0
+RING = 4
+AMPL = [1.0, 2.0, 3.0, 2.0]  # bend amplitude of frame i is KAPPA*AMPL[i % 4]: consecutive frames differ by KAPPA
+ALGO_BYTES_PER_VOXEL = 8     # 4 B read + 4 B write of the ushort2 voxel, full sweep
+
+
+def make_scene():
+    depth0 = synth.cylinder_depth()
+    canon = synth.backproject(depth0, synth.INTR)
+    pos, dq, dg_w = synth.cylinder_nodes(N_THETA, N_Y, EPSILON)
+    depths = [synth.cylinder_depth(kappa=KAPPA * a) for a in AMPL]
+    lives = [synth.bend(canon, KAPPA * a) for a in AMPL]
+    return dict(depth0=depth0, canon=canon, pos=pos, dq=dq, dg_w=dg_w, depths=depths, lives=lives)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
+        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU arm: the restated reference path (oracle), all host threads, bounded sample of the same frame
+def cpu_frame(scene, budget_planes=64):
+    from oracle import pyoracle
+
+    try:
+        o = pyoracle.Oracle("nanoflann")
+        knn = "reference nanoflann KD-tree (oracle/_ref)"
+    except FileNotFoundError:
+        o = pyoracle.Oracle("brute")
+        knn = "brute-force kNN (oracle/_ref absent)"
+    pos, dq, dg_w, canon = scene["pos"], scene["dq"], scene["dg_w"], scene["canon"]
+    live, depth = scene["lives"][0], scene["depths"][0]
+    t0 = time.perf_counter()
+    dists = o.compute_dists(depth, synth.INTR)
+    warped = o.warp(pos, dq, dg_w, canon)
+    prm = pyoracle.default_params(num_iter=GN_ITERS, nonlinear_iter=1, linear_iter=PCG_ITERS, lambda_=LAMBDA,
+                                  pcg_tol=0.0, early_out=0)
+    t_sol, dq_new, _ = o.solve(pos, dq, dg_w, warped, live, prm)
+    t_points = time.perf_counter() - t0
+    # warped integration on a bounded sample: every (DIM/budget)-th plane, extrapolated to DIM planes
+    vs = synth.voxel_size(DIM)
+    tr = o.trunc_dist(synth.TRUNC, vs)
+    stride = DIM // budget_planes
+    planes = list(range(stride // 2, DIM, stride))
+    vol = np.zeros((1, DIM, DIM), np.uint32)  # one plane of scratch, re-used (the C side offsets by z)
+    t1 = time.perf_counter()
+    for z in planes:
+        # shift the base pointer so that plane z lands in the scratch plane
+        base = vol.ctypes.data - z * DIM * DIM * 4
+        _integrate_plane(o, base, vs, tr, dists, (pos, dq_new, dg_w), z)
+    t_planes = time.perf_counter() - t1
+    t_int = t_planes * DIM / len(planes)
+    total = t_points + t_int
+    return dict(frames_per_s=1.0 / total, cores=o.num_threads(), t_points=t_points, t_integrate_est=t_int,
+                sample="1 frame: compute_dists + warp of %d points + %dx%d GN/PCG in full, warped integrate timed on %d of %d "
+                       "z-planes (every %dth) and extrapolated; kNN = %s" %
+                       (len(canon), GN_ITERS, PCG_ITERS, len(planes), DIM, stride, knn))
+
+
+def _integrate_plane(o, base_ptr, vs, tr, dists, nodes, z):
+    import ctypes as C
+    from oracle.pyoracle import _f, _f32
+
+    dims = np.array([DIM, DIM, DIM], np.int32)
+    pos, dq, dg_w = _f32(nodes[0], (-1, 3)), _f32(nodes[1], (-1, 8)), _f32(nodes[2])
+    v2c, intr = _f32(synth.VOL2CAM), _f32(synth.INTR)
+    d = np.ascontiguousarray(dists, np.uint16)
+    o.lib.orc_tsdf_integrate(C.cast(base_ptr, C.POINTER(C.c_uint32)), dims.ctypes.data_as(C.POINTER(C.c_int32)), _f(vs),
+                             tr, synth.MAX_WEIGHT, _f(v2c), _f(intr), d.ctypes.data_as(C.POINTER(C.c_uint16)),
+                             d.shape[1] * 2, d.shape[0], d.shape[1], _f(pos), _f(dq), _f(dg_w), pos.shape[0], 0, z, z + 1,
+                             None)
+
+
+def config_dict(n_gpus, P):
+    return {"workload": "C3 full per-frame loop at C2 size: compute_dists + warpToLive(8-NN+DQB) + %d GN x %d PCG + warped "
+                        "TSDF integrate, %d^3 volume, %d nodes, %d surface points, 640x480 depth, bending cylinder" %
+                        (GN_ITERS, PCG_ITERS, DIM, N_THETA * N_Y, P),
+            "volume": "%d^3 ushort2 (512 MiB, larger than the 126 MB L2: no L2 flush needed between steps)" % DIM,
+            "blend": "REF_COMPOSE (reference calcDQB)", "lambda": LAMBDA, "parallelism":
+            "z-slabs x point partitions over %d GPU(s)" % n_gpus}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    scene = make_scene()
+    for _ in range(min(args.warmup, 1)):
+        cpu_frame(scene, budget_planes=4)
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        vals.append(cpu_frame(scene, budget_planes=64))
+    best = max(vals, key=lambda r: r["frames_per_s"])
+    fps = float(np.mean([r["frames_per_s"] for r in vals]))
+    line = {"impl": "reference", "metric": "frames/sec (512^3 TSDF, 4096 nodes)", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / fps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args.gpus, len(scene["canon"])),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": best["cores"], "kind": "port",
+                             "sample": best["sample"]},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    import dynfu_b200 as dfu
+    from dynfu_b200._lib import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU: the product has no CPU fallback"
+    torch.cuda.set_device(local)
+    devs = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=devs)
+
+    scene = make_scene()
+    P_all = len(scene["canon"])
+    # z-slab of this rank (multiples of 8 planes) and its contiguous point partition
+    planes = DIM // 8
+    z0 = (planes * rank // world) * 8
+    z1 = (planes * (rank + 1) // world) * 8
+    p0, p1 = P_all * rank // world, P_all * (rank + 1) // world
+
+    def dev(a, dt=torch.float32):
+        return torch.as_tensor(np.ascontiguousarray(a)).to(devs, dtype=dt)
+
+    prm = dfu.DynFuParams(kinfuParams=dfu.KinFuParams(volume_dims=(DIM, DIM, DIM)), epsilon=EPSILON, lambda_=LAMBDA,
+                          solver=dfu.CombinedSolverParameters(numIter=GN_ITERS, nonLinearIter=1, linearIter=PCG_ITERS,
+                                                              earlyOut=False, pcgTolerance=0.0))
+    df = dfu.DynFusion(prm, device=devs, z0=z0, z1=z1)
+    if world > 1:
+        df.allreduce = lambda t: dist.all_reduce(t)
+    df.init(dev(scene["canon"][p0:p1]), None, nodes=(dev(scene["pos"]), dev(scene["dq"]), dev(scene["dg_w"])))
+
+    depth_host = [torch.from_numpy(d.view(np.int16)).pin_memory() for d in scene["depths"]]
+    live_host = [torch.from_numpy(np.ascontiguousarray(l[p0:p1])).pin_memory() for l in scene["lives"]]
+    depth_dev = [d.to(devs) for d in depth_host]
+    live_dev = [l.to(devs) for l in live_host]
+    live_stage = torch.empty_like(live_dev[0])
+    dq_out_host = torch.empty((N_THETA * N_Y, 8), dtype=torch.float32).pin_memory()
+    kp = prm.kinfuParams
+
+    # frame 0 (untimed): the canonical volume, rigid integration of the undeformed surface
+    df(torch.from_numpy(scene["depth0"].view(np.int16)).pin_memory())
+    torch.cuda.synchronize()
+
+    ev_int = []
+
+    def step_device(i, timed=False):
+        """inputs already in HBM"""
+        dfu.compute_dists(depth_dev[i % RING], kp.intr, out=df._dists)
+        df.warpCanonicalToLiveOpt(live_dev[i % RING])
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        df.volume.integrate(df._dists, df.camera_pose, kp.intr, df.warpfield, prm.blend_mode)
+        if timed:
+            b.record()
+            ev_int.append((a, b))
+
+    def step_host(i):
+        """public API with host buffers: depth + live points up, energy + node transforms down"""
+        live_stage.copy_(live_host[i % RING], non_blocking=True)
+        df(depth_host[i % RING], live_stage)
+        stats = df.solver.getStats()  # D2H of the solver scalars (synchronises)
+        _, dq, _ = df.warpfield.getNodes()
+        dq_out_host.copy_(dq, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn, K, **kw):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(K):
+            fn(i, **kw)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=devs)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        step_device(i)
+        step_host(i)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.dfu_launch_count()
+    ms_dev = timed_loop(step_device, args.steps, timed=True)
+    launches = lib.dfu_launch_count() - launches0
+    ms_e2e = timed_loop(step_host, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    stats = df.solver.getStats()
+
+    # dominant kernel: integrate_kernel, timed with CUDA events on the launching stream inside the timed region
+    int_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_int]))
+    int_ms_t = torch.tensor([int_ms], device=devs)
+    if world > 1:
+        dist.all_reduce(int_ms_t, op=dist.ReduceOp.MAX)
+    int_ms = float(int_ms_t.item())
+    voxels_rank = DIM * DIM * (z1 - z0)
+    hbm_peak, peak_src = peaks()
+    achieved = voxels_rank * ALGO_BYTES_PER_VOXEL / (int_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        fps = args.steps / (ms_dev * 1e-3)
+        fps_e2e = args.steps / (ms_e2e * 1e-3)
+        line = {
+            "metric": "frames/sec (512^3 TSDF, 4096 nodes)", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(world, P_all),
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(depth_host[0].numel() * 2 + live_host[0].numel() * 4),
+                    "d2h_bytes_per_step": int(dq_out_host.numel() * 4 + 48)},
+            "gpu_launches": int(launches),
+            "voxels_per_s": DIM ** 3 * fps,
+            "roofline": {"kernel": "integrate_kernel (warped projective TSDF integration)", "bound": "hbm",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": int_ms,
+                         "algorithmic_bytes_per_launch": voxels_rank * ALGO_BYTES_PER_VOXEL,
+                         "share_of_step": int_ms / (ms_dev / args.steps)},
+            "solver": {"final_energy": stats["final_energy"], "initial_energy": stats["initial_energy"],
+                       "pcg_iterations": stats["pcg_iterations"], "gn_steps": stats["gn_steps"]},
+            "clocks": clocks,
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "integrate_traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if not args.no_cpu_baseline and world == 1:
+            c = cpu_frame(scene)
+            line["cpu_baseline"] = {"value": c["frames_per_s"], "unit": "frames/s", "cores": c["cores"], "kind": "port",
+                                    "sample": c["sample"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -46,6 +46,7 @@ _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _SIGS = {
     "dfu_version": ([], C.c_int),
     "dfu_last_error": ([], C.c_char_p),
+    "dfu_launch_count": ([], C.c_ulonglong),
     "dfu_device_check": ([_i], _i),
     "dfu_warpfield_create": ([C.POINTER(_vp), _i], _i),
     "dfu_warpfield_destroy": ([_vp], _i),

@@ -25,7 +25,13 @@ void dfu_set_error(const char* fmt, ...);
             return code;                                           \
         }                                                          \
     } while (0)
-#define DFU_LAUNCH_OK() DFU_CUDA_OK(cudaGetLastError())
+// every kernel launch of the library goes through this macro, so the counter is the number of OUR kernels launched
+extern unsigned long long g_dfu_launches;
+#define DFU_LAUNCH_OK()                     \
+    do {                                    \
+        ++g_dfu_launches;                   \
+        DFU_CUDA_OK(cudaGetLastError());    \
+    } while (0)
 
 static inline cudaStream_t as_stream(dfu_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int div_up(long a, long b) { return (int) ((a + b - 1) / b); }

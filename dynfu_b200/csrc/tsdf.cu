@@ -105,20 +105,37 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
     const size_t plane = (size_t) a.dx * a.dy;
 
     // ---- classify the four bricks of this tile ------------------------------------------------------
+    // A brick must run the exact per-voxel warp ("near") unless every voxel of it is PROVABLY left where it is:
+    //  (a) all 8 weights are exactly 0.f beyond sqrt(209)*dg_w of every node (dfu_math.cuh node_weight), or
+    //  (b) translation-only field: p' = fl(p + 2*acc) with |2*acc_c| <= 16*dmax*w, w <= exp(-dmin^2/(2 maxw^2));
+    //      when that is below p_c * 2^-26 (less than half an ulp of p_c >= voxel size) the addition returns p_c
+    //      bit for bit.  Bricks touching index 0 of an axis (p_c == 0) are excluded from (b).
     int near_mask = 0;
     bool translation_only = false;
+    float reff2 = 0.f;  // squared distance beyond which rule (b) holds for a single voxel (0: rule unavailable)
     const float r_brick = 3.5f * sqrtf(a.vsx * a.vsx + a.vsy * a.vsy + a.vsz * a.vsz);  // brick half diagonal
     const size_t brick0 = a.warped ? (size_t) (x0 / 8) + (size_t) a.bdx * ((y0 / 8) + (size_t) a.bdy * (zt / 8)) : 0;
     if (a.warped) {
         translation_only = a.flags[0] != 0;
         const float maxw = __int_as_float(a.flags[1]);
-        // a weight is exactly 0 beyond sqrt(209)*dg_w (dfu_math.cuh node_weight); 1.001 covers rounding
-        const float r_active = 14.4569f * maxw * 1.001f + 1e-6f;
+        const float dmax = __int_as_float(a.flags[2]);
+        const float r_zero = 14.4569f * maxw * 1.001f + 1e-6f;  // rule (a); 1.001 covers rounding
         const bool all_near = (a.blend_mode == DFU_BLEND_REF_COMPOSE) && !translation_only;
+        float r_eff = r_zero;
+        if (translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
+            const float vmin = fminf(a.vsx, fminf(a.vsy, a.vsz));
+            // 16*dmax*exp(-x) * 1.0001 < vmin * 2^-26  <=>  x > L
+            const float L = logf(fmaxf(16.f * dmax * 1.0001f, 1e-37f)) - logf(vmin * 1.4901161e-8f) + 1e-3f;
+            const float re = L > 0.f ? maxw * sqrtf(2.f * L) * 1.0001f + 1e-6f : 0.f;
+            r_eff = fminf(r_zero, re);
+            reff2 = r_eff * r_eff;
+        }
 #pragma unroll
         for (int sb = 0; sb < 4; ++sb) {
             const float2 b = __ldg(&a.bounds[brick0 + sb]);
-            if (all_near || (sqrtf(b.y) - r_brick <= r_active)) near_mask |= 1 << sb;
+            const float dmin = sqrtf(b.y) - r_brick;  // lower bound of voxel-to-node distance in this brick
+            const bool on_zero_plane = (x0 + sb * 8 == 0) || (y0 == 0) || (zt == 0);
+            if (all_near || dmin <= (on_zero_plane ? r_zero : r_eff)) near_mask |= 1 << sb;
         }
     }
 
@@ -158,10 +175,20 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
         const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
         float px[4];
         Top8 t[4];
+        const float d8c = sqrtf(__ldg(&a.bounds[brick0 + sb]).x);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             px[v] = fmul((float) (x + v), a.vsx);
-            top8_init(t[v]);
+            // the 8 nodes nearest to the brick centre are within d8c + |v - centre| of voxel v: start every
+            // slot at that (inflated) bound, so the bulk of the candidates fails the first compare
+            const float ex = px[v] - bcx, ey = py - bcy, ez = pz - bcz;
+            const float bnd = (d8c + sqrtf(ex * ex + ey * ey + ez * ez)) * 1.0001f + 1e-6f;
+            const float bnd2 = bnd * bnd;
+#pragma unroll
+            for (int k = 0; k < DFU_KNN; ++k) {
+                t[v].d[k] = bnd2;
+                t[v].i[k] = -1;
+            }
         }
 #pragma unroll 1
         for (int c0 = 0; c0 < a.N; c0 += CHUNK) {
@@ -213,7 +240,10 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
         for (int v = 0; v < 4; ++v) {
             V3 w;
             if (translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
-                w = warp_translation_only(t[v], px[v], py, pz, a.pos_w, a.dual);
+                if (t[v].d[0] > reff2 && x + v > 0 && y > 0 && z > 0)
+                    w = V3{px[v], py, pz};  // rule (b) for this voxel: the warp returns p bit for bit
+                else
+                    w = warp_translation_only(t[v], px[v], py, pz, a.pos_w, a.dual);
             } else {
                 const DQ b = blend(a.blend_mode, t[v], px[v], py, pz, a.pos_w, a.real, a.dual);
                 w = dq_transform_vertex(b, V3{px[v], py, pz});

@@ -21,6 +21,8 @@ void dfu_set_error(const char* fmt, ...) {
 }
 extern "C" const char* dfu_last_error(void) { return g_err; }
 extern "C" int dfu_version(void) { return DFU_VERSION; }
+unsigned long long g_dfu_launches = 0;
+extern "C" unsigned long long dfu_launch_count(void) { return g_dfu_launches; }
 
 extern "C" int dfu_device_check(int device) {
     int n = 0;
@@ -92,29 +94,34 @@ __global__ void unpack_nodes_kernel(const float4* __restrict__ pos_w, const floa
 }
 
 // flags[0] = 1 iff every node is a pure translation: real == (1,0,0,0) and dual.w == 0 (the only state the
-// reference ever produces, src/dynfu/utils/opt_solver.cpp:280-281); flags[1] = max dg_w (float bits)
+// reference ever produces, src/dynfu/utils/opt_solver.cpp:280-281); flags[1] = max dg_w (float bits);
+// flags[2] = max over nodes of max(|dual.x|,|dual.y|,|dual.z|) (float bits)
 __global__ void node_flags_kernel(const float4* __restrict__ pos_w, const float4* __restrict__ real,
                                   const float4* __restrict__ dual, int N, int* __restrict__ flags) {
     __shared__ int s_ok;
-    __shared__ unsigned s_maxw;
+    __shared__ unsigned s_maxw, s_maxd;
     if (threadIdx.x == 0) {
         s_ok = 1;
         s_maxw = 0u;
+        s_maxd = 0u;
     }
     __syncthreads();
     int ok = 1;
-    float mw = 0.f;
+    float mw = 0.f, md = 0.f;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const float4 r = real[i], d = dual[i];
         ok &= (r.x == 1.f && r.y == 0.f && r.z == 0.f && r.w == 0.f && d.x == 0.f);
         mw = fmaxf(mw, pos_w[i].w);
+        md = fmaxf(md, fmaxf(fabsf(d.y), fmaxf(fabsf(d.z), fabsf(d.w))));
     }
     if (!ok) atomicAnd(&s_ok, 0);
-    atomicMax(&s_maxw, __float_as_uint(mw));  // dg_w > 0: uint order == float order
+    atomicMax(&s_maxw, __float_as_uint(mw));  // non-negative floats: uint order == float order
+    atomicMax(&s_maxd, __float_as_uint(md));
     __syncthreads();
     if (threadIdx.x == 0) {
         flags[0] = s_ok;
         flags[1] = (int) s_maxw;
+        flags[2] = (int) s_maxd;
     }
 }
 

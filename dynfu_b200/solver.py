@@ -48,8 +48,12 @@ class CombinedSolver:
         def _cb(buf, count, _ctx, stream):
             try:
                 t = _tensor_from_ptr(buf, count, dev)
-                with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=dev)):
-                    fn(t)
+                if stream:  # NULL = the legacy default stream, which is torch's default stream too
+                    with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=dev)):
+                        fn(t)
+                else:
+                    with torch.cuda.stream(torch.cuda.default_stream(dev)):
+                        fn(t)
                 return 0
             except Exception:  # never let an exception cross the C boundary
                 import traceback

@@ -65,6 +65,8 @@ typedef void* dfu_stream;                   /* cudaStream_t */
 
 int dfu_version(void);
 const char* dfu_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (instrumentation) */
+unsigned long long dfu_launch_count(void);
 /* 0 if a usable sm_100 device is visible, DFU_ERR_CUDA otherwise */
 int dfu_device_check(int device);
 

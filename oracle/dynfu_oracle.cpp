@@ -488,7 +488,7 @@ long orc_tsdf_integrate(uint32_t* vol, const int dims[3], const float voxel[3], 
     const float trunc_inv = 1.f / trunc; /* tsdf_volume.cu:106 */
     const size_t plane = (size_t) dims[0] * dims[1];
     long touched = 0;
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : touched)
+#pragma omp parallel for collapse(2) schedule(dynamic, 4) reduction(+ : touched)
     for (int z = z0; z < z1; ++z)
         for (int y = 0; y < dims[1]; ++y)
             for (int x = 0; x < dims[0]; ++x) {

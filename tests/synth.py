@@ -54,18 +54,23 @@ def sphere_depth(rows=480, cols=640, intr=None, center=(0.0, 0.0, 2.0), radius=0
     return np.where(hit, np.clip(np.round(z * 1000.0), 0, 65535), 0).astype(np.uint16)
 
 
-def cylinder_depth(rows=480, cols=640, intr=None, center=(0.0, 0.0, 2.0), radius=0.3, length=1.6):
-    """Depth (uint16 mm) of a cylinder whose axis is parallel to y."""
+def cylinder_depth(rows=480, cols=640, intr=None, center=(0.0, 0.0, 2.0), radius=0.3, length=1.6, kappa=0.0):
+    """Depth (uint16 mm) of a cylinder whose axis is parallel to y, optionally bent by x += kappa*(y-cy)^2
+    (the axis becomes a parabola; solved per ray by fixed-point iteration from the straight cylinder)."""
     intr = intr_for(cols, rows) if intr is None else intr
     d = _rays(rows, cols, intr)
     c = np.asarray(center, np.float64)
     a = d[..., 0] ** 2 + d[..., 2] ** 2
-    b = -2.0 * (d[..., 0] * c[0] + d[..., 2] * c[2])
-    cc = c[0] ** 2 + c[2] ** 2 - radius * radius
-    disc = b * b - 4 * a * cc
-    hit = disc >= 0
-    s = np.where(hit, (-b - np.sqrt(np.where(hit, disc, 0))) / (2 * a), 0.0)
-    y = s * d[..., 1]
+    shift = np.zeros(d.shape[:2])
+    for _ in range(8 if kappa else 1):
+        cx = c[0] + shift
+        b = -2.0 * (d[..., 0] * cx + d[..., 2] * c[2])
+        cc = cx ** 2 + c[2] ** 2 - radius * radius
+        disc = b * b - 4 * a * cc
+        hit = disc >= 0
+        s = np.where(hit, (-b - np.sqrt(np.where(hit, disc, 0))) / (2 * a), 0.0)
+        y = s * d[..., 1]
+        shift = np.where(hit, kappa * (y - c[1]) ** 2, shift)
     hit &= np.abs(y - c[1]) <= length / 2
     z = s * d[..., 2]
     return np.where(hit, np.clip(np.round(z * 1000.0), 0, 65535), 0).astype(np.uint16)
