@@ -5,19 +5,31 @@
 
 namespace dfu {
 
-// ---- blending ------------------------------------------------------------------------------------
+// Node::getTransformationWeight for the 8 neighbours of p (missing neighbours, idx < 0, get weight 0)
+DFU_DEV void neighbour_weights(const Top8& t, float px, float py, float pz, const float4* __restrict__ pos_w,
+                               float (&w)[DFU_KNN]) {
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) {
+        const int j = t.i[k];
+        if (j < 0) {
+            w[k] = 0.f;
+        } else {
+            const float4 nd = __ldg(&pos_w[j]);
+            w[k] = node_weight(nd.x, nd.y, nd.z, nd.w, px, py, pz, t.d[k]);
+        }
+    }
+}
+
 // Warpfield::calcDQB (src/dynfu/warp_field.cpp:127-148)
-DFU_DEV DQ blend_ref_compose(const Top8& t, float px, float py, float pz, const float4* __restrict__ pos_w,
-                             const float4* __restrict__ real, const float4* __restrict__ dual) {
+DFU_DEV DQ blend_ref_compose(const Top8& t, const float (&w)[DFU_KNN], const float4* __restrict__ real,
+                             const float4* __restrict__ dual) {
     DQ sum = dq_from_translation(0.f, 0.f, 0.f);  // DualQuaternion(0,0,0,0,0,0), warp_field.cpp:133
 #pragma unroll
     for (int k = 0; k < DFU_KNN; ++k) {
         const int j = t.i[k];
         if (j < 0) break;  // fewer than 8 nodes: the reference loops over what knnSearch returned
-        const float4 nd = __ldg(&pos_w[j]);
-        const float w = node_weight(nd.x, nd.y, nd.z, nd.w, px, py, pz, t.d[k]);
         const Quat nr = make_quat(__ldg(&real[j]));
-        const Quat wd = qscale(make_quat(__ldg(&dual[j])), w);  // operator*(T): dual only (dual_quaternion.hpp:120)
+        const Quat wd = qscale(make_quat(__ldg(&dual[j])), w[k]);  // operator*(T): dual only (dual_quaternion.hpp:120)
         // operator*=(DQ): dual first with the OLD real, then real (dual_quaternion.hpp:131-135)
         const Quat ndual = qadd(qmul(sum.real, wd), qmul(sum.dual, nr));
         sum.real = qmul(sum.real, nr);
@@ -31,18 +43,16 @@ DFU_DEV DQ blend_ref_compose(const Top8& t, float px, float py, float pz, const 
 
 // True dual-quaternion blending (north-star mode; no reference implementation): sign-aligned weighted
 // sum, both parts divided by |real|; no support (all weights underflow to 0) -> identity.
-DFU_DEV DQ blend_dqb_sum(const Top8& t, float px, float py, float pz, const float4* __restrict__ pos_w,
-                         const float4* __restrict__ real, const float4* __restrict__ dual) {
+DFU_DEV DQ blend_dqb_sum(const Top8& t, const float (&w)[DFU_KNN], const float4* __restrict__ real,
+                         const float4* __restrict__ dual) {
     Quat ar{0.f, 0.f, 0.f, 0.f}, ad{0.f, 0.f, 0.f, 0.f}, r0{1.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < DFU_KNN; ++k) {
         const int j = t.i[k];
         if (j < 0) break;
-        const float4 nd = __ldg(&pos_w[j]);
-        const float w = node_weight(nd.x, nd.y, nd.z, nd.w, px, py, pz, t.d[k]);
         const Quat nr = make_quat(__ldg(&real[j]));
         if (k == 0) r0 = nr;
-        const float ws = qdot(nr, r0) < 0.f ? -w : w;
+        const float ws = qdot(nr, r0) < 0.f ? -w[k] : w[k];
         ar = qadd(ar, qscale(nr, ws));
         ad = qadd(ad, qscale(make_quat(__ldg(&dual[j])), ws));
     }
@@ -52,12 +62,10 @@ DFU_DEV DQ blend_dqb_sum(const Top8& t, float px, float py, float pz, const floa
     return DQ{qscale(ar, inv), qscale(ad, inv)};
 }
 
-DFU_DEV DQ blend(int mode, const Top8& t, float px, float py, float pz, const float4* __restrict__ pos_w,
-                 const float4* __restrict__ real, const float4* __restrict__ dual) {
-    return mode == DFU_BLEND_REF_COMPOSE ? blend_ref_compose(t, px, py, pz, pos_w, real, dual)
-                                         : blend_dqb_sum(t, px, py, pz, pos_w, real, dual);
+DFU_DEV DQ blend(int mode, const Top8& t, const float (&w)[DFU_KNN], const float4* __restrict__ real,
+                 const float4* __restrict__ dual) {
+    return mode == DFU_BLEND_REF_COMPOSE ? blend_ref_compose(t, w, real, dual) : blend_dqb_sum(t, w, real, dual);
 }
-
 
 // Fast path for a translation-only field (every node real == (1,0,0,0), dual.w == 0 -- the only state
 // the reference ever produces, src/dynfu/utils/opt_solver.cpp:280-281).  Bit-identical to

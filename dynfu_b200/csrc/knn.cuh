@@ -100,4 +100,95 @@ DFU_DEV void knn8_scan_block(KnnSmem& sm, const float4* __restrict__ nodes, int 
     }
 }
 
+
+// ---- G lanes per query ------------------------------------------------------------------------------
+// The serial scan above has a critical path of N dependent compare/insert steps per thread.  For point
+// queries (tens of thousands, not millions) the node range is split over G consecutive lanes: lane `sub`
+// scans nodes sub, sub+G, ... (the G lanes read G consecutive float4 = conflict-free, other groups of the
+// warp get the same addresses by broadcast) and the G sorted lists are merged with warp shuffles.
+DFU_DEV bool lex_less(float d1, int i1, float d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
+
+DFU_DEV void lex_cswap(float& d1, int& i1, float& d2, int& i2) {
+    if (lex_less(d2, i2, d1, i1)) {
+        const float td = d1; d1 = d2; d2 = td;
+        const int ti = i1; i1 = i2; i2 = ti;
+    }
+}
+
+// merge the sorted top-8 lists of the G lanes of a group; afterwards every lane holds the group's top-8,
+// ascending by (dist2, idx)
+template <int G>
+DFU_DEV void top8_merge_group(Top8& t) {
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+        float od[DFU_KNN];
+        int oi[DFU_KNN];
+#pragma unroll
+        for (int k = 0; k < DFU_KNN; ++k) {  // partner's list, reversed
+            od[k] = __shfl_xor_sync(0xffffffffu, t.d[DFU_KNN - 1 - k], off);
+            oi[k] = __shfl_xor_sync(0xffffffffu, t.i[DFU_KNN - 1 - k], off);
+        }
+#pragma unroll
+        for (int k = 0; k < DFU_KNN; ++k)  // the 8 smallest of the union, as a bitonic sequence
+            if (lex_less(od[k], oi[k], t.d[k], t.i[k])) {
+                t.d[k] = od[k];
+                t.i[k] = oi[k];
+            }
+#pragma unroll
+        for (int st = DFU_KNN / 2; st > 0; st >>= 1)  // bitonic merge network
+#pragma unroll
+            for (int k = 0; k < DFU_KNN; ++k)
+                if ((k & st) == 0) lex_cswap(t.d[k], t.i[k], t.d[k + st], t.i[k + st]);
+    }
+}
+
+template <int G>
+DFU_DEV void knn8_scan_block_split(KnnSmem& sm, const float4* __restrict__ nodes, int Npad, float qx, float qy, float qz,
+                                   bool active, int sub, Top8& t) {
+    const int ntiles = (Npad + KNN_TILE - 1) / KNN_TILE;
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2 && s < ntiles; ++s) {
+            const int cnt = min(KNN_TILE, Npad - s * KNN_TILE);
+            mbar_expect_tx(&sm.bar[s], (uint32_t) cnt * 16u);
+            tma_bulk_g2s(sm.tile[s], nodes + (size_t) s * KNN_TILE, (uint32_t) cnt * 16u, &sm.bar[s]);
+        }
+    }
+    top8_init(t);
+    for (int tl = 0; tl < ntiles; ++tl) {
+        const int s = tl & 1;
+        const int cnt = min(KNN_TILE, Npad - tl * KNN_TILE);
+        mbar_wait(&sm.bar[s], (uint32_t) ((tl >> 1) & 1));
+        if (active) {
+            const float4* __restrict__ tile = sm.tile[s];
+            const int base = tl * KNN_TILE;
+#pragma unroll 1
+            for (int j = sub; j < cnt; j += 4 * G) {  // cnt % 32 == 0 and G | 8
+                float dd[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 p = tile[j + u * G];
+                    dd[u] = dist2(qx, qy, qz, p.x, p.y, p.z);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (dd[u] < t.d[DFU_KNN - 1]) top8_insert(t, dd[u], base + j + u * G);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && tl + 2 < ntiles) {
+            const int c2 = min(KNN_TILE, Npad - (tl + 2) * KNN_TILE);
+            fence_proxy_async();
+            mbar_expect_tx(&sm.bar[s], (uint32_t) c2 * 16u);
+            tma_bulk_g2s(sm.tile[s], nodes + (size_t) (tl + 2) * KNN_TILE, (uint32_t) c2 * 16u, &sm.bar[s]);
+        }
+    }
+    top8_merge_group<G>(t);
+}
+
 }  // namespace dfu

@@ -8,61 +8,97 @@
 // (opt_solver.cpp:30).  The residuals are linear in t, so one GN step is one SPD solve
 // (W^T Theta W + w_reg^2 L) delta = -J^T r, done matrix-free by block-Jacobi-preconditioned CG.
 //
-// Device layout: per point 8 neighbour ids + 8 weights (two 128-bit loads each), d = live - canon, tukey;
-// per node t, delta, r, z, p, q (N*3 floats each) and the normal-equation buffer
-//   nbuf = [ b = -J^T r : 3N | D = diag(J^T J) : N | E : 4 ]
-// which is the ONE buffer a data-parallel run all-reduces per GN step; the PCG all-reduces q (3N floats)
-// per iteration.  Per-point contributions reach the per-node blocks with float atomics (red.global.add);
-// everything that follows the all-reduce (regularisation term, dot products, vector updates) is
-// evaluated in a fixed order, so every rank computes bit-identical iterates.
-// No host synchronisation happens inside solve_all unless early_out / pcg_tol ask for it.
+// Data layout in HBM (all L2-resident at the sizes of BASELINE.json):
+//   per point   nbr[8] i32, wts[8] f32 (two 128-bit loads each), dvec = live - canon, theta (tukey),
+//               s4 = float4 scratch (theta*e | theta  during assembly, theta*W p during PCG)
+//   transposed  tptr[N+1], tv[8P], tw[8P]: for every node the (point, weight) pairs that reference it,
+//               sorted by point -- the per-node J^T J / J^T r blocks and the PCG product W^T(...) are GATHERS
+//               over these lists in a fixed order: no atomics in the iteration loop, bit-reproducible
+//   per node    t, delta, r, z, p, q (3 floats), nbuf = [ b = -J^T r : 3N | D = diag(J^T J) : N | E : 4 ]
+//
+// Two execution paths, same arithmetic phases:
+//   * single rank: ONE persistent cooperative kernel runs every outer / GN / PCG iteration with grid-wide
+//     barriers between phases (3 per PCG iteration) and decides convergence on the device -- no launches and
+//     no host round trips inside solveAll;
+//   * data-parallel ranks (all-reduce hook set): one kernel per phase, nbuf all-reduced once per GN step
+//     and q (3N floats) once per PCG iteration; everything after an all-reduce is evaluated in a fixed
+//     order, so all ranks compute bit-identical iterates.
+#include <cooperative_groups.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "dfu_internal.h"
 #include "dfu_math.cuh"
 
+namespace cg = cooperative_groups;
 using namespace dfu;
 
 namespace {
 
-constexpr int TPB = 256;
+constexpr int TPB = 256;           // multi-kernel path
+constexpr int PTPB = 512;          // persistent kernel
 constexpr int MAX_PARTIALS = 1024;
 
 struct Scalars {
-    double rz[2];        // r.z of PCG iteration it is rz[it & 1]
-    double rz_ref;       // r.z of the first GN step of this solve (< 0: unset)
-    double E;            // energy at the last assemble (data + reg)
-    double E0;           // energy at t = 0
-    int done_it;         // PCG iterations >= done_it of the current GN step are skipped
-    int pcg_iters;       // total PCG iterations executed
-    int first;           // 1 until E0 has been recorded
+    double rz[2];   // multi-kernel path: r.z of PCG iteration it is rz[it & 1]
+    double rz_ref;  // r.z of the first GN step of this solve (< 0: unset)
+    double E;       // energy at the last evaluation (data + reg)
+    double E0;      // energy at t = 0
+    int done_it;    // multi-kernel path: PCG iterations >= done_it of the current GN step are skipped
+    int pcg_iters;  // total PCG iterations executed
+    int gn_steps;   // total GN steps executed
+    int first;      // 1 until E0 has been recorded
 };
 
-DFU_DEV double block_sum(double v, double* sh) {
+struct Problem {
+    int N, P;
+    // data graph
+    const int32_t* nbr;
+    const float* wts;
+    const float* dvec;
+    float* theta;
+    float4* s4;
+    const int* tptr;
+    const int32_t* tv;
+    const float* tw;
+    // regularisation graph: out-edges n -> nnbr[n][i], in-edges rin[rin_ptr[n]..) (sources, ascending)
+    const int32_t* nnbr;
+    const int* rin_ptr;
+    const int32_t* rin;
+    float wreg2;
+    // unknowns and PCG vectors
+    float *t, *dl, *r, *z, *p, *q;
+    float* nbuf;   // b [3N] | D [N] | E [4]
+    double* part;  // 4 * MAX_PARTIALS
+    float tukey_offset, psi_data;
+};
+
+// ---------------------------------------------------------------------------------------------------
+DFU_DEV double warp_sum(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+DFU_DEV float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sum over the CTA, result broadcast to every thread; fixed reduction tree (deterministic)
+DFU_DEV double block_sum(double v, double* sh) {
+    v = warp_sum(v);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
     if (l == 0) sh[w] = v;
     __syncthreads();
-    double r = 0.0;
-    if (w == 0) {
-        r = l < (blockDim.x >> 5) ? sh[l] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
-    }
-    __syncthreads();
-    return r;  // valid in thread 0
+    double r = l < (int) (blockDim.x >> 5) ? sh[l] : 0.0;
+    return warp_sum(r);
 }
-
-// fixed-order sum of per-block partials, computed redundantly by every block (deterministic)
-DFU_DEV double sum_partials(const double* __restrict__ part, int n, double* sh) {
+// fixed-order sum of per-block partials, computed redundantly by every block
+DFU_DEV double sum_partials(const double* part, int n, double* sh) {
     double v = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
-    double r = block_sum(v, sh);
-    __shared__ double bc;
-    if (threadIdx.x == 0) bc = r;
-    __syncthreads();
-    return bc;
+    return block_sum(v, sh);
 }
 
 // calcTukeyBiweight (src/dynfu/utils/opt_solver.cpp:204-212)
@@ -75,262 +111,263 @@ DFU_DEV float tukey_biweight(float tukey_offset, float c, float ex, float ey, fl
     return 0.f;
 }
 
-struct PointData {
-    const int32_t* nbr;
-    const float* wts;
-    const float* dvec;
-    float* theta;
-    int P;
-};
-
 DFU_DEV void load8(const int32_t* nbr, const float* wts, int v, int (&nb)[8], float (&w)[8]) {
-    const int4 a = __ldg(reinterpret_cast<const int4*>(nbr) + 2 * (size_t) v);
-    const int4 b = __ldg(reinterpret_cast<const int4*>(nbr) + 2 * (size_t) v + 1);
-    const float4 c = __ldg(reinterpret_cast<const float4*>(wts) + 2 * (size_t) v);
-    const float4 d = __ldg(reinterpret_cast<const float4*>(wts) + 2 * (size_t) v + 1);
+    const int4 a = *(reinterpret_cast<const int4*>(nbr) + 2 * (size_t) v);
+    const int4 b = *(reinterpret_cast<const int4*>(nbr) + 2 * (size_t) v + 1);
+    const float4 c = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) v);
+    const float4 d = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) v + 1);
     nb[0] = a.x; nb[1] = a.y; nb[2] = a.z; nb[3] = a.w; nb[4] = b.x; nb[5] = b.y; nb[6] = b.z; nb[7] = b.w;
     w[0] = c.x; w[1] = c.y; w[2] = c.z; w[3] = c.w; w[4] = d.x; w[5] = d.y; w[6] = d.z; w[7] = d.w;
 }
 
-// Residual + Jacobian evaluation and per-node block assembly (data term).  J_vk = -sqrt(tukey) w_vk I3, so
-// b[n] += tukey w e, D[n] += tukey w^2 (the 3x3 diagonal block is D*I3), E += tukey |e|^2.
-__global__ void __launch_bounds__(TPB) assemble_data_kernel(PointData pd, const float* __restrict__ t, float* __restrict__ nbuf,
-                                                            int N, int update_tukey, float tukey_offset, float psi_data) {
-    __shared__ double sh[TPB / 32];
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    double e2 = 0.0;
-    if (v < pd.P) {
-        int nb[8];
-        float w[8];
-        load8(pd.nbr, pd.wts, v, nb, w);
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float* tk = t + 3 * (size_t) nb[k];
-            sx = __fmaf_rn(w[k], tk[0], sx);
-            sy = __fmaf_rn(w[k], tk[1], sy);
-            sz = __fmaf_rn(w[k], tk[2], sz);
-        }
-        const float ex = pd.dvec[3 * (size_t) v] - sx, ey = pd.dvec[3 * (size_t) v + 1] - sy, ez = pd.dvec[3 * (size_t) v + 2] - sz;
-        float th;
-        if (update_tukey) {
-            th = tukey_biweight(tukey_offset, psi_data, ex, ey, ez);
-            pd.theta[v] = th;
-        } else {
-            th = pd.theta[v];
-        }
-        e2 = (double) th * ((double) ex * ex + (double) ey * ey + (double) ez * ez);
-        if (th != 0.f) {
-            float* b = nbuf;
-            float* D = nbuf + 3 * (size_t) N;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float c = th * w[k];
-                if (c != 0.f) {
-                    atomicAdd(b + 3 * (size_t) nb[k], c * ex);
-                    atomicAdd(b + 3 * (size_t) nb[k] + 1, c * ey);
-                    atomicAdd(b + 3 * (size_t) nb[k] + 2, c * ez);
-                    atomicAdd(D + nb[k], c * w[k]);
-                }
-            }
-        }
-    }
-    const double bs = block_sum(e2, sh);
-    if (threadIdx.x == 0 && bs != 0.0) atomicAdd(nbuf + 4 * (size_t) N, (float) bs);
-}
-
-struct RegGraph {
-    const int32_t* nnbr;   // N*8 out-edges (n -> m)
-    const int* rin_ptr;    // N+1
-    const int32_t* rin;    // in-edges (sources m' that list n), sorted ascending
-    float wreg2;
-};
-
-// regularisation part of b, D, E -- gather form over out- and in-edges, no atomics, fixed order
-__global__ void __launch_bounds__(TPB) assemble_reg_kernel(RegGraph rg, const float* __restrict__ t, float* __restrict__ nbuf,
-                                                           int N, double* __restrict__ partE) {
-    __shared__ double sh[TPB / 32];
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    double e = 0.0;
-    if (n < N && rg.wreg2 > 0.f) {
-        const float tx = t[3 * (size_t) n], ty = t[3 * (size_t) n + 1], tz = t[3 * (size_t) n + 2];
-        float bx = 0.f, by = 0.f, bz = 0.f, dd = 0.f;
-        for (int i = 0; i < 8; ++i) {
-            const int m = rg.nnbr[(size_t) n * 8 + i];
-            if (m == n) continue;
-            const float dx = t[3 * (size_t) m] - tx, dy = t[3 * (size_t) m + 1] - ty, dz = t[3 * (size_t) m + 2] - tz;
-            bx += dx; by += dy; bz += dz;
-            dd += 1.f;
-            e += (double) dx * dx + (double) dy * dy + (double) dz * dz;
-        }
-        for (int j = rg.rin_ptr[n]; j < rg.rin_ptr[n + 1]; ++j) {
-            const int m = rg.rin[j];
-            if (m == n) continue;
-            bx += t[3 * (size_t) m] - tx; by += t[3 * (size_t) m + 1] - ty; bz += t[3 * (size_t) m + 2] - tz;
-            dd += 1.f;
-        }
-        nbuf[3 * (size_t) n] += rg.wreg2 * bx;
-        nbuf[3 * (size_t) n + 1] += rg.wreg2 * by;
-        nbuf[3 * (size_t) n + 2] += rg.wreg2 * bz;
-        nbuf[3 * (size_t) N + n] += rg.wreg2 * dd;
-        e *= (double) rg.wreg2;
-    }
-    const double bs = block_sum(e, sh);
-    if (threadIdx.x == 0) partE[blockIdx.x] = bs;
-}
-
-struct Vecs {
-    float *t, *dl, *r, *z, *p, *q;
-    const float* nbuf;
-    int N;
-};
-
-// r = b, z = M^-1 r, p = z, delta = 0, q = 0, partial r.z
-__global__ void __launch_bounds__(TPB) pcg_init_kernel(Vecs x, double* __restrict__ part_rz) {
-    __shared__ double sh[TPB / 32];
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    double rz = 0.0;
-    if (n < x.N) {
-        const float D = x.nbuf[3 * (size_t) x.N + n];
-        const float inv = D > 0.f ? 1.f / D : 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const size_t i = 3 * (size_t) n + c;
-            const float r = x.nbuf[i], z = r * inv;
-            x.r[i] = r; x.z[i] = z; x.p[i] = z; x.dl[i] = 0.f; x.q[i] = 0.f;
-            rz += (double) r * z;
-        }
-    }
-    const double bs = block_sum(rz, sh);
-    if (threadIdx.x == 0) part_rz[blockIdx.x] = bs;
-}
-
-// single-thread bookkeeping after pcg_init: total energy, r.z, convergence of this GN step
-__global__ void pcg_init_scalars_kernel(Scalars* sc, const float* __restrict__ nbuf, int N, const double* __restrict__ partE,
-                                        const double* __restrict__ part_rz, int nblk, double tol2) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double E = (double) nbuf[4 * (size_t) N], rz = 0.0;
-    for (int i = 0; i < nblk; ++i) {
-        E += partE[i];
-        rz += part_rz[i];
-    }
-    sc->E = E;
-    if (sc->first) {
-        sc->E0 = E;
-        sc->first = 0;
-    }
-    if (sc->rz_ref < 0.0) sc->rz_ref = rz;
-    sc->rz[0] = rz;
-    sc->done_it = (!(rz > 0.0) || rz <= tol2 * sc->rz_ref) ? 0 : INT_MAX;
-}
-
-// q += W^T Theta W p   (this rank's points)
-__global__ void __launch_bounds__(TPB) apply_data_kernel(PointData pd, const float* __restrict__ p, float* __restrict__ q,
-                                                         const Scalars* __restrict__ sc, int it) {
-    if (it >= sc->done_it) return;
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= pd.P) return;
-    const float th = pd.theta[v];
-    if (th == 0.f) return;
+// sum_k w_k x[n_k] for one point
+DFU_DEV void point_gather(const Problem& pb, int v, const float* x, float& sx, float& sy, float& sz) {
     int nb[8];
     float w[8];
-    load8(pd.nbr, pd.wts, v, nb, w);
-    float sx = 0.f, sy = 0.f, sz = 0.f;
+    load8(pb.nbr, pb.wts, v, nb, w);
+    sx = sy = sz = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float* pk = p + 3 * (size_t) nb[k];
-        sx = __fmaf_rn(w[k], pk[0], sx);
-        sy = __fmaf_rn(w[k], pk[1], sy);
-        sz = __fmaf_rn(w[k], pk[2], sz);
-    }
-    sx *= th; sy *= th; sz *= th;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (w[k] != 0.f) {
-            atomicAdd(q + 3 * (size_t) nb[k], w[k] * sx);
-            atomicAdd(q + 3 * (size_t) nb[k] + 1, w[k] * sy);
-            atomicAdd(q + 3 * (size_t) nb[k] + 2, w[k] * sz);
-        }
+        const float* xk = x + 3 * (size_t) nb[k];
+        sx = __fmaf_rn(w[k], xk[0], sx);
+        sy = __fmaf_rn(w[k], xk[1], sy);
+        sz = __fmaf_rn(w[k], xk[2], sz);
     }
 }
 
-// q += w_reg^2 L p (gather, fixed order), partial p.q
-__global__ void __launch_bounds__(TPB) apply_reg_dot_kernel(RegGraph rg, Vecs x, const Scalars* __restrict__ sc, int it,
-                                                            double* __restrict__ part_pq) {
+// ---- phases (grid-stride; tid/nthreads describe the whole launch) --------------------------------------
+// Residual evaluation (energy.t:47-55): e = d - W t, tukey re-weighting, s4 = (theta e, theta).
+// Returns this thread's share of sum theta |e|^2.
+DFU_DEV double phase_point_residual(const Problem& pb, bool update_tukey, int tid, int nthreads) {
+    double e2 = 0.0;
+    for (int v = tid; v < pb.P; v += nthreads) {
+        float sx, sy, sz;
+        point_gather(pb, v, pb.t, sx, sy, sz);
+        const float ex = pb.dvec[3 * (size_t) v] - sx, ey = pb.dvec[3 * (size_t) v + 1] - sy,
+                    ez = pb.dvec[3 * (size_t) v + 2] - sz;
+        float th;
+        if (update_tukey) {
+            th = tukey_biweight(pb.tukey_offset, pb.psi_data, ex, ey, ez);
+            pb.theta[v] = th;
+        } else {
+            th = pb.theta[v];
+        }
+        pb.s4[v] = make_float4(th * ex, th * ey, th * ez, th);
+        e2 += (double) th * ((double) ex * ex + (double) ey * ey + (double) ez * ez);
+    }
+    return e2;
+}
+
+// s4 = theta * W p
+DFU_DEV void phase_point_apply(const Problem& pb, int tid, int nthreads) {
+    for (int v = tid; v < pb.P; v += nthreads) {
+        const float th = pb.theta[v];
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        if (th != 0.f) point_gather(pb, v, pb.p, sx, sy, sz);
+        pb.s4[v] = make_float4(th * sx, th * sy, th * sz, th);
+    }
+}
+
+// per-node gather of the data term over the transposed graph (one warp per node): returns, in every lane,
+// sum_j tw_j * s4[tv_j].xyz and (with_diag) sum_j tw_j^2 * s4[tv_j].w -- lane-strided, then a fixed xor tree
+DFU_DEV void node_gather_data(const Problem& pb, int n, int lane, bool with_diag, float& ax, float& ay, float& az, float& ad) {
+    ax = ay = az = ad = 0.f;
+    const int lo = pb.tptr[n], hi = pb.tptr[n + 1];
+    for (int j = lo + lane; j < hi; j += 32) {
+        const float w = pb.tw[j];
+        const float4 s = pb.s4[pb.tv[j]];
+        ax = __fmaf_rn(w, s.x, ax);
+        ay = __fmaf_rn(w, s.y, ay);
+        az = __fmaf_rn(w, s.z, az);
+        if (with_diag) ad = __fmaf_rn(w * w, s.w, ad);
+    }
+}
+
+// lane-parallel regularisation gather for node n on vector x: sum over out- and in-edges (m != n) of
+// (x[n] - x[m]) in (gx,gy,gz), the edge count in cnt and (out-edges only) the squared differences in e2
+DFU_DEV void node_gather_reg(const Problem& pb, int n, int lane, const float* x, float& gx, float& gy, float& gz, float& cnt,
+                             float& e2) {
+    gx = gy = gz = cnt = e2 = 0.f;
+    const float xn0 = x[3 * (size_t) n], xn1 = x[3 * (size_t) n + 1], xn2 = x[3 * (size_t) n + 2];
+    const int lo = pb.rin_ptr[n], hi = pb.rin_ptr[n + 1];
+    for (int j = lane; j < 8 + (hi - lo); j += 32) {
+        const bool out = j < 8;
+        const int m = out ? pb.nnbr[(size_t) n * 8 + j] : pb.rin[lo + j - 8];
+        if (m == n) continue;
+        const float d0 = xn0 - x[3 * (size_t) m], d1 = xn1 - x[3 * (size_t) m + 1], d2 = xn2 - x[3 * (size_t) m + 2];
+        gx += d0; gy += d1; gz += d2;
+        cnt += 1.f;
+        if (out) e2 += d0 * d0 + d1 * d1 + d2 * d2;
+    }
+}
+
+// =====================================================================================================
+// multi-kernel path (data-parallel ranks with an all-reduce hook)
+
+__global__ void __launch_bounds__(TPB) k_point_residual(Problem pb, int update_tukey) {
+    __shared__ double sh[TPB / 32];
+    const double e2 = phase_point_residual(pb, update_tukey != 0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    const double bs = block_sum(e2, sh);
+    if (threadIdx.x == 0) pb.part[blockIdx.x] = bs;
+}
+// data part of b, D into nbuf; block 0 also folds the energy partials into nbuf[4N]
+__global__ void __launch_bounds__(TPB) k_node_assemble_data(Problem pb, int n_epart) {
+    __shared__ double sh[TPB / 32];
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int n = gw; n < pb.N; n += nw) {
+        float ax, ay, az, ad;
+        node_gather_data(pb, n, lane, true, ax, ay, az, ad);
+        ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az); ad = warp_sum(ad);
+        if (lane == 0) {
+            pb.nbuf[3 * (size_t) n] = ax; pb.nbuf[3 * (size_t) n + 1] = ay; pb.nbuf[3 * (size_t) n + 2] = az;
+            pb.nbuf[3 * (size_t) pb.N + n] = ad;
+        }
+    }
+    if (blockIdx.x == 0) {
+        const double E = sum_partials(pb.part, n_epart, sh);
+        if (threadIdx.x == 0) {
+            pb.nbuf[4 * (size_t) pb.N] = (float) E;
+            pb.nbuf[4 * (size_t) pb.N + 1] = pb.nbuf[4 * (size_t) pb.N + 2] = pb.nbuf[4 * (size_t) pb.N + 3] = 0.f;
+        }
+    }
+}
+// after the all-reduce: regularisation part of b, D, E; r = b, z = M^-1 r, p = z, delta = 0; partial r.z, E_reg
+__global__ void __launch_bounds__(TPB) k_node_reg_init(Problem pb) {
+    __shared__ double sh[TPB / 32];
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    double rz = 0.0, er = 0.0;
+    for (int n = gw; n < pb.N; n += nw) {
+        float gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
+        if (pb.wreg2 > 0.f) {
+            node_gather_reg(pb, n, lane, pb.t, gx, gy, gz, cnt, e2);
+            gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz); cnt = warp_sum(cnt); e2 = warp_sum(e2);
+        }
+        if (lane == 0) {
+            // d/dt_n of w^2 |t_m - t_n|^2 (both edge directions): b gets w^2 * sum (t_m - t_n) = -w^2 * g
+            const float b0 = pb.nbuf[3 * (size_t) n] - pb.wreg2 * gx, b1 = pb.nbuf[3 * (size_t) n + 1] - pb.wreg2 * gy,
+                        b2 = pb.nbuf[3 * (size_t) n + 2] - pb.wreg2 * gz;
+            const float D = pb.nbuf[3 * (size_t) pb.N + n] + pb.wreg2 * cnt;
+            pb.nbuf[3 * (size_t) n] = b0; pb.nbuf[3 * (size_t) n + 1] = b1; pb.nbuf[3 * (size_t) n + 2] = b2;
+            pb.nbuf[3 * (size_t) pb.N + n] = D;
+            const float inv = D > 0.f ? 1.f / D : 0.f;
+            const float bb[3] = {b0, b1, b2};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const size_t i = 3 * (size_t) n + c;
+                const float z = bb[c] * inv;
+                pb.r[i] = bb[c]; pb.z[i] = z; pb.p[i] = z; pb.dl[i] = 0.f;
+                rz += (double) bb[c] * z;
+            }
+            er += (double) pb.wreg2 * e2;
+        }
+    }
+    const double a = block_sum(rz, sh), b = block_sum(er, sh);
+    if (threadIdx.x == 0) {
+        pb.part[MAX_PARTIALS + blockIdx.x] = a;
+        pb.part[2 * MAX_PARTIALS + blockIdx.x] = b;
+    }
+}
+__global__ void k_init_scalars(Problem pb, Scalars* sc, int nblk, double tol2) {
+    __shared__ double sh[1];
+    if (blockIdx.x != 0) return;
+    const double rz = sum_partials(pb.part + MAX_PARTIALS, nblk, sh);
+    const double er = sum_partials(pb.part + 2 * MAX_PARTIALS, nblk, sh);
+    if (threadIdx.x == 0) {
+        const double E = (double) pb.nbuf[4 * (size_t) pb.N] + er;
+        sc->E = E;
+        if (sc->first) {
+            sc->E0 = E;
+            sc->first = 0;
+        }
+        if (sc->rz_ref < 0.0) sc->rz_ref = rz;
+        sc->rz[0] = rz;
+        sc->done_it = (!(rz > 0.0) || rz <= tol2 * sc->rz_ref) ? 0 : INT_MAX;
+    }
+}
+__global__ void __launch_bounds__(TPB) k_point_apply(Problem pb, const Scalars* sc, int it) {
+    if (it >= sc->done_it) return;
+    phase_point_apply(pb, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+__global__ void __launch_bounds__(TPB) k_node_apply_data(Problem pb, const Scalars* sc, int it) {
+    if (it >= sc->done_it) return;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int n = gw; n < pb.N; n += nw) {
+        float ax, ay, az, ad;
+        node_gather_data(pb, n, lane, false, ax, ay, az, ad);
+        ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+        if (lane == 0) {
+            pb.q[3 * (size_t) n] = ax; pb.q[3 * (size_t) n + 1] = ay; pb.q[3 * (size_t) n + 2] = az;
+        }
+    }
+}
+// after the all-reduce of q: q += w_reg^2 L p, partial p.q
+__global__ void __launch_bounds__(TPB) k_node_apply_reg_dot(Problem pb, const Scalars* sc, int it) {
     if (it >= sc->done_it) return;
     __shared__ double sh[TPB / 32];
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     double pq = 0.0;
-    if (n < x.N) {
-        const float px = x.p[3 * (size_t) n], py = x.p[3 * (size_t) n + 1], pz = x.p[3 * (size_t) n + 2];
-        float qx = x.q[3 * (size_t) n], qy = x.q[3 * (size_t) n + 1], qz = x.q[3 * (size_t) n + 2];
-        if (rg.wreg2 > 0.f) {
-            float ax = 0.f, ay = 0.f, az = 0.f;
-            for (int i = 0; i < 8; ++i) {
-                const int m = rg.nnbr[(size_t) n * 8 + i];
-                if (m == n) continue;
-                ax += px - x.p[3 * (size_t) m]; ay += py - x.p[3 * (size_t) m + 1]; az += pz - x.p[3 * (size_t) m + 2];
-            }
-            for (int j = rg.rin_ptr[n]; j < rg.rin_ptr[n + 1]; ++j) {
-                const int m = rg.rin[j];
-                if (m == n) continue;
-                ax += px - x.p[3 * (size_t) m]; ay += py - x.p[3 * (size_t) m + 1]; az += pz - x.p[3 * (size_t) m + 2];
-            }
-            qx += rg.wreg2 * ax; qy += rg.wreg2 * ay; qz += rg.wreg2 * az;
-            x.q[3 * (size_t) n] = qx; x.q[3 * (size_t) n + 1] = qy; x.q[3 * (size_t) n + 2] = qz;
+    for (int n = gw; n < pb.N; n += nw) {
+        float gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
+        if (pb.wreg2 > 0.f) {
+            node_gather_reg(pb, n, lane, pb.p, gx, gy, gz, cnt, e2);
+            gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
         }
-        pq = (double) px * qx + (double) py * qy + (double) pz * qz;
+        if (lane == 0) {
+            const float q0 = pb.q[3 * (size_t) n] + pb.wreg2 * gx, q1 = pb.q[3 * (size_t) n + 1] + pb.wreg2 * gy,
+                        q2 = pb.q[3 * (size_t) n + 2] + pb.wreg2 * gz;
+            pb.q[3 * (size_t) n] = q0; pb.q[3 * (size_t) n + 1] = q1; pb.q[3 * (size_t) n + 2] = q2;
+            pq += (double) pb.p[3 * (size_t) n] * q0 + (double) pb.p[3 * (size_t) n + 1] * q1 + (double) pb.p[3 * (size_t) n + 2] * q2;
+        }
     }
     const double bs = block_sum(pq, sh);
-    if (threadIdx.x == 0) part_pq[blockIdx.x] = bs;
+    if (threadIdx.x == 0) pb.part[blockIdx.x] = bs;
 }
-
-// alpha = r.z / p.q ; delta += alpha p ; r -= alpha q ; z = M^-1 r ; q = 0 ; partial r.z
-__global__ void __launch_bounds__(TPB) pcg_update_kernel(Vecs x, const Scalars* __restrict__ sc, int it,
-                                                         const double* __restrict__ part_pq, int nblk,
-                                                         double* __restrict__ part_rz) {
+// alpha = r.z / p.q ; delta += alpha p ; r -= alpha q ; z = M^-1 r ; partial r.z
+__global__ void __launch_bounds__(TPB) k_pcg_update(Problem pb, const Scalars* sc, int it, int nblk_pq) {
     if (it >= sc->done_it) return;
     __shared__ double sh[TPB / 32];
-    const double pq = sum_partials(part_pq, nblk, sh);
+    const double pq = sum_partials(pb.part, nblk_pq, sh);
     const double rz = sc->rz[it & 1];
     const float alpha = pq > 0.0 ? (float) (rz / pq) : 0.f;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     double rzn = 0.0;
-    if (n < x.N) {
-        const float D = x.nbuf[3 * (size_t) x.N + n];
+    if (n < pb.N) {
+        const float D = pb.nbuf[3 * (size_t) pb.N + n];
         const float inv = D > 0.f ? 1.f / D : 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const size_t i = 3 * (size_t) n + c;
-            x.dl[i] = __fmaf_rn(alpha, x.p[i], x.dl[i]);
-            const float r = __fmaf_rn(-alpha, x.q[i], x.r[i]);
+            pb.dl[i] = __fmaf_rn(alpha, pb.p[i], pb.dl[i]);
+            const float r = __fmaf_rn(-alpha, pb.q[i], pb.r[i]);
             const float z = r * inv;
-            x.r[i] = r; x.z[i] = z; x.q[i] = 0.f;
+            pb.r[i] = r; pb.z[i] = z;
             rzn += (double) r * z;
         }
     }
     const double bs = block_sum(rzn, sh);
-    if (threadIdx.x == 0) part_rz[blockIdx.x] = bs;
+    if (threadIdx.x == 0) pb.part[MAX_PARTIALS + blockIdx.x] = bs;
 }
-
 // beta = r.z_new / r.z ; p = z + beta p ; block 0 publishes r.z_new and the stop decision for it+1
-__global__ void __launch_bounds__(TPB) pcg_direction_kernel(Vecs x, Scalars* sc, int it, const double* __restrict__ part_rz,
-                                                            const double* __restrict__ part_pq, int nblk, double tol2) {
+__global__ void __launch_bounds__(TPB) k_pcg_direction(Problem pb, Scalars* sc, int it, int nblk, int nblk_pq, double tol2) {
     if (it >= sc->done_it) return;
     __shared__ double sh[TPB / 32];
-    const double rzn = sum_partials(part_rz, nblk, sh);
+    const double rzn = sum_partials(pb.part + MAX_PARTIALS, nblk, sh);
     const double rz = sc->rz[it & 1];
     const float beta = rz > 0.0 ? (float) (rzn / rz) : 0.f;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < x.N) {
+    if (n < pb.N) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const size_t i = 3 * (size_t) n + c;
-            x.p[i] = __fmaf_rn(beta, x.p[i], x.z[i]);
+            pb.p[i] = __fmaf_rn(beta, pb.p[i], pb.z[i]);
         }
     }
     if (blockIdx.x == 0) {
-        const double pq = sum_partials(part_pq, nblk, sh);
+        const double pq = sum_partials(pb.part, nblk_pq, sh);
         if (threadIdx.x == 0) {
             sc->rz[(it + 1) & 1] = rzn;
             sc->pcg_iters += 1;
@@ -338,28 +375,212 @@ __global__ void __launch_bounds__(TPB) pcg_direction_kernel(Vecs x, Scalars* sc,
         }
     }
 }
-
-__global__ void gn_update_kernel(float* __restrict__ t, const float* __restrict__ dl, int n3) {
+__global__ void k_axpy(float* __restrict__ t, const float* __restrict__ dl, int n3) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n3) t[i] += dl[i];
 }
 
-// ---- transposed regularisation graph (in-edges), deterministic ------------------------------------
-__global__ void reg_indegree_kernel(const int32_t* __restrict__ nnbr, int N, int* __restrict__ deg) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < N * 8) atomicAdd(&deg[nnbr[e]], 1);
+// =====================================================================================================
+// persistent cooperative kernel (single rank): the whole of solveAll in one launch
+
+struct SolveCtl {
+    int num_iter, nonlinear_iter, linear_iter, early_out;
+    double tol2;
+};
+
+__global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveCtl ctl, Scalars* sc) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[PTPB / 32];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, gw = tid >> 5, nw = nthreads >> 5;
+    const int nb = gridDim.x, n3 = 3 * pb.N;
+    double* part0 = pb.part;
+    double* part1 = pb.part + MAX_PARTIALS;
+    double* part2 = pb.part + 2 * MAX_PARTIALS;
+    double* part3 = pb.part + 3 * MAX_PARTIALS;
+
+    for (int i = tid; i < n3; i += nthreads) pb.t[i] = 0.f;  // unknowns := 0 (opt_solver.cpp:192-193)
+    grid.sync();
+
+    double rz_ref = -1.0, E = 0.0, E0 = 0.0;
+    int pcg_total = 0, gn_total = 0;
+    bool first = true, stop_all = false;
+
+    for (int outer = 0; outer < ctl.num_iter && !stop_all; ++outer) {
+        for (int gn = 0; gn < ctl.nonlinear_iter; ++gn) {
+            // ---- residuals + tukey (re-weighted once per outer iteration, opt_solver.cpp:135-140) -----
+            {
+                const double e2 = block_sum(phase_point_residual(pb, gn == 0, tid, nthreads), sh);
+                if (threadIdx.x == 0) part0[blockIdx.x] = e2;
+            }
+            grid.sync();
+            // ---- per-node blocks: b = -J^T r, D = diag(J^T J) (+ regularisation), PCG initialisation --------
+            {
+                double rz = 0.0, er = 0.0;
+                for (int n = gw; n < pb.N; n += nw) {
+                    float ax, ay, az, ad, gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
+                    node_gather_data(pb, n, lane, true, ax, ay, az, ad);
+                    if (pb.wreg2 > 0.f) {
+                        node_gather_reg(pb, n, lane, pb.t, gx, gy, gz, cnt, e2);
+                        ax -= pb.wreg2 * gx; ay -= pb.wreg2 * gy; az -= pb.wreg2 * gz;
+                        ad += pb.wreg2 * cnt;
+                        e2 = warp_sum(e2);
+                    }
+                    ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az); ad = warp_sum(ad);
+                    if (lane == 0) {
+                        const float inv = ad > 0.f ? 1.f / ad : 0.f;
+                        const double invd = ad > 0.f ? 1.0 / (double) ad : 0.0;
+                        const float bb[3] = {ax, ay, az};
+                        pb.nbuf[3 * (size_t) pb.N + n] = ad;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const size_t i = 3 * (size_t) n + c;
+                            pb.nbuf[i] = bb[c]; pb.r[i] = bb[c]; pb.p[i] = bb[c] * inv; pb.dl[i] = 0.f;
+                            rz += (double) bb[c] * (double) bb[c] * invd;
+                        }
+                        er += (double) pb.wreg2 * e2;
+                    }
+                }
+                const double a = block_sum(rz, sh), b = block_sum(er, sh);
+                if (threadIdx.x == 0) {
+                    part1[blockIdx.x] = a;
+                    part2[blockIdx.x] = b;
+                }
+            }
+            grid.sync();
+            double rz = sum_partials(part1, nb, sh);
+            E = sum_partials(part0, nb, sh) + sum_partials(part2, nb, sh);
+            if (first) {
+                E0 = E;
+                first = false;
+            }
+            if (rz_ref < 0.0) rz_ref = rz;
+            const bool conv0 = !(rz > 0.0) || rz <= ctl.tol2 * rz_ref;
+            grid.sync();  // every CTA has read the partials: they may be re-used
+            if (ctl.early_out && conv0) {  // converged at this linearisation point
+                if (gn == 0 && outer > 0) stop_all = true;
+                break;
+            }
+            // ---- PCG ---------------------------------------------------------------------------------------
+            if (!conv0) {
+                for (int it = 0; it < ctl.linear_iter; ++it) {
+                    phase_point_apply(pb, tid, nthreads);  // s4 = Theta W p
+                    grid.sync();
+                    // p.q, r.M^-1 r, r.M^-1 q, q.M^-1 q.  r.M^-1 r is re-measured from the stored float r every
+                    // iteration, so the recurrence below never drifts away from the actual residual.
+                    double pq = 0.0, rr = 0.0, rmq = 0.0, qmq = 0.0;
+                    for (int n = gw; n < pb.N; n += nw) {
+                        float ax, ay, az, ad, gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
+                        node_gather_data(pb, n, lane, false, ax, ay, az, ad);
+                        if (pb.wreg2 > 0.f) {
+                            node_gather_reg(pb, n, lane, pb.p, gx, gy, gz, cnt, e2);
+                            ax += pb.wreg2 * gx; ay += pb.wreg2 * gy; az += pb.wreg2 * gz;
+                        }
+                        ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+                        if (lane == 0) {
+                            const float D = pb.nbuf[3 * (size_t) pb.N + n];
+                            const double inv = D > 0.f ? 1.0 / (double) D : 0.0;
+                            const float qq[3] = {ax, ay, az};
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const size_t i = 3 * (size_t) n + c;
+                                pb.q[i] = qq[c];
+                                const double ri = (double) pb.r[i];
+                                pq += (double) pb.p[i] * qq[c];
+                                rr += ri * ri * inv;
+                                rmq += ri * qq[c] * inv;
+                                qmq += (double) qq[c] * qq[c] * inv;
+                            }
+                        }
+                    }
+                    {
+                        const double a = block_sum(pq, sh), b = block_sum(rmq, sh), c = block_sum(qmq, sh), d = block_sum(rr, sh);
+                        if (threadIdx.x == 0) {
+                            part0[blockIdx.x] = a;
+                            part1[blockIdx.x] = b;
+                            part2[blockIdx.x] = c;
+                            part3[blockIdx.x] = d;
+                        }
+                    }
+                    grid.sync();
+                    pq = sum_partials(part0, nb, sh);
+                    rmq = sum_partials(part1, nb, sh);
+                    qmq = sum_partials(part2, nb, sh);
+                    rz = sum_partials(part3, nb, sh);
+                    ++pcg_total;
+                    if (!(pq > 0.0) || !(rz > 0.0)) {
+                        grid.sync();
+                        break;
+                    }
+                    // r' = r - alpha q, z' = M^-1 r'  =>  r'.z' = r.z - 2 alpha r.M^-1 q + alpha^2 q.M^-1 q
+                    const double alpha = rz / pq;
+                    double rzn = rz - 2.0 * alpha * rmq + alpha * alpha * qmq;
+                    if (!(rzn > 0.0)) rzn = 0.0;
+                    const float af = (float) alpha, bf = (float) (rzn / rz);
+                    for (int i = tid; i < n3; i += nthreads) {
+                        const float D = pb.nbuf[3 * (size_t) pb.N + i / 3];
+                        const float inv = D > 0.f ? 1.f / D : 0.f;
+                        const float p = pb.p[i];
+                        pb.dl[i] = __fmaf_rn(af, p, pb.dl[i]);
+                        const float r = __fmaf_rn(-af, pb.q[i], pb.r[i]);
+                        pb.r[i] = r;
+                        pb.p[i] = __fmaf_rn(bf, p, r * inv);
+                    }
+                    rz = rzn;
+                    grid.sync();
+                    if (!(rz > 0.0) || rz <= ctl.tol2 * rz_ref) break;
+                }
+            }
+            for (int i = tid; i < n3; i += nthreads) pb.t[i] += pb.dl[i];
+            ++gn_total;
+            grid.sync();
+        }
+    }
+    // ---- final energy at the solution, Tukey weights of the last outer iteration -------------------------
+    {
+        const double e2 = block_sum(phase_point_residual(pb, false, tid, nthreads), sh);
+        double er = 0.0;
+        if (pb.wreg2 > 0.f)
+            for (int n = gw; n < pb.N; n += nw) {
+                float gx, gy, gz, cnt, r2;
+                node_gather_reg(pb, n, lane, pb.t, gx, gy, gz, cnt, r2);
+                r2 = warp_sum(r2);
+                if (lane == 0) er += (double) pb.wreg2 * r2;
+            }
+        const double b = block_sum(er, sh);
+        if (threadIdx.x == 0) {
+            part0[blockIdx.x] = e2;
+            part2[blockIdx.x] = b;
+        }
+    }
+    grid.sync();
+    E = sum_partials(part0, nb, sh) + sum_partials(part2, nb, sh);
+    if (tid == 0) {
+        sc->E = E;
+        sc->E0 = first ? E : E0;
+        sc->rz_ref = rz_ref;
+        sc->pcg_iters = pcg_total;
+        sc->gn_steps = gn_total;
+        sc->first = 0;
+    }
+}
+
+// ---- graph construction ------------------------------------------------------------------------------------
+__global__ void k_count(const int32_t* __restrict__ key, long n, int* __restrict__ deg) {
+    const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) atomicAdd(&deg[key[e]], 1);
 }
 // exclusive scan of deg[0..N) -> ptr[0..N], single block
-__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ deg, int N, int* __restrict__ ptr) {
+__global__ void __launch_bounds__(1024) k_scan(const int* __restrict__ deg, int N, int* __restrict__ ptr) {
     __shared__ int sh[1024];
     const int per = (N + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(N, lo + per);
+    const int lo = min(N, (int) threadIdx.x * per), hi = min(N, lo + per);
     int s = 0;
     for (int i = lo; i < hi; ++i) s += deg[i];
     sh[threadIdx.x] = s;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
-        const int v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        const int v = (int) threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
         __syncthreads();
         sh[threadIdx.x] += v;
         __syncthreads();
@@ -371,26 +592,45 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ deg,
     }
     if (threadIdx.x == 1023) ptr[N] = sh[1023];
 }
-__global__ void reg_fill_kernel(const int32_t* __restrict__ nnbr, int N, const int* __restrict__ ptr, int* __restrict__ cursor,
-                                int32_t* __restrict__ rin) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < N * 8) {
-        const int m = nnbr[e];
-        rin[ptr[m] + atomicAdd(&cursor[m], 1)] = e / 8;
+// scatter entry ids into their node's segment (arrival order; sorted afterwards)
+__global__ void k_fill(const int32_t* __restrict__ key, long n, const int* __restrict__ ptr, int* __restrict__ cursor,
+                       int32_t* __restrict__ out, int shift) {
+    const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) {
+        const int m = key[e];
+        out[ptr[m] + atomicAdd(&cursor[m], 1)] = (int32_t) (e >> shift);
     }
 }
-__global__ void reg_sort_kernel(const int* __restrict__ ptr, int N, int32_t* __restrict__ rin) {
+// in-edge lists of the regularisation graph are short: insertion sort, one thread per node
+__global__ void k_sort_small(const int* __restrict__ ptr, int N, int32_t* __restrict__ a) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const int lo = ptr[n], hi = ptr[n + 1];
-    for (int i = lo + 1; i < hi; ++i) {  // insertion sort: in-degree is small
-        const int key = rin[i];
+    for (int i = lo + 1; i < hi; ++i) {
+        const int key = a[i];
         int j = i - 1;
-        while (j >= lo && rin[j] > key) {
-            rin[j + 1] = rin[j];
+        while (j >= lo && a[j] > key) {
+            a[j + 1] = a[j];
             --j;
         }
-        rin[j + 1] = key;
+        a[j + 1] = key;
+    }
+}
+// transposed data graph: rank-sort each node's entry ids (one warp per node) and emit (point, weight) pairs
+__global__ void __launch_bounds__(TPB) k_sort_emit(const int* __restrict__ ptr, int N, const int32_t* __restrict__ ent,
+                                                   const float* __restrict__ wts, int32_t* __restrict__ tv,
+                                                   float* __restrict__ tw) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int n = gw; n < N; n += nw) {
+        const int lo = ptr[n], hi = ptr[n + 1];
+        for (int i = lo + lane; i < hi; i += 32) {
+            const int key = ent[i];
+            int rank = 0;
+            for (int j = lo; j < hi; ++j) rank += ent[j] < key;
+            tv[lo + rank] = key >> 3;
+            tw[lo + rank] = wts[key];
+        }
     }
 }
 
@@ -406,32 +646,44 @@ struct dfu_solver {
     // per point
     int32_t* nbr = nullptr;
     float *wts = nullptr, *dvec = nullptr, *theta = nullptr;
+    float4* s4 = nullptr;
+    int32_t *tent = nullptr, *tv = nullptr;
+    float* tw = nullptr;
     // per node
+    int* tptr = nullptr;
+    int* tmp = nullptr;  // [deg N | cursor N]
     int32_t* nnbr = nullptr;
-    int *rin_ptr = nullptr, *rin_tmp = nullptr;  // rin_tmp: [deg N | cursor N]
+    int* rin_ptr = nullptr;
     int32_t* rin = nullptr;
     float* vec = nullptr;   // t, dl, r, z, p, q : 6 * 3N
     float* nbuf = nullptr;  // 4N + 4
-    double* part = nullptr;  // 3 * MAX_PARTIALS : E, rz, pq
+    double* part = nullptr;
     Scalars* sc = nullptr;
     Scalars* sc_host = nullptr;  // pinned
+    uint64_t reg_epoch = 0;      // node-position epoch the regularisation graph was built for (0: never)
     bool problem_ready = false;
-    int gn_steps = 0;  // GN steps launched by the last solve_all
+    int coop_blocks = 0;         // co-resident CTAs for the persistent kernel (0: not available)
+    int gn_steps_host = 0;
 };
 
 namespace {
 
-int free_point_arrays(dfu_solver* s) {
-    cudaFree(s->nbr); cudaFree(s->wts); cudaFree(s->dvec); cudaFree(s->theta);
-    s->nbr = nullptr; s->wts = s->dvec = s->theta = nullptr;
+void free_point_arrays(dfu_solver* s) {
+    cudaFree(s->nbr); cudaFree(s->wts); cudaFree(s->dvec); cudaFree(s->theta); cudaFree(s->s4);
+    cudaFree(s->tent); cudaFree(s->tv); cudaFree(s->tw);
+    s->nbr = s->tent = s->tv = nullptr;
+    s->wts = s->dvec = s->theta = s->tw = nullptr;
+    s->s4 = nullptr;
     s->capP = 0;
-    return DFU_OK;
 }
-int free_node_arrays(dfu_solver* s) {
-    cudaFree(s->nnbr); cudaFree(s->rin_ptr); cudaFree(s->rin_tmp); cudaFree(s->rin); cudaFree(s->vec); cudaFree(s->nbuf);
-    s->nnbr = nullptr; s->rin_ptr = s->rin_tmp = nullptr; s->rin = nullptr; s->vec = s->nbuf = nullptr;
+void free_node_arrays(dfu_solver* s) {
+    cudaFree(s->tptr); cudaFree(s->tmp); cudaFree(s->nnbr); cudaFree(s->rin_ptr); cudaFree(s->rin); cudaFree(s->vec);
+    cudaFree(s->nbuf);
+    s->tptr = s->tmp = s->rin_ptr = nullptr;
+    s->nnbr = s->rin = nullptr;
+    s->vec = s->nbuf = nullptr;
     s->capN = 0;
-    return DFU_OK;
+    s->reg_epoch = 0;
 }
 
 int read_scalars(dfu_solver* s, cudaStream_t st) {
@@ -440,39 +692,119 @@ int read_scalars(dfu_solver* s, cudaStream_t st) {
     return DFU_OK;
 }
 
-Vecs make_vecs(const dfu_solver* s) {
+Problem make_problem(const dfu_solver* s) {
     const size_t n3 = 3 * (size_t) s->N;
-    Vecs x;
-    x.t = s->vec; x.dl = s->vec + n3; x.r = s->vec + 2 * n3; x.z = s->vec + 3 * n3; x.p = s->vec + 4 * n3; x.q = s->vec + 5 * n3;
-    x.nbuf = s->nbuf;
-    x.N = s->N;
-    return x;
+    Problem pb{};
+    pb.N = s->N; pb.P = s->P;
+    pb.nbr = s->nbr; pb.wts = s->wts; pb.dvec = s->dvec; pb.theta = s->theta; pb.s4 = s->s4;
+    pb.tptr = s->tptr; pb.tv = s->tv; pb.tw = s->tw;
+    pb.nnbr = s->nnbr; pb.rin_ptr = s->rin_ptr; pb.rin = s->rin;
+    pb.wreg2 = s->prm.lambda / ((float) s->N * 8.f);  // w_reg^2 (opt_solver.cpp:30)
+    pb.t = s->vec; pb.dl = s->vec + n3; pb.r = s->vec + 2 * n3; pb.z = s->vec + 3 * n3; pb.p = s->vec + 4 * n3;
+    pb.q = s->vec + 5 * n3;
+    pb.nbuf = s->nbuf;
+    pb.part = s->part;
+    pb.tukey_offset = s->prm.tukey_offset;
+    pb.psi_data = s->prm.psi_data;
+    return pb;
 }
 
-// one residual/Jacobian evaluation + block assembly (+ all-reduce) + regularisation + PCG initialisation
-int assemble(dfu_solver* s, bool update_tukey, cudaStream_t st) {
-    const int N = s->N, P = s->P, nblk = div_up(N, TPB);
-    Vecs x = make_vecs(s);
-    PointData pd{s->nbr, s->wts, s->dvec, s->theta, P};
-    RegGraph rg{s->nnbr, s->rin_ptr, s->rin, s->prm.lambda / ((float) N * 8.f)};
-    const size_t nbuf_count = 4 * (size_t) N + 4;
-    DFU_CUDA_OK(cudaMemsetAsync(s->nbuf, 0, nbuf_count * sizeof(float), st));
+// multi-kernel path: residuals + block assembly (+ all-reduce) + regularisation + PCG initialisation
+int assemble_mk(dfu_solver* s, const Problem& pb, bool update_tukey, cudaStream_t st) {
+    const int N = s->N, P = s->P;
+    const int nblk_p = P > 0 ? min(div_up(P, TPB), MAX_PARTIALS) : 0;
+    const int nblk_w = min(div_up((long) N * 32, TPB), MAX_PARTIALS);
     if (P > 0) {
-        assemble_data_kernel<<<div_up(P, TPB), TPB, 0, st>>>(pd, x.t, s->nbuf, N, update_tukey ? 1 : 0, s->prm.tukey_offset,
-                                                            s->prm.psi_data);
+        k_point_residual<<<nblk_p, TPB, 0, st>>>(pb, update_tukey ? 1 : 0);
         DFU_LAUNCH_OK();
     }
+    k_node_assemble_data<<<nblk_w, TPB, 0, st>>>(pb, nblk_p);
+    DFU_LAUNCH_OK();
     if (s->allreduce) {
-        int rc = s->allreduce(s->nbuf, nbuf_count, s->allreduce_ctx, (dfu_stream) st);
+        int rc = s->allreduce(s->nbuf, 4 * (size_t) N + 4, s->allreduce_ctx, (dfu_stream) st);
         DFU_REQUIRE(rc == 0, DFU_ERR_CUDA, "all-reduce hook failed");
     }
-    assemble_reg_kernel<<<nblk, TPB, 0, st>>>(rg, x.t, s->nbuf, N, s->part);
-    DFU_LAUNCH_OK();
-    pcg_init_kernel<<<nblk, TPB, 0, st>>>(x, s->part + MAX_PARTIALS);
+    k_node_reg_init<<<nblk_w, TPB, 0, st>>>(pb);
     DFU_LAUNCH_OK();
     const double tol2 = (double) s->prm.pcg_tol * (double) s->prm.pcg_tol;
-    pcg_init_scalars_kernel<<<1, 32, 0, st>>>(s->sc, s->nbuf, N, s->part, s->part + MAX_PARTIALS, nblk, tol2);
+    k_init_scalars<<<1, 32, 0, st>>>(pb, s->sc, nblk_w, tol2);
     DFU_LAUNCH_OK();
+    return DFU_OK;
+}
+
+int solve_multi_kernel(dfu_solver* s, cudaStream_t st) {
+    const int N = s->N, P = s->P;
+    const dfu_solver_params& prm = s->prm;
+    const Problem pb = make_problem(s);
+    const int nblk_n = div_up(N, TPB);
+    const int nblk_p = P > 0 ? min(div_up(P, TPB), MAX_PARTIALS) : 0;
+    const int nblk_w = min(div_up((long) N * 32, TPB), MAX_PARTIALS);
+    const double tol2 = (double) prm.pcg_tol * (double) prm.pcg_tol;
+    const bool host_checks = prm.early_out != 0;
+
+    Scalars init{};
+    init.rz_ref = -1.0;
+    init.first = 1;
+    init.done_it = INT_MAX;
+    *s->sc_host = init;
+    DFU_CUDA_OK(cudaMemcpyAsync(s->sc, s->sc_host, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+    DFU_CUDA_OK(cudaMemsetAsync(pb.t, 0, 3 * (size_t) N * sizeof(float), st));
+    if (host_checks) DFU_CUDA_OK(cudaStreamSynchronize(st));  // sc_host is re-used for read-backs below
+
+    bool stop_all = false;
+    s->gn_steps_host = 0;
+    for (int outer = 0; outer < prm.num_iter && !stop_all; ++outer) {
+        for (int gn = 0; gn < prm.nonlinear_iter; ++gn) {
+            int rc = assemble_mk(s, pb, gn == 0, st);  // preNonlinearSolve re-weights once per outer iteration
+            if (rc != DFU_OK) return rc;
+            if (host_checks) {
+                rc = read_scalars(s, st);
+                if (rc != DFU_OK) return rc;
+                if (s->sc_host->done_it == 0) {  // already converged at this linearisation point
+                    if (gn == 0 && outer > 0) stop_all = true;
+                    break;
+                }
+            }
+            for (int it = 0; it < prm.linear_iter; ++it) {
+                if (P > 0) {
+                    k_point_apply<<<nblk_p, TPB, 0, st>>>(pb, s->sc, it);
+                    DFU_LAUNCH_OK();
+                }
+                k_node_apply_data<<<nblk_w, TPB, 0, st>>>(pb, s->sc, it);
+                DFU_LAUNCH_OK();
+                if (s->allreduce) {
+                    rc = s->allreduce(pb.q, 3 * (size_t) N, s->allreduce_ctx, (dfu_stream) st);
+                    DFU_REQUIRE(rc == 0, DFU_ERR_CUDA, "all-reduce hook failed");
+                }
+                k_node_apply_reg_dot<<<nblk_w, TPB, 0, st>>>(pb, s->sc, it);
+                DFU_LAUNCH_OK();
+                k_pcg_update<<<nblk_n, TPB, 0, st>>>(pb, s->sc, it, nblk_w);
+                DFU_LAUNCH_OK();
+                k_pcg_direction<<<nblk_n, TPB, 0, st>>>(pb, s->sc, it, nblk_n, nblk_w, tol2);
+                DFU_LAUNCH_OK();
+                if (host_checks && (it & 7) == 7) {
+                    rc = read_scalars(s, st);
+                    if (rc != DFU_OK) return rc;
+                    if (s->sc_host->done_it <= it + 1) break;
+                }
+            }
+            k_axpy<<<div_up(3L * N, TPB), TPB, 0, st>>>(pb.t, pb.dl, 3 * N);
+            DFU_LAUNCH_OK();
+            s->gn_steps_host += 1;
+        }
+    }
+    return assemble_mk(s, pb, false, st);  // final energy at the solution
+}
+
+int solve_persistent(dfu_solver* s, cudaStream_t st) {
+    Problem pb = make_problem(s);
+    SolveCtl ctl{s->prm.num_iter, s->prm.nonlinear_iter, s->prm.linear_iter, s->prm.early_out,
+                 (double) s->prm.pcg_tol * (double) s->prm.pcg_tol};
+    Scalars* sc = s->sc;
+    void* args[] = {&pb, &ctl, &sc};
+    DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent, dim3(s->coop_blocks), dim3(PTPB), args, 0, st));
+    ++g_dfu_launches;
+    s->gn_steps_host = -1;  // read from the device scalars
     return DFU_OK;
 }
 
@@ -492,7 +824,12 @@ int dfu_solver_create(dfu_solver** out, dfu_warpfield* wf, const dfu_solver_para
     cudaSetDevice(wf->device);
     cudaError_t e1 = cudaMalloc(&s->sc, sizeof(Scalars));
     cudaError_t e2 = cudaMallocHost(&s->sc_host, sizeof(Scalars));
-    cudaError_t e3 = cudaMalloc(&s->part, 3 * MAX_PARTIALS * sizeof(double));
+    cudaError_t e3 = cudaMalloc(&s->part, 4 * MAX_PARTIALS * sizeof(double));
+    int coop = 0, sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, wf->device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wf->device);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, PTPB, 0) == cudaSuccess && per_sm >= 1)
+        s->coop_blocks = min(sms, MAX_PARTIALS);  // one CTA per SM
     cudaSetDevice(prev);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
         dfu_set_error("dfu_solver_create: allocation failed");
@@ -533,7 +870,7 @@ int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* ca
     dfu_warpfield* wf = s->wf;
     DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
     DFU_REQUIRE(wf->N >= DFU_KNN, DFU_ERR_PRECONDITION, "the solver needs at least 8 nodes (reference UB, opt_solver.cpp:63-66)");
-    DFU_REQUIRE(div_up(wf->N, TPB) <= MAX_PARTIALS, DFU_ERR_INVALID, "too many nodes");
+    DFU_REQUIRE((long) P * 8 < 0x7fffffffL, DFU_ERR_INVALID, "too many points");
     int prev = 0;
     cudaGetDevice(&prev);
     if (prev != wf->device) DFU_CUDA_OK(cudaSetDevice(wf->device));
@@ -546,14 +883,19 @@ int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* ca
         DFU_CUDA_OK(cudaMalloc(&s->wts, cap * 8 * sizeof(float)));
         DFU_CUDA_OK(cudaMalloc(&s->dvec, cap * 3 * sizeof(float)));
         DFU_CUDA_OK(cudaMalloc(&s->theta, cap * sizeof(float)));
+        DFU_CUDA_OK(cudaMalloc(&s->s4, cap * sizeof(float4)));
+        DFU_CUDA_OK(cudaMalloc(&s->tent, cap * 8 * sizeof(int32_t)));
+        DFU_CUDA_OK(cudaMalloc(&s->tv, cap * 8 * sizeof(int32_t)));
+        DFU_CUDA_OK(cudaMalloc(&s->tw, cap * 8 * sizeof(float)));
         s->capP = cap;
     }
     if ((size_t) N > s->capN) {
         free_node_arrays(s);
         const size_t cap = (size_t) N;
+        DFU_CUDA_OK(cudaMalloc(&s->tptr, (cap + 1) * sizeof(int)));
+        DFU_CUDA_OK(cudaMalloc(&s->tmp, 2 * cap * sizeof(int)));
         DFU_CUDA_OK(cudaMalloc(&s->nnbr, cap * 8 * sizeof(int32_t)));
         DFU_CUDA_OK(cudaMalloc(&s->rin_ptr, (cap + 1) * sizeof(int)));
-        DFU_CUDA_OK(cudaMalloc(&s->rin_tmp, 2 * cap * sizeof(int)));
         DFU_CUDA_OK(cudaMalloc(&s->rin, cap * 8 * sizeof(int32_t)));
         DFU_CUDA_OK(cudaMalloc(&s->vec, 18 * cap * sizeof(float)));
         DFU_CUDA_OK(cudaMalloc(&s->nbuf, (4 * cap + 4) * sizeof(float)));
@@ -562,18 +904,42 @@ int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* ca
     s->N = N;
     s->P = P;
     int rc = DFU_OK;
-    if (P > 0) rc = dfu_wf_build_data_graph(wf, canon_v, live_v, P, s->nbr, s->wts, s->dvec, st);  // opt_solver.cpp:56-72
-    if (rc == DFU_OK) rc = dfu_wf_build_node_graph(wf, s->nnbr, st);                             // opt_solver.cpp:74-105
-    if (rc != DFU_OK) return rc;
-    DFU_CUDA_OK(cudaMemsetAsync(s->rin_tmp, 0, 2 * (size_t) N * sizeof(int), st));
-    reg_indegree_kernel<<<div_up((long) N * 8, TPB), TPB, 0, st>>>(s->nnbr, N, s->rin_tmp);
+    // regularisation graph (opt_solver.cpp:74-105) and its transpose: depend on node POSITIONS only, so they are
+    // rebuilt exactly when the reference would see a different KD-tree (Warpfield::init / update)
+    if (s->reg_epoch != wf->node_epoch) {
+        rc = dfu_wf_build_node_graph(wf, s->nnbr, st);
+        if (rc != DFU_OK) return rc;
+        const long ne = (long) N * 8;
+        DFU_CUDA_OK(cudaMemsetAsync(s->tmp, 0, 2 * (size_t) N * sizeof(int), st));
+        k_count<<<div_up(ne, TPB), TPB, 0, st>>>(s->nnbr, ne, s->tmp);
+        DFU_LAUNCH_OK();
+        k_scan<<<1, 1024, 0, st>>>(s->tmp, N, s->rin_ptr);
+        DFU_LAUNCH_OK();
+        k_fill<<<div_up(ne, TPB), TPB, 0, st>>>(s->nnbr, ne, s->rin_ptr, s->tmp + N, s->rin, 3);
+        DFU_LAUNCH_OK();
+        k_sort_small<<<div_up(N, TPB), TPB, 0, st>>>(s->rin_ptr, N, s->rin);
+        DFU_LAUNCH_OK();
+        s->reg_epoch = wf->node_epoch;
+    }
+    // data graph (opt_solver.cpp:56-72) with the per-edge weights, and its transpose
+    if (P > 0) {
+        rc = dfu_wf_build_data_graph(wf, canon_v, live_v, P, s->nbr, s->wts, s->dvec, st);
+        if (rc != DFU_OK) return rc;
+    }
+    const long ne = (long) P * 8;
+    DFU_CUDA_OK(cudaMemsetAsync(s->tmp, 0, 2 * (size_t) N * sizeof(int), st));
+    if (P > 0) {
+        k_count<<<div_up(ne, TPB), TPB, 0, st>>>(s->nbr, ne, s->tmp);
+        DFU_LAUNCH_OK();
+    }
+    k_scan<<<1, 1024, 0, st>>>(s->tmp, N, s->tptr);
     DFU_LAUNCH_OK();
-    scan_kernel<<<1, 1024, 0, st>>>(s->rin_tmp, N, s->rin_ptr);
-    DFU_LAUNCH_OK();
-    reg_fill_kernel<<<div_up((long) N * 8, TPB), TPB, 0, st>>>(s->nnbr, N, s->rin_ptr, s->rin_tmp + N, s->rin);
-    DFU_LAUNCH_OK();
-    reg_sort_kernel<<<div_up(N, TPB), TPB, 0, st>>>(s->rin_ptr, N, s->rin);
-    DFU_LAUNCH_OK();
+    if (P > 0) {
+        k_fill<<<div_up(ne, TPB), TPB, 0, st>>>(s->nbr, ne, s->tptr, s->tmp + N, s->tent, 0);
+        DFU_LAUNCH_OK();
+        k_sort_emit<<<min(div_up((long) N * 32, TPB), 65535), TPB, 0, st>>>(s->tptr, N, s->tent, s->wts, s->tv, s->tw);
+        DFU_LAUNCH_OK();
+    }
     DFU_CUDA_OK(cudaMemsetAsync(s->vec, 0, 18 * (size_t) N * sizeof(float), st));  // unknowns := 0 (opt_solver.cpp:192-193)
     s->problem_ready = true;
     if (prev != wf->device) cudaSetDevice(prev);
@@ -587,74 +953,14 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream) {
     cudaGetDevice(&prev);
     if (prev != s->wf->device) DFU_CUDA_OK(cudaSetDevice(s->wf->device));
     cudaStream_t st = as_stream(stream);
-    const int N = s->N, P = s->P, nblk = div_up(N, TPB);
-    const dfu_solver_params& prm = s->prm;
-    Vecs x = make_vecs(s);
-    PointData pd{s->nbr, s->wts, s->dvec, s->theta, P};
-    RegGraph rg{s->nnbr, s->rin_ptr, s->rin, prm.lambda / ((float) N * 8.f)};
-    const double tol2 = (double) prm.pcg_tol * (double) prm.pcg_tol;
-    const bool host_checks = prm.early_out != 0;
-    double* partE = s->part;
-    double* part_rz = s->part + MAX_PARTIALS;
-    double* part_pq = s->part + 2 * MAX_PARTIALS;
-
-    Scalars init{};
-    init.rz_ref = -1.0;
-    init.first = 1;
-    init.done_it = INT_MAX;
-    *s->sc_host = init;
-    DFU_CUDA_OK(cudaMemcpyAsync(s->sc, s->sc_host, sizeof(Scalars), cudaMemcpyHostToDevice, st));
-    DFU_CUDA_OK(cudaMemsetAsync(x.t, 0, 3 * (size_t) N * sizeof(float), st));
-    if (host_checks) DFU_CUDA_OK(cudaStreamSynchronize(st));  // sc_host is reused for read-backs below
-
-    bool stop_all = false;
-    s->gn_steps = 0;
-    for (int outer = 0; outer < prm.num_iter && !stop_all; ++outer) {
-        for (int gn = 0; gn < prm.nonlinear_iter; ++gn) {
-            // preNonlinearSolve re-weights once per outer iteration (opt_solver.cpp:135-140)
-            int rc = assemble(s, gn == 0, st);
-            if (rc != DFU_OK) return rc;
-            if (host_checks) {
-                rc = read_scalars(s, st);
-                if (rc != DFU_OK) return rc;
-                if (s->sc_host->done_it == 0) {  // already converged at this linearisation point
-                    if (gn == 0 && outer > 0) stop_all = true;
-                    break;
-                }
-            }
-            for (int it = 0; it < prm.linear_iter; ++it) {
-                if (P > 0) {
-                    apply_data_kernel<<<div_up(P, TPB), TPB, 0, st>>>(pd, x.p, x.q, s->sc, it);
-                    DFU_LAUNCH_OK();
-                }
-                if (s->allreduce) {
-                    rc = s->allreduce(x.q, 3 * (size_t) N, s->allreduce_ctx, (dfu_stream) st);
-                    DFU_REQUIRE(rc == 0, DFU_ERR_CUDA, "all-reduce hook failed");
-                }
-                apply_reg_dot_kernel<<<nblk, TPB, 0, st>>>(rg, x, s->sc, it, part_pq);
-                DFU_LAUNCH_OK();
-                pcg_update_kernel<<<nblk, TPB, 0, st>>>(x, s->sc, it, part_pq, nblk, part_rz);
-                DFU_LAUNCH_OK();
-                pcg_direction_kernel<<<nblk, TPB, 0, st>>>(x, s->sc, it, part_rz, part_pq, nblk, tol2);
-                DFU_LAUNCH_OK();
-                if (host_checks && (it & 7) == 7) {
-                    rc = read_scalars(s, st);
-                    if (rc != DFU_OK) return rc;
-                    if (s->sc_host->done_it <= it + 1) break;
-                }
-            }
-            gn_update_kernel<<<div_up(3L * N, TPB), TPB, 0, st>>>(x.t, x.dl, 3 * N);
-            DFU_LAUNCH_OK();
-            s->gn_steps += 1;
-        }
-    }
-    // final energy at the solution (Tukey weights of the last outer iteration), then write back ONCE:
-    // dg_se3 := DQ(0,0,0,t) * dg_se3 (opt_solver.cpp:270-285, node.cpp:19-23)
-    int rc = assemble(s, false, st);
+    // DFU_SOLVER_PATH=multi forces the one-kernel-per-phase path (used by the tests to cover both)
+    const char* force = getenv("DFU_SOLVER_PATH");
+    const bool multi = s->allreduce != nullptr || s->coop_blocks == 0 || (force && force[0] == 'm');
+    int rc = multi ? solve_multi_kernel(s, st) : solve_persistent(s, st);
     if (rc != DFU_OK) return rc;
-    rc = dfu_warpfield_update_translations(s->wf, x.t, stream);
+    // write back ONCE: dg_se3 := DQ(0,0,0,t) * dg_se3 (opt_solver.cpp:270-285, node.cpp:19-23)
+    rc = dfu_warpfield_update_translations(s->wf, s->vec, stream);
     if (prev != s->wf->device) cudaSetDevice(prev);
-    (void) partE;
     return rc;
 }
 
@@ -673,7 +979,7 @@ int dfu_solver_get_stats_host(const dfu_solver* s, double stats_host[4], dfu_str
     stats_host[0] = s->sc_host->E0;
     stats_host[1] = s->sc_host->E;
     stats_host[2] = (double) s->sc_host->pcg_iters;
-    stats_host[3] = (double) s->gn_steps;
+    stats_host[3] = (double) (s->gn_steps_host >= 0 ? s->gn_steps_host : s->sc_host->gn_steps);
     return DFU_OK;
 }
 

@@ -245,7 +245,9 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
                 else
                     w = warp_translation_only(t[v], px[v], py, pz, a.pos_w, a.dual);
             } else {
-                const DQ b = blend(a.blend_mode, t[v], px[v], py, pz, a.pos_w, a.real, a.dual);
+                float wk[DFU_KNN];
+                neighbour_weights(t[v], px[v], py, pz, a.pos_w, wk);
+                const DQ b = blend(a.blend_mode, t[v], wk, a.real, a.dual);
                 w = dq_transform_vertex(b, V3{px[v], py, pz});
             }
             hit[v] = voxel_tsdf(a, w.x, w.y, w.z, ts[v]);

@@ -162,16 +162,35 @@ struct PointArgs {
     float voxel[3];
 };
 
+// G = 8 consecutive lanes cooperate on one query: split scan + shuffle merge (knn.cuh), then lane `sub`
+// evaluates the (FP64) weight of neighbour `sub` -- 8 lanes, 8 neighbours -- and the lanes share them by shuffle.
+constexpr int QG = 8;                  // lanes per query
+constexpr int QPB = 256 / QG;          // queries per CTA
+
+DFU_DEV float pick(const float (&a)[DFU_KNN], int k) {
+    float r = a[0];
+#pragma unroll
+    for (int i = 1; i < DFU_KNN; ++i) r = (i == k) ? a[i] : r;
+    return r;
+}
+DFU_DEV int pick(const int (&a)[DFU_KNN], int k) {
+    int r = a[0];
+#pragma unroll
+    for (int i = 1; i < DFU_KNN; ++i) r = (i == k) ? a[i] : r;
+    return r;
+}
+
 template <int OP>
 __global__ void __launch_bounds__(256) points_kernel(const PointArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     KnnSmem& sm = *reinterpret_cast<KnnSmem*>(smem_raw);
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = threadIdx.x & (QG - 1);
+    const long q = (long) blockIdx.x * QPB + (threadIdx.x / QG);
     const bool active = q < a.Q;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (active) {
         if (OP == OP_BOUNDS) {
-            const int bx = q % a.bdim[0], by = (q / a.bdim[0]) % a.bdim[1], bz = q / (a.bdim[0] * a.bdim[1]);
+            const int bx = (int) (q % a.bdim[0]), by = (int) ((q / a.bdim[0]) % a.bdim[1]), bz = (int) (q / ((long) a.bdim[0] * a.bdim[1]));
             qx = (bx * 8 + 3.5f) * a.voxel[0];
             qy = (by * 8 + 3.5f) * a.voxel[1];
             qz = (bz * 8 + 3.5f) * a.voxel[2];
@@ -184,56 +203,58 @@ __global__ void __launch_bounds__(256) points_kernel(const PointArgs a) {
             qz = a.q[3 * (size_t) q + 2];
         }
     }
+    V3 nn{0.f, 0.f, 0.f};  // read before anything is written: v_out / n_out may alias the inputs
+    if (OP == OP_WARP && active && a.n_in) nn = V3{a.n_in[3 * (size_t) q], a.n_in[3 * (size_t) q + 1], a.n_in[3 * (size_t) q + 2]};
     Top8 t;
-    knn8_scan_block(sm, a.pos_w, a.Npad, qx, qy, qz, active, t);
-    if (!active) return;
+    knn8_scan_block_split<QG>(sm, a.pos_w, a.Npad, qx, qy, qz, active, sub, t);
+    // a warp holds 4 queries; inactive queries only exist in the last CTA and come in whole groups of 8 lanes,
+    // so the full-mask shuffles below are executed by every lane of the warp
+    const int my_i = pick(t.i, sub);
+    const float my_d = pick(t.d, sub);
 
+    if (OP == OP_KNN || OP == OP_NODEGRAPH) {
+        if (active) {
+            a.idx[(size_t) q * DFU_KNN + sub] = my_i;
+            if (a.dist2) a.dist2[(size_t) q * DFU_KNN + sub] = my_d;
+        }
+        return;
+    }
+    if (OP == OP_BOUNDS) {
+        if (active && sub == 0) a.bounds[q] = make_float2(t.d[DFU_KNN - 1], t.d[0]);
+        return;
+    }
+    // weight of neighbour `sub` (Node::getTransformationWeight)
+    float my_w = 0.f;
+    if (active && my_i >= 0) {
+        const float4 nd = __ldg(&a.pos_w[my_i]);
+        my_w = node_weight(nd.x, nd.y, nd.z, nd.w, qx, qy, qz, my_d);
+    }
     if (OP == OP_GRAPH) {
         // CombinedSolver::initializeDataGraph (src/dynfu/utils/opt_solver.cpp:56-72) + the per-edge weight of
         // energy.t:15-17,49-52 + (live - canon) of energy.t:55
-        int32_t* o = a.idx + (size_t) q * DFU_KNN;
-        float* w = a.wts + (size_t) q * DFU_KNN;
-#pragma unroll
-        for (int k = 0; k < DFU_KNN; ++k) {
-            const int j = t.i[k];
-            o[k] = j;
-            const float4 nd = __ldg(&a.pos_w[j]);
-            w[k] = node_weight(nd.x, nd.y, nd.z, nd.w, qx, qy, qz, t.d[k]);
+        if (active) {
+            a.idx[(size_t) q * DFU_KNN + sub] = my_i;
+            a.wts[(size_t) q * DFU_KNN + sub] = my_w;
+            if (sub < 3) a.dvec[3 * (size_t) q + sub] = a.live[3 * (size_t) q + sub] - (sub == 0 ? qx : (sub == 1 ? qy : qz));
         }
-        a.dvec[3 * (size_t) q] = a.live[3 * (size_t) q] - qx;
-        a.dvec[3 * (size_t) q + 1] = a.live[3 * (size_t) q + 1] - qy;
-        a.dvec[3 * (size_t) q + 2] = a.live[3 * (size_t) q + 2] - qz;
-    } else if (OP == OP_KNN || OP == OP_NODEGRAPH) {
-        int32_t* o = a.idx + (size_t) q * DFU_KNN;
+        return;
+    }
+    float w[DFU_KNN];
+    const int base = (threadIdx.x & 31) & ~(QG - 1);
 #pragma unroll
-        for (int k = 0; k < DFU_KNN; ++k) o[k] = t.i[k];
-        if (a.dist2) {
-            float* d = a.dist2 + (size_t) q * DFU_KNN;
-#pragma unroll
-            for (int k = 0; k < DFU_KNN; ++k) d[k] = t.d[k];
-        }
-    } else if (OP == OP_BOUNDS) {
-        a.bounds[q] = make_float2(t.d[DFU_KNN - 1], t.d[0]);
+    for (int k = 0; k < DFU_KNN; ++k) w[k] = __shfl_sync(0xffffffffu, my_w, base + k);
+    if (!active) return;
+    const DQ b = blend(a.blend_mode, t, w, a.real, a.dual);  // all 8 lanes compute the same chain
+    if (OP == OP_BLEND) {
+        const float o[8] = {b.real.w, b.real.x, b.real.y, b.real.z, b.dual.w, b.dual.x, b.dual.y, b.dual.z};
+        a.dq_out[(size_t) q * 8 + sub] = pick(o, sub);
     } else {
-        const DQ b = blend(a.blend_mode, t, qx, qy, qz, a.pos_w, a.real, a.dual);
-        if (OP == OP_BLEND) {
-            float* o = a.dq_out + (size_t) q * 8;
-            o[0] = b.real.w; o[1] = b.real.x; o[2] = b.real.y; o[3] = b.real.z;
-            o[4] = b.dual.w; o[5] = b.dual.x; o[6] = b.dual.y; o[7] = b.dual.z;
-        } else {
-            // Warpfield::warpToLive (src/dynfu/warp_field.cpp:150-171)
-            V3 nn{0.f, 0.f, 0.f};
-            if (a.n_in) nn = V3{a.n_in[3 * (size_t) q], a.n_in[3 * (size_t) q + 1], a.n_in[3 * (size_t) q + 2]};
-            const V3 r = dq_transform_vertex(b, V3{qx, qy, qz});
-            a.v_out[3 * (size_t) q] = r.x;
-            a.v_out[3 * (size_t) q + 1] = r.y;
-            a.v_out[3 * (size_t) q + 2] = r.z;
-            if (a.n_in && a.n_out) {
-                const V3 rn = a.normal_mode == DFU_NORMAL_REF ? dq_transform_vertex(b, nn) : dq_rotate(b, nn);
-                a.n_out[3 * (size_t) q] = rn.x;
-                a.n_out[3 * (size_t) q + 1] = rn.y;
-                a.n_out[3 * (size_t) q + 2] = rn.z;
-            }
+        // Warpfield::warpToLive (src/dynfu/warp_field.cpp:150-171)
+        const V3 r = dq_transform_vertex(b, V3{qx, qy, qz});
+        if (sub < 3) a.v_out[3 * (size_t) q + sub] = sub == 0 ? r.x : (sub == 1 ? r.y : r.z);
+        if (a.n_in && a.n_out) {
+            const V3 rn = a.normal_mode == DFU_NORMAL_REF ? dq_transform_vertex(b, nn) : dq_rotate(b, nn);
+            if (sub >= 3 && sub < 6) a.n_out[3 * (size_t) q + sub - 3] = sub == 3 ? rn.x : (sub == 4 ? rn.y : rn.z);
         }
     }
 }
@@ -251,7 +272,7 @@ int launch_points(const dfu_warpfield* wf, PointArgs& a, cudaStream_t st) {
                                          (int) sizeof(KnnSmem)));
         attr_set = true;
     }
-    points_kernel<OP><<<div_up(a.Q, 256), 256, sizeof(KnnSmem), st>>>(a);
+    points_kernel<OP><<<div_up(a.Q, QPB), 256, sizeof(KnnSmem), st>>>(a);
     DFU_LAUNCH_OK();
     return DFU_OK;
 }
