@@ -47,6 +47,11 @@ struct BrickTable {            // per-volume-geometry acceleration data for the 
     float voxel[3] = {0, 0, 0};
     uint64_t node_epoch = 0;   // positions epoch the table was built for
     bool valid = false;
+    // per-voxel 8-NN cache (filled lazily by the integrator, valid while node positions are unchanged):
+    // 512 voxels x 8 u16 node ids = 8 KB per brick, brick-major; built[brick] != 0 once a brick is filled
+    uint4* knn_pool = nullptr;
+    unsigned char* built = nullptr;
+    size_t pool_bricks = 0;    // bricks the pool has room for (0: cache disabled)
 };
 
 struct dfu_warpfield {

@@ -16,8 +16,21 @@
 namespace dfu {
 
 DFU_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
-DFU_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
-DFU_DEV float fsub(float a, float b) { return __fsub_rn(a, b); }
+// a + b and a - b, rounded once, issued as FFMA with a unit multiplier.  fma(a, 1, b) == a + b and
+// fma(b, -1, a) == a - b bit for bit (the product is exact; signed zeros, infinities and NaNs behave alike).
+// Why: on sm_100 FADD/FSETP/FSEL issue on the half-rate ALU pipe while FFMA/FMUL use the full-rate FMA pipe
+// (ncu: alu 67 % vs fma 14 % busy in the voxel kNN loop before this change) -- the distance / quaternion
+// arithmetic is add-heavy, so the adds are moved to the FMA pipe.
+DFU_DEV float fadd(float a, float b) {
+    float r;
+    asm("fma.rn.f32 %0, %1, 0f3F800000, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+DFU_DEV float fsub(float a, float b) {
+    float r;
+    asm("fma.rn.f32 %0, %1, 0fBF800000, %2;" : "=f"(r) : "f"(b), "f"(a));
+    return r;
+}
 
 struct Quat {
     float w, x, y, z;

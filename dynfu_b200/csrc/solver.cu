@@ -638,6 +638,7 @@ __global__ void __launch_bounds__(TPB) k_sort_emit(const int* __restrict__ ptr, 
 
 struct dfu_solver {
     dfu_warpfield* wf = nullptr;
+    int device = 0;
     dfu_solver_params prm{};
     dfu_allreduce_fn allreduce = nullptr;
     void* allreduce_ctx = nullptr;
@@ -818,6 +819,7 @@ int dfu_solver_create(dfu_solver** out, dfu_warpfield* wf, const dfu_solver_para
     DFU_REQUIRE(prm->tukey_offset > 0.f && prm->psi_data > 0.f && prm->lambda >= 0.f, DFU_ERR_INVALID, "bad robust/regularisation parameter");
     dfu_solver* s = new dfu_solver();
     s->wf = wf;
+    s->device = wf->device;
     s->prm = *prm;
     int prev = 0;
     cudaGetDevice(&prev);
@@ -844,7 +846,7 @@ int dfu_solver_destroy(dfu_solver* s) {
     if (!s) return DFU_OK;
     int prev = 0;
     cudaGetDevice(&prev);
-    cudaSetDevice(s->wf->device);
+    cudaSetDevice(s->device);  // not s->wf->device: the warp field may already be gone
     free_point_arrays(s);
     free_node_arrays(s);
     cudaFree(s->sc);
@@ -874,6 +876,7 @@ int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* ca
     int prev = 0;
     cudaGetDevice(&prev);
     if (prev != wf->device) DFU_CUDA_OK(cudaSetDevice(wf->device));
+    (void) cudaGetLastError();  // drop stale errors of other libraries
     cudaStream_t st = as_stream(stream);
     const int N = wf->N;
     if ((size_t) P > s->capP) {
@@ -952,6 +955,7 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream) {
     int prev = 0;
     cudaGetDevice(&prev);
     if (prev != s->wf->device) DFU_CUDA_OK(cudaSetDevice(s->wf->device));
+    (void) cudaGetLastError();
     cudaStream_t st = as_stream(stream);
     // DFU_SOLVER_PATH=multi forces the one-kernel-per-phase path (used by the tests to cover both)
     const char* force = getenv("DFU_SOLVER_PATH");

@@ -37,6 +37,8 @@ struct IntegrateArgs {
     const int* flags;
     const float2* bounds;
     int bdx, bdy;
+    uint4* knn_pool;       // per-voxel 8-NN cache (null: disabled), see BrickTable
+    unsigned char* built;
 };
 
 DFU_DEV uint4 ld_stream(const uint4* p) { return __ldcs(p); }
@@ -175,63 +177,98 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
         const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
         float px[4];
         Top8 t[4];
-        const float d8c = sqrtf(__ldg(&a.bounds[brick0 + sb]).x);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            px[v] = fmul((float) (x + v), a.vsx);
-            // the 8 nodes nearest to the brick centre are within d8c + |v - centre| of voxel v: start every
-            // slot at that (inflated) bound, so the bulk of the candidates fails the first compare
-            const float ex = px[v] - bcx, ey = py - bcy, ez = pz - bcz;
-            const float bnd = (d8c + sqrtf(ex * ex + ey * ey + ez * ez)) * 1.0001f + 1e-6f;
-            const float bnd2 = bnd * bnd;
+        for (int v = 0; v < 4; ++v) px[v] = fmul((float) (x + v), a.vsx);
+        const size_t brick = brick0 + sb;
+        uint4* cache = a.knn_pool ? a.knn_pool + brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4) : nullptr;
+        if (cache && a.built[brick]) {
+            // node positions have not changed since this brick's 8-NN were computed: read the ids back and
+            // re-evaluate the 8 squared distances (same expression as the scan -> same bits)
 #pragma unroll
-            for (int k = 0; k < DFU_KNN; ++k) {
-                t[v].d[k] = bnd2;
-                t[v].i[k] = -1;
-            }
-        }
-#pragma unroll 1
-        for (int c0 = 0; c0 < a.N; c0 += CHUNK) {
-            // each warp compacts its 256-node slice, in index order, into its own segment
-            int n = 0;
-#pragma unroll 1
-            for (int j = 0; j < SEG; j += 32) {
-                const int idx = c0 + warp * SEG + j + lane;
-                bool keep = false;
-                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (idx < a.N) {
-                    p = __ldg(&a.pos_w[idx]);
-                    const float ddx = p.x - bcx, ddy = p.y - bcy, ddz = p.z - bcz;
-                    keep = (ddx * ddx + ddy * ddy + ddz * ddz) <= thr2;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    p.w = __int_as_float(idx);
-                    sm.cand[warp * SEG + n + __popc(m & ((1u << lane) - 1u))] = p;
-                }
-                n += __popc(m);
-            }
-            if (lane == 0) sm.cnt[warp] = n;
-            __syncthreads();
-#pragma unroll 1
-            for (int sg = 0; sg < 4; ++sg) {
-                const int cn = sm.cnt[sg];
-                const float4* __restrict__ cl = sm.cand + sg * SEG;
-#pragma unroll 1
-                for (int j = 0; j < cn; ++j) {
-                    const float4 p = cl[j];  // warp-wide broadcast
-                    const int idx = __float_as_int(p.w);
-                    const float dy = fsub(py, p.y), dz = fsub(pz, p.z);
-                    const float dy2 = fmul(dy, dy), dz2 = fmul(dz, dz);
+            for (int v = 0; v < 4; ++v) {
+                const uint4 c = cache[v];
+                const unsigned u[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const float dxv = fsub(px[v], p.x);
-                        const float d = fadd(fadd(fmul(dxv, dxv), dy2), dz2);  // nanoflann metric, bit exact
-                        if (d < t[v].d[DFU_KNN - 1]) top8_insert(t[v], d, idx);
+                for (int k = 0; k < DFU_KNN; ++k) {
+                    const int id = (int) ((u[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+                    t[v].i[k] = id == 0xffff ? -1 : id;
+                    t[v].d[k] = INFINITY;
+                    if (id != 0xffff) {
+                        const float4 p = __ldg(&a.pos_w[id]);
+                        t[v].d[k] = dist2(px[v], py, pz, p.x, p.y, p.z);
                     }
                 }
             }
-            __syncthreads();
+        } else {
+            const float d8c = sqrtf(__ldg(&a.bounds[brick]).x);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                // the 8 nodes nearest to the brick centre are within d8c + |v - centre| of voxel v: start every
+                // slot at that (inflated) bound, so the bulk of the candidates fails the first compare
+                const float ex = px[v] - bcx, ey = py - bcy, ez = pz - bcz;
+                const float bnd = (d8c + sqrtf(ex * ex + ey * ey + ez * ez)) * 1.0001f + 1e-6f;
+                const float bnd2 = bnd * bnd;
+#pragma unroll
+                for (int k = 0; k < DFU_KNN; ++k) {
+                    t[v].d[k] = bnd2;
+                    t[v].i[k] = -1;
+                }
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < a.N; c0 += CHUNK) {
+                // each warp compacts its 256-node slice, in index order, into its own segment
+                int n = 0;
+#pragma unroll 1
+                for (int j = 0; j < SEG; j += 32) {
+                    const int idx = c0 + warp * SEG + j + lane;
+                    bool keep = false;
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < a.N) {
+                        p = __ldg(&a.pos_w[idx]);
+                        const float ddx = p.x - bcx, ddy = p.y - bcy, ddz = p.z - bcz;
+                        keep = (ddx * ddx + ddy * ddy + ddz * ddz) <= thr2;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        p.w = __int_as_float(idx);
+                        sm.cand[warp * SEG + n + __popc(m & ((1u << lane) - 1u))] = p;
+                    }
+                    n += __popc(m);
+                }
+                if (lane == 0) sm.cnt[warp] = n;
+                __syncthreads();
+#pragma unroll 1
+                for (int sg = 0; sg < 4; ++sg) {
+                    const int cn = sm.cnt[sg];
+                    const float4* __restrict__ cl = sm.cand + sg * SEG;
+#pragma unroll 1
+                    for (int j = 0; j < cn; ++j) {
+                        const float4 p = cl[j];  // warp-wide broadcast
+                        const int idx = __float_as_int(p.w);
+                        const float dy = fsub(py, p.y), dz = fsub(pz, p.z);
+                        const float dy2 = fmul(dy, dy), dz2 = fmul(dz, dz);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float dxv = fsub(px[v], p.x);
+                            const float d = fadd(fadd(fmul(dxv, dxv), dy2), dz2);  // nanoflann metric, bit exact
+                            if (d < t[v].d[DFU_KNN - 1]) top8_insert(t[v], d, idx);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (cache) {  // fill the cache: 8 u16 ids per voxel, 64 contiguous bytes per thread
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    unsigned u[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        u[k] = ((unsigned) t[v].i[2 * k] & 0xffffu) | (((unsigned) t[v].i[2 * k + 1] & 0xffffu) << 16);
+                    cache[v] = make_uint4(u[0], u[1], u[2], u[3]);
+                }
+                __syncthreads();
+                if (tid == 0) a.built[brick] = 1;
+            }
         }
         if (z < a.z0 || z >= a.z1) continue;
         bool hit[4];
@@ -314,6 +351,7 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
     DFU_REQUIRE(((uintptr_t) volume & 15) == 0, DFU_ERR_INVALID, "volume must be 16-byte aligned");
     DFU_REQUIRE(blend_mode == DFU_BLEND_REF_COMPOSE || blend_mode == DFU_BLEND_DQB_SUM, DFU_ERR_INVALID, "bad blend_mode");
     if (z0 == z1) return DFU_OK;
+    (void) cudaGetLastError();  // drop stale errors of other libraries
     cudaStream_t st = as_stream(stream);
     IntegrateArgs a{};
     a.vol = reinterpret_cast<uint32_t*>(volume);
@@ -349,6 +387,8 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
         a.bounds = wf->bricks.bounds;
         a.bdx = dims[0] / 8;
         a.bdy = dims[1] / 8;
+        a.knn_pool = wf->bricks.knn_pool;
+        a.built = wf->bricks.built;
     }
     const long nblocks = (long) a.ntx * a.nty * ntz;
     DFU_REQUIRE(nblocks <= 0x7fffffffL, DFU_ERR_INVALID, "volume too large for one launch");

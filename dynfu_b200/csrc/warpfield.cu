@@ -3,6 +3,7 @@
 // (src/dynfu/utils/node.cpp) and the DualQuaternion arithmetic they call, for whole arrays of points.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "dfu_internal.h"
 #include "blend.cuh"
@@ -48,12 +49,15 @@ struct DeviceGuard {
         if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
     }
 };
+// also drops any stale, non-sticky error another library left in the runtime, so that the launch checks
+// below report only this library's own failures
 #define DFU_GUARD(dev)                                                     \
     DeviceGuard _guard(dev);                                               \
     if (!_guard.ok) {                                                      \
         dfu_set_error("%s: cannot select CUDA device %d", __func__, dev);  \
         return DFU_ERR_CUDA;                                               \
-    }
+    }                                                                      \
+    (void) cudaGetLastError();
 
 // ---- node packing ------------------------------------------------------------------------------
 __global__ void pack_nodes_kernel(const float* __restrict__ pos, const float* __restrict__ dq,
@@ -345,6 +349,29 @@ int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float v
     }
     int rc = launch_points<OP_BOUNDS>(wf, a, st);
     if (rc != DFU_OK) return rc;
+    // voxel kNN cache: node ids fit u16, 8 KB per brick, at most 4 GiB (512^3 needs 2 GiB of the 180 GB);
+    // DFU_VOXEL_KNN_CACHE=0 turns it off (every frame then recomputes the per-voxel 8-NN)
+    const char* env = getenv("DFU_VOXEL_KNN_CACHE");
+    const bool want = !(env && env[0] == '0') && wf->N <= 65535 && nb * 8192ull <= (4ull << 30);
+    if (!want) {
+        if (bt.knn_pool) cudaFree(bt.knn_pool);
+        if (bt.built) cudaFree(bt.built);
+        bt.knn_pool = nullptr;
+        bt.built = nullptr;
+        bt.pool_bricks = 0;
+    } else {
+        if (nb > bt.pool_bricks) {
+            if (bt.knn_pool) cudaFree(bt.knn_pool);
+            if (bt.built) cudaFree(bt.built);
+            bt.knn_pool = nullptr;
+            bt.built = nullptr;
+            bt.pool_bricks = 0;
+            DFU_CUDA_OK(cudaMalloc(&bt.knn_pool, nb * 8192ull));
+            DFU_CUDA_OK(cudaMalloc(&bt.built, nb));
+            bt.pool_bricks = nb;
+        }
+        DFU_CUDA_OK(cudaMemsetAsync(bt.built, 0, nb, st));
+    }
     bt.node_epoch = wf->node_epoch;
     bt.valid = true;
     return DFU_OK;
@@ -391,6 +418,8 @@ int dfu_warpfield_destroy(dfu_warpfield* wf) {
     cudaFree(wf->flags);
     cudaFree(wf->staging);
     cudaFree(wf->bricks.bounds);
+    cudaFree(wf->bricks.knn_pool);
+    cudaFree(wf->bricks.built);
     delete wf;
     return DFU_OK;
 }

@@ -237,6 +237,24 @@ def test_tsdf_properties_at_full_size(dfu, dists_np):
     assert torch.equal(part.data, full.data[224:288])
 
 
+def test_tsdf_voxel_knn_cache_on_equals_off(dfu, dists_np, monkeypatch):
+    """the lazily filled per-voxel 8-NN cache (second and later frames) gives the same bits as recomputing"""
+    dim = 128
+    d = dev(dists_np.view(np.int16), torch.int16)
+    pos, dq, dg_w, _ = synth.sphere_nodes(1024, 0.025)
+    vols = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DFU_VOXEL_KNN_CACHE", flag)
+        wf = make_wf(dfu, pos, dq, dg_w, 0.025)
+        vol = _volume(dfu, dim)
+        for frame in range(3):
+            vol.integrate(d, np.eye(4), synth.INTR, wf)
+            if frame == 1:  # new transforms, same positions: the cache stays valid
+                wf.updateTranslations(dev(np.full((1024, 3), 0.002, np.float32)))
+        vols.append(vol.data.clone())
+    assert torch.equal(vols[0], vols[1])
+
+
 def test_tsdf_bad_arguments(dfu, dists_np):
     d = dev(dists_np.view(np.int16), torch.int16)
     with pytest.raises(dfu.DfuError):  # dims.x % 32 (src/kfusion/kinfu.cpp:47)
