@@ -222,10 +222,9 @@ def main():
     scene = make_scene()
     P_all = len(scene["canon"])
     # z-slab of this rank (multiples of 8 planes) and its contiguous point partition
-    planes = DIM // 8
-    z0 = (planes * rank // world) * 8
-    z1 = (planes * (rank + 1) // world) * 8
-    p0, p1 = P_all * rank // world, P_all * (rank + 1) // world
+    from dynfu_b200 import dist as dfu_dist
+    z0, z1 = dfu_dist.slab_range(rank, world, DIM)
+    p0, p1 = dfu_dist.point_range(rank, world, P_all)
 
     def dev(a, dt=torch.float32):
         return torch.as_tensor(np.ascontiguousarray(a)).to(devs, dtype=dt)
@@ -235,7 +234,7 @@ def main():
                                                               earlyOut=False, pcgTolerance=0.0))
     df = dfu.DynFusion(prm, device=devs, z0=z0, z1=z1)
     if world > 1:
-        df.allreduce = lambda t: dist.all_reduce(t)
+        df.allreduce = dfu_dist.make_allreduce()
     df.init(dev(scene["canon"][p0:p1]), None, nodes=(dev(scene["pos"]), dev(scene["dq"]), dev(scene["dg_w"])))
 
     depth_host = [torch.from_numpy(d.view(np.int16)).pin_memory() for d in scene["depths"]]

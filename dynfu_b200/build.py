@@ -54,5 +54,21 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_cpp_tests(verbose=False):
+    """tests/cpp/opt_test: the reference's gtest cases compiled against the adapter header + the C-ABI library."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tests", "cpp", "opt_test.cpp")
+    out = os.path.join(root, "tests", "cpp", "opt_test")
+    deps = [src, os.path.join(root, "tests", "cpp", "mini_gtest.h"), os.path.join(HERE, "adapter", "dynfu_adapter.hpp"), OUT]
+    if _stale(out, deps):
+        cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-I/usr/local/cuda/include", "-o", out, src, "-L" + HERE, "-ldynfu_b200",
+               "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN/../../dynfu_b200", "-Wl,-rpath,/usr/local/cuda/lib64"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building tests/cpp/opt_test failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_cpp_tests())

@@ -1,0 +1,77 @@
+"""torchrun worker: the sharded hot path (z-slabs + point partitions + all-reduced normal equations) on
+WORLD_SIZE GPUs must equal the single-GPU run: TSDF slabs bit for bit, node transforms within 1e-5 relative."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import dynfu_b200 as dfu  # noqa: E402
+from dynfu_b200 import dist as dd  # noqa: E402
+from tests import synth  # noqa: E402
+
+
+def run(scene, rank, world, dim, device, frames=3):
+    z0, z1 = dd.slab_range(rank, world, dim)
+    p0, p1 = dd.point_range(rank, world, len(scene["canon"]))
+
+    def dev(a, dt=torch.float32):
+        return torch.as_tensor(np.ascontiguousarray(a)).to(device, dtype=dt)
+
+    prm = dfu.DynFuParams(kinfuParams=dfu.KinFuParams(volume_dims=(dim, dim, dim)), epsilon=0.03, lambda_=200.0,
+                          solver=dfu.CombinedSolverParameters(numIter=5, nonLinearIter=1, linearIter=10, earlyOut=False,
+                                                              pcgTolerance=0.0))
+    df = dfu.DynFusion(prm, device=device, z0=z0, z1=z1)
+    if world > 1:
+        df.allreduce = dd.make_allreduce()
+    df.init(dev(scene["canon"][p0:p1]), None, nodes=(dev(scene["pos"]), dev(scene["dq"]), dev(scene["dg_w"])))
+    depth = torch.from_numpy(scene["depth"].view(np.int16)).pin_memory()
+    df(depth)
+    for f in range(frames):
+        df(depth, dev(scene["lives"][f][p0:p1]))
+    torch.cuda.synchronize()
+    return df.volume.data.clone(), df.warpfield.getNodes()[1].clone(), (z0, z1)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+    dim = 128
+    depth = synth.sphere_depth()
+    pos, _, dg_w, t_true = synth.sphere_nodes(1024, 0.03)
+    canon = synth.backproject(depth, synth.INTR, stride=2)
+    lives = [canon + (0.004 * (f + 1)) * np.sin(3 * canon[:, [1, 2, 0]]).astype(np.float32) for f in range(3)]
+    scene = dict(depth=depth, pos=pos, dq=synth.identity_dq(1024), dg_w=dg_w, canon=canon, lives=lives)
+    vol_s, dq_s, (z0, z1) = run(scene, rank, world, dim, device)
+    ok = torch.tensor([1], device=device)
+    # every rank repeats the single-GPU run and compares its own slab + the node transforms
+    vol_f, dq_f, _ = run(scene, 0, 1, dim, device)
+    if not torch.equal(vol_s, vol_f[z0:z1]):
+        print("rank %d: slab [%d,%d) differs from the single-GPU volume in %d voxels" %
+              (rank, z0, z1, int((vol_s != vol_f[z0:z1]).sum())))
+        ok[0] = 0
+    scale = float(dq_f[:, 5:].abs().max())
+    err = float((dq_s - dq_f).abs().max())
+    if not err <= 1e-5 * scale:
+        print("rank %d: node transforms differ: %.3e (scale %.3e)" % (rank, err, scale))
+        ok[0] = 0
+    # all ranks must hold bit-identical node transforms
+    ref = dq_s.clone()
+    dist.broadcast(ref, 0)
+    if not torch.equal(ref, dq_s):
+        print("rank %d: node transforms are not bit-identical to rank 0" % rank)
+        ok[0] = 0
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MGPU_OK" if int(ok.item()) == 1 else "MGPU_FAIL", "world", world, "dq err", err, "scale", scale)
+    dist.destroy_process_group()
+    return 0 if int(ok.item()) == 1 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -447,3 +447,32 @@ def test_frame_operator_end_to_end(dfu, oracle):
     # the fused volume: replay the oracle integrator with the GPU's own solved transforms -> bit exact
     _oracle_integrate(oracle, ref, dists, nodes=(pos, dq_g, dg_w))
     assert _mismatch(df.volume.data.cpu().numpy().view(np.uint32), ref) == 0
+
+
+# ----------------------------------------------------------------- the reference's own tests, in C++
+def test_reference_gtest_cases_through_the_cpp_adapter(dfu):
+    """tests/cpp/opt_test.cpp = test/opt_optimisation_test.cpp:212-698 written against the same class names
+    (Warpfield, Node, DualQuaternion, CombinedSolver, dynfu::Frame) via dynfu_b200/adapter/dynfu_adapter.hpp."""
+    import os
+    import subprocess
+    from dynfu_b200 import build as b
+
+    exe = b.build_cpp_tests()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(exe))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "9 tests, 0 failed" in r.stdout, r.stdout
+
+
+def test_two_gpus_equal_one_gpu(dfu):
+    """z-slab + point-partition sharding over 2 GPUs == the single-GPU run (needs >= 2 GPUs on the box)"""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_worker.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
