@@ -50,14 +50,22 @@ def main():
     vol_s, dq_s, (z0, z1) = run(scene, rank, world, dim, device)
     ok = torch.tensor([1], device=device)
     # every rank repeats the single-GPU run and compares its own slab + the node transforms
+    # (the single-GPU reference uses the same one-kernel-per-phase solver path as the ranks, so that the only
+    #  difference left is the order of the partition sums; the persistent-kernel path is compared for information)
+    os.environ["DFU_SOLVER_PATH"] = "multi"
     vol_f, dq_f, _ = run(scene, 0, 1, dim, device)
+    os.environ["DFU_SOLVER_PATH"] = "persistent"
+    _, dq_p, _ = run(scene, 0, 1, dim, device)
     if not torch.equal(vol_s, vol_f[z0:z1]):
         print("rank %d: slab [%d,%d) differs from the single-GPU volume in %d voxels" %
               (rank, z0, z1, int((vol_s != vol_f[z0:z1]).sum())))
         ok[0] = 0
     scale = float(dq_f[:, 5:].abs().max())
     err = float((dq_s - dq_f).abs().max())
-    if not err <= 1e-5 * scale:
+    err_p = float((dq_s - dq_p).abs().max())
+    # float32 coordinates of ~1.5 m carry 1.2e-7 m of rounding, which is what the partition-sum order perturbs:
+    # bar = 5e-7 m absolute on the dual parts (1e-6 of the scene scale), like-for-like and vs the persistent kernel
+    if not (err <= 5e-7 and err_p <= 5e-7):
         print("rank %d: node transforms differ: %.3e (scale %.3e)" % (rank, err, scale))
         ok[0] = 0
     # all ranks must hold bit-identical node transforms
@@ -68,7 +76,8 @@ def main():
         ok[0] = 0
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("MGPU_OK" if int(ok.item()) == 1 else "MGPU_FAIL", "world", world, "dq err", err, "scale", scale)
+        print("MGPU_OK" if int(ok.item()) == 1 else "MGPU_FAIL", "world", world, "dq err vs 1 GPU (same path)", err,
+              "vs 1 GPU persistent kernel", err_p, "scale", scale)
     dist.destroy_process_group()
     return 0 if int(ok.item()) == 1 else 1
 
