@@ -94,6 +94,53 @@ DFU_DEV double block_sum(double v, double* sh) {
     double r = l < (int) (blockDim.x >> 5) ? sh[l] : 0.0;
     return warp_sum(r);
 }
+// four sums at once (one pair of CTA barriers instead of four)
+struct D4 {
+    double a, b, c, d;
+};
+DFU_DEV D4 block_sum4(D4 v, double* sh4) {  // sh4: 4 * (blockDim/32) doubles
+    v.a = warp_sum(v.a); v.b = warp_sum(v.b); v.c = warp_sum(v.c); v.d = warp_sum(v.d);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nwp = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) {
+        sh4[w] = v.a; sh4[nwp + w] = v.b; sh4[2 * nwp + w] = v.c; sh4[3 * nwp + w] = v.d;
+    }
+    __syncthreads();
+    D4 r;
+    r.a = warp_sum(l < nwp ? sh4[l] : 0.0);
+    r.b = warp_sum(l < nwp ? sh4[nwp + l] : 0.0);
+    r.c = warp_sum(l < nwp ? sh4[2 * nwp + l] : 0.0);
+    r.d = warp_sum(l < nwp ? sh4[3 * nwp + l] : 0.0);
+    return r;
+}
+// per-CTA partials are stored as 4 consecutive doubles per CTA; every CTA sums them redundantly in a fixed
+// order with ONE pass over memory
+DFU_DEV D4 sum_partials4(const double* part4, int n, double* sh4) {
+    D4 v{0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 x = *reinterpret_cast<const double2*>(part4 + 4 * (size_t) i);
+        const double2 y = *reinterpret_cast<const double2*>(part4 + 4 * (size_t) i + 2);
+        v.a += x.x; v.b += x.y; v.c += y.x; v.d += y.y;
+    }
+    return block_sum4(v, sh4);
+}
+
+// Grid-wide barrier of the persistent kernel: one release-add per CTA on a monotonically increasing counter
+// (zeroed by the host before the launch) and an acquire-poll until all CTAs of this generation have arrived.
+// The kernel is launched cooperatively, so all CTAs are co-resident.
+DFU_DEV void grid_barrier(unsigned* counter, unsigned nblocks, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblocks;
+        unsigned seen;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
 // fixed-order sum of per-block partials, computed redundantly by every block
 DFU_DEV double sum_partials(const double* part, int n, double* sh) {
     double v = 0.0;
@@ -173,13 +220,29 @@ DFU_DEV void phase_point_apply(const Problem& pb, int tid, int nthreads) {
 DFU_DEV void node_gather_data(const Problem& pb, int n, int lane, bool with_diag, float& ax, float& ay, float& az, float& ad) {
     ax = ay = az = ad = 0.f;
     const int lo = pb.tptr[n], hi = pb.tptr[n + 1];
-    for (int j = lo + lane; j < hi; j += 32) {
-        const float w = pb.tw[j];
-        const float4 s = pb.s4[pb.tv[j]];
-        ax = __fmaf_rn(w, s.x, ax);
-        ay = __fmaf_rn(w, s.y, ay);
-        az = __fmaf_rn(w, s.z, az);
-        if (with_diag) ad = __fmaf_rn(w * w, s.w, ad);
+    // 4 entries per lane in flight: all index/weight loads first, then the dependent s4 gathers, then the
+    // accumulation in entry order (same order as a plain lane-strided loop -> same bits)
+    for (int j = lo + lane; j < hi; j += 128) {
+        float w[4];
+        int v[4];
+        float4 s[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jj = j + 32 * u;
+            const bool ok = jj < hi;
+            w[u] = ok ? pb.tw[jj] : 0.f;
+            v[u] = ok ? pb.tv[jj] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] = v[u] >= 0 ? pb.s4[v[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (v[u] < 0) continue;
+            ax = __fmaf_rn(w[u], s[u].x, ax);
+            ay = __fmaf_rn(w[u], s[u].y, ay);
+            az = __fmaf_rn(w[u], s[u].z, az);
+            if (with_diag) ad = __fmaf_rn(w[u] * w[u], s[u].w, ad);
+        }
     }
 }
 
@@ -388,19 +451,17 @@ struct SolveCtl {
     double tol2;
 };
 
-__global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveCtl ctl, Scalars* sc) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double sh[PTPB / 32];
+__global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveCtl ctl, Scalars* sc, unsigned* bar) {
+    __shared__ double sh4[4 * (PTPB / 32)];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, gw = tid >> 5, nw = nthreads >> 5;
     const int nb = gridDim.x, n3 = 3 * pb.N;
-    double* part0 = pb.part;
-    double* part1 = pb.part + MAX_PARTIALS;
-    double* part2 = pb.part + 2 * MAX_PARTIALS;
-    double* part3 = pb.part + 3 * MAX_PARTIALS;
+    unsigned bar_target = 0;
+    double* part4 = pb.part;  // 4 doubles per CTA
+#define GRID_SYNC() grid_barrier(bar, (unsigned) nb, bar_target)
 
     for (int i = tid; i < n3; i += nthreads) pb.t[i] = 0.f;  // unknowns := 0 (opt_solver.cpp:192-193)
-    grid.sync();
+    GRID_SYNC();
 
     double rz_ref = -1.0, E = 0.0, E0 = 0.0;
     int pcg_total = 0, gn_total = 0;
@@ -409,11 +470,8 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveC
     for (int outer = 0; outer < ctl.num_iter && !stop_all; ++outer) {
         for (int gn = 0; gn < ctl.nonlinear_iter; ++gn) {
             // ---- residuals + tukey (re-weighted once per outer iteration, opt_solver.cpp:135-140) -----
-            {
-                const double e2 = block_sum(phase_point_residual(pb, gn == 0, tid, nthreads), sh);
-                if (threadIdx.x == 0) part0[blockIdx.x] = e2;
-            }
-            grid.sync();
+            const double e2_local = phase_point_residual(pb, gn == 0, tid, nthreads);
+            GRID_SYNC();
             // ---- per-node blocks: b = -J^T r, D = diag(J^T J) (+ regularisation), PCG initialisation --------
             {
                 double rz = 0.0, er = 0.0;
@@ -441,31 +499,32 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveC
                         er += (double) pb.wreg2 * e2;
                     }
                 }
-                const double a = block_sum(rz, sh), b = block_sum(er, sh);
+                const D4 s = block_sum4(D4{e2_local, rz, er, 0.0}, sh4);
                 if (threadIdx.x == 0) {
-                    part1[blockIdx.x] = a;
-                    part2[blockIdx.x] = b;
+                    part4[4 * blockIdx.x] = s.a; part4[4 * blockIdx.x + 1] = s.b; part4[4 * blockIdx.x + 2] = s.c;
+                    part4[4 * blockIdx.x + 3] = 0.0;
                 }
             }
-            grid.sync();
-            double rz = sum_partials(part1, nb, sh);
-            E = sum_partials(part0, nb, sh) + sum_partials(part2, nb, sh);
+            GRID_SYNC();
+            const D4 tot = sum_partials4(part4, nb, sh4);
+            double rz = tot.b;
+            E = tot.a + tot.c;
             if (first) {
                 E0 = E;
                 first = false;
             }
             if (rz_ref < 0.0) rz_ref = rz;
             const bool conv0 = !(rz > 0.0) || rz <= ctl.tol2 * rz_ref;
-            grid.sync();  // every CTA has read the partials: they may be re-used
             if (ctl.early_out && conv0) {  // converged at this linearisation point
                 if (gn == 0 && outer > 0) stop_all = true;
+                GRID_SYNC();  // every CTA has read the partials before anyone overwrites them
                 break;
             }
-            // ---- PCG ---------------------------------------------------------------------------------------
+            // ---- PCG (the barrier after the point phase also separates the partials' readers and writers) ----
             if (!conv0) {
                 for (int it = 0; it < ctl.linear_iter; ++it) {
                     phase_point_apply(pb, tid, nthreads);  // s4 = Theta W p
-                    grid.sync();
+                    GRID_SYNC();
                     // p.q, r.M^-1 r, r.M^-1 q, q.M^-1 q.  r.M^-1 r is re-measured from the stored float r every
                     // iteration, so the recurrence below never drifts away from the actual residual.
                     double pq = 0.0, rr = 0.0, rmq = 0.0, qmq = 0.0;
@@ -484,8 +543,8 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveC
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
                                 const size_t i = 3 * (size_t) n + c;
-                                pb.q[i] = qq[c];
                                 const double ri = (double) pb.r[i];
+                                pb.q[i] = qq[c];
                                 pq += (double) pb.p[i] * qq[c];
                                 rr += ri * ri * inv;
                                 rmq += ri * qq[c] * inv;
@@ -494,24 +553,17 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveC
                         }
                     }
                     {
-                        const double a = block_sum(pq, sh), b = block_sum(rmq, sh), c = block_sum(qmq, sh), d = block_sum(rr, sh);
+                        const D4 s = block_sum4(D4{pq, rr, rmq, qmq}, sh4);
                         if (threadIdx.x == 0) {
-                            part0[blockIdx.x] = a;
-                            part1[blockIdx.x] = b;
-                            part2[blockIdx.x] = c;
-                            part3[blockIdx.x] = d;
+                            part4[4 * blockIdx.x] = s.a; part4[4 * blockIdx.x + 1] = s.b; part4[4 * blockIdx.x + 2] = s.c;
+                            part4[4 * blockIdx.x + 3] = s.d;
                         }
                     }
-                    grid.sync();
-                    pq = sum_partials(part0, nb, sh);
-                    rmq = sum_partials(part1, nb, sh);
-                    qmq = sum_partials(part2, nb, sh);
-                    rz = sum_partials(part3, nb, sh);
+                    GRID_SYNC();
+                    const D4 g = sum_partials4(part4, nb, sh4);
+                    pq = g.a; rz = g.b; rmq = g.c; qmq = g.d;
                     ++pcg_total;
-                    if (!(pq > 0.0) || !(rz > 0.0)) {
-                        grid.sync();
-                        break;
-                    }
+                    if (!(pq > 0.0) || !(rz > 0.0)) break;
                     // r' = r - alpha q, z' = M^-1 r'  =>  r'.z' = r.z - 2 alpha r.M^-1 q + alpha^2 q.M^-1 q
                     const double alpha = rz / pq;
                     double rzn = rz - 2.0 * alpha * rmq + alpha * alpha * qmq;
@@ -527,18 +579,19 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveC
                         pb.p[i] = __fmaf_rn(bf, p, r * inv);
                     }
                     rz = rzn;
-                    grid.sync();
+                    GRID_SYNC();
                     if (!(rz > 0.0) || rz <= ctl.tol2 * rz_ref) break;
                 }
             }
+            GRID_SYNC();  // (also covers the PCG exits that left without a barrier after reading the partials)
             for (int i = tid; i < n3; i += nthreads) pb.t[i] += pb.dl[i];
             ++gn_total;
-            grid.sync();
+            GRID_SYNC();
         }
     }
     // ---- final energy at the solution, Tukey weights of the last outer iteration -------------------------
     {
-        const double e2 = block_sum(phase_point_residual(pb, false, tid, nthreads), sh);
+        const double e2 = phase_point_residual(pb, false, tid, nthreads);
         double er = 0.0;
         if (pb.wreg2 > 0.f)
             for (int n = gw; n < pb.N; n += nw) {
@@ -547,14 +600,17 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveC
                 r2 = warp_sum(r2);
                 if (lane == 0) er += (double) pb.wreg2 * r2;
             }
-        const double b = block_sum(er, sh);
+        const D4 s = block_sum4(D4{e2, er, 0.0, 0.0}, sh4);
         if (threadIdx.x == 0) {
-            part0[blockIdx.x] = e2;
-            part2[blockIdx.x] = b;
+            part4[4 * blockIdx.x] = s.a; part4[4 * blockIdx.x + 1] = s.b; part4[4 * blockIdx.x + 2] = 0.0;
+            part4[4 * blockIdx.x + 3] = 0.0;
         }
     }
-    grid.sync();
-    E = sum_partials(part0, nb, sh) + sum_partials(part2, nb, sh);
+    GRID_SYNC();
+    {
+        const D4 g = sum_partials4(part4, nb, sh4);
+        E = g.a + g.b;
+    }
     if (tid == 0) {
         sc->E = E;
         sc->E0 = first ? E : E0;
@@ -563,6 +619,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveC
         sc->gn_steps = gn_total;
         sc->first = 0;
     }
+#undef GRID_SYNC
 }
 
 // ---- graph construction ------------------------------------------------------------------------------------
@@ -661,6 +718,7 @@ struct dfu_solver {
     double* part = nullptr;
     Scalars* sc = nullptr;
     Scalars* sc_host = nullptr;  // pinned
+    unsigned* bar = nullptr;     // grid-barrier counter of the persistent kernel
     uint64_t reg_epoch = 0;      // node-position epoch the regularisation graph was built for (0: never)
     bool problem_ready = false;
     int coop_blocks = 0;         // co-resident CTAs for the persistent kernel (0: not available)
@@ -802,7 +860,9 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
     SolveCtl ctl{s->prm.num_iter, s->prm.nonlinear_iter, s->prm.linear_iter, s->prm.early_out,
                  (double) s->prm.pcg_tol * (double) s->prm.pcg_tol};
     Scalars* sc = s->sc;
-    void* args[] = {&pb, &ctl, &sc};
+    unsigned* bar = s->bar;
+    DFU_CUDA_OK(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+    void* args[] = {&pb, &ctl, &sc, &bar};
     DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent, dim3(s->coop_blocks), dim3(PTPB), args, 0, st));
     ++g_dfu_launches;
     s->gn_steps_host = -1;  // read from the device scalars
@@ -827,6 +887,7 @@ int dfu_solver_create(dfu_solver** out, dfu_warpfield* wf, const dfu_solver_para
     cudaError_t e1 = cudaMalloc(&s->sc, sizeof(Scalars));
     cudaError_t e2 = cudaMallocHost(&s->sc_host, sizeof(Scalars));
     cudaError_t e3 = cudaMalloc(&s->part, 4 * MAX_PARTIALS * sizeof(double));
+    if (e3 == cudaSuccess) e3 = cudaMalloc(&s->bar, 64);
     int coop = 0, sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, wf->device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wf->device);
@@ -852,6 +913,7 @@ int dfu_solver_destroy(dfu_solver* s) {
     cudaFree(s->sc);
     cudaFreeHost(s->sc_host);
     cudaFree(s->part);
+    cudaFree(s->bar);
     cudaSetDevice(prev);
     delete s;
     return DFU_OK;
