@@ -35,7 +35,7 @@ from tests import synth  # noqa: E402
 DIM = 512
 N_THETA, N_Y = 64, 64
 EPSILON = 0.0125
-KAPPA = 0.05
+KAPPA = 0.02   # bend x += KAPPA*a*(y-cy)^2: the largest displacement (a = 3, |y| = 0.8 m) is 0.038 m ~ dg_w, i.e. trackable
 GN_ITERS, PCG_ITERS = 5, 10
 LAMBDA = 200.0
 RING = 4

@@ -54,6 +54,26 @@ struct BrickTable {            // per-volume-geometry acceleration data for the 
     size_t pool_bricks = 0;    // bricks the pool has room for (0: cache disabled)
 };
 
+// Uniform grid over the node positions for the point-query kNN (rebuilt when positions change)
+struct GridDesc {
+    float ox, oy, oz;  // origin (bbox min)
+    float h, inv_h;    // cell edge
+    int nx, ny, nz;
+    int n_occ;         // number of non-empty cells (entries of NodeGrid::occ)
+};
+constexpr int DFU_GRID_MAX_DIM = 128;
+constexpr int DFU_GRID_MAX_CELLS = DFU_GRID_MAX_DIM * DFU_GRID_MAX_DIM * DFU_GRID_MAX_DIM;
+struct NodeGrid {
+    GridDesc* desc = nullptr;     // device
+    int* cell_start = nullptr;    // DFU_GRID_MAX_CELLS + 1
+    int* cell_count = nullptr;    // DFU_GRID_MAX_CELLS (scratch during the build)
+    float4* sorted = nullptr;     // nodes ordered by cell: (x, y, z, index bits)
+    int* occ = nullptr;           // ids of the non-empty cells (at most N)
+    int capacity = 0;             // entries of `sorted`
+    uint64_t node_epoch = 0;
+    bool valid = false;
+};
+
 struct dfu_warpfield {
     int device = 0;
     int N = 0;            // nodes
@@ -70,6 +90,7 @@ struct dfu_warpfield {
     size_t staging_cap = 0;
     uint64_t node_epoch = 0;   // bumped when positions change
     BrickTable bricks;
+    NodeGrid grid;
     bool initialised = false;
 };
 

@@ -263,6 +263,320 @@ __global__ void __launch_bounds__(256) points_kernel(const PointArgs a) {
     }
 }
 
+// =====================================================================================================
+// Grid-bucketed exact kNN for point queries (the north-star's "(1) grid-bucketed ... kNN").
+//
+// Nodes are binned into a uniform grid (cell edge ~2.5 mean nearest-neighbour distances).  A query visits the
+// cells in shells of growing Chebyshev radius around its own cell and stops as soon as its current 8th
+// distance is smaller than the distance to everything not yet visited, so it evaluates tens of candidates
+// instead of all N.  Distances use the same expression as everywhere else (bit-exact) and the top-8 is kept
+// by the (dist2, index) key explicitly, because cells are not visited in index order.
+
+// bbox, mean nearest-neighbour distance (sampled) -> grid descriptor.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) grid_desc_kernel(const float4* __restrict__ pos_w, int N, GridDesc* __restrict__ g) {
+    __shared__ float s_min[3][32], s_max[3][32], s_nn[32];
+    __shared__ int s_cnt[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < N; i += 1024) {
+        const float4 p = pos_w[i];
+        mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+        mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    }
+    // nearest-neighbour distance of up to 1024 sample nodes
+    float nn = 0.f;
+    int cnt = 0;
+    const int stride = max(1, N / 1024);
+    const int i0 = tid * stride;
+    if (i0 < N && N > 1) {
+        const float4 q = pos_w[i0];
+        float best = INFINITY;
+        for (int j = 0; j < N; ++j) {
+            if (j == i0) continue;
+            const float4 p = pos_w[j];
+            const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+            best = fminf(best, dx * dx + dy * dy + dz * dz);
+        }
+        nn = sqrtf(best);
+        cnt = 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int c = 0; c < 3; ++c) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) {
+        for (int c = 0; c < 3; ++c) {
+            s_min[c][wid] = mn[c];
+            s_max[c][wid] = mx[c];
+        }
+        s_nn[wid] = nn;
+        s_cnt[wid] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float nnsum = 0.f;
+        int c_ = 0;
+        for (int w = 0; w < 32; ++w) {
+            for (int c = 0; c < 3; ++c) {
+                mn[c] = fminf(mn[c], s_min[c][w]);
+                mx[c] = fmaxf(mx[c], s_max[c][w]);
+            }
+            nnsum += s_nn[w];
+            c_ += s_cnt[w];
+        }
+        const float ext = fmaxf(mx[0] - mn[0], fmaxf(mx[1] - mn[1], mx[2] - mn[2]));
+        float h = c_ > 0 ? 2.5f * nnsum / (float) c_ : 1.f;
+        h = fmaxf(h, ext / (float) (DFU_GRID_MAX_DIM - 1));
+        h = fmaxf(h, 1e-6f);
+        g->ox = mn[0]; g->oy = mn[1]; g->oz = mn[2];
+        g->h = h;
+        g->inv_h = 1.f / h;
+        g->nx = min(DFU_GRID_MAX_DIM, (int) ((mx[0] - mn[0]) * g->inv_h) + 1);
+        g->ny = min(DFU_GRID_MAX_DIM, (int) ((mx[1] - mn[1]) * g->inv_h) + 1);
+        g->nz = min(DFU_GRID_MAX_DIM, (int) ((mx[2] - mn[2]) * g->inv_h) + 1);
+        g->n_occ = 0;
+    }
+}
+
+DFU_DEV int grid_coord(float v, float o, float inv_h, int n) { return min(n - 1, max(0, (int) floorf((v - o) * inv_h))); }
+DFU_DEV int grid_cell_of(const GridDesc& g, float x, float y, float z) {
+    return grid_coord(x, g.ox, g.inv_h, g.nx) + g.nx * (grid_coord(y, g.oy, g.inv_h, g.ny) + g.ny * grid_coord(z, g.oz, g.inv_h, g.nz));
+}
+__global__ void grid_count_kernel(const float4* __restrict__ pos_w, int N, const GridDesc* __restrict__ gd, int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const GridDesc g = *gd;
+    const float4 p = pos_w[i];
+    atomicAdd(&count[grid_cell_of(g, p.x, p.y, p.z)], 1);
+}
+// exclusive scan of count[0..ncells) -> start[0..ncells]; single CTA, ncells read from the descriptor
+__global__ void __launch_bounds__(1024) grid_scan_kernel(const int* __restrict__ count, const GridDesc* __restrict__ gd, int* __restrict__ start) {
+    __shared__ int sh[1024];
+    const int n = gd->nx * gd->ny * gd->nz;
+    const int per = (n + 1023) / 1024;
+    const int lo = min(n, (int) threadIdx.x * per), hi = min(n, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += count[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = (int) threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = sh[threadIdx.x] - s;
+    for (int i = lo; i < hi; ++i) {
+        start[i] = run;
+        run += count[i];
+    }
+    if (threadIdx.x == 1023) start[n] = sh[1023];
+}
+__global__ void grid_fill_kernel(const float4* __restrict__ pos_w, int N, const GridDesc* __restrict__ gd, const int* __restrict__ start,
+                                 int* __restrict__ count, float4* __restrict__ sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const GridDesc g = *gd;
+    const float4 p = pos_w[i];
+    const int c = grid_cell_of(g, p.x, p.y, p.z);
+    const int slot = atomicSub(&count[c], 1) - 1;  // order inside a cell is irrelevant: the search uses the (dist2, idx) key
+    sorted[start[c] + slot] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+}
+
+// list of the non-empty cells (order arbitrary: it only affects the visiting order, never the result)
+__global__ void grid_occ_kernel(const int* __restrict__ start, GridDesc* __restrict__ gd, int* __restrict__ occ) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = gd->nx * gd->ny * gd->nz;
+    if (c < n && start[c + 1] > start[c]) occ[atomicAdd(&gd->n_occ, 1)] = c;
+}
+
+// top-8 insertion by the explicit key (dist2, idx)
+DFU_DEV void top8_insert_lex(Top8& t, float dist, int idx) {
+#pragma unroll
+    for (int k = DFU_KNN - 1; k > 0; --k) {
+        const bool shift = lex_less(dist, idx, t.d[k - 1], t.i[k - 1]);
+        const bool here = !shift && lex_less(dist, idx, t.d[k], t.i[k]);
+        t.i[k] = shift ? t.i[k - 1] : (here ? idx : t.i[k]);
+        t.d[k] = shift ? t.d[k - 1] : (here ? dist : t.d[k]);
+    }
+    if (lex_less(dist, idx, t.d[0], t.i[0])) {
+        t.d[0] = dist;
+        t.i[0] = idx;
+    }
+}
+
+DFU_DEV void grid_visit_cell(const int* __restrict__ start, const float4* __restrict__ sorted, int cell, float qx, float qy, float qz, Top8& t) {
+    const int lo = __ldg(&start[cell]), hi = __ldg(&start[cell + 1]);
+    for (int j = lo; j < hi; ++j) {
+        const float4 p = __ldg(&sorted[j]);
+        const float d = dist2(qx, qy, qz, p.x, p.y, p.z);
+        if (d <= t.d[DFU_KNN - 1]) {
+            const int idx = __float_as_int(p.w);
+            if (lex_less(d, idx, t.d[DFU_KNN - 1], t.i[DFU_KNN - 1])) top8_insert_lex(t, d, idx);
+        }
+    }
+}
+
+// exact 8-NN of one query through the grid.  Shells of growing Chebyshev radius around the query's cell (a
+// query near the nodes is done after 1-2); once the next shell would cost more cell visits than there are
+// NON-EMPTY cells, a query that is still not settled sweeps the list of non-empty cells instead, pruning each
+// by its box distance, so the cost stays bounded however far the query is from the nodes.
+DFU_DEV void knn8_grid(const GridDesc& g, const int* __restrict__ start, const float4* __restrict__ sorted,
+                       const int* __restrict__ occ, float qx, float qy, float qz, Top8& t) {
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) {
+        t.d[k] = INFINITY;
+        t.i[k] = 0x7fffffff;  // "no node": loses every tie
+    }
+    const int cx = grid_coord(qx, g.ox, g.inv_h, g.nx), cy = grid_coord(qy, g.oy, g.inv_h, g.ny), cz = grid_coord(qz, g.oz, g.inv_h, g.nz);
+    bool settled = false;
+    int r = 0, rd = -1;  // rd: every cell within this Chebyshev radius has been visited
+    for (; (2 * r + 1) * (2 * r + 1) * (2 * r + 1) <= 2 * g.n_occ + 27; ++r) {
+        rd = r;
+        const int z0 = max(0, cz - r), z1 = min(g.nz - 1, cz + r);
+        const int y0 = max(0, cy - r), y1 = min(g.ny - 1, cy + r);
+        const int x0 = max(0, cx - r), x1 = min(g.nx - 1, cx + r);
+        for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y) {
+                const bool face = (abs(z - cz) == r) || (abs(y - cy) == r);
+                const int row = g.nx * (y + g.ny * z);
+                if (face) {
+                    for (int x = x0; x <= x1; ++x) grid_visit_cell(start, sorted, row + x, qx, qy, qz, t);
+                } else {  // interior rows of the shell: only the two end cells
+                    if (cx - r >= 0) grid_visit_cell(start, sorted, row + cx - r, qx, qy, qz, t);
+                    if (cx + r < g.nx) grid_visit_cell(start, sorted, row + cx + r, qx, qy, qz, t);
+                }
+            }
+        // distance from the query to everything not visited yet: the nearest face of the visited box that
+        // still has cells beyond it
+        float L = INFINITY;
+        if (cx - r > 0) L = fminf(L, qx - (g.ox + (float) (cx - r) * g.h));
+        if (cx + r < g.nx - 1) L = fminf(L, (g.ox + (float) (cx + r + 1) * g.h) - qx);
+        if (cy - r > 0) L = fminf(L, qy - (g.oy + (float) (cy - r) * g.h));
+        if (cy + r < g.ny - 1) L = fminf(L, (g.oy + (float) (cy + r + 1) * g.h) - qy);
+        if (cz - r > 0) L = fminf(L, qz - (g.oz + (float) (cz - r) * g.h));
+        if (cz + r < g.nz - 1) L = fminf(L, (g.oz + (float) (cz + r + 1) * g.h) - qz);
+        // margin: binning and face coordinates are rounded (coordinates are O(1) m: 1e-5 m is > 100 ulp)
+        const float Ls = L - 1e-5f - 1e-5f * g.h;
+        if (L == INFINITY || (Ls > 0.f && t.d[DFU_KNN - 1] < Ls * Ls)) {
+            settled = true;
+            break;
+        }
+    }
+    if (!settled) {
+        const int n_occ = g.n_occ;
+        for (int e = 0; e < n_occ; ++e) {
+            const int c = __ldg(&occ[e]);
+            const int ix = c % g.nx, iy = (c / g.nx) % g.ny, iz = c / (g.nx * g.ny);
+            if (abs(ix - cx) <= rd && abs(iy - cy) <= rd && abs(iz - cz) <= rd) continue;
+            const float lx = g.ox + (float) ix * g.h, ly = g.oy + (float) iy * g.h, lz = g.oz + (float) iz * g.h;
+            const float ddx = fmaxf(0.f, fmaxf(lx - qx, qx - (lx + g.h))), ddy = fmaxf(0.f, fmaxf(ly - qy, qy - (ly + g.h))),
+                        ddz = fmaxf(0.f, fmaxf(lz - qz, qz - (lz + g.h)));
+            const float dl = fmaxf(0.f, sqrtf(ddx * ddx + ddy * ddy + ddz * ddz) - 1e-5f - 1e-5f * g.h);
+            if (dl * dl <= t.d[DFU_KNN - 1]) grid_visit_cell(start, sorted, c, qx, qy, qz, t);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k)
+        if (t.i[k] == 0x7fffffff) t.i[k] = -1;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(128) points_grid_kernel(const PointArgs a, const GridDesc* __restrict__ gd, const int* __restrict__ start,
+                                                          const float4* __restrict__ sorted, const int* __restrict__ occ) {
+    const long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.Q) return;
+    const GridDesc g = *gd;
+    float qx, qy, qz;
+    if (OP == OP_NODEGRAPH) {
+        const float4 p = a.pos_w[q];
+        qx = p.x; qy = p.y; qz = p.z;
+    } else {
+        qx = a.q[3 * (size_t) q]; qy = a.q[3 * (size_t) q + 1]; qz = a.q[3 * (size_t) q + 2];
+    }
+    V3 nn{0.f, 0.f, 0.f};
+    if (OP == OP_WARP && a.n_in) nn = V3{a.n_in[3 * (size_t) q], a.n_in[3 * (size_t) q + 1], a.n_in[3 * (size_t) q + 2]};
+    Top8 t;
+    knn8_grid(g, start, sorted, occ, qx, qy, qz, t);
+    if (OP == OP_KNN || OP == OP_NODEGRAPH) {
+        int4* o = reinterpret_cast<int4*>(a.idx + (size_t) q * DFU_KNN);
+        o[0] = make_int4(t.i[0], t.i[1], t.i[2], t.i[3]);
+        o[1] = make_int4(t.i[4], t.i[5], t.i[6], t.i[7]);
+        if (a.dist2) {
+            float4* d = reinterpret_cast<float4*>(a.dist2 + (size_t) q * DFU_KNN);
+            d[0] = make_float4(t.d[0], t.d[1], t.d[2], t.d[3]);
+            d[1] = make_float4(t.d[4], t.d[5], t.d[6], t.d[7]);
+        }
+        return;
+    }
+    float w[DFU_KNN];
+    neighbour_weights(t, qx, qy, qz, a.pos_w, w);
+    if (OP == OP_GRAPH) {
+        int4* o = reinterpret_cast<int4*>(a.idx + (size_t) q * DFU_KNN);
+        o[0] = make_int4(t.i[0], t.i[1], t.i[2], t.i[3]);
+        o[1] = make_int4(t.i[4], t.i[5], t.i[6], t.i[7]);
+        float4* ww = reinterpret_cast<float4*>(a.wts + (size_t) q * DFU_KNN);
+        ww[0] = make_float4(w[0], w[1], w[2], w[3]);
+        ww[1] = make_float4(w[4], w[5], w[6], w[7]);
+        a.dvec[3 * (size_t) q] = a.live[3 * (size_t) q] - qx;
+        a.dvec[3 * (size_t) q + 1] = a.live[3 * (size_t) q + 1] - qy;
+        a.dvec[3 * (size_t) q + 2] = a.live[3 * (size_t) q + 2] - qz;
+        return;
+    }
+    const DQ b = blend(a.blend_mode, t, w, a.real, a.dual);
+    if (OP == OP_BLEND) {
+        float4* o = reinterpret_cast<float4*>(a.dq_out + (size_t) q * 8);
+        o[0] = make_float4(b.real.w, b.real.x, b.real.y, b.real.z);
+        o[1] = make_float4(b.dual.w, b.dual.x, b.dual.y, b.dual.z);
+    } else {
+        const V3 r = dq_transform_vertex(b, V3{qx, qy, qz});
+        a.v_out[3 * (size_t) q] = r.x; a.v_out[3 * (size_t) q + 1] = r.y; a.v_out[3 * (size_t) q + 2] = r.z;
+        if (a.n_in && a.n_out) {
+            const V3 rn = a.normal_mode == DFU_NORMAL_REF ? dq_transform_vertex(b, nn) : dq_rotate(b, nn);
+            a.n_out[3 * (size_t) q] = rn.x; a.n_out[3 * (size_t) q + 1] = rn.y; a.n_out[3 * (size_t) q + 2] = rn.z;
+        }
+    }
+}
+
+int build_node_grid(dfu_warpfield* wf, cudaStream_t st) {
+    NodeGrid& ng = wf->grid;
+    if (ng.valid && ng.node_epoch == wf->node_epoch) return DFU_OK;
+    if (!ng.desc) {
+        DFU_CUDA_OK(cudaMalloc(&ng.desc, sizeof(GridDesc)));
+        DFU_CUDA_OK(cudaMalloc(&ng.cell_start, ((size_t) DFU_GRID_MAX_CELLS + 1) * sizeof(int)));
+        DFU_CUDA_OK(cudaMalloc(&ng.cell_count, (size_t) DFU_GRID_MAX_CELLS * sizeof(int)));
+    }
+    if (wf->N > ng.capacity) {
+        if (ng.sorted) cudaFree(ng.sorted);
+        ng.sorted = nullptr;
+        ng.capacity = 0;
+        DFU_CUDA_OK(cudaMalloc(&ng.sorted, (size_t) wf->N * sizeof(float4)));
+        if (ng.occ) cudaFree(ng.occ);
+        ng.occ = nullptr;
+        DFU_CUDA_OK(cudaMalloc(&ng.occ, (size_t) wf->N * sizeof(int)));
+        ng.capacity = wf->N;
+    }
+    grid_desc_kernel<<<1, 1024, 0, st>>>(wf->pos_w, wf->N, ng.desc);
+    DFU_LAUNCH_OK();
+    DFU_CUDA_OK(cudaMemsetAsync(ng.cell_count, 0, (size_t) DFU_GRID_MAX_CELLS * sizeof(int), st));
+    grid_count_kernel<<<div_up(wf->N, 256), 256, 0, st>>>(wf->pos_w, wf->N, ng.desc, ng.cell_count);
+    DFU_LAUNCH_OK();
+    grid_scan_kernel<<<1, 1024, 0, st>>>(ng.cell_count, ng.desc, ng.cell_start);
+    DFU_LAUNCH_OK();
+    grid_fill_kernel<<<div_up(wf->N, 256), 256, 0, st>>>(wf->pos_w, wf->N, ng.desc, ng.cell_start, ng.cell_count, ng.sorted);
+    DFU_LAUNCH_OK();
+    grid_occ_kernel<<<div_up(DFU_GRID_MAX_CELLS, 256), 256, 0, st>>>(ng.cell_start, ng.desc, ng.occ);
+    DFU_LAUNCH_OK();
+    ng.node_epoch = wf->node_epoch;
+    ng.valid = true;
+    return DFU_OK;
+}
+
 template <int OP>
 int launch_points(const dfu_warpfield* wf, PointArgs& a, cudaStream_t st) {
     a.pos_w = wf->pos_w;
@@ -270,6 +584,15 @@ int launch_points(const dfu_warpfield* wf, PointArgs& a, cudaStream_t st) {
     a.dual = wf->dual;
     a.Npad = wf->Npad;
     if (a.Q == 0) return DFU_OK;
+    // point queries go through the node grid (exact, tens of candidates per query); the smem-tiled brute force
+    // stays for the brick-centre queries (most are far from every node), tiny node sets and DFU_POINT_KNN=brute
+    if (OP != OP_BOUNDS && wf->N >= 64 && wf->grid.valid && wf->grid.node_epoch == wf->node_epoch &&
+        ((reinterpret_cast<uintptr_t>(a.idx) | reinterpret_cast<uintptr_t>(a.dist2) | reinterpret_cast<uintptr_t>(a.wts) |
+          reinterpret_cast<uintptr_t>(a.dq_out)) & 15) == 0) {
+        points_grid_kernel<OP><<<div_up(a.Q, 128), 128, 0, st>>>(a, wf->grid.desc, wf->grid.cell_start, wf->grid.sorted, wf->grid.occ);
+        DFU_LAUNCH_OK();
+        return DFU_OK;
+    }
     static bool attr_set = false;  // per template instantiation
     if (!attr_set) {
         DFU_CUDA_OK(cudaFuncSetAttribute(points_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -420,6 +743,11 @@ int dfu_warpfield_destroy(dfu_warpfield* wf) {
     cudaFree(wf->bricks.bounds);
     cudaFree(wf->bricks.knn_pool);
     cudaFree(wf->bricks.built);
+    cudaFree(wf->grid.desc);
+    cudaFree(wf->grid.cell_start);
+    cudaFree(wf->grid.cell_count);
+    cudaFree(wf->grid.sorted);
+    cudaFree(wf->grid.occ);
     delete wf;
     return DFU_OK;
 }
@@ -438,6 +766,12 @@ int dfu_warpfield_init(dfu_warpfield* wf, float epsilon, const float* pos_xyz, c
     DFU_LAUNCH_OK();
     wf->node_epoch++;
     wf->initialised = true;
+    const char* env = getenv("DFU_POINT_KNN");
+    wf->grid.valid = false;
+    if (!(env && env[0] == 'b') && N >= 64) {
+        rc = build_node_grid(wf, st);
+        if (rc != DFU_OK) return rc;
+    }
     return dfu_wf_refresh_flags(wf, st);
 }
 

@@ -476,3 +476,18 @@ def test_two_gpus_equal_one_gpu(dfu):
                         "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_worker.py")],
                        capture_output=True, text=True, timeout=600)
     assert "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_knn_far_queries_grid_fallback(dfu, oracle):
+    """queries many cell sizes away from every node (the grid search falls back to sweeping the occupied cells)
+    and queries outside the nodes' bounding box: still bit-exact"""
+    rng = np.random.default_rng(77)
+    pos, dq, dg_w, _ = synth.sphere_nodes(2048, 0.02)
+    q = np.concatenate([pos[rng.integers(0, 2048, 500)] + rng.normal(0, 0.3, (500, 3)),
+                        rng.uniform(-3, 6, (300, 3)), pos[:200] * 1.0]).astype(np.float32)
+    q[-200:] += rng.normal(0, 1e-3, (200, 3)).astype(np.float32)
+    idx_o, d_o, ties = oracle.knn(pos, q, return_dist=True)
+    assert ties == 0
+    wf = make_wf(dfu, pos, dq, dg_w)
+    idx_g, d_g = wf.findNeighborsIndex(8, dev(q), return_dist=True)
+    assert np.array_equal(idx_g.cpu().numpy(), idx_o) and np.array_equal(d_g.cpu().numpy(), d_o)
