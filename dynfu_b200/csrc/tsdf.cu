@@ -39,7 +39,11 @@ struct IntegrateArgs {
     int bdx, bdy;
     uint4* knn_pool;       // per-voxel 8-NN cache (null: disabled), see BrickTable
     unsigned char* built;
+    const float* dmax_tiles;  // max ray length per 16x16-pixel tile of the dists image (0: no depth in the tile)
+    int dtx, dty;             // tiles per row / column
 };
+
+constexpr int DT = 16;  // pixels per side of a depth tile
 
 DFU_DEV uint4 ld_stream(const uint4* p) { return __ldcs(p); }
 DFU_DEV void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
@@ -141,9 +145,60 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
         }
     }
 
+    // ---- hierarchical cull of the rigid part of the tile ------------------------------------------------
+    // The tile's voxels are un-warped in the rigid pass, so their camera-space positions lie in the convex hull
+    // of the 8 transformed tile corners.  If that hull is behind the camera, projects outside the image, projects
+    // only onto pixels without depth, or lies entirely more than trunc behind the farthest depth it can see,
+    // no voxel of it can pass the per-voxel tests (tsdf_volume.cu:70-79) and the rigid pass is skipped.  All
+    // bounds carry margins far above the rounding of the per-voxel arithmetic, so the result is bit-identical.
+    bool rigid_skip = false;
+    {
+        float zmin = INFINITY, zmax = -INFINITY, umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
+        float cxs = 0.f, cys = 0.f, czs = 0.f, cor[8][3];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float px = (float) (x0 + ((c & 1) ? 31 : 0)) * a.vsx, py = (float) (y0 + ((c & 2) ? 7 : 0)) * a.vsy,
+                        pz = (float) (zt + ((c & 4) ? 7 : 0)) * a.vsz;
+            cor[c][0] = a.R[0] * px + a.R[1] * py + a.R[2] * pz + a.T[0];
+            cor[c][1] = a.R[3] * px + a.R[4] * py + a.R[5] * pz + a.T[1];
+            cor[c][2] = a.R[6] * px + a.R[7] * py + a.R[8] * pz + a.T[2];
+            cxs += cor[c][0]; cys += cor[c][1]; czs += cor[c][2];
+            zmin = fminf(zmin, cor[c][2]);
+            zmax = fmaxf(zmax, cor[c][2]);
+        }
+        if (zmax <= -1e-4f) {
+            rigid_skip = true;  // every voxel has vc.z <= 0
+        } else if (zmin > 1e-3f) {
+            cxs *= 0.125f; cys *= 0.125f; czs *= 0.125f;
+            float rad = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float iz = 1.f / cor[c][2];
+                const float u = a.fx * cor[c][0] * iz + a.cx, v = a.fy * cor[c][1] * iz + a.cy;
+                umin = fminf(umin, u); umax = fmaxf(umax, u);
+                vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+                const float ex = cor[c][0] - cxs, ey = cor[c][1] - cys, ez = cor[c][2] - czs;
+                rad = fmaxf(rad, sqrtf(ex * ex + ey * ey + ez * ez));
+            }
+            // pixel rectangle the tile can project to, one pixel of margin
+            const int pu0 = max(0, (int) floorf(umin) - 1), pu1 = min(a.cols - 1, (int) floorf(umax) + 1);
+            const int pv0 = max(0, (int) floorf(vmin) - 1), pv1 = min(a.rows - 1, (int) floorf(vmax) + 1);
+            if (pu0 > pu1 || pv0 > pv1 || !(umax >= -1.f) || !(vmax >= -1.f)) {
+                rigid_skip = true;  // projects outside the image
+            } else {
+                float dfar = 0.f;
+                for (int ty = pv0 / DT; ty <= pv1 / DT; ++ty)
+                    for (int tx = pu0 / DT; tx <= pu1 / DT; ++tx) dfar = fmaxf(dfar, __ldg(&a.dmax_tiles[ty * a.dtx + tx]));
+                const float near_dist = sqrtf(cxs * cxs + cys * cys + czs * czs) - rad;  // <= |vc| of every voxel
+                // dfar == 0: no depth anywhere it projects to; else sdf = Dp - |vc| <= dfar - near_dist < -trunc
+                if (dfar == 0.f || dfar - near_dist < -a.trunc - 1e-3f) rigid_skip = true;
+            }
+        }
+    }
+
     // ---- rigid pass: every quad of a brick that is not near ------------------------------------------
 #pragma unroll 1
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < (rigid_skip ? 0 : 4); ++it) {
         const int lin = it * 128 + tid;
         const int qx = lin & 7, yy = (lin >> 3) & 7, zz = lin >> 6;
         const int z = zt + zz;
@@ -293,6 +348,26 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
     }
 }
 
+// max ray length per 16x16-pixel tile of the dists image (for the hierarchical cull of integrate_kernel)
+__global__ void __launch_bounds__(DT * DT) depth_tiles_kernel(const uint16_t* __restrict__ dists, size_t pitch, int rows, int cols,
+                                                              float* __restrict__ out, int dtx) {
+    __shared__ float sh[DT * DT / 32];
+    const int x = blockIdx.x * DT + (threadIdx.x % DT), y = blockIdx.y * DT + (threadIdx.x / DT);
+    float d = 0.f;
+    if (x < cols && y < rows)
+        d = __half2float(__ushort_as_half(*reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(dists) + (size_t) y * pitch + 2 * (size_t) x)));
+    if (!(d == d)) d = INFINITY;  // NaN depth: never cull
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.f;
+        for (int i = 0; i < DT * DT / 32; ++i) m = fmaxf(m, sh[i]);
+        out[blockIdx.y * dtx + blockIdx.x] = m;
+    }
+}
+
 // compute_dists_kernel (src/kfusion/cuda/imgproc.cu:233-245); the reference's guard uses || (:237, a
 // latent out-of-bounds access) -- the bounds check here is the intended &&.
 __global__ void compute_dists_kernel(const uint16_t* __restrict__ depth, size_t dpitch, uint16_t* __restrict__ dists,
@@ -392,8 +467,17 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
     }
     const long nblocks = (long) a.ntx * a.nty * ntz;
     DFU_REQUIRE(nblocks <= 0x7fffffffL, DFU_ERR_INVALID, "volume too large for one launch");
+    // coarse max-depth map for the hierarchical cull (stream-ordered scratch: safe with concurrent streams)
+    a.dtx = div_up(cols, DT);
+    a.dty = div_up(rows, DT);
+    float* tiles = nullptr;
+    DFU_CUDA_OK(cudaMallocAsync(&tiles, (size_t) a.dtx * a.dty * sizeof(float), st));
+    depth_tiles_kernel<<<dim3(a.dtx, a.dty), DT * DT, 0, st>>>(dists, pitch, rows, cols, tiles, a.dtx);
+    DFU_LAUNCH_OK();
+    a.dmax_tiles = tiles;
     integrate_kernel<<<(unsigned) nblocks, 128, 0, st>>>(a);
     DFU_LAUNCH_OK();
+    DFU_CUDA_OK(cudaFreeAsync(tiles, st));
     return DFU_OK;
 }
 
