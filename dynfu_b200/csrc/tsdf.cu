@@ -39,6 +39,7 @@ struct IntegrateArgs {
     int bdx, bdy;
     uint4* knn_pool;       // per-voxel 8-NN cache (null: disabled), see BrickTable
     unsigned char* built;
+    const unsigned char* tile_skip;  // per 32x8x8 tile: 1 = the rigid pass cannot touch any voxel (tile_cull_kernel)
     const float* dmax_tiles;  // max ray length per 16x16-pixel tile of the dists image (0: no depth in the tile)
     int dtx, dty;             // tiles per row / column
 };
@@ -99,112 +100,73 @@ struct IntegrateSmem {
     int cnt[4];
 };
 
-__global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ IntegrateArgs a) {
-    __shared__ IntegrateSmem sm;
-    const int tid = threadIdx.x;
+// what one CTA needs to know about its 32x8x8 tile
+struct TileInfo {
+    int x0, y0, zt;
+    size_t brick0;          // index of the tile's first brick in the brick table
+    int near_mask;          // bit sb set: brick sb needs the exact per-voxel warp
+    bool translation_only;  // every node is a pure translation
+    float reff2;            // squared distance beyond which rule (b) below holds for a single voxel
+    float r_brick;
+};
+
+// A brick must run the exact per-voxel warp ("near") unless every voxel of it is PROVABLY left where it is:
+//  (a) all 8 weights are exactly 0.f beyond sqrt(209)*dg_w of every node (dfu_math.cuh node_weight), or
+//  (b) translation-only field: p' = fl(p + 2*acc) with |2*acc_c| <= 16*dmax*w, w <= exp(-dmin^2/(2 maxw^2));
+//      when that is below p_c * 2^-26 (less than half an ulp of p_c >= voxel size) the addition returns p_c
+//      bit for bit.  Bricks touching index 0 of an axis (p_c == 0) are excluded from (b).
+DFU_DEV TileInfo tile_info(const IntegrateArgs& a) {
+    TileInfo ti;
     int bid = blockIdx.x;
     const int tile_x = bid % a.ntx;
     bid /= a.ntx;
     const int tile_y = bid % a.nty;
     const int tile_z = bid / a.nty;
-    const int x0 = tile_x * 32, y0 = tile_y * 8, zt = a.zt0 + tile_z * 8;
-    const size_t plane = (size_t) a.dx * a.dy;
-
-    // ---- classify the four bricks of this tile ------------------------------------------------------
-    // A brick must run the exact per-voxel warp ("near") unless every voxel of it is PROVABLY left where it is:
-    //  (a) all 8 weights are exactly 0.f beyond sqrt(209)*dg_w of every node (dfu_math.cuh node_weight), or
-    //  (b) translation-only field: p' = fl(p + 2*acc) with |2*acc_c| <= 16*dmax*w, w <= exp(-dmin^2/(2 maxw^2));
-    //      when that is below p_c * 2^-26 (less than half an ulp of p_c >= voxel size) the addition returns p_c
-    //      bit for bit.  Bricks touching index 0 of an axis (p_c == 0) are excluded from (b).
-    int near_mask = 0;
-    bool translation_only = false;
-    float reff2 = 0.f;  // squared distance beyond which rule (b) holds for a single voxel (0: rule unavailable)
-    const float r_brick = 3.5f * sqrtf(a.vsx * a.vsx + a.vsy * a.vsy + a.vsz * a.vsz);  // brick half diagonal
-    const size_t brick0 = a.warped ? (size_t) (x0 / 8) + (size_t) a.bdx * ((y0 / 8) + (size_t) a.bdy * (zt / 8)) : 0;
+    ti.x0 = tile_x * 32;
+    ti.y0 = tile_y * 8;
+    ti.zt = a.zt0 + tile_z * 8;
+    ti.near_mask = 0;
+    ti.translation_only = false;
+    ti.reff2 = 0.f;
+    ti.r_brick = 3.5f * sqrtf(a.vsx * a.vsx + a.vsy * a.vsy + a.vsz * a.vsz);  // brick half diagonal
+    ti.brick0 = a.warped ? (size_t) (ti.x0 / 8) + (size_t) a.bdx * ((ti.y0 / 8) + (size_t) a.bdy * (ti.zt / 8)) : 0;
     if (a.warped) {
-        translation_only = a.flags[0] != 0;
+        ti.translation_only = a.flags[0] != 0;
         const float maxw = __int_as_float(a.flags[1]);
         const float dmax = __int_as_float(a.flags[2]);
         const float r_zero = 14.4569f * maxw * 1.001f + 1e-6f;  // rule (a); 1.001 covers rounding
-        const bool all_near = (a.blend_mode == DFU_BLEND_REF_COMPOSE) && !translation_only;
+        const bool all_near = (a.blend_mode == DFU_BLEND_REF_COMPOSE) && !ti.translation_only;
         float r_eff = r_zero;
-        if (translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
+        if (ti.translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
             const float vmin = fminf(a.vsx, fminf(a.vsy, a.vsz));
             // 16*dmax*exp(-x) * 1.0001 < vmin * 2^-26  <=>  x > L
             const float L = logf(fmaxf(16.f * dmax * 1.0001f, 1e-37f)) - logf(vmin * 1.4901161e-8f) + 1e-3f;
             const float re = L > 0.f ? maxw * sqrtf(2.f * L) * 1.0001f + 1e-6f : 0.f;
             r_eff = fminf(r_zero, re);
-            reff2 = r_eff * r_eff;
+            ti.reff2 = r_eff * r_eff;
         }
 #pragma unroll
         for (int sb = 0; sb < 4; ++sb) {
-            const float2 b = __ldg(&a.bounds[brick0 + sb]);
-            const float dmin = sqrtf(b.y) - r_brick;  // lower bound of voxel-to-node distance in this brick
-            const bool on_zero_plane = (x0 + sb * 8 == 0) || (y0 == 0) || (zt == 0);
-            if (all_near || dmin <= (on_zero_plane ? r_zero : r_eff)) near_mask |= 1 << sb;
+            const float2 b = __ldg(&a.bounds[ti.brick0 + sb]);
+            const float dmin = sqrtf(b.y) - ti.r_brick;  // lower bound of voxel-to-node distance in this brick
+            const bool on_zero_plane = (ti.x0 + sb * 8 == 0) || (ti.y0 == 0) || (ti.zt == 0);
+            if (all_near || dmin <= (on_zero_plane ? r_zero : r_eff)) ti.near_mask |= 1 << sb;
         }
     }
+    return ti;
+}
 
-    // ---- hierarchical cull of the rigid part of the tile ------------------------------------------------
-    // The tile's voxels are un-warped in the rigid pass, so their camera-space positions lie in the convex hull
-    // of the 8 transformed tile corners.  If that hull is behind the camera, projects outside the image, projects
-    // only onto pixels without depth, or lies entirely more than trunc behind the farthest depth it can see,
-    // no voxel of it can pass the per-voxel tests (tsdf_volume.cu:70-79) and the rigid pass is skipped.  All
-    // bounds carry margins far above the rounding of the per-voxel arithmetic, so the result is bit-identical.
-    bool rigid_skip = false;
-    {
-        float zmin = INFINITY, zmax = -INFINITY, umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
-        float cxs = 0.f, cys = 0.f, czs = 0.f, cor[8][3];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float px = (float) (x0 + ((c & 1) ? 31 : 0)) * a.vsx, py = (float) (y0 + ((c & 2) ? 7 : 0)) * a.vsy,
-                        pz = (float) (zt + ((c & 4) ? 7 : 0)) * a.vsz;
-            cor[c][0] = a.R[0] * px + a.R[1] * py + a.R[2] * pz + a.T[0];
-            cor[c][1] = a.R[3] * px + a.R[4] * py + a.R[5] * pz + a.T[1];
-            cor[c][2] = a.R[6] * px + a.R[7] * py + a.R[8] * pz + a.T[2];
-            cxs += cor[c][0]; cys += cor[c][1]; czs += cor[c][2];
-            zmin = fminf(zmin, cor[c][2]);
-            zmax = fmaxf(zmax, cor[c][2]);
-        }
-        if (zmax <= -1e-4f) {
-            rigid_skip = true;  // every voxel has vc.z <= 0
-        } else if (zmin > 1e-3f) {
-            cxs *= 0.125f; cys *= 0.125f; czs *= 0.125f;
-            float rad = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float iz = 1.f / cor[c][2];
-                const float u = a.fx * cor[c][0] * iz + a.cx, v = a.fy * cor[c][1] * iz + a.cy;
-                umin = fminf(umin, u); umax = fmaxf(umax, u);
-                vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
-                const float ex = cor[c][0] - cxs, ey = cor[c][1] - cys, ez = cor[c][2] - czs;
-                rad = fmaxf(rad, sqrtf(ex * ex + ey * ey + ez * ez));
-            }
-            // pixel rectangle the tile can project to, one pixel of margin
-            const int pu0 = max(0, (int) floorf(umin) - 1), pu1 = min(a.cols - 1, (int) floorf(umax) + 1);
-            const int pv0 = max(0, (int) floorf(vmin) - 1), pv1 = min(a.rows - 1, (int) floorf(vmax) + 1);
-            if (pu0 > pu1 || pv0 > pv1 || !(umax >= -1.f) || !(vmax >= -1.f)) {
-                rigid_skip = true;  // projects outside the image
-            } else {
-                float dfar = 0.f;
-                for (int ty = pv0 / DT; ty <= pv1 / DT; ++ty)
-                    for (int tx = pu0 / DT; tx <= pu1 / DT; ++tx) dfar = fmaxf(dfar, __ldg(&a.dmax_tiles[ty * a.dtx + tx]));
-                const float near_dist = sqrtf(cxs * cxs + cys * cys + czs * czs) - rad;  // <= |vc| of every voxel
-                // dfar == 0: no depth anywhere it projects to; else sdf = Dp - |vc| <= dfar - near_dist < -trunc
-                if (dfar == 0.f || dfar - near_dist < -a.trunc - 1e-3f) rigid_skip = true;
-            }
-        }
-    }
-
-    // ---- rigid pass: every quad of a brick that is not near ------------------------------------------
+// rigid pass over the quads of the bricks that are not near
+DFU_DEV void rigid_pass(const IntegrateArgs& a, const TileInfo& ti) {
+    const size_t plane = (size_t) a.dx * a.dy;
 #pragma unroll 1
-    for (int it = 0; it < (rigid_skip ? 0 : 4); ++it) {
-        const int lin = it * 128 + tid;
+    for (int it = 0; it < 4; ++it) {
+        const int lin = it * 128 + threadIdx.x;
         const int qx = lin & 7, yy = (lin >> 3) & 7, zz = lin >> 6;
-        const int z = zt + zz;
-        if ((near_mask >> (qx >> 1)) & 1) continue;
+        const int z = ti.zt + zz;
+        if ((ti.near_mask >> (qx >> 1)) & 1) continue;
         if (z < a.z0 || z >= a.z1) continue;
-        const int x = x0 + qx * 4, y = y0 + yy;
+        const int x = ti.x0 + qx * 4, y = ti.y0 + yy;
         const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
         bool hit[4];
         float ts[4];
@@ -212,140 +174,264 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
         for (int v = 0; v < 4; ++v) hit[v] = voxel_tsdf(a, fmul((float) (x + v), a.vsx), py, pz, ts[v]);
         quad_commit(a, (size_t) x + (size_t) y * a.dx + plane * (size_t) z, hit, ts);
     }
-    if (near_mask == 0) return;
+}
 
-    // ---- near pass: exact per-voxel 8-NN over a culled candidate list, blend, integrate -----------------
-    const int warp = tid >> 5, lane = tid & 31;
-    const int qx2 = tid & 1, yy = (tid >> 1) & 7, zz = tid >> 4;
-#pragma unroll 1
-    for (int sb = 0; sb < 4; ++sb) {
-        if (!((near_mask >> sb) & 1)) continue;  // uniform over the CTA
-        // any node among the 8 nearest of ANY voxel of the brick lies within d8(centre) + 2r of the centre
-        float thr2;
-        {
-            const float th = (sqrtf(__ldg(&a.bounds[brick0 + sb]).x) + 2.f * r_brick) * 1.0001f + 1e-6f;
-            thr2 = th * th;
+// exact 8-NN of the thread's 4 voxels of brick sb: cull the N nodes to the brick's candidates (every warp compacts
+// its slice in index order with ballots), then scan them with the nanoflann metric.  All 128 threads take part.
+DFU_DEV void brick_knn_scan(const IntegrateArgs& a, const TileInfo& ti, IntegrateSmem& sm, int sb, const float (&px)[4], float py,
+                            float pz, Top8 (&t)[4]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float bcx = (ti.x0 + sb * 8 + 3.5f) * a.vsx, bcy = (ti.y0 + 3.5f) * a.vsy, bcz = (ti.zt + 3.5f) * a.vsz;
+    const float d8c = sqrtf(__ldg(&a.bounds[ti.brick0 + sb]).x);
+    // any node among the 8 nearest of ANY voxel of the brick lies within d8(centre) + 2r of the centre
+    const float th = (d8c + 2.f * ti.r_brick) * 1.0001f + 1e-6f;
+    const float thr2 = th * th;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        // the 8 nodes nearest to the brick centre are within d8c + |v - centre| of voxel v: start every
+        // slot at that (inflated) bound, so the bulk of the candidates fails the first compare
+        const float ex = px[v] - bcx, ey = py - bcy, ez = pz - bcz;
+        const float bnd = (d8c + sqrtf(ex * ex + ey * ey + ez * ez)) * 1.0001f + 1e-6f;
+        const float bnd2 = bnd * bnd;
+#pragma unroll
+        for (int k = 0; k < DFU_KNN; ++k) {
+            t[v].d[k] = bnd2;
+            t[v].i[k] = -1;
         }
-        const int z = zt + zz;
-        const int x = x0 + sb * 8 + qx2 * 4, y = y0 + yy;
-        const float bcx = (x0 + sb * 8 + 3.5f) * a.vsx, bcy = (y0 + 3.5f) * a.vsy, bcz = (zt + 3.5f) * a.vsz;
-        const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
-        float px[4];
-        Top8 t[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) px[v] = fmul((float) (x + v), a.vsx);
-        const size_t brick = brick0 + sb;
-        uint4* cache = a.knn_pool ? a.knn_pool + brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4) : nullptr;
-        if (cache && a.built[brick]) {
-            // node positions have not changed since this brick's 8-NN were computed: read the ids back and
-            // re-evaluate the 8 squared distances (same expression as the scan -> same bits)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const uint4 c = cache[v];
-                const unsigned u[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-                for (int k = 0; k < DFU_KNN; ++k) {
-                    const int id = (int) ((u[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
-                    t[v].i[k] = id == 0xffff ? -1 : id;
-                    t[v].d[k] = INFINITY;
-                    if (id != 0xffff) {
-                        const float4 p = __ldg(&a.pos_w[id]);
-                        t[v].d[k] = dist2(px[v], py, pz, p.x, p.y, p.z);
-                    }
-                }
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < a.N; c0 += CHUNK) {
+        int n = 0;
+#pragma unroll 1
+        for (int j = 0; j < SEG; j += 32) {
+            const int idx = c0 + warp * SEG + j + lane;
+            bool keep = false;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < a.N) {
+                p = __ldg(&a.pos_w[idx]);
+                const float ddx = p.x - bcx, ddy = p.y - bcy, ddz = p.z - bcz;
+                keep = (ddx * ddx + ddy * ddy + ddz * ddz) <= thr2;
             }
-        } else {
-            const float d8c = sqrtf(__ldg(&a.bounds[brick]).x);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                // the 8 nodes nearest to the brick centre are within d8c + |v - centre| of voxel v: start every
-                // slot at that (inflated) bound, so the bulk of the candidates fails the first compare
-                const float ex = px[v] - bcx, ey = py - bcy, ez = pz - bcz;
-                const float bnd = (d8c + sqrtf(ex * ex + ey * ey + ez * ez)) * 1.0001f + 1e-6f;
-                const float bnd2 = bnd * bnd;
-#pragma unroll
-                for (int k = 0; k < DFU_KNN; ++k) {
-                    t[v].d[k] = bnd2;
-                    t[v].i[k] = -1;
-                }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                p.w = __int_as_float(idx);
+                sm.cand[warp * SEG + n + __popc(m & ((1u << lane) - 1u))] = p;
             }
+            n += __popc(m);
+        }
+        if (lane == 0) sm.cnt[warp] = n;
+        __syncthreads();
 #pragma unroll 1
-            for (int c0 = 0; c0 < a.N; c0 += CHUNK) {
-                // each warp compacts its 256-node slice, in index order, into its own segment
-                int n = 0;
+        for (int sg = 0; sg < 4; ++sg) {
+            const int cn = sm.cnt[sg];
+            const float4* __restrict__ cl = sm.cand + sg * SEG;
 #pragma unroll 1
-                for (int j = 0; j < SEG; j += 32) {
-                    const int idx = c0 + warp * SEG + j + lane;
-                    bool keep = false;
-                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < a.N) {
-                        p = __ldg(&a.pos_w[idx]);
-                        const float ddx = p.x - bcx, ddy = p.y - bcy, ddz = p.z - bcz;
-                        keep = (ddx * ddx + ddy * ddy + ddz * ddz) <= thr2;
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    if (keep) {
-                        p.w = __int_as_float(idx);
-                        sm.cand[warp * SEG + n + __popc(m & ((1u << lane) - 1u))] = p;
-                    }
-                    n += __popc(m);
-                }
-                if (lane == 0) sm.cnt[warp] = n;
-                __syncthreads();
-#pragma unroll 1
-                for (int sg = 0; sg < 4; ++sg) {
-                    const int cn = sm.cnt[sg];
-                    const float4* __restrict__ cl = sm.cand + sg * SEG;
-#pragma unroll 1
-                    for (int j = 0; j < cn; ++j) {
-                        const float4 p = cl[j];  // warp-wide broadcast
-                        const int idx = __float_as_int(p.w);
-                        const float dy = fsub(py, p.y), dz = fsub(pz, p.z);
-                        const float dy2 = fmul(dy, dy), dz2 = fmul(dz, dz);
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            const float dxv = fsub(px[v], p.x);
-                            const float d = fadd(fadd(fmul(dxv, dxv), dy2), dz2);  // nanoflann metric, bit exact
-                            if (d < t[v].d[DFU_KNN - 1]) top8_insert(t[v], d, idx);
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-            if (cache) {  // fill the cache: 8 u16 ids per voxel, 64 contiguous bytes per thread
+            for (int j = 0; j < cn; ++j) {
+                const float4 p = cl[j];  // warp-wide broadcast
+                const int idx = __float_as_int(p.w);
+                const float dy = fsub(py, p.y), dz = fsub(pz, p.z);
+                const float dy2 = fmul(dy, dy), dz2 = fmul(dz, dz);
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    unsigned u[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        u[k] = ((unsigned) t[v].i[2 * k] & 0xffffu) | (((unsigned) t[v].i[2 * k + 1] & 0xffffu) << 16);
-                    cache[v] = make_uint4(u[0], u[1], u[2], u[3]);
+                    const float dxv = fsub(px[v], p.x);
+                    const float d = fadd(fadd(fmul(dxv, dxv), dy2), dz2);  // nanoflann metric, bit exact
+                    if (d < t[v].d[DFU_KNN - 1]) top8_insert(t[v], d, idx);
                 }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// warped position of one voxel from its 8 neighbour ids (ascending by (dist2, idx)); distances are re-evaluated
+// with the scan's expression.  Translation-only fields take the reduced chain (blend.cuh), everything else the
+// general blend.  The 8 FP64 weights are evaluated as independent straight-line chains.
+DFU_DEV V3 warp_voxel(const IntegrateArgs& a, const TileInfo& ti, const int (&id)[DFU_KNN], float px, float py, float pz,
+                      bool off_zero_planes) {
+    float4 nd[DFU_KNN];
+    float d2[DFU_KNN];
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) {
+        nd[k] = id[k] >= 0 ? __ldg(&a.pos_w[id[k]]) : make_float4(INFINITY, INFINITY, INFINITY, 1.f);
+        d2[k] = dist2(px, py, pz, nd[k].x, nd[k].y, nd[k].z);
+    }
+    const bool fast = ti.translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE;
+    if (fast && d2[0] > ti.reff2 && off_zero_planes) return V3{px, py, pz};  // rule (b): p' == p bit for bit
+    float w[DFU_KNN];
+    double arg[DFU_KNN];
+    bool zero[DFU_KNN];
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) {  // Node::getTransformationWeight (node.cpp:29-36), see dfu_math.cuh node_weight
+        zero[k] = id[k] < 0 || d2[k] > fmul(209.f, fmul(nd[k].w, nd[k].w));
+        const double dx = (double) fsub(nd[k].x, px), dy = (double) fsub(nd[k].y, py), dz = (double) fsub(nd[k].z, pz);
+        const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        const double w2 = __dmul_rn((double) nd[k].w, (double) nd[k].w);
+        arg[k] = zero[k] ? 0.0 : __ddiv_rn(-distSq, __dmul_rn(2.0, w2));
+    }
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) w[k] = zero[k] ? 0.f : __double2float_rn(exp(arg[k]));
+    if (fast) {
+        float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+        for (int k = 0; k < DFU_KNN; ++k) {
+            if (id[k] < 0) break;
+            if (w[k] != 0.f) {
+                const float4 du = __ldg(&a.dual[id[k]]);  // (w,x,y,z) stored in (x,y,z,w)
+                ax = fadd(fmul(du.y, w[k]), ax);
+                ay = fadd(fmul(du.z, w[k]), ay);
+                az = fadd(fmul(du.w, w[k]), az);
+            }
+        }
+        return V3{fadd(px, fmul(2.f, ax)), fadd(py, fmul(2.f, ay)), fadd(pz, fmul(2.f, az))};
+    }
+    Top8 t;
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) {
+        t.i[k] = id[k];
+        t.d[k] = d2[k];
+    }
+    const DQ b = blend(a.blend_mode, t, w, a.real, a.dual);
+    return dq_transform_vertex(b, V3{px, py, pz});
+}
+
+DFU_DEV uint4 pack_ids(const Top8& t) {
+    unsigned u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = ((unsigned) t.i[2 * k] & 0xffffu) | (((unsigned) t.i[2 * k + 1] & 0xffffu) << 16);
+    return make_uint4(u[0], u[1], u[2], u[3]);
+}
+DFU_DEV void unpack_ids(uint4 c, int (&id)[DFU_KNN]) {
+    const unsigned u[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) {
+        const int v = (int) ((u[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+        id[k] = v == 0xffff ? -1 : v;
+    }
+}
+
+enum { MODE_ONTHEFLY = 0, MODE_FILL = 1, MODE_CACHED = 2 };
+
+// MODE_ONTHEFLY: rigid pass + per-voxel 8-NN recomputed for every near brick (no cache)
+// MODE_FILL    : only computes and stores the 8-NN of near bricks that are not in the cache yet (no TSDF work)
+// MODE_CACHED  : rigid pass + near bricks from the cache (filled by a MODE_FILL launch earlier in the stream);
+//                no per-thread top-8 lists -> half the registers, twice the resident warps
+template <int MODE>
+__global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_kernel(const __grid_constant__ IntegrateArgs a) {
+    const int tid = threadIdx.x;
+    const TileInfo ti = tile_info(a);
+    const size_t plane = (size_t) a.dx * a.dy;
+    if (MODE != MODE_FILL && !(a.tile_skip && a.tile_skip[blockIdx.x])) rigid_pass(a, ti);
+    if (ti.near_mask == 0) return;
+
+    const int qx2 = tid & 1, yy = (tid >> 1) & 7, zz = tid >> 4;
+    const int z = ti.zt + zz, y = ti.y0 + yy;
+    const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
+#pragma unroll 1
+    for (int sb = 0; sb < 4; ++sb) {
+        if (!((ti.near_mask >> sb) & 1)) continue;  // uniform over the CTA
+        const int x = ti.x0 + sb * 8 + qx2 * 4;
+        const size_t brick = ti.brick0 + sb;
+        const size_t lin = (size_t) x + (size_t) y * a.dx + plane * (size_t) z;
+        float px[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) px[v] = fmul((float) (x + v), a.vsx);
+
+        if (MODE == MODE_CACHED) {
+            if (z < a.z0 || z >= a.z1) continue;
+            const uint4* cache = a.knn_pool + brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4);
+            bool hit[4];
+            float ts[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                int id[DFU_KNN];
+                unpack_ids(cache[v], id);
+                const V3 w = warp_voxel(a, ti, id, px[v], py, pz, x + v > 0 && y > 0 && z > 0);
+                hit[v] = voxel_tsdf(a, w.x, w.y, w.z, ts[v]);
+            }
+            quad_commit(a, lin, hit, ts);
+        } else {
+            __shared__ IntegrateSmem sm;
+            if (MODE == MODE_FILL && a.built[brick]) continue;  // uniform over the CTA
+            Top8 t[4];
+            brick_knn_scan(a, ti, sm, sb, px, py, pz, t);
+            if (MODE == MODE_FILL) {
+                // 8 u16 ids per voxel, 64 contiguous bytes per thread
+                uint4* cache = a.knn_pool + brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) cache[v] = pack_ids(t[v]);
                 __syncthreads();
                 if (tid == 0) a.built[brick] = 1;
-            }
-        }
-        if (z < a.z0 || z >= a.z1) continue;
-        bool hit[4];
-        float ts[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            V3 w;
-            if (translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
-                if (t[v].d[0] > reff2 && x + v > 0 && y > 0 && z > 0)
-                    w = V3{px[v], py, pz};  // rule (b) for this voxel: the warp returns p bit for bit
-                else
-                    w = warp_translation_only(t[v], px[v], py, pz, a.pos_w, a.dual);
             } else {
-                float wk[DFU_KNN];
-                neighbour_weights(t[v], px[v], py, pz, a.pos_w, wk);
-                const DQ b = blend(a.blend_mode, t[v], wk, a.real, a.dual);
-                w = dq_transform_vertex(b, V3{px[v], py, pz});
+                if (z < a.z0 || z >= a.z1) continue;
+                bool hit[4];
+                float ts[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const V3 w = warp_voxel(a, ti, t[v].i, px[v], py, pz, x + v > 0 && y > 0 && z > 0);
+                    hit[v] = voxel_tsdf(a, w.x, w.y, w.z, ts[v]);
+                }
+                quad_commit(a, lin, hit, ts);
             }
-            hit[v] = voxel_tsdf(a, w.x, w.y, w.z, ts[v]);
         }
-        quad_commit(a, (size_t) x + (size_t) y * a.dx + plane * (size_t) z, hit, ts);
     }
+}
+
+// Hierarchical cull of the RIGID part of every tile, one thread per tile.  The tile's un-warped voxels lie in the
+// convex hull of its 8 transformed corners.  If that hull is behind the camera, projects outside the image, projects
+// only onto pixels without depth, or lies entirely more than trunc behind the farthest depth it can see, no voxel of
+// it can pass the per-voxel tests (tsdf_volume.cu:70-79) and the rigid pass is skipped.  All bounds carry margins far
+// above the rounding of the per-voxel arithmetic, so the result is bit-identical.
+__global__ void tile_cull_kernel(const __grid_constant__ IntegrateArgs a, int ntiles, unsigned char* __restrict__ skip) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= ntiles) return;
+    int bid = tile;
+    const int x0 = (bid % a.ntx) * 32;
+    bid /= a.ntx;
+    const int y0 = (bid % a.nty) * 8;
+    const int zt = a.zt0 + (bid / a.nty) * 8;
+    bool rigid_skip = false;
+    float zmin = INFINITY, zmax = -INFINITY, umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
+    float cxs = 0.f, cys = 0.f, czs = 0.f, cor[8][3];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float px = (float) (x0 + ((c & 1) ? 31 : 0)) * a.vsx, py = (float) (y0 + ((c & 2) ? 7 : 0)) * a.vsy,
+                    pz = (float) (zt + ((c & 4) ? 7 : 0)) * a.vsz;
+        cor[c][0] = a.R[0] * px + a.R[1] * py + a.R[2] * pz + a.T[0];
+        cor[c][1] = a.R[3] * px + a.R[4] * py + a.R[5] * pz + a.T[1];
+        cor[c][2] = a.R[6] * px + a.R[7] * py + a.R[8] * pz + a.T[2];
+        cxs += cor[c][0]; cys += cor[c][1]; czs += cor[c][2];
+        zmin = fminf(zmin, cor[c][2]);
+        zmax = fmaxf(zmax, cor[c][2]);
+    }
+    if (zmax <= -1e-4f) {
+        rigid_skip = true;  // every voxel has vc.z <= 0
+    } else if (zmin > 1e-3f) {
+        cxs *= 0.125f; cys *= 0.125f; czs *= 0.125f;
+        float rad = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float iz = 1.f / cor[c][2];
+            const float u = a.fx * cor[c][0] * iz + a.cx, v = a.fy * cor[c][1] * iz + a.cy;
+            umin = fminf(umin, u); umax = fmaxf(umax, u);
+            vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+            const float ex = cor[c][0] - cxs, ey = cor[c][1] - cys, ez = cor[c][2] - czs;
+            rad = fmaxf(rad, sqrtf(ex * ex + ey * ey + ez * ez));
+        }
+        // pixel rectangle the tile can project to, one pixel of margin
+        const int pu0 = max(0, (int) floorf(fmaxf(umin, -1e6f)) - 1), pu1 = min(a.cols - 1, (int) floorf(fminf(umax, 1e6f)) + 1);
+        const int pv0 = max(0, (int) floorf(fmaxf(vmin, -1e6f)) - 1), pv1 = min(a.rows - 1, (int) floorf(fminf(vmax, 1e6f)) + 1);
+        if (pu0 > pu1 || pv0 > pv1) {
+            rigid_skip = true;  // projects outside the image
+        } else {
+            float dfar = 0.f;
+            for (int ty = pv0 / DT; ty <= pv1 / DT; ++ty)
+                for (int tx = pu0 / DT; tx <= pu1 / DT; ++tx) dfar = fmaxf(dfar, __ldg(&a.dmax_tiles[ty * a.dtx + tx]));
+            const float near_dist = sqrtf(cxs * cxs + cys * cys + czs * czs) - rad;  // <= |vc| of every voxel
+            // dfar == 0: no depth anywhere it projects to; else sdf = Dp - |vc| <= dfar - near_dist < -trunc
+            if (dfar == 0.f || dfar - near_dist < -a.trunc - 1e-3f) rigid_skip = true;
+        }
+    }
+    skip[tile] = rigid_skip ? 1 : 0;
 }
 
 // max ray length per 16x16-pixel tile of the dists image (for the hierarchical cull of integrate_kernel)
@@ -382,6 +468,30 @@ __global__ void compute_dists_kernel(const uint16_t* __restrict__ depth, size_t 
         *reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(dists) + (size_t) y * opitch + 2 * (size_t) x) =
             __half_as_ushort(__float2half_rn(fmul(fmul((float) d, lambda), 0.001f)));
     }
+}
+
+// Private stream-ordered pool for the per-call scratch (depth tiles + cull flags).  The default pool hands its
+// memory back at every synchronisation (release threshold 0), which would turn each call after a sync into a real
+// allocation; this one keeps up to 64 MiB cached and leaves the application's pools alone.
+cudaMemPool_t scratch_pool(int device) {
+    static cudaMemPool_t pools[64] = {};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t p = nullptr;
+        if (cudaMemPoolCreate(&p, &props) != cudaSuccess) {
+            (void) cudaGetLastError();
+            return nullptr;
+        }
+        unsigned long long keep = 64ull << 20;
+        cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[device] = p;
+    }
+    return pools[device];
 }
 
 }  // namespace
@@ -467,16 +577,34 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
     }
     const long nblocks = (long) a.ntx * a.nty * ntz;
     DFU_REQUIRE(nblocks <= 0x7fffffffL, DFU_ERR_INVALID, "volume too large for one launch");
-    // coarse max-depth map for the hierarchical cull (stream-ordered scratch: safe with concurrent streams)
+    // coarse max-depth map + per-tile cull flags (stream-ordered scratch: safe with concurrent streams)
     a.dtx = div_up(cols, DT);
     a.dty = div_up(rows, DT);
     float* tiles = nullptr;
-    DFU_CUDA_OK(cudaMallocAsync(&tiles, (size_t) a.dtx * a.dty * sizeof(float), st));
+    const size_t tile_bytes = ((size_t) a.dtx * a.dty * sizeof(float) + 255) / 256 * 256;
+    int device = 0;
+    DFU_CUDA_OK(cudaGetDevice(&device));
+    cudaMemPool_t pool = scratch_pool(device);
+    if (pool)
+        DFU_CUDA_OK(cudaMallocFromPoolAsync(&tiles, tile_bytes + (size_t) nblocks, pool, st));
+    else
+        DFU_CUDA_OK(cudaMallocAsync(&tiles, tile_bytes + (size_t) nblocks, st));
+    unsigned char* skip = reinterpret_cast<unsigned char*>(tiles) + tile_bytes;
     depth_tiles_kernel<<<dim3(a.dtx, a.dty), DT * DT, 0, st>>>(dists, pitch, rows, cols, tiles, a.dtx);
     DFU_LAUNCH_OK();
     a.dmax_tiles = tiles;
-    integrate_kernel<<<(unsigned) nblocks, 128, 0, st>>>(a);
+    tile_cull_kernel<<<div_up(nblocks, 128), 128, 0, st>>>(a, (int) nblocks, skip);
     DFU_LAUNCH_OK();
+    a.tile_skip = skip;
+    if (!a.warped || a.knn_pool == nullptr) {
+        integrate_kernel<MODE_ONTHEFLY><<<(unsigned) nblocks, 128, 0, st>>>(a);
+        DFU_LAUNCH_OK();
+    } else {
+        integrate_kernel<MODE_FILL><<<(unsigned) nblocks, 128, 0, st>>>(a);  // a no-op once the cache is warm
+        DFU_LAUNCH_OK();
+        integrate_kernel<MODE_CACHED><<<(unsigned) nblocks, 128, 0, st>>>(a);
+        DFU_LAUNCH_OK();
+    }
     DFU_CUDA_OK(cudaFreeAsync(tiles, st));
     return DFU_OK;
 }
