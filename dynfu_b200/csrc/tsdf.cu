@@ -10,6 +10,8 @@
 // traffic is 128-bit ld/st (streaming, evict-first) and a warp of the rigid pass covers whole 128-byte
 // lines.  A brick is "near" when some voxel of it may have a non-zero node weight; near bricks run the
 // exact per-voxel 8-NN + blend, all other bricks are provably un-warped and take the rigid path.
+#include <algorithm>
+
 #include "blend.cuh"
 #include "dfu_internal.h"
 
@@ -39,7 +41,13 @@ struct IntegrateArgs {
     int bdx, bdy;
     uint4* knn_pool;       // per-voxel 8-NN cache (null: disabled), see BrickTable
     unsigned char* built;
-    const unsigned char* tile_skip;  // per 32x8x8 tile: 1 = the rigid pass cannot touch any voxel (tile_cull_kernel)
+    // per-call scratch written by tile_classify_kernel
+    unsigned char* tile_flags;  // per 32x8x8 tile: bits 0-3 = near mask of its 4 bricks, bit 4 = rigid pass cannot touch a voxel
+    int* work_count;            // [0] tiles with any work, [1] tiles with a near brick missing from the 8-NN cache,
+                                // [2],[3] ticket counters of the two lists
+    int* work_tiles;            // ids of the tiles with work
+    int* fill_tiles;            // ids of the tiles to fill
+    int ntiles;
     const float* dmax_tiles;  // max ray length per 16x16-pixel tile of the dists image (0: no depth in the tile)
     int dtx, dty;             // tiles per row / column
 };
@@ -110,14 +118,40 @@ struct TileInfo {
     float r_brick;
 };
 
+// uniform per-call scalars of the warp field (rule (b) radius etc.)
+struct FieldInfo {
+    bool translation_only;
+    bool all_near;
+    float r_zero, r_eff, reff2;
+};
 // A brick must run the exact per-voxel warp ("near") unless every voxel of it is PROVABLY left where it is:
 //  (a) all 8 weights are exactly 0.f beyond sqrt(209)*dg_w of every node (dfu_math.cuh node_weight), or
 //  (b) translation-only field: p' = fl(p + 2*acc) with |2*acc_c| <= 16*dmax*w, w <= exp(-dmin^2/(2 maxw^2));
 //      when that is below p_c * 2^-26 (less than half an ulp of p_c >= voxel size) the addition returns p_c
 //      bit for bit.  Bricks touching index 0 of an axis (p_c == 0) are excluded from (b).
-DFU_DEV TileInfo tile_info(const IntegrateArgs& a) {
+DFU_DEV FieldInfo field_info(const IntegrateArgs& a) {
+    FieldInfo f{false, false, 0.f, 0.f, 0.f};
+    if (!a.warped) return f;
+    f.translation_only = a.flags[0] != 0;
+    const float maxw = __int_as_float(a.flags[1]);
+    const float dmax = __int_as_float(a.flags[2]);
+    f.r_zero = 14.4569f * maxw * 1.001f + 1e-6f;  // rule (a); 1.001 covers rounding
+    f.all_near = (a.blend_mode == DFU_BLEND_REF_COMPOSE) && !f.translation_only;
+    f.r_eff = f.r_zero;
+    if (f.translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
+        const float vmin = fminf(a.vsx, fminf(a.vsy, a.vsz));
+        // 16*dmax*exp(-x) * 1.0001 < vmin * 2^-26  <=>  x > L
+        const float L = logf(fmaxf(16.f * dmax * 1.0001f, 1e-37f)) - logf(vmin * 1.4901161e-8f) + 1e-3f;
+        const float re = L > 0.f ? maxw * sqrtf(2.f * L) * 1.0001f + 1e-6f : 0.f;
+        f.r_eff = fminf(f.r_zero, re);
+        f.reff2 = f.r_eff * f.r_eff;
+    }
+    return f;
+}
+
+DFU_DEV TileInfo tile_info(const IntegrateArgs& a, int tile, const FieldInfo& f) {
     TileInfo ti;
-    int bid = blockIdx.x;
+    int bid = tile;
     const int tile_x = bid % a.ntx;
     bid /= a.ntx;
     const int tile_y = bid % a.nty;
@@ -125,34 +159,11 @@ DFU_DEV TileInfo tile_info(const IntegrateArgs& a) {
     ti.x0 = tile_x * 32;
     ti.y0 = tile_y * 8;
     ti.zt = a.zt0 + tile_z * 8;
-    ti.near_mask = 0;
-    ti.translation_only = false;
-    ti.reff2 = 0.f;
+    ti.near_mask = a.tile_flags[tile] & 15;
+    ti.translation_only = f.translation_only;
+    ti.reff2 = f.reff2;
     ti.r_brick = 3.5f * sqrtf(a.vsx * a.vsx + a.vsy * a.vsy + a.vsz * a.vsz);  // brick half diagonal
     ti.brick0 = a.warped ? (size_t) (ti.x0 / 8) + (size_t) a.bdx * ((ti.y0 / 8) + (size_t) a.bdy * (ti.zt / 8)) : 0;
-    if (a.warped) {
-        ti.translation_only = a.flags[0] != 0;
-        const float maxw = __int_as_float(a.flags[1]);
-        const float dmax = __int_as_float(a.flags[2]);
-        const float r_zero = 14.4569f * maxw * 1.001f + 1e-6f;  // rule (a); 1.001 covers rounding
-        const bool all_near = (a.blend_mode == DFU_BLEND_REF_COMPOSE) && !ti.translation_only;
-        float r_eff = r_zero;
-        if (ti.translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
-            const float vmin = fminf(a.vsx, fminf(a.vsy, a.vsz));
-            // 16*dmax*exp(-x) * 1.0001 < vmin * 2^-26  <=>  x > L
-            const float L = logf(fmaxf(16.f * dmax * 1.0001f, 1e-37f)) - logf(vmin * 1.4901161e-8f) + 1e-3f;
-            const float re = L > 0.f ? maxw * sqrtf(2.f * L) * 1.0001f + 1e-6f : 0.f;
-            r_eff = fminf(r_zero, re);
-            ti.reff2 = r_eff * r_eff;
-        }
-#pragma unroll
-        for (int sb = 0; sb < 4; ++sb) {
-            const float2 b = __ldg(&a.bounds[ti.brick0 + sb]);
-            const float dmin = sqrtf(b.y) - ti.r_brick;  // lower bound of voxel-to-node distance in this brick
-            const bool on_zero_plane = (ti.x0 + sb * 8 == 0) || (ti.y0 == 0) || (ti.zt == 0);
-            if (all_near || dmin <= (on_zero_plane ? r_zero : r_eff)) ti.near_mask |= 1 << sb;
-        }
-    }
     return ti;
 }
 
@@ -318,59 +329,73 @@ enum { MODE_ONTHEFLY = 0, MODE_FILL = 1, MODE_CACHED = 2 };
 template <int MODE>
 __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_kernel(const __grid_constant__ IntegrateArgs a) {
     const int tid = threadIdx.x;
-    const TileInfo ti = tile_info(a);
+    const FieldInfo fi = field_info(a);
     const size_t plane = (size_t) a.dx * a.dy;
-    if (MODE != MODE_FILL && !(a.tile_skip && a.tile_skip[blockIdx.x])) rigid_pass(a, ti);
-    if (ti.near_mask == 0) return;
-
+    const int n_work = a.work_count[MODE == MODE_FILL ? 1 : 0];
+    const int* __restrict__ list = MODE == MODE_FILL ? a.fill_tiles : a.work_tiles;
     const int qx2 = tid & 1, yy = (tid >> 1) & 7, zz = tid >> 4;
-    const int z = ti.zt + zz, y = ti.y0 + yy;
-    const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
+    // persistent CTAs pull tiles from the compacted list of tiles that have work (tile_classify_kernel); a shared
+    // ticket counter balances the very uneven tiles (rigid-only vs near bricks)
+    __shared__ int s_ticket;
 #pragma unroll 1
-    for (int sb = 0; sb < 4; ++sb) {
-        if (!((ti.near_mask >> sb) & 1)) continue;  // uniform over the CTA
-        const int x = ti.x0 + sb * 8 + qx2 * 4;
-        const size_t brick = ti.brick0 + sb;
-        const size_t lin = (size_t) x + (size_t) y * a.dx + plane * (size_t) z;
-        float px[4];
+    for (;;) {
+        if (tid == 0) s_ticket = atomicAdd(&a.work_count[MODE == MODE_FILL ? 3 : 2], 1);
+        __syncthreads();
+        const int wi = s_ticket;
+        __syncthreads();
+        if (wi >= n_work) break;
+        const int tile = list[wi];
+        const TileInfo ti = tile_info(a, tile, fi);
+        if (MODE != MODE_FILL && !(a.tile_flags[tile] & 16)) rigid_pass(a, ti);
+        if (ti.near_mask == 0) continue;
+        const int z = ti.zt + zz, y = ti.y0 + yy;
+        const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
+#pragma unroll 1
+        for (int sb = 0; sb < 4; ++sb) {
+            if (!((ti.near_mask >> sb) & 1)) continue;  // uniform over the CTA
+            const int x = ti.x0 + sb * 8 + qx2 * 4;
+            const size_t brick = ti.brick0 + sb;
+            const size_t lin = (size_t) x + (size_t) y * a.dx + plane * (size_t) z;
+            float px[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) px[v] = fmul((float) (x + v), a.vsx);
+            for (int v = 0; v < 4; ++v) px[v] = fmul((float) (x + v), a.vsx);
 
-        if (MODE == MODE_CACHED) {
-            if (z < a.z0 || z >= a.z1) continue;
-            const uint4* cache = a.knn_pool + brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4);
-            bool hit[4];
-            float ts[4];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                int id[DFU_KNN];
-                unpack_ids(cache[v], id);
-                const V3 w = warp_voxel(a, ti, id, px[v], py, pz, x + v > 0 && y > 0 && z > 0);
-                hit[v] = voxel_tsdf(a, w.x, w.y, w.z, ts[v]);
-            }
-            quad_commit(a, lin, hit, ts);
-        } else {
-            __shared__ IntegrateSmem sm;
-            if (MODE == MODE_FILL && a.built[brick]) continue;  // uniform over the CTA
-            Top8 t[4];
-            brick_knn_scan(a, ti, sm, sb, px, py, pz, t);
-            if (MODE == MODE_FILL) {
-                // 8 u16 ids per voxel, 64 contiguous bytes per thread
-                uint4* cache = a.knn_pool + brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4);
-#pragma unroll
-                for (int v = 0; v < 4; ++v) cache[v] = pack_ids(t[v]);
-                __syncthreads();
-                if (tid == 0) a.built[brick] = 1;
-            } else {
+            if (MODE == MODE_CACHED) {
                 if (z < a.z0 || z >= a.z1) continue;
+                const uint4* cache = a.knn_pool + brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4);
                 bool hit[4];
                 float ts[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    const V3 w = warp_voxel(a, ti, t[v].i, px[v], py, pz, x + v > 0 && y > 0 && z > 0);
+                    int id[DFU_KNN];
+                    unpack_ids(cache[v], id);
+                    const V3 w = warp_voxel(a, ti, id, px[v], py, pz, x + v > 0 && y > 0 && z > 0);
                     hit[v] = voxel_tsdf(a, w.x, w.y, w.z, ts[v]);
                 }
                 quad_commit(a, lin, hit, ts);
+            } else {
+                __shared__ IntegrateSmem sm;
+                if (MODE == MODE_FILL && a.built[brick]) continue;  // uniform over the CTA
+                Top8 t[4];
+                brick_knn_scan(a, ti, sm, sb, px, py, pz, t);
+                if (MODE == MODE_FILL) {
+                    // 8 u16 ids per voxel, 64 contiguous bytes per thread
+                    uint4* cache = a.knn_pool + brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) cache[v] = pack_ids(t[v]);
+                    __syncthreads();
+                    if (tid == 0) a.built[brick] = 1;
+                } else {
+                    if (z < a.z0 || z >= a.z1) continue;
+                    bool hit[4];
+                    float ts[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const V3 w = warp_voxel(a, ti, t[v].i, px[v], py, pz, x + v > 0 && y > 0 && z > 0);
+                        hit[v] = voxel_tsdf(a, w.x, w.y, w.z, ts[v]);
+                    }
+                    quad_commit(a, lin, hit, ts);
+                }
             }
         }
     }
@@ -381,9 +406,11 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
 // only onto pixels without depth, or lies entirely more than trunc behind the farthest depth it can see, no voxel of
 // it can pass the per-voxel tests (tsdf_volume.cu:70-79) and the rigid pass is skipped.  All bounds carry margins far
 // above the rounding of the per-voxel arithmetic, so the result is bit-identical.
-__global__ void tile_cull_kernel(const __grid_constant__ IntegrateArgs a, int ntiles, unsigned char* __restrict__ skip) {
+// The same thread classifies the tile's 4 bricks as near / not near (rules (a),(b) above) and appends the tile to the
+// work list (anything to do) and to the fill list (a near brick missing from the 8-NN cache).
+__global__ void tile_classify_kernel(const __grid_constant__ IntegrateArgs a) {
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile >= ntiles) return;
+    if (tile >= a.ntiles) return;
     int bid = tile;
     const int x0 = (bid % a.ntx) * 32;
     bid /= a.ntx;
@@ -431,7 +458,25 @@ __global__ void tile_cull_kernel(const __grid_constant__ IntegrateArgs a, int nt
             if (dfar == 0.f || dfar - near_dist < -a.trunc - 1e-3f) rigid_skip = true;
         }
     }
-    skip[tile] = rigid_skip ? 1 : 0;
+    int near_mask = 0, need_fill = 0;
+    if (a.warped) {
+        const FieldInfo f = field_info(a);
+        const float r_brick = 3.5f * sqrtf(a.vsx * a.vsx + a.vsy * a.vsy + a.vsz * a.vsz);
+        const size_t brick0 = (size_t) (x0 / 8) + (size_t) a.bdx * ((y0 / 8) + (size_t) a.bdy * (zt / 8));
+#pragma unroll
+        for (int sb = 0; sb < 4; ++sb) {
+            const float2 b = __ldg(&a.bounds[brick0 + sb]);
+            const float dmin = sqrtf(b.y) - r_brick;  // lower bound of voxel-to-node distance in this brick
+            const bool on_zero_plane = (x0 + sb * 8 == 0) || (y0 == 0) || (zt == 0);
+            if (f.all_near || dmin <= (on_zero_plane ? f.r_zero : f.r_eff)) {
+                near_mask |= 1 << sb;
+                if (a.knn_pool && !a.built[brick0 + sb]) need_fill = 1;
+            }
+        }
+    }
+    a.tile_flags[tile] = (unsigned char) (near_mask | (rigid_skip ? 16 : 0));
+    if (near_mask || !rigid_skip) a.work_tiles[atomicAdd(&a.work_count[0], 1)] = tile;
+    if (need_fill) a.fill_tiles[atomicAdd(&a.work_count[1], 1)] = tile;
 }
 
 // max ray length per 16x16-pixel tile of the dists image (for the hierarchical cull of integrate_kernel)
@@ -577,32 +622,44 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
     }
     const long nblocks = (long) a.ntx * a.nty * ntz;
     DFU_REQUIRE(nblocks <= 0x7fffffffL, DFU_ERR_INVALID, "volume too large for one launch");
-    // coarse max-depth map + per-tile cull flags (stream-ordered scratch: safe with concurrent streams)
+    // per-call scratch (stream-ordered: safe with concurrent streams): coarse max-depth map, per-tile flags, work lists
     a.dtx = div_up(cols, DT);
     a.dty = div_up(rows, DT);
-    float* tiles = nullptr;
-    const size_t tile_bytes = ((size_t) a.dtx * a.dty * sizeof(float) + 255) / 256 * 256;
+    a.ntiles = (int) nblocks;
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t o_flags = up((size_t) a.dtx * a.dty * sizeof(float));
+    const size_t o_count = o_flags + up((size_t) nblocks);
+    const size_t o_work = o_count + 256;
+    const size_t o_fill = o_work + up((size_t) nblocks * sizeof(int));
+    const size_t total = o_fill + up((size_t) nblocks * sizeof(int));
+    char* tiles = nullptr;
     int device = 0;
     DFU_CUDA_OK(cudaGetDevice(&device));
     cudaMemPool_t pool = scratch_pool(device);
     if (pool)
-        DFU_CUDA_OK(cudaMallocFromPoolAsync(&tiles, tile_bytes + (size_t) nblocks, pool, st));
+        DFU_CUDA_OK(cudaMallocFromPoolAsync((void**) &tiles, total, pool, st));
     else
-        DFU_CUDA_OK(cudaMallocAsync(&tiles, tile_bytes + (size_t) nblocks, st));
-    unsigned char* skip = reinterpret_cast<unsigned char*>(tiles) + tile_bytes;
-    depth_tiles_kernel<<<dim3(a.dtx, a.dty), DT * DT, 0, st>>>(dists, pitch, rows, cols, tiles, a.dtx);
+        DFU_CUDA_OK(cudaMallocAsync((void**) &tiles, total, st));
+    a.dmax_tiles = reinterpret_cast<float*>(tiles);
+    a.tile_flags = reinterpret_cast<unsigned char*>(tiles + o_flags);
+    a.work_count = reinterpret_cast<int*>(tiles + o_count);
+    a.work_tiles = reinterpret_cast<int*>(tiles + o_work);
+    a.fill_tiles = reinterpret_cast<int*>(tiles + o_fill);
+    DFU_CUDA_OK(cudaMemsetAsync(a.work_count, 0, 4 * sizeof(int), st));
+    depth_tiles_kernel<<<dim3(a.dtx, a.dty), DT * DT, 0, st>>>(dists, pitch, rows, cols, reinterpret_cast<float*>(tiles), a.dtx);
     DFU_LAUNCH_OK();
-    a.dmax_tiles = tiles;
-    tile_cull_kernel<<<div_up(nblocks, 128), 128, 0, st>>>(a, (int) nblocks, skip);
+    tile_classify_kernel<<<div_up(nblocks, 128), 128, 0, st>>>(a);
     DFU_LAUNCH_OK();
-    a.tile_skip = skip;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const unsigned grid8 = (unsigned) std::min<long>(nblocks, (long) sms * 8), grid4 = (unsigned) std::min<long>(nblocks, (long) sms * 4);
     if (!a.warped || a.knn_pool == nullptr) {
-        integrate_kernel<MODE_ONTHEFLY><<<(unsigned) nblocks, 128, 0, st>>>(a);
+        integrate_kernel<MODE_ONTHEFLY><<<grid4, 128, 0, st>>>(a);
         DFU_LAUNCH_OK();
     } else {
-        integrate_kernel<MODE_FILL><<<(unsigned) nblocks, 128, 0, st>>>(a);  // a no-op once the cache is warm
+        integrate_kernel<MODE_FILL><<<grid4, 128, 0, st>>>(a);  // its work list is empty once the cache is warm
         DFU_LAUNCH_OK();
-        integrate_kernel<MODE_CACHED><<<(unsigned) nblocks, 128, 0, st>>>(a);
+        integrate_kernel<MODE_CACHED><<<grid8, 128, 0, st>>>(a);
         DFU_LAUNCH_OK();
     }
     DFU_CUDA_OK(cudaFreeAsync(tiles, st));
