@@ -47,11 +47,15 @@ struct BrickTable {            // per-volume-geometry acceleration data for the 
     float voxel[3] = {0, 0, 0};
     uint64_t node_epoch = 0;   // positions epoch the table was built for
     bool valid = false;
-    // per-voxel 8-NN cache (filled lazily by the integrator, valid while node positions are unchanged):
-    // 512 voxels x 8 u16 node ids = 8 KB per brick, brick-major; built[brick] != 0 once a brick is filled
+    // per-voxel 8-NN + weight cache (filled lazily by the integrator, valid while node POSITIONS are unchanged: ids
+    // and Gaussian weights depend only on the canonical voxel and node positions, never on the node transforms):
+    // per brick 512 voxels x (8 u16 ids = 16 B | 8 f32 weights = 32 B) = 24 KB; built[brick] != 0 once filled.
+    // The pools cover the brick planes [pool_zb0, pool_zb1) (the z-slab this rank integrates).
     uint4* knn_pool = nullptr;
+    float4* w_pool = nullptr;
     unsigned char* built = nullptr;
-    size_t pool_bricks = 0;    // bricks the pool has room for (0: cache disabled)
+    size_t pool_bricks = 0;    // bricks the pools have room for (0: cache disabled)
+    int pool_zb0 = 0, pool_zb1 = 0;
 };
 
 // Uniform grid over the node positions for the point-query kNN (rebuilt when positions change)
@@ -96,7 +100,7 @@ struct dfu_warpfield {
 
 // kernels living in warpfield.cu that tsdf.cu / solver.cu launch
 int dfu_wf_refresh_flags(dfu_warpfield* wf, cudaStream_t st);
-int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float voxel[3], cudaStream_t st);
+int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float voxel[3], int z0, int z1, cudaStream_t st);
 int dfu_wf_build_data_graph(const dfu_warpfield* wf, const float* canon, const float* live, int P, int32_t* nbr,
                             float* wts, float* dvec, cudaStream_t st);
 int dfu_wf_build_node_graph(const dfu_warpfield* wf, int32_t* nnbr, cudaStream_t st);

@@ -39,7 +39,8 @@ struct IntegrateArgs {
     const int* flags;
     const float2* bounds;
     int bdx, bdy;
-    uint4* knn_pool;       // per-voxel 8-NN cache (null: disabled), see BrickTable
+    uint4* knn_pool;       // per-voxel 8-NN id cache (null: disabled), see BrickTable; indexed by GLOBAL brick id
+    float4* w_pool;        // per-voxel weight cache (two float4 per voxel)
     unsigned char* built;
     // per-call scratch written by tile_classify_kernel
     unsigned char* tile_flags;  // per 32x8x8 tile: bits 0-3 = near mask of its 4 bricks, bit 4 = rigid pass cannot touch a voxel
@@ -305,6 +306,33 @@ DFU_DEV V3 warp_voxel(const IntegrateArgs& a, const TileInfo& ti, const int (&id
     return dq_transform_vertex(b, V3{px, py, pz});
 }
 
+// warped position of one voxel from its cached 8 neighbour ids and weights (no distance or weight evaluation:
+// both depend on positions only and were computed when the brick was filled)
+DFU_DEV V3 warp_voxel_weights(const IntegrateArgs& a, const TileInfo& ti, const int (&id)[DFU_KNN], const float (&w)[DFU_KNN],
+                              float px, float py, float pz) {
+    if (ti.translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
+        float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+        for (int k = 0; k < DFU_KNN; ++k) {
+            if (id[k] >= 0 && w[k] != 0.f) {
+                const float4 du = __ldg(&a.dual[id[k]]);  // (w,x,y,z) stored in (x,y,z,w)
+                ax = fadd(fmul(du.y, w[k]), ax);
+                ay = fadd(fmul(du.z, w[k]), ay);
+                az = fadd(fmul(du.w, w[k]), az);
+            }
+        }
+        return V3{fadd(px, fmul(2.f, ax)), fadd(py, fmul(2.f, ay)), fadd(pz, fmul(2.f, az))};
+    }
+    Top8 t;
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) {
+        t.i[k] = id[k];
+        t.d[k] = 0.f;  // not used by blend() once the weights are known
+    }
+    const DQ b = blend(a.blend_mode, t, w, a.real, a.dual);
+    return dq_transform_vertex(b, V3{px, py, pz});
+}
+
 DFU_DEV uint4 pack_ids(const Top8& t) {
     unsigned u[4];
 #pragma unroll
@@ -362,15 +390,19 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
 
             if (MODE == MODE_CACHED) {
                 if (z < a.z0 || z >= a.z1) continue;
-                const uint4* cache = a.knn_pool + brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4);
+                const size_t slot = brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4);
+                const uint4* cache = a.knn_pool + slot;
+                const float4* wcache = a.w_pool + 2 * slot;
                 bool hit[4];
                 float ts[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     int id[DFU_KNN];
                     unpack_ids(cache[v], id);
-                    const V3 w = warp_voxel(a, ti, id, px[v], py, pz, x + v > 0 && y > 0 && z > 0);
-                    hit[v] = voxel_tsdf(a, w.x, w.y, w.z, ts[v]);
+                    const float4 w0 = wcache[2 * v], w1 = wcache[2 * v + 1];
+                    const float w[DFU_KNN] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    const V3 p = warp_voxel_weights(a, ti, id, w, px[v], py, pz);
+                    hit[v] = voxel_tsdf(a, p.x, p.y, p.z, ts[v]);
                 }
                 quad_commit(a, lin, hit, ts);
             } else {
@@ -380,9 +412,17 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
                 brick_knn_scan(a, ti, sm, sb, px, py, pz, t);
                 if (MODE == MODE_FILL) {
                     // 8 u16 ids per voxel, 64 contiguous bytes per thread
-                    uint4* cache = a.knn_pool + brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4);
+                    const size_t slot = brick * 512 + ((zz * 8 + yy) * 8 + qx2 * 4);
+                    uint4* cache = a.knn_pool + slot;
+                    float4* wcache = a.w_pool + 2 * slot;
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) cache[v] = pack_ids(t[v]);
+                    for (int v = 0; v < 4; ++v) {
+                        cache[v] = pack_ids(t[v]);
+                        float w[DFU_KNN];
+                        neighbour_weights(t[v], px[v], py, pz, a.pos_w, w);  // the FP64 evaluation, once per voxel
+                        wcache[2 * v] = make_float4(w[0], w[1], w[2], w[3]);
+                        wcache[2 * v + 1] = make_float4(w[4], w[5], w[6], w[7]);
+                    }
                     __syncthreads();
                     if (tid == 0) a.built[brick] = 1;
                 } else {
@@ -605,7 +645,7 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
     const int ntz = (z1 - a.zt0 + 7) / 8;
     if (wf) {
         DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
-        int rc = dfu_wf_build_brick_table(wf, dims, vs, st);
+        int rc = dfu_wf_build_brick_table(wf, dims, vs, z0, z1, st);
         if (rc != DFU_OK) return rc;
         a.warped = 1;
         a.blend_mode = blend_mode;
@@ -617,8 +657,12 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
         a.bounds = wf->bricks.bounds;
         a.bdx = dims[0] / 8;
         a.bdy = dims[1] / 8;
-        a.knn_pool = wf->bricks.knn_pool;
-        a.built = wf->bricks.built;
+        if (wf->bricks.knn_pool) {  // pools start at brick plane pool_zb0: shift so that they index by global brick id
+            const size_t off = (size_t) (dims[0] / 8) * (dims[1] / 8) * (size_t) wf->bricks.pool_zb0;
+            a.knn_pool = wf->bricks.knn_pool - off * 512;
+            a.w_pool = wf->bricks.w_pool - off * 1024;
+            a.built = wf->bricks.built - off;
+        }
     }
     const long nblocks = (long) a.ntx * a.nty * ntz;
     DFU_REQUIRE(nblocks <= 0x7fffffffL, DFU_ERR_INVALID, "volume too large for one launch");

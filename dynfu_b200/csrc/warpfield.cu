@@ -646,54 +646,63 @@ int dfu_wf_refresh_flags(dfu_warpfield* wf, cudaStream_t st) {
 // from its centre to the 8th and to the 1st nearest node.  Depends only on node POSITIONS and the volume
 // geometry, so it is cached until either changes (the reference rebuilds its KD-tree at the same moments,
 // src/dynfu/warp_field.cpp:24-27,85-94).
-int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float voxel[3], cudaStream_t st) {
+int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float voxel[3], int z0, int z1, cudaStream_t st) {
     BrickTable& bt = wf->bricks;
+    const int zb0 = z0 / 8, zb1 = (z1 + 7) / 8;
     const bool same = bt.valid && bt.node_epoch == wf->node_epoch && bt.dims[0] == dims[0] && bt.dims[1] == dims[1] &&
                       bt.dims[2] == dims[2] && bt.voxel[0] == voxel[0] && bt.voxel[1] == voxel[1] &&
                       bt.voxel[2] == voxel[2];
-    if (same) return DFU_OK;
+    const bool pool_covers = bt.pool_bricks == 0 || (zb0 >= bt.pool_zb0 && zb1 <= bt.pool_zb1);
+    if (same && pool_covers) return DFU_OK;
     const int bd[3] = {dims[0] / 8, dims[1] / 8, (dims[2] + 7) / 8};
     const size_t nb = (size_t) bd[0] * bd[1] * bd[2];
-    if (nb > bt.capacity) {
-        if (bt.bounds) cudaFree(bt.bounds);
-        bt.bounds = nullptr;
-        bt.capacity = 0;
-        DFU_CUDA_OK(cudaMalloc(&bt.bounds, nb * sizeof(float2)));
-        bt.capacity = nb;
+    if (!same) {
+        if (nb > bt.capacity) {
+            if (bt.bounds) cudaFree(bt.bounds);
+            bt.bounds = nullptr;
+            bt.capacity = 0;
+            DFU_CUDA_OK(cudaMalloc(&bt.bounds, nb * sizeof(float2)));
+            bt.capacity = nb;
+        }
+        PointArgs a{};
+        a.Q = (int) nb;
+        a.bounds = bt.bounds;
+        for (int i = 0; i < 3; ++i) {
+            a.bdim[i] = bd[i];
+            a.voxel[i] = voxel[i];
+            bt.dims[i] = dims[i];
+            bt.voxel[i] = voxel[i];
+        }
+        int rc = launch_points<OP_BOUNDS>(wf, a, st);
+        if (rc != DFU_OK) return rc;
     }
-    PointArgs a{};
-    a.Q = (int) nb;
-    a.bounds = bt.bounds;
-    for (int i = 0; i < 3; ++i) {
-        a.bdim[i] = bd[i];
-        a.voxel[i] = voxel[i];
-        bt.dims[i] = dims[i];
-        bt.voxel[i] = voxel[i];
-    }
-    int rc = launch_points<OP_BOUNDS>(wf, a, st);
-    if (rc != DFU_OK) return rc;
-    // voxel kNN cache: node ids fit u16, 8 KB per brick, at most 4 GiB (512^3 needs 2 GiB of the 180 GB);
-    // DFU_VOXEL_KNN_CACHE=0 turns it off (every frame then recomputes the per-voxel 8-NN)
+    // voxel cache for the brick planes of this z-slab: 24 KB per brick (512^3 full volume: 6 GiB of the 180 GB).
+    // Budget DFU_VOXEL_CACHE_GB (default 16); DFU_VOXEL_KNN_CACHE=0 turns the cache off (every frame then recomputes
+    // the per-voxel 8-NN and weights).
     const char* env = getenv("DFU_VOXEL_KNN_CACHE");
-    const bool want = !(env && env[0] == '0') && wf->N <= 65535 && nb * 8192ull <= (4ull << 30);
-    if (!want) {
+    const char* gb = getenv("DFU_VOXEL_CACHE_GB");
+    const double budget = (gb ? atof(gb) : 16.0) * 1073741824.0;
+    const size_t nbp = (size_t) bd[0] * bd[1] * (size_t) (zb1 - zb0);
+    const bool want = !(env && env[0] == '0') && wf->N <= 65535 && (double) nbp * 24576.0 <= budget;
+    if (!want || nbp > bt.pool_bricks) {
         if (bt.knn_pool) cudaFree(bt.knn_pool);
+        if (bt.w_pool) cudaFree(bt.w_pool);
         if (bt.built) cudaFree(bt.built);
         bt.knn_pool = nullptr;
+        bt.w_pool = nullptr;
         bt.built = nullptr;
         bt.pool_bricks = 0;
-    } else {
-        if (nb > bt.pool_bricks) {
-            if (bt.knn_pool) cudaFree(bt.knn_pool);
-            if (bt.built) cudaFree(bt.built);
-            bt.knn_pool = nullptr;
-            bt.built = nullptr;
-            bt.pool_bricks = 0;
-            DFU_CUDA_OK(cudaMalloc(&bt.knn_pool, nb * 8192ull));
-            DFU_CUDA_OK(cudaMalloc(&bt.built, nb));
-            bt.pool_bricks = nb;
+    }
+    if (want) {
+        if (bt.pool_bricks == 0) {
+            DFU_CUDA_OK(cudaMalloc(&bt.knn_pool, nbp * 8192ull));
+            DFU_CUDA_OK(cudaMalloc(&bt.w_pool, nbp * 16384ull));
+            DFU_CUDA_OK(cudaMalloc(&bt.built, nbp));
+            bt.pool_bricks = nbp;
         }
-        DFU_CUDA_OK(cudaMemsetAsync(bt.built, 0, nb, st));
+        DFU_CUDA_OK(cudaMemsetAsync(bt.built, 0, bt.pool_bricks, st));
+        bt.pool_zb0 = zb0;
+        bt.pool_zb1 = zb1;
     }
     bt.node_epoch = wf->node_epoch;
     bt.valid = true;
@@ -742,6 +751,7 @@ int dfu_warpfield_destroy(dfu_warpfield* wf) {
     cudaFree(wf->staging);
     cudaFree(wf->bricks.bounds);
     cudaFree(wf->bricks.knn_pool);
+    cudaFree(wf->bricks.w_pool);
     cudaFree(wf->bricks.built);
     cudaFree(wf->grid.desc);
     cudaFree(wf->grid.cell_start);
