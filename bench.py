@@ -61,7 +61,9 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 50 ms in the background; samples are kept with their wall-clock time so that only the
+    ones taken inside the timed region are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -71,37 +73,44 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
+
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        inside = [r for r in rows if t0 is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+        use = inside if inside else rows
+        reasons = set()
+        for r in use:
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        hi = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
-        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": max(r[2] for r in use), "reasons": sorted(reasons),
+                "samples": len(use), "window": "timed region" if inside else "whole run (timed region shorter than the sampling period)"}
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -195,7 +204,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -250,11 +259,21 @@ def main():
     torch.cuda.synchronize()
 
     ev_int = []
+    ev_sol = []
 
     def step_device(i, timed=False):
         """inputs already in HBM"""
         dfu.compute_dists(depth_dev[i % RING], kp.intr, out=df._dists)
-        df.warpCanonicalToLiveOpt(live_dev[i % RING])
+        if timed:
+            df.canonicalWarpedToLive, _ = df.warpfield.warpToLive(df.canonicalVertices, None, prm.blend_mode)
+            df.solver.initializeProblemInstance(df.canonicalWarpedToLive, live_dev[i % RING])
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            df.solver.solveAll()
+            s1.record()
+            ev_sol.append((s0, s1))
+        else:
+            df.warpCanonicalToLiveOpt(live_dev[i % RING])
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -278,13 +297,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    cpu_submit = {}
+
     def timed_loop(fn, K, **kw):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_cpu = time.perf_counter()
         a.record()
         for i in range(K):
             fn(i, **kw)
         b.record()
+        cpu_submit[fn.__name__] = (time.perf_counter() - t_cpu) * 1e3 / K  # host time to enqueue one step
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=devs)
         if world > 1:
@@ -299,11 +322,14 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.25)  # let nvidia-smi start sampling
     launches0 = lib.dfu_launch_count()
+    t_wall0 = time.time()
     ms_dev = timed_loop(step_device, args.steps, timed=True)
     launches = lib.dfu_launch_count() - launches0
     ms_e2e = timed_loop(step_host, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     stats = df.solver.getStats()
 
     # dominant kernel: integrate_kernel, timed with CUDA events on the launching stream inside the timed region
@@ -315,6 +341,11 @@ def main():
     voxels_rank = DIM * DIM * (z1 - z0)
     hbm_peak, peak_src = peaks()
     achieved = voxels_rank * ALGO_BYTES_PER_VOXEL / (int_ms * 1e-3) / 1e9
+    sol_ms = dfu_dist.max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev_sol])), devs)
+    # per GN iteration the assembly reads ~100 B/point, per PCG iteration ~100 B/point + N*(6+27)*4 B
+    P_rank = p1 - p0
+    sol_bytes = GN_ITERS * P_rank * 100 + GN_ITERS * PCG_ITERS * (P_rank * 100 + N_THETA * N_Y * 33 * 4)
+    sol_achieved = sol_bytes / (sol_ms * 1e-3) / 1e9
 
     if rank == 0:
         fps = args.steps / (ms_dev * 1e-3)
@@ -327,23 +358,34 @@ def main():
             "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(depth_host[0].numel() * 2 + live_host[0].numel() * 4),
                     "d2h_bytes_per_step": int(dq_out_host.numel() * 4 + 48)},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": cpu_submit.get("step_device"),
             "voxels_per_s": DIM ** 3 * fps,
-            "roofline": {"kernel": "integrate_kernel (warped projective TSDF integration)", "bound": "hbm",
-                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": int_ms,
-                         "algorithmic_bytes_per_launch": voxels_rank * ALGO_BYTES_PER_VOXEL,
-                         "share_of_step": int_ms / (ms_dev / args.steps)},
+            "roofline": None,
+            "roofline_kernels": [
+                {"kernel": "integrate (depth_tiles + tile_classify + integrate_kernel<FILL> + integrate_kernel<CACHED>): "
+                           "warped projective TSDF integration", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": int_ms,
+                 "algorithmic_bytes_per_launch": voxels_rank * ALGO_BYTES_PER_VOXEL, "share_of_step": int_ms / (ms_dev / args.steps)},
+                {"kernel": "k_solve_persistent (5 GN x 10 PCG, one cooperative launch)" if world == 1 else
+                           "solver phase kernels + NCCL all-reduces (5 GN x 10 PCG)", "bound": "hbm", "achieved": sol_achieved,
+                 "peak": hbm_peak, "unit": "GB/s", "frac": sol_achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                 "kernel_ms": sol_ms, "algorithmic_bytes_per_launch": sol_bytes, "share_of_step": sol_ms / (ms_dev / args.steps),
+                 "note": "L2-resident and bound by grid-barrier / L2 latency, not by HBM (SURVEY 8d): frac is reported "
+                         "for completeness"}],
             "solver": {"final_energy": stats["final_energy"], "initial_energy": stats["initial_energy"],
                        "pcg_iterations": stats["pcg_iterations"], "gn_steps": stats["gn_steps"]},
             "clocks": clocks,
         }
-        traffic_file = os.path.join(ROOT, "profiles", "integrate_traffic.json")
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
             try:
-                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+                tr = json.load(open(traffic_file))
+                line["roofline_kernels"][0]["traffic"] = tr.get("integrate_dram_bytes_per_launch")
+                line["roofline_kernels"][1]["traffic"] = tr.get("solver_dram_bytes_per_launch")
             except Exception:
                 pass
+        # the contract's `roofline` object is the dominant kernel of the step
+        line["roofline"] = max(line["roofline_kernels"], key=lambda r: r["kernel_ms"])
         if not args.no_cpu_baseline and world == 1:
             c = cpu_frame(scene)
             line["cpu_baseline"] = {"value": c["frames_per_s"], "unit": "frames/s", "cores": c["cores"], "kind": "port",
