@@ -208,6 +208,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver-parallel", default="auto", choices=["auto", "replicated", "partitioned"],
+                    help="N > 1: every rank solves all points (no exchange) or the points are partitioned and the "
+                         "normal-equation buffers all-reduced over NCCL; auto = partitioned from 100k points per rank")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -233,7 +236,15 @@ def main():
     # z-slab of this rank (multiples of 8 planes) and its contiguous point partition
     from dynfu_b200 import dist as dfu_dist
     z0, z1 = dfu_dist.slab_range(rank, world, DIM)
-    p0, p1 = dfu_dist.point_range(rank, world, P_all)
+    # the solve is latency-bound at this size (76k points, 4096 nodes): partitioning the points only adds one
+    # all-reduce per PCG iteration, so by default every rank solves the whole (small) problem and only the volume
+    # is sharded; the partitioned + all-reduce mode is what larger problems (BASELINE configs[4]) use
+    mode = args.solver_parallel
+    if mode == "auto":
+        mode = "partitioned" if (world > 1 and P_all // world >= 100000) else "replicated"
+    if world == 1:
+        mode = "single"
+    p0, p1 = dfu_dist.point_range(rank, world, P_all) if mode == "partitioned" else (0, P_all)
 
     def dev(a, dt=torch.float32):
         return torch.as_tensor(np.ascontiguousarray(a)).to(devs, dtype=dt)
@@ -242,8 +253,8 @@ def main():
                           solver=dfu.CombinedSolverParameters(numIter=GN_ITERS, nonLinearIter=1, linearIter=PCG_ITERS,
                                                               earlyOut=False, pcgTolerance=0.0))
     df = dfu.DynFusion(prm, device=devs, z0=z0, z1=z1)
-    if world > 1:
-        df.allreduce = dfu_dist.make_allreduce()
+    if mode == "partitioned":
+        df.comm = dfu_dist.Communicator(devs)
     df.init(dev(scene["canon"][p0:p1]), None, nodes=(dev(scene["pos"]), dev(scene["dq"]), dev(scene["dg_w"])))
 
     depth_host = [torch.from_numpy(d.view(np.int16)).pin_memory() for d in scene["depths"]]
@@ -354,7 +365,7 @@ def main():
             "metric": "frames/sec (512^3 TSDF, 4096 nodes)", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(world, P_all),
+            "config": dict(config_dict(world, P_all), solver_parallel=mode),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(depth_host[0].numel() * 2 + live_host[0].numel() * 4),
                     "d2h_bytes_per_step": int(dq_out_host.numel() * 4 + 48)},

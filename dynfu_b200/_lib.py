@@ -69,6 +69,11 @@ _SIGS = {
     "dfu_solver_create": ([C.POINTER(_vp), _vp, C.POINTER(SolverParams)], _i),
     "dfu_solver_destroy": ([_vp], _i),
     "dfu_solver_set_allreduce": ([_vp, ALLREDUCE_FN, _vp], _i),
+    "dfu_comm_unique_id": ([C.c_char_p], _i),
+    "dfu_comm_create": ([C.POINTER(_vp), C.c_char_p, _i, _i], _i),
+    "dfu_comm_destroy": ([_vp], _i),
+    "dfu_comm_allreduce": ([_vp, _sz, _vp, _vp], _i),
+    "dfu_solver_set_comm": ([_vp, _vp], _i),
     "dfu_solver_init_problem": ([_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), _vp], _i),
     "dfu_solver_solve_all": ([_vp, _vp], _i),
     "dfu_solver_get_translations": ([_vp, _vp, _vp], _i),

@@ -35,3 +35,37 @@ def max_over_ranks(value, device):
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class Communicator:
+    """NCCL communicator owned by libdynfu_b200.so (created over torch.distributed's rendezvous), so that the
+    solver issues its all-reduces from C++ on its own stream -- no Python inside the PCG loop."""
+
+    def __init__(self, device=None):
+        import ctypes as C
+
+        from ._lib import check, lib
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            check(lib.dfu_comm_unique_id(buf))
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0)
+        h = C.c_void_p()
+        if device is not None:
+            torch.cuda.set_device(device)
+        check(lib.dfu_comm_create(C.byref(h), box[0], rank, world))
+        self._h = h
+        self.rank, self.world = rank, world
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        from ._lib import lib
+
+        if getattr(self, "_h", None):
+            lib.dfu_comm_destroy(self._h)
+            self._h = None

@@ -63,7 +63,8 @@ class DynFusion:
         self.canonicalWarpedToLive = None
         self._depth_dev = torch.empty((kp.rows, kp.cols), dtype=torch.int16, device=self.device)
         self._dists = torch.empty_like(self._depth_dev)
-        self.allreduce = None
+        self.allreduce = None  # python all-reduce hook (tests)
+        self.comm = None       # dynfu_b200.dist.Communicator: NCCL issued from C++
 
     # DynFusion::init (src/dynfu/dyn_fusion.cpp:147-168); explicit nodes may be given instead of the 128-stride pick
     def init(self, canonicalVertices, canonicalNormals=None, nodes=None):
@@ -83,7 +84,9 @@ class DynFusion:
         self.warpfield.init(self.params.epsilon, pos, dq, w)
         self.solver = CombinedSolver(self.warpfield, self.params.solver, self.params.tukeyOffset, self.params.psi_data,
                                      self.params.lambda_, self.params.psi_reg)  # dyn_fusion.cpp:193
-        if self.allreduce is not None:
+        if self.comm is not None:
+            self.solver.setCommunicator(self.comm)
+        elif self.allreduce is not None:
             self.solver.setAllReduce(self.allreduce)
 
     def uploadDepth(self, depth_host):

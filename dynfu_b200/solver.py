@@ -63,6 +63,11 @@ class CombinedSolver:
         self._cb = _lib.ALLREDUCE_FN(_cb)
         check(lib.dfu_solver_set_allreduce(self._h, self._cb, None))
 
+    def setCommunicator(self, comm):
+        """dynfu_b200.dist.Communicator: all-reduces issued by the library itself through NCCL"""
+        self._comm = comm
+        check(lib.dfu_solver_set_comm(self._h, comm.handle if comm is not None else None))
+
     # CombinedSolver::initializeProblemInstance (src/dynfu/utils/opt_solver.cpp:15-54)
     def initializeProblemInstance(self, canonicalVertices, liveVertices, canonicalNormals=None, liveNormals=None,
                                   affine=None):

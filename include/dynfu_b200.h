@@ -168,6 +168,18 @@ int dfu_solver_destroy(dfu_solver* s);
 /* ranks hold disjoint point partitions; fn sums the per-node normal-equation buffers over ranks */
 int dfu_solver_set_allreduce(dfu_solver* s, dfu_allreduce_fn fn, void* ctx);
 
+/* NCCL communicator owned by the library (libnccl.so.2 is opened at run time; nothing to link).  Rank 0 calls
+ * dfu_comm_unique_id and ships the 128 bytes to the other ranks (e.g. through torch.distributed); every rank then
+ * calls dfu_comm_create with its CUDA device current.  dfu_solver_set_comm makes the solver issue ncclAllReduce on
+ * its own stream instead of calling a host callback; dfu_comm_allreduce is that callback (a dfu_allreduce_fn with
+ * ctx = the dfu_comm). */
+typedef struct dfu_comm dfu_comm;
+int dfu_comm_unique_id(char id_host[128]);
+int dfu_comm_create(dfu_comm** out, const char id_host[128], int rank, int world);
+int dfu_comm_destroy(dfu_comm* c);
+int dfu_comm_allreduce(float* buf, size_t count, void* ctx, dfu_stream stream);
+int dfu_solver_set_comm(dfu_solver* s, dfu_comm* c);
+
 /* CombinedSolver::initializeProblemInstance(canonicalFrame, liveFrame, affine)
  * (src/dynfu/utils/opt_solver.cpp:15-54): uploads nothing (pointers are device), builds the kNN data
  * graph (:56-72) and regularisation graph (:74-105), zeroes the unknowns (:192-193).

@@ -13,6 +13,8 @@ import dynfu_b200 as dfu  # noqa: E402
 from dynfu_b200 import dist as dd  # noqa: E402
 from tests import synth  # noqa: E402
 
+COMM = None
+
 
 def run(scene, rank, world, dim, device, frames=3):
     z0, z1 = dd.slab_range(rank, world, dim)
@@ -26,7 +28,7 @@ def run(scene, rank, world, dim, device, frames=3):
                                                               pcgTolerance=0.0))
     df = dfu.DynFusion(prm, device=device, z0=z0, z1=z1)
     if world > 1:
-        df.allreduce = dd.make_allreduce()
+        df.comm = COMM  # NCCL all-reduces issued by the library itself
     df.init(dev(scene["canon"][p0:p1]), None, nodes=(dev(scene["pos"]), dev(scene["dq"]), dev(scene["dg_w"])))
     depth = torch.from_numpy(scene["depth"].view(np.int16)).pin_memory()
     df(depth)
@@ -41,6 +43,8 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
+    global COMM
+    COMM = dd.Communicator(device)
     dim = 128
     depth = synth.sphere_depth()
     pos, _, dg_w, t_true = synth.sphere_nodes(1024, 0.03)
