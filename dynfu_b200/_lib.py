@@ -76,6 +76,8 @@ _SIGS = {
     "dfu_solver_set_comm": ([_vp, _vp], _i),
     "dfu_solver_init_problem": ([_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), _vp], _i),
     "dfu_solver_solve_all": ([_vp, _vp], _i),
+    "dfu_solver_huber_weights": ([_vp, _vp, _vp], _i),
+    "dfu_solver_tukey_weights": ([_vp, _vp, _vp], _i),
     "dfu_solver_get_translations": ([_vp, _vp, _vp], _i),
     "dfu_solver_get_stats_host": ([_vp, C.POINTER(C.c_double), _vp], _i),
 }

@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent(Problem pb, SolveC
     }
     // ---- final energy at the solution, Tukey weights of the last outer iteration -------------------------
     {
-        const double e2 = phase_point_residual(pb, false, tid, nthreads);
+        const double e2 = phase_point_residual(pb, first, tid, nthreads);  // no GN step ran: weights at t = 0
         double er = 0.0;
         if (pb.wreg2 > 0.f)
             for (int n = gw; n < pb.N; n += nw) {
@@ -950,7 +950,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent2(Problem pb, Solve
     }
     // ---- final energy at the solution, Tukey weights of the last outer iteration -------------------------
     {
-        const double e2 = residual_phase(false);
+        const double e2 = residual_phase(first);  // no GN step ran: weights at t = 0
         double er = 0.0;
         if (pb.wreg2 > 0.f) {
 #pragma unroll
@@ -1217,7 +1217,7 @@ int solve_multi_kernel(dfu_solver* s, cudaStream_t st) {
             s->gn_steps_host += 1;
         }
     }
-    return assemble_mk(s, pb, false, st);  // final energy at the solution
+    return assemble_mk(s, pb, s->gn_steps_host == 0, st);  // final energy at the solution (tukey weights at t = 0 if no step ran)
 }
 
 int solve_persistent(dfu_solver* s, cudaStream_t st) {
@@ -1405,6 +1405,39 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream) {
     rc = dfu_warpfield_update_translations(s->wf, s->vec, stream);
     if (prev != s->wf->device) cudaSetDevice(prev);
     return rc;
+}
+
+// CombinedSolver::updateHuberWeights (opt_solver.cpp:241-268): for node i the loop over its 8 neighbours overwrites
+// h[i] every time, so the value that survives is the one of the LAST (8th nearest) neighbour j:
+//   e = | T_i(dg_v[j]) - T_j(dg_v[j]) |,  h = e <= psi_reg ? 1 : psi_reg / e
+// The reference computes it and never reads it (energy.t:76-77); provided for API completeness.
+__global__ void k_huber(const float4* __restrict__ pos_w, const float4* __restrict__ real, const float4* __restrict__ dual,
+                        const int32_t* __restrict__ nnbr, int N, float psi_reg, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int j = nnbr[(size_t) i * 8 + 7];
+    const float4 pj = pos_w[j];
+    const V3 c{pj.x, pj.y, pj.z};
+    const V3 a = dq_transform_vertex(DQ{make_quat(real[i]), make_quat(dual[i])}, c);
+    const V3 b = dq_transform_vertex(DQ{make_quat(real[j]), make_quat(dual[j])}, c);
+    const float ex = fsub(a.x, b.x), ey = fsub(a.y, b.y), ez = fsub(a.z, b.z);
+    const float e = __fsqrt_rn(fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(ez, ez)));
+    out[i] = e <= psi_reg ? 1.f : __fdiv_rn(psi_reg, e);
+}
+
+int dfu_solver_huber_weights(const dfu_solver* s, float* huber, dfu_stream stream) {
+    DFU_REQUIRE(s && huber, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(s->problem_ready, DFU_ERR_NOT_INIT, "no problem instance");
+    k_huber<<<div_up(s->N, TPB), TPB, 0, as_stream(stream)>>>(s->wf->pos_w, s->wf->real, s->wf->dual, s->nnbr, s->N, s->prm.psi_reg, huber);
+    DFU_LAUNCH_OK();
+    return DFU_OK;
+}
+
+int dfu_solver_tukey_weights(const dfu_solver* s, float* tukey, dfu_stream stream) {
+    DFU_REQUIRE(s && tukey, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(s->problem_ready, DFU_ERR_NOT_INIT, "no problem instance");
+    DFU_CUDA_OK(cudaMemcpyAsync(tukey, s->theta, (size_t) s->P * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return DFU_OK;
 }
 
 int dfu_solver_get_translations(const dfu_solver* s, float* t_xyz, dfu_stream stream) {

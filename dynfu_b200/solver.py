@@ -83,6 +83,18 @@ class CombinedSolver:
     def solveAll(self):
         check(lib.dfu_solver_solve_all(self._h, stream_ptr()))
 
+    # CombinedSolver::updateHuberWeights (src/dynfu/utils/opt_solver.cpp:241-268)
+    def huberWeights(self):
+        h = torch.empty((self.warpfield.numNodes(),), dtype=torch.float32, device=self.warpfield.device)
+        check(lib.dfu_solver_huber_weights(self._h, dptr(h), stream_ptr()))
+        return h
+
+    # the tukey biweights (src/dynfu/utils/opt_solver.cpp:204-231) the last solve ended with
+    def tukeyWeights(self):
+        t = torch.empty((self._keep[0].shape[0],), dtype=torch.float32, device=self.warpfield.device)
+        check(lib.dfu_solver_tukey_weights(self._h, dptr(t), stream_ptr()))
+        return t
+
     def getTranslations(self):
         n = self.warpfield.numNodes()
         t = torch.empty((n, 3), dtype=torch.float32, device=self.warpfield.device)

@@ -196,6 +196,12 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream);
 int dfu_solver_get_translations(const dfu_solver* s, float* t_xyz, dfu_stream stream);
 int dfu_solver_get_stats_host(const dfu_solver* s, double stats_host[4], dfu_stream stream);
 
+/* CombinedSolver::updateHuberWeights (opt_solver.cpp:241-268): huber[N], the value the reference's loop leaves
+ * behind (its last neighbour); computed but never read by the reference's energy.  tukey[P] are the
+ * calcTukeyBiweight values (opt_solver.cpp:204-231) the last solve ended with. */
+int dfu_solver_huber_weights(const dfu_solver* s, float* huber, dfu_stream stream);
+int dfu_solver_tukey_weights(const dfu_solver* s, float* tukey, dfu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

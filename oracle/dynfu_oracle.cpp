@@ -536,6 +536,26 @@ float orc_huber(float k, float e) {
     return k / std::fabs(e);
 }
 
+/* opt_solver.cpp:241-268 : the inner loop overwrites h[i] for every neighbour, the last one survives */
+void orc_huber_weights(const float* pos, const float* dq, int N, float psi_reg, float* out) {
+    KnnIndex index(pos, N);
+    for (int i = 0; i < N; ++i) {
+        int32_t nb[KNN];
+        int n = index.query(pos + 3 * (size_t) i, KNN, nb, nullptr);
+        float h = 0.f;
+        for (int k = 0; k < n; ++k) {
+            const int j = nb[k];
+            V3 c{pos[3 * (size_t) j], pos[3 * (size_t) j + 1], pos[3 * (size_t) j + 2]};
+            V3 a = dq_transform_vertex(load_dq(dq + 8 * (size_t) i), c);
+            V3 b = dq_transform_vertex(load_dq(dq + 8 * (size_t) j), c);
+            float ex = a.x - b.x, ey = a.y - b.y, ez = a.z - b.z;
+            float e = sqrtf(ex * ex + ey * ey + ez * ez);
+            h = orc_huber(psi_reg, e);
+        }
+        out[i] = h;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* Solver: energy.t restated as a sparse linear least-squares problem, double precision        */
 

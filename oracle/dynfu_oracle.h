@@ -96,6 +96,7 @@ float orc_trunc_dist(float requested, const float voxel[3]); /* tsdf_volume.cpp:
 /* ---- robust weights (src/dynfu/utils/opt_solver.cpp:204-212, 233-239) ---- */
 float orc_tukey(float tukey_offset, float c, const float err[3]);
 float orc_huber(float k, float e);
+void orc_huber_weights(const float* pos, const float* dq, int N, float psi_reg, float* out); /* opt_solver.cpp:241-268 */
 
 /* ---- solver (opt_solver.cpp + energy.t; contract in DESIGN.md) ---- */
 typedef struct {

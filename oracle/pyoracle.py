@@ -111,6 +111,7 @@ class Oracle:
         L.orc_tukey.restype = C.c_float
         L.orc_huber.argtypes = [C.c_float, C.c_float]
         L.orc_huber.restype = C.c_float
+        L.orc_huber_weights.argtypes = [_fp, _fp, C.c_int, C.c_float, _fp]
         L.orc_solve.argtypes = [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_long, C.POINTER(SolverParams), _dp, _dp]
         L.orc_solve.restype = C.c_int
         L.orc_energy.argtypes = [_fp, _fp, C.c_int, _fp, _fp, C.c_long, C.POINTER(SolverParams), _dp, _dp]
@@ -300,6 +301,12 @@ class Oracle:
 
     def huber(self, k, e):
         return self.lib.orc_huber(k, e)
+
+    def huber_weights(self, pos, dq, psi_reg):
+        pos, dq = _f32(pos, (-1, 3)), _f32(dq, (-1, 8))
+        out = np.empty(pos.shape[0], np.float32)
+        self.lib.orc_huber_weights(_f(pos), _f(dq), pos.shape[0], psi_reg, _f(out))
+        return out
 
     def solve(self, pos, dq, dg_w, canon, live, params):
         """Returns (t[N,3] float64, dq_new[N,8] float32, stats[4])."""

@@ -308,6 +308,25 @@ def test_opt_warp_twice_thrice_reverse(dfu):
     assert np.max(np.abs(_warp(wfr, fx.WARP_SRC) - fx.WARP_SRC)) <= fx.MAX_ERROR
 
 
+def test_huber_and_tukey_weights(dfu, oracle):
+    """updateHuberWeights / updateTukeyBiweights (opt_solver.cpp:204-268): computed-but-unused in the reference"""
+    pos, dq, dg_w, t_true = synth.sphere_nodes(512, 0.03, rotations=True)
+    rng = np.random.default_rng(8)
+    canon = (pos[rng.integers(0, 512, 2000)] + rng.normal(0, 0.01, (2000, 3))).astype(np.float32)
+    live = (canon + rng.normal(0, 0.004, canon.shape)).astype(np.float32)
+    wf = make_wf(dfu, pos, dq, dg_w, 0.03)
+    s = dfu.CombinedSolver(wf, dfu.CombinedSolverParameters(numIter=0, nonLinearIter=0, linearIter=0, earlyOut=False), 4.652, 1e-2,
+                           200.0, 1e-4)
+    s.initializeProblemInstance(dev(canon), dev(live))
+    h = s.huberWeights().cpu().numpy()
+    assert np.array_equal(h, oracle.huber_weights(pos, dq, 1e-4))
+    assert h.min() < 1.0  # rotated neighbours disagree by more than psi_reg
+    s.solveAll()  # zero iterations: the final evaluation still computes the residuals (tukey weights at t = 0)
+    th = s.tukeyWeights().cpu().numpy()
+    exp = np.array([oracle.tukey(4.652, 1e-2, live[v] - canon[v]) for v in range(2000)], np.float32)
+    assert np.allclose(th, exp, rtol=1e-6, atol=1e-7)
+
+
 def test_solver_needs_8_nodes(dfu):
     with pytest.raises(dfu.DfuError) as e:
         _gpu_solve(dfu, fx.NODES_GROUP1[:5], fx.identity_dq(5), fx.WARP_SRC, fx.WARP_T1)
