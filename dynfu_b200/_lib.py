@@ -80,6 +80,13 @@ _SIGS = {
     "dfu_solver_tukey_weights": ([_vp, _vp, _vp], _i),
     "dfu_solver_get_translations": ([_vp, _vp, _vp], _i),
     "dfu_solver_get_stats_host": ([_vp, C.POINTER(C.c_double), _vp], _i),
+    "dfu_compute_points_normals": ([_vp, _sz, _i, _i, C.POINTER(_f), _vp, _sz, _vp, _sz, _vp], _i),
+    "dfu_compact_points": ([_vp, _sz, _vp, _sz, _i, _i, C.POINTER(_f), _vp, _vp, _i, _vp, _vp], _i),
+    "dfu_pointindex_create": ([C.POINTER(_vp), _i], _i),
+    "dfu_pointindex_destroy": ([_vp], _i),
+    "dfu_pointindex_build": ([_vp, _vp, _i, _vp], _i),
+    "dfu_pointindex_nearest": ([_vp, _vp, _i, _vp, _vp, _vp], _i),
+    "dfu_find_corresponding": ([_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp], _i),
 }
 EXPORTS = sorted(_SIGS)
 for _name, (_args, _res) in _SIGS.items():
@@ -116,6 +123,18 @@ def dptr(t):
         raise DfuError(1, "expected a CUDA tensor: this package has no CPU path")
     if not t.is_contiguous():
         raise DfuError(1, "expected a contiguous tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def dptr2d(t):
+    """Device pointer of a row-pitched image (rows may be strided, everything inside a row is dense)."""
+    if not t.is_cuda:
+        raise DfuError(1, "expected a CUDA tensor: this package has no CPU path")
+    inner = 1
+    for d in range(t.dim() - 1, 0, -1):
+        if t.stride(d) != inner:
+            raise DfuError(1, "expected dense rows")
+        inner *= t.shape[d]
     return C.c_void_p(t.data_ptr())
 
 

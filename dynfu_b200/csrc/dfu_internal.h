@@ -35,6 +35,14 @@ extern unsigned long long g_dfu_launches;
 
 static inline cudaStream_t as_stream(dfu_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int div_up(long a, long b) { return (int) ((a + b - 1) / b); }
+cudaMemPool_t scratch_pool(int device);  // tsdf.cu: private stream-ordered pool for per-call scratch
+static inline cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool = scratch_pool(device);
+    return pool ? cudaMallocFromPoolAsync(p, bytes, pool, st) : cudaMallocAsync(p, bytes, st);
+}
 
 // ---- the warp field handle ---------------------------------------------------------------------------
 // Node state in HBM (DESIGN.md "data layout"): three float4 arrays padded to a multiple of 32 entries.

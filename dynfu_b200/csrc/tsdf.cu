@@ -555,6 +555,8 @@ __global__ void compute_dists_kernel(const uint16_t* __restrict__ depth, size_t 
     }
 }
 
+}  // namespace
+
 // Private stream-ordered pool for the per-call scratch (depth tiles + cull flags).  The default pool hands its
 // memory back at every synchronisation (release threshold 0), which would turn each call after a sync into a real
 // allocation; this one keeps up to 64 MiB cached and leaves the application's pools alone.
@@ -578,8 +580,6 @@ cudaMemPool_t scratch_pool(int device) {
     }
     return pools[device];
 }
-
-}  // namespace
 
 extern "C" {
 

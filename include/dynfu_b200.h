@@ -202,6 +202,42 @@ int dfu_solver_get_stats_host(const dfu_solver* s, double stats_host[4], dfu_str
 int dfu_solver_huber_weights(const dfu_solver* s, float* huber, dfu_stream stream);
 int dfu_solver_tukey_weights(const dfu_solver* s, float* tukey, dfu_stream stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Front end of the frame loop (the callers either side of the hot path)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* cuda::computePointNormals (src/kfusion/imgproc.cpp:27-36 -> src/kfusion/cuda/imgproc.cu:187-226): depth u16 mm
+ * -> camera-space points and normals, float4 images (x,y,z,0), all-NaN where a pixel or its right/lower neighbour
+ * has no depth and in the last row/column.  Normalisation is cross / sqrt(dot) in IEEE arithmetic (the reference
+ * uses the approximate rsqrt; difference <= 2 ulp). */
+int dfu_compute_points_normals(const uint16_t* depth, size_t depth_pitch_bytes, int rows, int cols,
+                               const float intr_host[4], float* points4, size_t points_pitch_bytes, float* normals4,
+                               size_t normals_pitch_bytes, dfu_stream stream);
+
+/* Packs the valid (non-NaN) pixels of a points image (and, if given, normals image) into xyz arrays in raster
+ * order -- the device-side equivalent of downloading the cloud and pushing the valid entries into a
+ * dynfu::Frame (src/dynfu/dyn_fusion.cpp:120-134, src/dynfu/utils/frame.cpp:3-18).  xform_host (NULL = none) is
+ * a rigid transform {R row-major, t} applied to the points (rotation only to the normals), e.g. camera ->
+ * volume-local.  *count_out (device int) receives the number of valid pixels; at most `capacity` are written. */
+int dfu_compact_points(const float* points4, size_t points_pitch_bytes, const float* normals4,
+                       size_t normals_pitch_bytes, int rows, int cols, const float xform_host[12], float* out_v,
+                       float* out_n, int capacity, int* count_out, dfu_stream stream);
+
+/* Exact nearest-neighbour index over an arbitrary point set: replaces the nanoflann KD-tree that
+ * DynFusion::findCorrespondingFrame builds per frame (src/dynfu/dyn_fusion.cpp:212-242).  Ties resolve to the
+ * lower index; distances use nanoflann's L2_Simple_Adaptor accumulation order. */
+typedef struct dfu_pointindex dfu_pointindex;
+int dfu_pointindex_create(dfu_pointindex** out, int device);
+int dfu_pointindex_destroy(dfu_pointindex* pi);
+int dfu_pointindex_build(dfu_pointindex* pi, const float* pts_xyz, int P, dfu_stream stream);
+int dfu_pointindex_nearest(const dfu_pointindex* pi, const float* q_xyz, int Q, int32_t* idx, float* dist2,
+                           dfu_stream stream);
+/* findCorrespondingFrame in one call: out_v[i] / out_n[i] = canonical vertex / normal nearest to live_v[i].
+ * canon_n, out_n, idx_out may be NULL. */
+int dfu_find_corresponding(dfu_pointindex* pi, const float* canon_v, const float* canon_n, int P_canon,
+                           const float* live_v, int P_live, float* out_v, float* out_n, int32_t* idx_out,
+                           dfu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -453,6 +453,98 @@ void orc_compute_dists(const uint16_t* depth, size_t depth_pitch_bytes, uint16_t
     }
 }
 
+/* src/kfusion/cuda/imgproc.cu:187-215 (points_normals_kernel) with Reprojector::operator()
+ * (include/kfusion/cuda/device.hpp:50-54).  points/normals: rows*cols float4, NaN where invalid.
+ * normalized() (include/kfusion/cuda/temp_utils.hpp:91) is v * rsqrt(dot) with the GPU's approximate rsqrt; the
+ * restatement divides by the IEEE square root (documented deviation, <= 2 ulp). */
+void orc_points_normals(const uint16_t* depth, size_t depth_pitch_bytes, int rows, int cols, const float intr[4],
+                        float* points4, float* normals4) {
+    const float finvx = 1.f / intr[0], finvy = 1.f / intr[1], cx = intr[2], cy = intr[3];
+    const float qnan = std::numeric_limits<float>::quiet_NaN();
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < rows; ++y) {
+        const uint16_t* r0 = (const uint16_t*) ((const char*) depth + (size_t) y * depth_pitch_bytes);
+        const uint16_t* r1 = (const uint16_t*) ((const char*) depth + (size_t) (y + 1 < rows ? y + 1 : y) * depth_pitch_bytes);
+        for (int x = 0; x < cols; ++x) {
+            float* P = points4 + 4 * ((size_t) y * cols + x);
+            float* Nn = normals4 + 4 * ((size_t) y * cols + x);
+            for (int c = 0; c < 4; ++c) P[c] = Nn[c] = qnan;
+            if (x >= cols - 1 || y >= rows - 1) continue;
+            const float z00 = (float) r0[x] * 0.001f, z01 = (float) r0[x + 1] * 0.001f, z10 = (float) r1[x] * 0.001f;
+            if (z00 * z01 * z10 != 0) {
+                auto reproj = [&](int u, int v, float z, float o[3]) {
+                    o[0] = z * ((float) u - cx) * finvx;
+                    o[1] = z * ((float) v - cy) * finvy;
+                    o[2] = z;
+                };
+                float v00[3], v01[3], v10[3];
+                reproj(x, y, z00, v00);
+                reproj(x + 1, y, z01, v01);
+                reproj(x, y + 1, z10, v10);
+                const float a[3] = {v01[0] - v00[0], v01[1] - v00[1], v01[2] - v00[2]};
+                const float b[3] = {v10[0] - v00[0], v10[1] - v00[1], v10[2] - v00[2]};
+                const float c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+                const float len = sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+                Nn[0] = -(c[0] / len); Nn[1] = -(c[1] / len); Nn[2] = -(c[2] / len); Nn[3] = 0.f;
+                P[0] = v00[0]; P[1] = v00[1]; P[2] = v00[2]; P[3] = 0.f;
+            }
+        }
+    }
+}
+
+/* The valid entries of a points(/normals) image in raster order, as the reference collects them on the host
+ * (src/dynfu/dyn_fusion.cpp:120-134 pushes every downloaded vertex; src/dynfu/utils/frame.cpp keeps them as
+ * given); xform = {R row-major, t} or NULL.  Returns the number of valid pixels. */
+long orc_compact_points(const float* points4, const float* normals4_or_null, int rows, int cols, const float* xform,
+                        float* out_v, float* out_n_or_null) {
+    long n = 0;
+    for (long i = 0; i < (long) rows * cols; ++i) {
+        const float* p = points4 + 4 * i;
+        const float* q = normals4_or_null ? normals4_or_null + 4 * i : nullptr;
+        if (p[0] != p[0] || p[1] != p[1] || p[2] != p[2]) continue;
+        if (q && (q[0] != q[0] || q[1] != q[1] || q[2] != q[2])) continue;
+        float v[3] = {p[0], p[1], p[2]}, m[3] = {q ? q[0] : 0.f, q ? q[1] : 0.f, q ? q[2] : 0.f};
+        if (xform) {
+            for (int r = 0; r < 3; ++r) {
+                v[r] = fmaf(xform[3 * r + 2], p[2], fmaf(xform[3 * r + 1], p[1], fmaf(xform[3 * r], p[0], xform[9 + r])));
+                if (q) m[r] = fmaf(xform[3 * r + 2], q[2], fmaf(xform[3 * r + 1], q[1], xform[3 * r] * q[0]));
+            }
+        }
+        for (int c = 0; c < 3; ++c) {
+            out_v[3 * n + c] = v[c];
+            if (out_n_or_null) out_n_or_null[3 * n + c] = m[c];
+        }
+        ++n;
+    }
+    return n;
+}
+
+/* DynFusion::findCorrespondingFrame (src/dynfu/dyn_fusion.cpp:212-242): a KD-tree over the canonical vertices,
+ * 1-NN per live vertex, gather vertex and normal.  Returns the number of live vertices whose two nearest
+ * canonical vertices are at bit-equal distance (0 when built against nanoflann, which cannot tell). */
+long orc_find_corresponding(const float* canon_v, const float* canon_n_or_null, int P_canon, const float* live_v, long P_live,
+                            float* out_v, float* out_n_or_null, int32_t* idx_out_or_null) {
+    KnnIndex index(canon_v, P_canon);
+    long ties = 0;
+#pragma omp parallel for schedule(static) reduction(+ : ties)
+    for (long i = 0; i < P_live; ++i) {
+        int32_t idx[2];
+        float d2[2];
+#ifdef ORC_USE_NANOFLANN
+        index.query(live_v + 3 * i, 1, idx, d2);
+#else
+        int n = index.query(live_v + 3 * i, std::min(2, P_canon), idx, d2);
+        if (n == 2 && d2[0] == d2[1]) ++ties;
+#endif
+        for (int c = 0; c < 3; ++c) {
+            out_v[3 * i + c] = canon_v[3 * (size_t) idx[0] + c];
+            if (canon_n_or_null && out_n_or_null) out_n_or_null[3 * i + c] = canon_n_or_null[3 * (size_t) idx[0] + c];
+        }
+        if (idx_out_or_null) idx_out_or_null[i] = idx[0];
+    }
+    return ties;
+}
+
 uint16_t orc_float2half(float f) { return float2half(f); }
 float orc_half2float(uint16_t h) { return half2float(h); }
 

@@ -78,6 +78,14 @@ void orc_compute_dists(const uint16_t* depth, size_t depth_pitch_bytes, uint16_t
                        size_t dists_pitch_bytes, int rows, int cols, const float intr[4]);
 
 /* ---- half helpers (include/kfusion/cuda/device.hpp:59-67) ---- */
+/* ---- depth -> points + normals (src/kfusion/cuda/imgproc.cu:187-215) ---- */
+void orc_points_normals(const uint16_t* depth, size_t depth_pitch_bytes, int rows, int cols, const float intr[4],
+                        float* points4, float* normals4);
+long orc_compact_points(const float* points4, const float* normals4_or_null, int rows, int cols, const float* xform,
+                        float* out_v, float* out_n_or_null);
+/* ---- live -> canonical correspondences (src/dynfu/dyn_fusion.cpp:212-242) ---- */
+long orc_find_corresponding(const float* canon_v, const float* canon_n_or_null, int P_canon, const float* live_v,
+                            long P_live, float* out_v, float* out_n_or_null, int32_t* idx_out_or_null);
 uint16_t orc_float2half(float f);
 float    orc_half2float(uint16_t h);
 

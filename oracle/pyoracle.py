@@ -97,6 +97,11 @@ class Oracle:
         L.orc_blend.argtypes = [_fp, _fp, _fp, C.c_int, _fp, C.c_long, C.c_int, _fp]
         L.orc_warp.argtypes = [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_long, C.c_int, C.c_int, _fp, _fp]
         L.orc_compute_dists.argtypes = [_u16p, C.c_size_t, _u16p, C.c_size_t, C.c_int, C.c_int, _fp]
+        L.orc_points_normals.argtypes = [_u16p, C.c_size_t, C.c_int, C.c_int, _fp, _fp, _fp]
+        L.orc_compact_points.argtypes = [_fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp]
+        L.orc_compact_points.restype = C.c_long
+        L.orc_find_corresponding.argtypes = [_fp, _fp, C.c_int, _fp, C.c_long, _fp, _fp, _ip]
+        L.orc_find_corresponding.restype = C.c_long
         L.orc_float2half.argtypes = [C.c_float]
         L.orc_float2half.restype = C.c_uint16
         L.orc_half2float.argtypes = [C.c_uint16]
@@ -258,6 +263,37 @@ class Oracle:
         self.lib.orc_compute_dists(depth.ctypes.data_as(_u16p), cols * 2, out.ctypes.data_as(_u16p), cols * 2, rows,
                                    cols, _f(intr))
         return out
+
+    def points_normals(self, depth, intr):
+        """cuda::computePointNormals: (rows, cols, 4) points and normals, NaN where invalid."""
+        depth = np.ascontiguousarray(depth, np.uint16)
+        rows, cols = depth.shape
+        pts = np.empty((rows, cols, 4), np.float32)
+        nrm = np.empty((rows, cols, 4), np.float32)
+        self.lib.orc_points_normals(depth.ctypes.data_as(_u16p), cols * 2, rows, cols, _f(_f32(intr)), _f(pts), _f(nrm))
+        return pts, nrm
+
+    def compact_points(self, pts4, nrm4=None, xform=None):
+        pts4 = _f32(pts4)
+        rows, cols = pts4.shape[:2]
+        nrm4 = _f32(nrm4) if nrm4 is not None else None
+        xf = _f32(xform) if xform is not None else None
+        v = np.empty((rows * cols, 3), np.float32)
+        n = np.empty((rows * cols, 3), np.float32) if nrm4 is not None else None
+        cnt = self.lib.orc_compact_points(_f(pts4), _f(nrm4), rows, cols, _f(xf), _f(v), _f(n))
+        return (v[:cnt].copy(), n[:cnt].copy()) if n is not None else v[:cnt].copy()
+
+    def find_corresponding(self, canon_v, canon_n, live_v):
+        """DynFusion::findCorrespondingFrame: (vertices, normals, indices, ties)."""
+        canon_v, live_v = _f32(canon_v, (-1, 3)), _f32(live_v, (-1, 3))
+        canon_n = _f32(canon_n, (-1, 3)) if canon_n is not None else None
+        P = live_v.shape[0]
+        ov = np.empty((P, 3), np.float32)
+        on = np.empty((P, 3), np.float32) if canon_n is not None else None
+        idx = np.empty(P, np.int32)
+        ties = self.lib.orc_find_corresponding(_f(canon_v), _f(canon_n), canon_v.shape[0], _f(live_v), P, _f(ov), _f(on),
+                                               idx.ctypes.data_as(_ip))
+        return ov, on, idx, ties
 
     def float2half(self, f):
         return self.lib.orc_float2half(f)
