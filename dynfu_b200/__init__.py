@@ -13,3 +13,4 @@ from .warpfield import Warpfield  # noqa: F401
 from .tsdf_volume import TsdfVolume, compute_dists  # noqa: F401
 from .solver import CombinedSolver, CombinedSolverParameters  # noqa: F401
 from .dyn_fusion import DynFusion, DynFuParams, KinFuParams  # noqa: F401
+from . import frontend  # noqa: F401

@@ -82,6 +82,10 @@ _SIGS = {
     "dfu_solver_get_stats_host": ([_vp, C.POINTER(C.c_double), _vp], _i),
     "dfu_compute_points_normals": ([_vp, _sz, _i, _i, C.POINTER(_f), _vp, _sz, _vp, _sz, _vp], _i),
     "dfu_compact_points": ([_vp, _sz, _vp, _sz, _i, _i, C.POINTER(_f), _vp, _vp, _i, _vp, _vp], _i),
+    "dfu_warpfield_unsupported": ([_vp, _vp, _i, _vp, _vp], _i),
+    "dfu_voxel_grid_filter": ([_vp, _i, _f, _vp, C.POINTER(_i), _vp], _i),
+    "dfu_warpfield_update": ([_vp, _vp, _i, _i, C.POINTER(_i), C.POINTER(_i), _vp], _i),
+    "dfu_warpfield_cache_stats": ([_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _vp], _i),
     "dfu_pointindex_create": ([C.POINTER(_vp), _i], _i),
     "dfu_pointindex_destroy": ([_vp], _i),
     "dfu_pointindex_build": ([_vp, _vp, _i, _vp], _i),

@@ -53,7 +53,8 @@ struct BrickTable {            // per-volume-geometry acceleration data for the 
     size_t capacity = 0;       // bricks allocated
     int dims[3] = {0, 0, 0};
     float voxel[3] = {0, 0, 0};
-    uint64_t node_epoch = 0;   // positions epoch the table was built for
+    uint64_t node_epoch = 0;   // positions epoch the bounds were built for
+    uint64_t cache_epoch = 0;  // positions epoch the built[] flags of the voxel cache are valid for
     bool valid = false;
     // per-voxel 8-NN + weight cache (filled lazily by the integrator, valid while node POSITIONS are unchanged: ids
     // and Gaussian weights depend only on the canonical voxel and node positions, never on the node transforms):

@@ -12,6 +12,7 @@
 
 #include "dfu_internal.h"
 #include "dfu_math.cuh"
+#include "scan.cuh"
 
 using namespace dfu;
 
@@ -70,29 +71,6 @@ __global__ void chunk_count_kernel(const float4* __restrict__ points, size_t ppi
     const unsigned m = __ballot_sync(0xffffffffu, ok);
     if (lane == 0) counts[chunk] = __popc(m);
 }
-// exclusive scan of n counts (single CTA), total to *total
-__global__ void __launch_bounds__(1024) small_scan_kernel(int* __restrict__ counts, int n, int* __restrict__ total) {
-    __shared__ int sh[1024];
-    const int per = (n + 1023) / 1024;
-    const int lo = min(n, (int) threadIdx.x * per), hi = min(n, lo + per);
-    int s = 0;
-    for (int i = lo; i < hi; ++i) s += counts[i];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int v = (int) threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-        __syncthreads();
-        sh[threadIdx.x] += v;
-        __syncthreads();
-    }
-    int run = sh[threadIdx.x] - s;
-    for (int i = lo; i < hi; ++i) {
-        const int c = counts[i];
-        counts[i] = run;
-        run += c;
-    }
-    if (threadIdx.x == 1023) *total = sh[1023];
-}
 // one warp per chunk writes its valid pixels at the chunk's offset, in x order; optional rigid transform of the points
 // (rotation only for the normals)
 __global__ void chunk_emit_kernel(const float4* __restrict__ points, size_t ppitch, const float4* __restrict__ normals, size_t npitch,
@@ -134,13 +112,6 @@ struct PGrid {
 };
 constexpr int PG_MAX_DIM = 160;
 constexpr int PG_MAX_CELLS = PG_MAX_DIM * PG_MAX_DIM * PG_MAX_DIM;
-
-// order-preserving float <-> uint map for atomicMin/Max
-DFU_DEV unsigned f2ord(float f) {
-    const unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-DFU_DEV float ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
 // bbox[0..2] = min (ordered uint), bbox[3..5] = max, bbox[6] = CTAs done; the last CTA derives the first-guess grid
 __global__ void __launch_bounds__(256) pg_bbox_kernel(const float* __restrict__ pts, int P, unsigned* __restrict__ bbox,

@@ -649,11 +649,14 @@ int dfu_wf_refresh_flags(dfu_warpfield* wf, cudaStream_t st) {
 int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float voxel[3], int z0, int z1, cudaStream_t st) {
     BrickTable& bt = wf->bricks;
     const int zb0 = z0 / 8, zb1 = (z1 + 7) / 8;
-    const bool same = bt.valid && bt.node_epoch == wf->node_epoch && bt.dims[0] == dims[0] && bt.dims[1] == dims[1] &&
-                      bt.dims[2] == dims[2] && bt.voxel[0] == voxel[0] && bt.voxel[1] == voxel[1] &&
-                      bt.voxel[2] == voxel[2];
+    const bool geom = bt.valid && bt.dims[0] == dims[0] && bt.dims[1] == dims[1] && bt.dims[2] == dims[2] &&
+                      bt.voxel[0] == voxel[0] && bt.voxel[1] == voxel[1] && bt.voxel[2] == voxel[2];
+    const bool same = geom && bt.node_epoch == wf->node_epoch;
     const bool pool_covers = bt.pool_bricks == 0 || (zb0 >= bt.pool_zb0 && zb1 <= bt.pool_zb1);
-    if (same && pool_covers) return DFU_OK;
+    // the built[] flags survive a change of the node set when Warpfield::update has already cleared the bricks its
+    // new nodes can reach (cache_epoch is then the current epoch although the bounds are stale)
+    const bool cache_ok = geom && bt.cache_epoch == wf->node_epoch && pool_covers;
+    if (same && cache_ok) return DFU_OK;
     const int bd[3] = {dims[0] / 8, dims[1] / 8, (dims[2] + 7) / 8};
     const size_t nb = (size_t) bd[0] * bd[1] * bd[2];
     if (!same) {
@@ -694,16 +697,20 @@ int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float v
         bt.pool_bricks = 0;
     }
     if (want) {
-        if (bt.pool_bricks == 0) {
+        const bool fresh = bt.pool_bricks == 0;
+        if (fresh) {
             DFU_CUDA_OK(cudaMalloc(&bt.knn_pool, nbp * 8192ull));
             DFU_CUDA_OK(cudaMalloc(&bt.w_pool, nbp * 16384ull));
             DFU_CUDA_OK(cudaMalloc(&bt.built, nbp));
             bt.pool_bricks = nbp;
         }
-        DFU_CUDA_OK(cudaMemsetAsync(bt.built, 0, bt.pool_bricks, st));
-        bt.pool_zb0 = zb0;
-        bt.pool_zb1 = zb1;
+        if (fresh || !cache_ok) {
+            DFU_CUDA_OK(cudaMemsetAsync(bt.built, 0, bt.pool_bricks, st));
+            bt.pool_zb0 = zb0;
+            bt.pool_zb1 = zb1;
+        }
     }
+    bt.cache_epoch = wf->node_epoch;
     bt.node_epoch = wf->node_epoch;
     bt.valid = true;
     return DFU_OK;

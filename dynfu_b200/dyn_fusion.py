@@ -2,12 +2,17 @@
 src/kfusion/kinfu.cpp:140-234, src/dynfu/dyn_fusion.cpp:48-145), restricted to the steps SURVEY.md §8 puts in
 scope: computeDists -> warpToLive (kNN + DQB) -> CombinedSolver -> warped TSDF integration.
 
-Marching cubes, ICP and the 1-NN correspondence search are NOT on the path (§8f): canonical vertices and the
-live vertices paired with them are supplied by the caller, exactly like the reference's solver tests do."""
+The rows either side of the path (§8f) are wired in as well: live vertices come from the depth image
+(cuda::computePointNormals + compaction, in place of the reference's marching-cubes download with its faked
+normals, dyn_fusion.cpp:126-134), correspondences from the grid 1-NN (findCorrespondingFrame, :212-242) and the
+warp field grows through Warpfield::update (:142).  Marching cubes and ICP stay out (rendering / the reference
+skips ICP itself, :100-105); canonical vertices can still be supplied by the caller like the solver tests do."""
 from dataclasses import dataclass, field
 
+import numpy as np
 import torch
 
+from . import frontend
 from ._lib import BLEND_REF_COMPOSE
 from .solver import CombinedSolver, CombinedSolverParameters
 from .tsdf_volume import TsdfVolume, compute_dists
@@ -63,6 +68,11 @@ class DynFusion:
         self.canonicalWarpedToLive = None
         self._depth_dev = torch.empty((kp.rows, kp.cols), dtype=torch.int16, device=self.device)
         self._dists = torch.empty_like(self._depth_dev)
+        self._points = torch.empty((kp.rows, kp.cols, 4), dtype=torch.float32, device=self.device)
+        self._normals = torch.empty_like(self._points)
+        self._index = None     # frontend.PointIndex, built per frame like the reference's second KD-tree
+        self.liveVertices = None
+        self.liveNormals = None
         self.allreduce = None  # python all-reduce hook (tests)
         self.comm = None       # dynfu_b200.dist.Communicator: NCCL issued from C++
 
@@ -77,7 +87,8 @@ class DynFusion:
             n = pos.shape[0]
             dq = torch.zeros((n, 8), dtype=torch.float32, device=self.device)
             dq[:, 0] = 1.0
-            w = torch.full((n,), 3 * self.params.epsilon, dtype=torch.float32, device=self.device)  # :156
+            w = torch.full((n,), float(np.float32(3) * np.float32(self.params.epsilon)), dtype=torch.float32,
+                           device=self.device)  # :156, float arithmetic
         else:
             pos, dq, w = nodes
         self.warpfield = Warpfield(self.device)
@@ -96,10 +107,50 @@ class DynFusion:
         return self._depth_dev
 
     # DynFusion::warpCanonicalToLiveOpt (src/dynfu/dyn_fusion.cpp:182-210)
-    def warpCanonicalToLiveOpt(self, liveVertices):
-        self.canonicalWarpedToLive, _ = self.warpfield.warpToLive(self.canonicalVertices, None, self.params.blend_mode)
-        self.solver.initializeProblemInstance(self.canonicalWarpedToLive, liveVertices)
+    def warpCanonicalToLiveOpt(self, liveVertices, paired=True):
+        """paired=True: liveVertices[i] belongs to canonicalVertices[i] (the solver tests' convention).
+        paired=False: the reference's flow -- warp the canonical frame, then pick for every live vertex the nearest
+        warped canonical vertex (findCorrespondingFrame, :196-197) and solve on those pairs."""
+        self.canonicalWarpedToLive, warpedNormals = self.warpfield.warpToLive(self.canonicalVertices, self.canonicalNormals,
+                                                                              self.params.blend_mode)
+        if paired:
+            self.solver.initializeProblemInstance(self.canonicalWarpedToLive, liveVertices)
+        else:
+            corr_v, _ = self.findCorrespondingFrame(self.canonicalWarpedToLive, warpedNormals, liveVertices)
+            self.solver.initializeProblemInstance(corr_v, liveVertices)
         self.solver.solveAll()
+
+    # DynFusion::findCorrespondingFrame (src/dynfu/dyn_fusion.cpp:212-242)
+    def findCorrespondingFrame(self, canonicalVertices, canonicalNormals, liveVertices):
+        if self._index is None:
+            self._index = frontend.PointIndex(self.device)
+        return self._index.find_corresponding(canonicalVertices, canonicalNormals, liveVertices)
+
+    # live surface points of a depth frame in the frame of the volume (the nodes' frame): cuda::computePointNormals
+    # (kinfu.cpp:170-173) + compaction; replaces the marching-cubes download of dyn_fusion.cpp:120-134
+    def liveFrameFromDepth(self, depth_dev):
+        kp = self.params.kinfuParams
+        frontend.compute_points_normals(depth_dev, kp.intr, self._points, self._normals)
+        cam2vol = torch.linalg.inv(self.volume.pose) @ self.camera_pose
+        self.liveVertices, self.liveNormals = frontend.compact_points(self._points, self._normals, cam2vol)
+        return self.liveVertices, self.liveNormals
+
+    # one fully automatic frame: DynFusion::operator() with the front-end rows on the device
+    def processFrame(self, depth_host):
+        kp = self.params.kinfuParams
+        depth = self.uploadDepth(depth_host)
+        compute_dists(depth, kp.intr, out=self._dists)  # :55
+        live_v, live_n = self.liveFrameFromDepth(depth)
+        if self.frame_counter == 0 or self.warpfield is None:
+            self.volume.integrate(self._dists, self.camera_pose, kp.intr)  # :70
+            self.init(live_v, live_n)  # :88 (vertices of the first frame are the canonical frame)
+            self.frame_counter += 1
+            return False
+        self.warpCanonicalToLiveOpt(live_v, paired=False)  # :140
+        self.warpfield.update(self.canonicalWarpedToLive, self.params.blend_mode)  # :142
+        self.volume.integrate(self._dists, self.camera_pose, kp.intr, self.warpfield, self.params.blend_mode)
+        self.frame_counter += 1
+        return True
 
     # DynFusion::operator() (src/dynfu/dyn_fusion.cpp:48-145), hot-path steps
     def __call__(self, depth_host, liveVertices=None):

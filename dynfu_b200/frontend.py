@@ -4,6 +4,7 @@
     compact_points          the host-side collection of the downloaded cloud (src/dynfu/dyn_fusion.cpp:120-134)
     PointIndex              the per-frame nanoflann KD-tree of DynFusion::findCorrespondingFrame
     find_corresponding      DynFusion::findCorrespondingFrame (src/dynfu/dyn_fusion.cpp:212-242)
+    voxel_grid_filter       pcl::VoxelGrid as used by Warpfield::update (src/dynfu/warp_field.cpp:68-72)
 """
 import ctypes as C
 
@@ -50,6 +51,15 @@ def compact_points(points, normals=None, xform=None, capacity=None, sync=True):
         return out_v, out_n, count
     n = min(int(count.item()), cap)
     return out_v[:n], (out_n[:n] if out_n is not None else None)
+
+
+def voxel_grid_filter(points, leaf=0.05):
+    """pcl::VoxelGrid<PointXYZ> with a cubic leaf (src/dynfu/warp_field.cpp:68-72): centroids, ascending cell index."""
+    p = points.reshape(-1, 3).contiguous()
+    out = torch.empty_like(p)
+    m = C.c_int()
+    check(lib.dfu_voxel_grid_filter(dptr(p), p.shape[0], float(leaf), dptr(out), C.byref(m), stream_ptr()))
+    return out[:m.value]
 
 
 class PointIndex:

@@ -73,6 +73,27 @@ class Warpfield:
         t = _f32(translations, (self.numNodes(), 3), self.device)
         check(lib.dfu_warpfield_update_translations(self._h, dptr(t), stream_ptr()))
 
+    # Warpfield::getUnsupportedVertices (src/dynfu/warp_field.cpp:34-62): the unsupported vertices, in input order
+    def getUnsupportedVertices(self, vertices, return_mask=False):
+        v = _f32(vertices, (-1, 3), self.device)
+        flags = torch.empty(v.shape[0], dtype=torch.uint8, device=self.device)
+        check(lib.dfu_warpfield_unsupported(self._h, dptr(v), v.shape[0], dptr(flags), stream_ptr()))
+        mask = flags.bool()
+        return mask if return_mask else v[mask]
+
+    # Warpfield::update (src/dynfu/warp_field.cpp:64-95): returns (number of unsupported vertices, nodes added)
+    def update(self, vertices, blend_mode=BLEND_REF_COMPOSE):
+        v = _f32(vertices, (-1, 3), self.device)
+        nu, nn = C.c_int(), C.c_int()
+        check(lib.dfu_warpfield_update(self._h, dptr(v), v.shape[0], blend_mode, C.byref(nu), C.byref(nn), stream_ptr()))
+        return nu.value, nn.value
+
+    def cacheStats(self):
+        """(bricks the per-voxel neighbour cache holds, bricks currently valid) -- diagnostics"""
+        a, b = C.c_longlong(), C.c_longlong()
+        check(lib.dfu_warpfield_cache_stats(self._h, C.byref(a), C.byref(b), stream_ptr()))
+        return a.value, b.value
+
     # Warpfield::findNeighborsIndex (src/dynfu/warp_field.cpp:111-122), for [Q,3] vertices at once
     def findNeighborsIndex(self, numNeighbor, vertices, return_dist=False):
         if numNeighbor != KNN:

@@ -43,7 +43,8 @@ typedef enum {
     DFU_ERR_CUDA = 2,         /* CUDA runtime error; message in dfu_last_error()                    */
     DFU_ERR_PRECONDITION = 3, /* e.g. fewer than 8 nodes for the solver (reference UB,              */
                               /* src/dynfu/utils/opt_solver.cpp:63-66)                              */
-    DFU_ERR_NOT_INIT = 4      /* handle used before init (nanoflann throws, nanoflann.hpp:1209)     */
+    DFU_ERR_NOT_INIT = 4,     /* handle used before init (nanoflann throws, nanoflann.hpp:1209)     */
+    DFU_ERR_UNSUPPORTED = 5   /* input outside what the device tables hold (message says which)     */
 } dfu_status;
 
 /* how the 8 weighted node transforms are combined */
@@ -237,6 +238,30 @@ int dfu_pointindex_nearest(const dfu_pointindex* pi, const float* q_xyz, int Q, 
 int dfu_find_corresponding(dfu_pointindex* pi, const float* canon_v, const float* canon_n, int P_canon,
                            const float* live_v, int P_live, float* out_v, float* out_n, int32_t* idx_out,
                            dfu_stream stream);
+
+/* Warpfield::getUnsupportedVertices (src/dynfu/warp_field.cpp:34-62): flags[i] = 1 when
+ * min_k |v_i - n_k| / dg_w_k >= 1 over the 8 nearest nodes (distance in double, stored as float, like the
+ * reference's sqrt(pow()+pow()+pow())). */
+int dfu_warpfield_unsupported(const dfu_warpfield* wf, const float* verts_xyz, int P, uint8_t* flags,
+                              dfu_stream stream);
+
+/* pcl::VoxelGrid<pcl::PointXYZ> with a cubic leaf (PCL 1.8.1, filters/impl/voxel_grid.hpp:212-437; the filter
+ * Warpfield::update applies with a 5 cm leaf, src/dynfu/warp_field.cpp:68-72): one centroid per non-empty cell,
+ * cells in ascending linear index.  Inside a cell the points are added in ascending index (PCL's std::sort leaves
+ * that order implementation defined).  out_xyz needs room for U points; *M_host receives the number written.
+ * Synchronises the stream.  DFU_ERR_UNSUPPORTED if the cell table would exceed 2^21 cells. */
+int dfu_voxel_grid_filter(const float* pts_xyz, int U, float leaf, float* out_xyz, int* M_host, dfu_stream stream);
+
+/* Warpfield::update (src/dynfu/warp_field.cpp:64-95): finds the unsupported vertices of the frame, decimates them
+ * on a 5 cm grid, appends one node per centroid (dg_se3 = calcDQB(centroid) w.r.t. the nodes before the call,
+ * dg_w = 2*epsilon) and re-indexes.  Existing node indices are preserved.  The integrator's per-voxel neighbour
+ * cache is invalidated only for bricks a new node can reach.  Synchronises the stream (the node count changes). */
+int dfu_warpfield_update(dfu_warpfield* wf, const float* verts_xyz, int P, int blend_mode, int* num_unsupported_host,
+                         int* num_new_host, dfu_stream stream);
+
+/* Diagnostics of the integrator's per-voxel neighbour cache: bricks the pool holds, bricks currently valid. */
+int dfu_warpfield_cache_stats(const dfu_warpfield* wf, long long* pool_bricks_host, long long* built_bricks_host,
+                              dfu_stream stream);
 
 #ifdef __cplusplus
 }

@@ -545,6 +545,123 @@ long orc_find_corresponding(const float* canon_v, const float* canon_n_or_null, 
     return ties;
 }
 
+/* ---- Warpfield::update (src/dynfu/warp_field.cpp:34-95) ------------------------------------------------------ */
+
+/* getUnsupportedVertices (:34-62): a vertex is unsupported when min_k dist(v, n_k) / dg_w_k >= 1 over its 8 nearest
+ * nodes.  `sqrt(pow(dx,2)+pow(dy,2)+pow(dz,2))` is evaluated in double (std::pow(float,int) promotes) and stored in a
+ * float.  flags_out[P]; returns the number of unsupported vertices. */
+long orc_unsupported(const float* pos, const float* dg_w, int N, const float* verts, long P, uint8_t* flags_out) {
+    KnnIndex index(pos, N);
+    long count = 0;
+#pragma omp parallel for schedule(static) reduction(+ : count)
+    for (long i = 0; i < P; ++i) {
+        int32_t idx[16];
+        float d2[16];
+        const float* v = verts + 3 * i;
+        int n = index.query(v, std::min(8, N), idx, d2);
+        float mn = HUGE_VALF;
+        for (int k = 0; k < n; ++k) {
+            const float* c = pos + 3 * (size_t) idx[k];
+            const float dx = v[0] - c[0], dy = v[1] - c[1], dz = v[2] - c[2];
+            const double s = ((double) dx * (double) dx + (double) dy * (double) dy) + (double) dz * (double) dz;
+            const float dist = (float) std::sqrt(s);
+            const float r = dist / dg_w[idx[k]];
+            if (r <= mn) mn = r;
+        }
+        flags_out[i] = mn >= 1 ? 1 : 0;
+        count += flags_out[i];
+    }
+    return count;
+}
+
+/* pcl::VoxelGrid<pcl::PointXYZ>::applyFilter -- PCL 1.8.1 (CMakeLists.txt:63 of the reference; PCL is not vendored in
+ * the reference tree, so this restates filters/include/pcl/filters/impl/voxel_grid.hpp:212-437 from its published
+ * algorithm): bounding box -> integer cell of every point -> points grouped by cell -> one centroid per non-empty
+ * cell, cells in ascending linear index.  The centroid accumulates in float (AccumulatorXYZ) and divides by the
+ * count.  PCL groups with an UNSTABLE std::sort, so the order of the float additions inside a cell is
+ * implementation defined there; order_mode 0 adds in ascending point index (the canonical order the GPU path
+ * reproduces), order_mode 1 reproduces std::sort on (cell) keys with this libstdc++ to measure the difference.
+ * Returns the number of output points, or -1 if the grid would overflow int32 (PCL then returns its input). */
+long orc_voxel_grid(const float* pts, long U, const float leaf[3], float* out, int order_mode) {
+    if (U <= 0) return 0;
+    const float inv[3] = {1.f / leaf[0], 1.f / leaf[1], 1.f / leaf[2]};
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (long i = 0; i < U; ++i)
+        for (int c = 0; c < 3; ++c) {
+            mn[c] = std::min(mn[c], pts[3 * i + c]);
+            mx[c] = std::max(mx[c], pts[3 * i + c]);
+        }
+    int64_t d[3];
+    for (int c = 0; c < 3; ++c) d[c] = (int64_t) ((mx[c] - mn[c]) * inv[c]) + 1;
+    if (d[0] * d[1] * d[2] > (int64_t) INT32_MAX) return -1;
+    int min_b[3], div_b[3];
+    for (int c = 0; c < 3; ++c) {
+        min_b[c] = (int) floorf(mn[c] * inv[c]);
+        div_b[c] = (int) floorf(mx[c] * inv[c]) - min_b[c] + 1;
+    }
+    const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+    struct Entry {
+        unsigned idx;
+        unsigned pt;
+        bool operator<(const Entry& o) const { return idx < o.idx; }
+    };
+    std::vector<Entry> ev((size_t) U);
+    for (long i = 0; i < U; ++i) {
+        int ijk[3];
+        for (int c = 0; c < 3; ++c) ijk[c] = (int) (floorf(pts[3 * i + c] * inv[c]) - (float) min_b[c]);
+        ev[(size_t) i] = Entry{(unsigned) (ijk[0] * mul[0] + ijk[1] * mul[1] + ijk[2] * mul[2]), (unsigned) i};
+    }
+    if (order_mode == 1)
+        std::sort(ev.begin(), ev.end());
+    else
+        std::stable_sort(ev.begin(), ev.end());
+    long M = 0;
+    for (size_t a = 0; a < ev.size();) {
+        size_t b = a;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        while (b < ev.size() && ev[b].idx == ev[a].idx) {
+            sx += pts[3 * (size_t) ev[b].pt];
+            sy += pts[3 * (size_t) ev[b].pt + 1];
+            sz += pts[3 * (size_t) ev[b].pt + 2];
+            ++b;
+        }
+        const float n = (float) (b - a);
+        out[3 * M] = sx / n; out[3 * M + 1] = sy / n; out[3 * M + 2] = sz / n;
+        ++M;
+        a = b;
+    }
+    return M;
+}
+
+/* Warpfield::update (:64-95): unsupported vertices -> 5 cm voxel-grid decimation -> one new node per centroid with
+ * dg_se3 = calcDQB(centroid) against the OLD node set (the KD-tree is rebuilt only after the loop) and
+ * dg_w = 2 * epsilon; new nodes are appended.  Output arrays need room for N + P nodes; returns the new node count. */
+long orc_warpfield_update(const float* pos, const float* dq, const float* dg_w, int N, float epsilon, const float* verts,
+                          long P, int blend_mode, float* pos_out, float* dq_out, float* w_out) {
+    std::vector<uint8_t> flags((size_t) std::max<long>(P, 1));
+    orc_unsupported(pos, dg_w, N, verts, P, flags.data());
+    std::vector<float> uns;
+    for (long i = 0; i < P; ++i)
+        if (flags[(size_t) i]) uns.insert(uns.end(), verts + 3 * i, verts + 3 * i + 3);
+    const long U = (long) uns.size() / 3;
+    std::vector<float> cent((size_t) std::max<long>(3 * U, 3));
+    const float leaf[3] = {(float) 0.05, 0.05f, 0.05f};
+    long M = orc_voxel_grid(uns.data(), U, leaf, cent.data(), 0);
+    if (M < 0) {  // PCL hands the input back unfiltered
+        M = U;
+        cent = uns;
+    }
+    std::memcpy(pos_out, pos, (size_t) N * 3 * sizeof(float));
+    std::memcpy(dq_out, dq, (size_t) N * 8 * sizeof(float));
+    std::memcpy(w_out, dg_w, (size_t) N * sizeof(float));
+    if (M > 0) {
+        std::memcpy(pos_out + 3 * (size_t) N, cent.data(), (size_t) M * 3 * sizeof(float));
+        orc_blend(pos, dq, dg_w, N, cent.data(), M, blend_mode, dq_out + 8 * (size_t) N);
+        for (long i = 0; i < M; ++i) w_out[N + i] = 2 * epsilon;
+    }
+    return N + M;
+}
+
 uint16_t orc_float2half(float f) { return float2half(f); }
 float orc_half2float(uint16_t h) { return half2float(h); }
 

@@ -86,6 +86,11 @@ long orc_compact_points(const float* points4, const float* normals4_or_null, int
 /* ---- live -> canonical correspondences (src/dynfu/dyn_fusion.cpp:212-242) ---- */
 long orc_find_corresponding(const float* canon_v, const float* canon_n_or_null, int P_canon, const float* live_v,
                             long P_live, float* out_v, float* out_n_or_null, int32_t* idx_out_or_null);
+/* ---- Warpfield::update (src/dynfu/warp_field.cpp:34-95) ---- */
+long orc_unsupported(const float* pos, const float* dg_w, int N, const float* verts, long P, uint8_t* flags_out);
+long orc_voxel_grid(const float* pts, long U, const float leaf[3], float* out, int order_mode);
+long orc_warpfield_update(const float* pos, const float* dq, const float* dg_w, int N, float epsilon,
+                          const float* verts, long P, int blend_mode, float* pos_out, float* dq_out, float* w_out);
 uint16_t orc_float2half(float f);
 float    orc_half2float(uint16_t h);
 

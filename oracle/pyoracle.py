@@ -102,6 +102,12 @@ class Oracle:
         L.orc_compact_points.restype = C.c_long
         L.orc_find_corresponding.argtypes = [_fp, _fp, C.c_int, _fp, C.c_long, _fp, _fp, _ip]
         L.orc_find_corresponding.restype = C.c_long
+        L.orc_unsupported.argtypes = [_fp, _fp, C.c_int, _fp, C.c_long, C.POINTER(C.c_uint8)]
+        L.orc_unsupported.restype = C.c_long
+        L.orc_voxel_grid.argtypes = [_fp, C.c_long, _fp, _fp, C.c_int]
+        L.orc_voxel_grid.restype = C.c_long
+        L.orc_warpfield_update.argtypes = [_fp, _fp, _fp, C.c_int, C.c_float, _fp, C.c_long, C.c_int, _fp, _fp, _fp]
+        L.orc_warpfield_update.restype = C.c_long
         L.orc_float2half.argtypes = [C.c_float]
         L.orc_float2half.restype = C.c_uint16
         L.orc_half2float.argtypes = [C.c_uint16]
@@ -294,6 +300,30 @@ class Oracle:
         ties = self.lib.orc_find_corresponding(_f(canon_v), _f(canon_n), canon_v.shape[0], _f(live_v), P, _f(ov), _f(on),
                                                idx.ctypes.data_as(_ip))
         return ov, on, idx, ties
+
+    def unsupported(self, pos, dg_w, verts):
+        """Warpfield::getUnsupportedVertices: boolean mask over the vertices."""
+        pos, dg_w, verts = _f32(pos, (-1, 3)), _f32(dg_w), _f32(verts, (-1, 3))
+        flags = np.zeros(max(verts.shape[0], 1), np.uint8)
+        self.lib.orc_unsupported(_f(pos), _f(dg_w), pos.shape[0], _f(verts), verts.shape[0],
+                                 flags.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return flags[:verts.shape[0]].astype(bool)
+
+    def voxel_grid(self, pts, leaf=0.05, order_mode=0):
+        """pcl::VoxelGrid centroids (None if PCL would refuse the grid)."""
+        pts = _f32(pts, (-1, 3))
+        out = np.empty((max(pts.shape[0], 1), 3), np.float32)
+        lf = np.full(3, leaf, np.float32)
+        m = self.lib.orc_voxel_grid(_f(pts), pts.shape[0], _f(lf), _f(out), order_mode)
+        return None if m < 0 else out[:m].copy()
+
+    def warpfield_update(self, pos, dq, dg_w, epsilon, verts, blend_mode=BLEND_REF_COMPOSE):
+        pos, dq, dg_w, verts = _f32(pos, (-1, 3)), _f32(dq, (-1, 8)), _f32(dg_w), _f32(verts, (-1, 3))
+        N, P = pos.shape[0], verts.shape[0]
+        po, qo, wo = np.empty((N + P, 3), np.float32), np.empty((N + P, 8), np.float32), np.empty(N + P, np.float32)
+        n = self.lib.orc_warpfield_update(_f(pos), _f(dq), _f(dg_w), N, epsilon, _f(verts), P, blend_mode, _f(po), _f(qo),
+                                          _f(wo))
+        return po[:n].copy(), qo[:n].copy(), wo[:n].copy()
 
     def float2half(self, f):
         return self.lib.orc_float2half(f)

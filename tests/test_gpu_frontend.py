@@ -170,3 +170,191 @@ def test_depth_to_solver_pipeline(fe, oracle):
     assert cv.shape == live_v.shape and cn.shape == live_v.shape
     # every live vertex is within ~2 pixels' footprint of its partner
     assert float((cv - live_v).norm(dim=1).max()) < 0.05
+
+
+# ------------------------------------------------------------------------------------------------ f1
+def update_scene(n_nodes=300, rows=240, cols=320):
+    """a sphere surface seen by the camera, sparsely covered by nodes -> part of it is unsupported"""
+    intr = synth.intr_for(cols, rows)
+    depth = synth.sphere_depth(rows, cols, intr, bump=0.01)
+    pos, dq, w, _ = synth.sphere_nodes(n_nodes, 0.0125, rotations=True)
+    return depth, intr, pos, dq, w
+
+
+def make_wf(pos, dq, w, eps=0.0125):
+    import dynfu_b200
+
+    wf = dynfu_b200.Warpfield()
+    wf.init(eps, dev(pos), dev(dq), dev(w))
+    return wf
+
+
+def frame_vertices(oracle, depth, intr):
+    p, _ = oracle.points_normals(depth, intr)
+    return oracle.compact_points(p, None, np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 1.5, 1.5, -0.5], np.float32))
+
+
+def test_unsupported_vertices_bit_exact(fe, oracle):
+    depth, intr, pos, dq, w = update_scene()
+    v = frame_vertices(oracle, depth, intr)
+    mask_o = oracle.unsupported(pos, w, v)
+    assert 0 < mask_o.sum() < v.shape[0]  # the scene exercises both outcomes
+    wf = make_wf(pos, dq, w)
+    mask_g = wf.getUnsupportedVertices(dev(v), return_mask=True).cpu().numpy()
+    assert np.array_equal(mask_g, mask_o)
+    assert same_bits(wf.getUnsupportedVertices(dev(v)).cpu().numpy(), v[mask_o])
+    # vertices exactly one radius away from their nearest node: ratio == 1 counts as unsupported (>=)
+    edge = pos[:50] + np.float32([0.0375, 0, 0])
+    assert np.array_equal(wf.getUnsupportedVertices(dev(edge), return_mask=True).cpu().numpy(), oracle.unsupported(pos, w, edge))
+
+
+@pytest.mark.parametrize("kind", ["surface", "cube", "single", "negative"])
+def test_voxel_grid_bit_exact(fe, oracle, kind):
+    rng = np.random.default_rng(17)
+    if kind == "surface":
+        pts = surface_points(40000, 3)
+    elif kind == "cube":
+        pts = rng.uniform(0.2, 2.9, (30000, 3)).astype(np.float32)
+    elif kind == "single":
+        pts = np.float32([[0.31, 0.32, 0.33]])
+    else:  # coordinates straddling zero: floor() towards -inf, negative min_b
+        pts = rng.uniform(-1.0, 1.0, (20000, 3)).astype(np.float32)
+    c_o = oracle.voxel_grid(pts, 0.05)
+    c_g = fe.voxel_grid_filter(dev(pts), 0.05).cpu().numpy()
+    assert c_g.shape == c_o.shape
+    assert same_bits(c_g, c_o)
+
+
+def test_voxel_grid_many_points_per_cell_and_limits(fe, oracle):
+    rng = np.random.default_rng(23)
+    pts = (np.float32([1.0, 1.0, 1.0]) + rng.uniform(0, 0.1, (20000, 3))).astype(np.float32)  # ~2500 points per cell
+    c_o = oracle.voxel_grid(pts, 0.05)
+    c_g = fe.voxel_grid_filter(dev(pts), 0.05).cpu().numpy()
+    assert same_bits(c_g, c_o)
+    # the unstable std::sort of PCL changes the float sums by a few ulp only (measured, not asserted bit-exact)
+    assert np.abs(oracle.voxel_grid(pts, 0.05, order_mode=1) - c_o).max() < 1e-5
+    import dynfu_b200
+    with pytest.raises(dynfu_b200.DfuError):  # 2^21-cell table exceeded
+        fe.voxel_grid_filter(dev(np.float32([[0, 0, 0], [100, 100, 100]])), 0.05)
+    assert fe.voxel_grid_filter(dev(np.zeros((0, 3), np.float32)), 0.05).shape[0] == 0
+
+
+@pytest.mark.parametrize("n_nodes", [300, 8])
+def test_warpfield_update_bit_exact(fe, oracle, n_nodes):
+    depth, intr, pos, dq, w = update_scene(n_nodes)
+    v = frame_vertices(oracle, depth, intr)
+    po, qo, wo = oracle.warpfield_update(pos, dq, w, 0.0125, v)
+    wf = make_wf(pos, dq, w)
+    nu, nn = wf.update(dev(v))
+    assert nu == int(oracle.unsupported(pos, w, v).sum())
+    assert nn == po.shape[0] - n_nodes > 0
+    pg, qg, wg = [t.cpu().numpy() for t in wf.getNodes()]
+    assert same_bits(pg, po) and same_bits(wg, wo)
+    assert same_bits(qg[:n_nodes], qo[:n_nodes])
+    assert np.allclose(qg[n_nodes:], qo[n_nodes:], atol=2e-6)  # calcDQB tolerance of the blend tests (exp in double)
+    # the re-indexed field answers queries like a freshly initialised one with the same nodes
+    q = (v[::37] + np.float32(0.003)).astype(np.float32)
+    idx_o, _ = oracle.knn(po, q)
+    assert np.array_equal(wf.findNeighborsIndex(8, dev(q)).cpu().numpy(), idx_o)
+    # a second update with the same frame: the new nodes (dg_w = 2 eps = 2.5 cm, 5 cm grid) leave some gaps
+    po2, _, _ = oracle.warpfield_update(po, qo, wo, 0.0125, v)
+    wf.update(dev(v))
+    assert wf.numNodes() == po2.shape[0]
+    assert same_bits(wf.getNodes()[0].cpu().numpy(), po2)
+
+
+def test_update_without_unsupported_vertices_is_a_noop(fe, oracle):
+    depth, intr, pos, dq, w = update_scene()
+    wf = make_wf(pos, dq, w)
+    v = (pos[:100] + np.float32(0.001)).astype(np.float32)
+    assert wf.update(dev(v)) == (0, 0)
+    assert wf.numNodes() == pos.shape[0]
+
+
+def test_update_keeps_voxel_cache_consistent(fe, oracle):
+    """integrate (fills the per-voxel 8-NN cache) -> update (adds nodes, selective invalidation) -> integrate:
+    the volume must equal the one a fresh warp field with the same nodes produces."""
+    import dynfu_b200
+    dim = 128
+    intr = synth.intr_for(320, 240)
+    depth, _, pos, dq, w = update_scene(400)
+    rng = np.random.default_rng(2)
+    dq = synth.translations_to_dq(rng.normal(0, 0.004, (pos.shape[0], 3)).astype(np.float32))
+    v = frame_vertices(oracle, depth, intr)
+    dists = dynfu_b200.compute_dists(dev(depth.view(np.int16), torch.int16), intr)
+    pose = torch.eye(4, dtype=torch.float64)
+    pose[:3, 3] = torch.tensor([-1.5, -1.5, 0.5], dtype=torch.float64)
+
+    def volume():
+        vol = dynfu_b200.TsdfVolume((dim, dim, dim))
+        vol.setPose(pose)
+        vol.setTruncDist(0.06)
+        return vol
+
+    cam = torch.eye(4, dtype=torch.float64)
+    wf = make_wf(pos, dq, w)
+    vol_a = volume()
+    vol_a.integrate(dists, cam, intr, wf)            # warm cache with the old nodes
+    pool, built0 = wf.cacheStats()
+    nu, nn = wf.update(dev(v[::3]))
+    assert nn > 0
+    _, built1 = wf.cacheStats()
+    assert pool > 0 and 0 < built1 < built0          # only the bricks the new nodes can reach were dropped
+    vol_a.integrate(dists, cam, intr, wf)            # partially invalidated cache + new nodes
+    assert wf.cacheStats()[1] >= built0
+    p2, q2, w2 = wf.getNodes()
+    wf_b = dynfu_b200.Warpfield()
+    wf_b.init(0.0125, dev(pos), dev(dq), dev(w))
+    vol_b = volume()
+    vol_b.integrate(dists, cam, intr, wf_b)
+    wf_c = dynfu_b200.Warpfield()
+    wf_c.init(0.0125, p2, q2, w2)
+    vol_b.integrate(dists, cam, intr, wf_c)          # everything recomputed from scratch
+    assert torch.equal(vol_a.data, vol_b.data)
+
+
+# ------------------------------------------------------------------------------ the widened frame loop, end to end
+def test_process_frame_against_oracle_chain(fe, oracle):
+    """DynFusion.processFrame on two depth frames (the second one bulged): depth -> points -> canonical frame /
+    nodes -> warp -> correspondences -> solve -> Warpfield::update, replayed step by step with the oracle."""
+    import dynfu_b200 as dfu
+    from oracle import pyoracle
+
+    rows, cols = 120, 160
+    intr = synth.intr_for(cols, rows)
+    d0 = synth.sphere_depth(rows, cols, intr)
+    d1 = synth.sphere_depth(rows, cols, intr, radius=0.51)
+    kp = dfu.KinFuParams(cols=cols, rows=rows, intr=tuple(float(x) for x in intr), volume_dims=(64, 64, 64))
+    prm = dfu.DynFuParams(kinfuParams=kp, epsilon=0.03, lambda_=200.0, node_step=16,
+                          solver=dfu.CombinedSolverParameters(numIter=3, nonLinearIter=1, linearIter=10, earlyOut=False,
+                                                              pcgTolerance=0.0))
+    df = dfu.DynFusion(prm)
+    assert df.processFrame(torch.from_numpy(d0.view(np.int16)).pin_memory()) is False
+    n0 = df.warpfield.numNodes()
+    assert df.processFrame(torch.from_numpy(d1.view(np.int16)).pin_memory()) is True
+    torch.cuda.synchronize()
+
+    # ---- oracle replay
+    xf = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 1.5, 1.5, -0.5], np.float32)
+    p0, m0 = oracle.points_normals(d0, intr)
+    canon_v, canon_n = oracle.compact_points(p0, m0, xf)
+    assert same_bits(df.canonicalVertices.cpu().numpy(), canon_v)
+    pos = canon_v[::16].copy()
+    assert n0 == pos.shape[0]
+    dq = synth.identity_dq(n0)
+    w = np.full(n0, np.float32(3) * np.float32(0.03), np.float32)
+    p1, m1 = oracle.points_normals(d1, intr)
+    live_v, _ = oracle.compact_points(p1, m1, xf)
+    assert same_bits(df.liveVertices.cpu().numpy(), live_v)
+    warped_v, warped_n = oracle.warp(pos, dq, w, canon_v, canon_n)
+    corr_v, _, _, _ = oracle.find_corresponding(warped_v, warped_n, live_v)
+    prm_o = pyoracle.default_params(num_iter=3, nonlinear_iter=1, linear_iter=10, lambda_=200.0, pcg_tol=0.0, early_out=0)
+    t_o, dq_o, st_o = oracle.solve(pos, dq, w, corr_v, live_v, prm_o)
+    st = df.solver.getStats()
+    assert abs(st["final_energy"] - st_o[1]) <= 1e-4 * st_o[1]
+    assert st_o[1] < st_o[0]  # the solve did reduce the energy
+    po, qo, wo = oracle.warpfield_update(pos, dq_o, w, 0.03, warped_v)
+    pg, qg, wg = [t.cpu().numpy() for t in df.warpfield.getNodes()]
+    assert pg.shape == po.shape
+    assert same_bits(pg, po) and same_bits(wg, wo)
+    assert np.max(np.abs(qg - qo)) <= 1e-4 * max(np.abs(t_o).max(), 1e-3)

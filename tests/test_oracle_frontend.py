@@ -89,3 +89,62 @@ def test_find_corresponding_brute_equals_reference_kdtree(oracle, oracle_nf):
     assert ties == 0
     assert np.array_equal(i_b, i_k) and np.array_equal(v_b, v_k) and np.array_equal(n_b, n_k)
     assert np.array_equal(v_b, canon[i_b])
+
+
+# ---- Warpfield::update (src/dynfu/warp_field.cpp:34-95) -----------------------------------------------------------
+def test_unsupported_threshold(oracle):
+    pos = np.float32([[0, 0, 0]] + [[10 + i, 0, 0] for i in range(7)])
+    w = np.full(8, 0.5, np.float32)
+    verts = np.float32([[0.25, 0, 0], [0.5, 0, 0], [0.49999997, 0, 0], [0, 0.6, 0]])
+    # ratio 0.5 -> supported; exactly 1 -> unsupported (`min >= 1`, :56); just below 1 -> supported; 1.2 -> unsupported
+    assert oracle.unsupported(pos, w, verts).tolist() == [False, True, False, True]
+
+
+def np_voxel_grid(pts, leaf):
+    """independent numpy restatement of pcl::VoxelGrid (PCL 1.8.1 voxel_grid.hpp), ascending index inside a cell"""
+    f = np.float32
+    inv = f(1) / f(leaf)
+    mn, mx = pts.min(0), pts.max(0)
+    min_b = np.floor(mn * inv).astype(np.int64)
+    div_b = np.floor(mx * inv).astype(np.int64) - min_b + 1
+    ijk = (np.floor(pts * inv) - min_b.astype(np.float32)).astype(np.int64)
+    key = ijk[:, 0] + ijk[:, 1] * div_b[0] + ijk[:, 2] * div_b[0] * div_b[1]
+    out = []
+    for k in np.unique(key):
+        sel = pts[key == k]
+        s = np.zeros(3, np.float32)
+        for p in sel:
+            s = s + p
+        out.append(s / f(len(sel)))
+    return np.array(out, np.float32)
+
+
+def test_voxel_grid_against_numpy(oracle):
+    rng = np.random.default_rng(8)
+    for lo, hi, n in [(0.2, 1.4, 3000), (-0.7, 0.9, 2500)]:
+        pts = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+        c_o = oracle.voxel_grid(pts, 0.05)
+        c_n = np_voxel_grid(pts, 0.05)
+        assert c_o.shape == c_n.shape and np.array_equal(c_o, c_n)
+        # PCL's unstable std::sort only reorders float additions inside a cell
+        c_s = oracle.voxel_grid(pts, 0.05, order_mode=1)
+        assert c_s.shape == c_o.shape and np.abs(c_s - c_o).max() < 1e-6
+
+
+def test_voxel_grid_refuses_int32_overflow(oracle):
+    assert oracle.voxel_grid(np.float32([[0, 0, 0], [1e4, 1e4, 1e4]]), 0.001) is None  # PCL returns its input
+
+
+def test_update_appends_nodes(oracle):
+    pos, dq, w, _ = synth.sphere_nodes(64, 0.0125, rotations=True)
+    rng = np.random.default_rng(1)
+    verts = np.concatenate([pos[:20] + np.float32(0.002), pos[:5] + np.float32([0.3, 0.0, 0.0])]).astype(np.float32)
+    po, qo, wo = oracle.warpfield_update(pos, dq, w, 0.0125, verts)
+    n_new = po.shape[0] - 64
+    assert 1 <= n_new <= 5
+    assert np.array_equal(po[:64], pos) and np.array_equal(qo[:64], dq) and np.array_equal(wo[:64], w)
+    assert np.all(wo[64:] == np.float32(2 * 0.0125))                       # dg_w = 2 * epsilon (:80)
+    assert np.array_equal(qo[64:], oracle.blend(pos, dq, w, po[64:]))      # calcDQB against the OLD nodes (:79)
+    # supported-only frames add nothing
+    po2, _, _ = oracle.warpfield_update(pos, dq, w, 0.0125, verts[:20])
+    assert po2.shape[0] == 64
