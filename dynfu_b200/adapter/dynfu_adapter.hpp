@@ -43,6 +43,7 @@ struct Normal {
 };
 template <class T>
 struct PointCloud {
+    typedef std::shared_ptr<PointCloud<T>> Ptr;
     std::vector<T> points;
     void push_back(const T& p) { points.push_back(p); }
     size_t size() const { return points.size(); }
@@ -70,6 +71,7 @@ struct Affine3f {  // only carried around: the reference's solver never uses it 
     }
 };
 }  // namespace cv
+
 #endif
 
 namespace dfu_adapter {
@@ -265,6 +267,49 @@ public:
         return std::make_shared<dynfu::Frame>(0, wv, wn);
     }
 
+    void addNode(std::shared_ptr<Node> newNode) { nodes.emplace_back(std::move(newNode)); }  // warp_field.cpp:30
+
+    // warp_field.cpp:34-62
+    pcl::PointCloud<pcl::PointXYZ>::Ptr getUnsupportedVertices(std::shared_ptr<dynfu::Frame> frame) {
+        pushTransforms();
+        auto& V = frame->getVertices();
+        const int P = (int) V.size();
+        pcl::PointCloud<pcl::PointXYZ>::Ptr out(new pcl::PointCloud<pcl::PointXYZ>);
+        if (P == 0) return out;
+        std::vector<float> v(3 * (size_t) P);
+        for (int i = 0; i < P; ++i) { v[3 * i] = V[i].x; v[3 * i + 1] = V[i].y; v[3 * i + 2] = V[i].z; }
+        dfu_adapter::DevArray<float> dv;
+        dfu_adapter::DevArray<uint8_t> df((size_t) P);
+        dv.upload(v.data(), v.size());
+        dfu_adapter::check(dfu_warpfield_unsupported(handle.get(), dv.p, P, df.p, nullptr), "dfu_warpfield_unsupported");
+        std::vector<uint8_t> flags((size_t) P);
+        df.download(flags.data(), flags.size());
+        for (int i = 0; i < P; ++i)
+            if (flags[i]) out->push_back(V[i]);
+        return out;
+    }
+
+    // warp_field.cpp:64-95: new nodes appear at the end of getNodes(), existing shared Nodes are kept
+    void update(std::shared_ptr<dynfu::Frame> frame, int blend_mode = DFU_BLEND_REF_COMPOSE) {
+        pushTransforms();
+        auto& V = frame->getVertices();
+        const int P = (int) V.size();
+        if (P == 0) return;
+        std::vector<float> v(3 * (size_t) P);
+        for (int i = 0; i < P; ++i) { v[3 * i] = V[i].x; v[3 * i + 1] = V[i].y; v[3 * i + 2] = V[i].z; }
+        dfu_adapter::DevArray<float> dv;
+        dv.upload(v.data(), v.size());
+        int n_uns = 0, n_new = 0;
+        dfu_adapter::check(dfu_warpfield_update(handle.get(), dv.p, P, blend_mode, &n_uns, &n_new, nullptr), "dfu_warpfield_update");
+        if (n_new == 0) return;
+        const size_t N2 = nodes.size() + (size_t) n_new;
+        std::vector<float> pos(3 * N2), dq(8 * N2), w(N2);
+        dfu_adapter::check(dfu_warpfield_get_nodes_host(handle.get(), pos.data(), dq.data(), w.data(), nullptr), "dfu_warpfield_get_nodes_host");
+        for (size_t i = nodes.size(); i < N2; ++i)
+            addNode(std::make_shared<Node>(pcl::PointXYZ(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]),
+                                           std::make_shared<DualQuaternion<float>>(&dq[8 * i]), w[i]));
+    }
+
     // ---- not in the reference: the bridge between the shared host Nodes and the device copy ----
     dfu_warpfield* raw() const { return handle.get(); }
     // host Node transforms -> device (cheap: 32 B per node); called before every device operation because the
@@ -381,3 +426,40 @@ private:
 };
 }  // namespace cuda
 }  // namespace kfusion
+
+// DynFusion::findCorrespondingFrame (src/dynfu/dyn_fusion.cpp:212-242): for every live vertex the nearest canonical
+// vertex (and its normal), as a new Frame.  The reference builds a nanoflann KD-tree per call; this is one C-ABI call.
+inline std::shared_ptr<dynfu::Frame> findCorrespondingFrame(pcl::PointCloud<pcl::PointXYZ> canonicalVertices,
+                                                            pcl::PointCloud<pcl::Normal> canonicalNormals,
+                                                            pcl::PointCloud<pcl::PointXYZ> liveVertices) {
+    const int Pc = (int) canonicalVertices.size(), Pl = (int) liveVertices.size();
+    if (Pc == 0) throw std::runtime_error("findCorrespondingFrame: empty canonical cloud");  // nanoflann throws too
+    std::vector<float> c(3 * (size_t) Pc), cn(3 * (size_t) Pc), l(3 * (size_t) Pl);
+    for (int i = 0; i < Pc; ++i) {
+        c[3 * i] = canonicalVertices[i].x; c[3 * i + 1] = canonicalVertices[i].y; c[3 * i + 2] = canonicalVertices[i].z;
+        cn[3 * i] = canonicalNormals[i].normal_x; cn[3 * i + 1] = canonicalNormals[i].normal_y; cn[3 * i + 2] = canonicalNormals[i].normal_z;
+    }
+    for (int i = 0; i < Pl; ++i) { l[3 * i] = liveVertices[i].x; l[3 * i + 1] = liveVertices[i].y; l[3 * i + 2] = liveVertices[i].z; }
+    dfu_adapter::DevArray<float> dc, dcn, dl, dov((size_t) 3 * Pl + 1), don((size_t) 3 * Pl + 1);
+    dc.upload(c.data(), c.size());
+    dcn.upload(cn.data(), cn.size());
+    dl.upload(l.data(), l.size());
+    dfu_pointindex* pi = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dfu_adapter::check(dfu_pointindex_create(&pi, dev), "dfu_pointindex_create");
+    const int rc = dfu_find_corresponding(pi, dc.p, dcn.p, Pc, dl.p, Pl, dov.p, don.p, nullptr, nullptr);
+    if (rc == DFU_OK) cudaStreamSynchronize(nullptr);
+    dfu_pointindex_destroy(pi);
+    dfu_adapter::check(rc, "dfu_find_corresponding");
+    std::vector<float> ov(3 * (size_t) Pl), on(3 * (size_t) Pl);
+    dov.download(ov.data(), ov.size());
+    don.download(on.data(), on.size());
+    pcl::PointCloud<pcl::PointXYZ> rv;
+    pcl::PointCloud<pcl::Normal> rn;
+    for (int i = 0; i < Pl; ++i) {
+        rv.push_back(pcl::PointXYZ(ov[3 * i], ov[3 * i + 1], ov[3 * i + 2]));
+        rn.push_back(pcl::Normal(on[3 * i], on[3 * i + 1], on[3 * i + 2]));
+    }
+    return std::make_shared<dynfu::Frame>(0, rv, rn);
+}

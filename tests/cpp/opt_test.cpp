@@ -216,4 +216,63 @@ TEST_F(TsdfTest, IdentityWarpEqualsRigidIntegrate) {
     ASSERT_NEAR(touched > 1000 ? 1.0 : 0.0, 1.0, 0.0);
 }
 
+// ---- the rows around the solver, through the same class interface ------------------------------------------------
+class UpdateTest {
+public:
+    void SetUp() {}
+    void TearDown() {}
+};
+
+// Warpfield::getUnsupportedVertices / update (src/dynfu/warp_field.cpp:34-95) with hand-checkable numbers
+TEST_F(UpdateTest, UnsupportedVerticesBecomeNodes) {
+    std::vector<std::shared_ptr<Node>> nodes;
+    for (int i = 0; i < 9; ++i)  // a 3x3 patch of nodes, 10 cm apart, radius 0.15
+        nodes.push_back(std::make_shared<Node>(pcl::PointXYZ(1.0f + 0.1f * (i % 3), 1.0f + 0.1f * (i / 3), 1.0f),
+                                               std::make_shared<DualQuaternion<float>>(0.f, 0.f, 0.f, 0.01f, 0.02f, 0.03f), 0.15f));
+    Warpfield wf;
+    wf.init(0.05f, nodes);
+    pcl::PointCloud<pcl::PointXYZ> v;
+    pcl::PointCloud<pcl::Normal> n;
+    v.push_back(pcl::PointXYZ(1.05f, 1.05f, 1.0f));    // inside the patch: supported
+    v.push_back(pcl::PointXYZ(1.62f, 1.01f, 1.0f));    // 0.42 m from the nearest node: unsupported
+    v.push_back(pcl::PointXYZ(1.63f, 1.02f, 1.0f));    // same 5 cm cell as the previous one -> one centroid
+    v.push_back(pcl::PointXYZ(1.01f, 1.01f, 1.9f));    // unsupported, far away in z
+    for (int i = 0; i < 4; ++i) n.push_back(pcl::Normal(0, 0, 1));
+    auto frame = std::make_shared<dynfu::Frame>(1, v, n);
+    auto uns = wf.getUnsupportedVertices(frame);
+    ASSERT_NEAR((double) uns->size(), 3.0, 0.0);
+    ASSERT_NEAR((*uns)[0].x, 1.62f, 0.0);
+    wf.update(frame);
+    auto all = wf.getNodes();
+    ASSERT_NEAR((double) all.size(), 11.0, 0.0);
+    // cells in ascending linear index: the z = 1.0 cell comes before the z = 1.9 cell
+    ASSERT_NEAR(all[9]->getPosition().x, 1.625f, 1e-6);
+    ASSERT_NEAR(all[9]->getPosition().y, 1.015f, 1e-6);
+    ASSERT_NEAR(all[10]->getPosition().z, 1.9f, 1e-6);
+    ASSERT_NEAR(all[9]->getRadialBasisWeight(), 0.1f, 0.0);  // 2 * epsilon
+    // all old nodes carry the same translation -> calcDQB at the new node returns it (weights are ~0 far away, so
+    // the blend degenerates exactly like the reference's; just check the node is usable)
+    auto q = wf.findNeighborsIndex(KNN, pcl::PointXYZ(1.62f, 1.01f, 1.0f));
+    ASSERT_NEAR((double) q[0], 9.0, 0.0);  // the new node is now the nearest neighbour of the vertex it came from
+}
+
+// DynFusion::findCorrespondingFrame (src/dynfu/dyn_fusion.cpp:212-242)
+TEST_F(UpdateTest, FindCorrespondingFrame) {
+    pcl::PointCloud<pcl::PointXYZ> canon, live;
+    pcl::PointCloud<pcl::Normal> cn;
+    for (int i = 0; i < 100; ++i) {
+        canon.push_back(pcl::PointXYZ(0.01f * i, 0.5f, 2.f));
+        cn.push_back(pcl::Normal((float) i, 0, 0));
+    }
+    live.push_back(pcl::PointXYZ(0.302f, 0.6f, 2.1f));   // nearest: i = 30
+    live.push_back(pcl::PointXYZ(-5.f, 0.5f, 2.f));      // nearest: i = 0
+    live.push_back(pcl::PointXYZ(0.996f, 0.5f, 2.f));    // nearest: i = 99 (clamped at the end of the row)
+    auto f = findCorrespondingFrame(canon, cn, live);
+    ASSERT_NEAR((double) f->getVertices().size(), 3.0, 0.0);
+    ASSERT_NEAR(f->getNormals()[0].normal_x, 30.f, 0.0);
+    ASSERT_NEAR(f->getNormals()[1].normal_x, 0.f, 0.0);
+    ASSERT_NEAR(f->getNormals()[2].normal_x, 99.f, 0.0);
+    ASSERT_NEAR(f->getVertices()[0].x, 0.3f, 1e-7);
+}
+
 int main() { return RUN_ALL_TESTS(); }

@@ -479,7 +479,7 @@ def test_reference_gtest_cases_through_the_cpp_adapter(dfu):
     exe = b.build_cpp_tests()
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(exe))
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "9 tests, 0 failed" in r.stdout, r.stdout
+    assert "11 tests, 0 failed" in r.stdout, r.stdout
 
 
 def test_two_gpus_equal_one_gpu(dfu):
