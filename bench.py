@@ -35,7 +35,10 @@ from tests import synth  # noqa: E402
 DIM = 512
 N_THETA, N_Y = 64, 64
 EPSILON = 0.0125
-KAPPA = 0.02   # bend x += KAPPA*a*(y-cy)^2: the largest displacement (a = 3, |y| = 0.8 m) is 0.038 m ~ dg_w, i.e. trackable
+KAPPA = 0.005  # bend x += KAPPA*a*(y-cy)^2: the largest displacement (a = 3, |y| = 0.8 m) is 9.6 mm.  The reference evaluates
+               # node weights at the WARPED positions against static node positions (dyn_fusion.cpp:196-206), which only
+               # tracks deformations well below dg_w (37.5 mm): at 0.01 and above the frame-to-frame loop slowly diverges
+               # (measured over 260 frames), at 0.005 it settles into a periodic steady state
 GN_ITERS, PCG_ITERS = 5, 10
 LAMBDA = 200.0
 RING = 4

@@ -386,6 +386,31 @@ def test_solver_fixed_iteration_mode_is_async_and_matches_oracle(dfu, oracle):
     assert np.max(np.abs(t_g - t_o)) <= 1e-4 * np.abs(t_o).max()
 
 
+@pytest.mark.parametrize("path", ["p1", "p2", "p3", "p3g", "multi"])
+def test_solver_every_execution_path_matches_oracle(dfu, oracle, monkeypatch, path):
+    """the persistent kernels (1: matrix-free from L2, 2: matrix-free with the graph in registers, 3: explicit normal matrix +
+    pipelined PCG with the rows in registers, 3g: the same from L2) and the one-kernel-per-phase path solve the same problem"""
+    monkeypatch.setenv("DFU_SOLVER_PATH", path)
+    pos, dg_w, canon, t_true = _wellposed(seed=11, N=2048, P=40000)
+    N = len(pos)
+    live = oracle.warp(pos, synth.translations_to_dq(0.2 * t_true), dg_w, canon)
+    prm_o = pyoracle.default_params(num_iter=4, nonlinear_iter=2, linear_iter=12, lambda_=50.0, pcg_tol=0.0, early_out=0)
+    t_o, _, st_o = oracle.solve(pos, synth.identity_dq(N), dg_w, canon, live, prm_o)
+    wf = make_wf(dfu, pos, synth.identity_dq(N), dg_w, 0.025)
+    prm = dfu.CombinedSolverParameters(numIter=4, nonLinearIter=2, linearIter=12, earlyOut=False, pcgTolerance=0.0)
+    s = dfu.CombinedSolver(wf, prm, 4.652, 1e-2, 50.0, 1e-4)
+    s.initializeProblemInstance(dev(canon), dev(live))
+    s.solveAll()
+    st = s.getStats()
+    assert st["pcg_iterations"] == 96 and st["gn_steps"] == 8
+    assert abs(st["final_energy"] - st_o[1]) <= 1e-4 * st_o[1], (st, st_o)
+    t_g = s.getTranslations().cpu().numpy()
+    assert np.max(np.abs(t_g - t_o)) <= 1e-4 * np.abs(t_o).max()
+    # the tukey weights the solve ended with are readable whatever kernel kept them in registers
+    th = s.tukeyWeights().cpu().numpy()
+    assert th.shape == (40000,) and th.min() >= 0.0 and th.max() <= 1.0 and th.mean() > 0.5
+
+
 def test_solver_allreduce_hook_two_partitions(dfu, oracle):
     """data-parallel contract on one GPU: two solvers hold disjoint point partitions and exchange their
     normal-equation buffers through the all-reduce hook; the result equals the single-partition solve."""
