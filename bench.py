@@ -380,8 +380,8 @@ def main():
                            "warped projective TSDF integration", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                  "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": int_ms,
                  "algorithmic_bytes_per_launch": voxels_rank * ALGO_BYTES_PER_VOXEL, "share_of_step": int_ms / (ms_dev / args.steps)},
-                {"kernel": "k_solve_persistent (5 GN x 10 PCG, one cooperative launch)" if world == 1 else
-                           "solver phase kernels + NCCL all-reduces (5 GN x 10 PCG)", "bound": "hbm", "achieved": sol_achieved,
+                {"kernel": "k_solve_persistent3r: explicit normal matrix + pipelined PCG, 5 GN x 10 PCG in one cooperative launch"
+                           if mode != "partitioned" else "solver phase kernels + NCCL all-reduces (5 GN x 10 PCG)", "bound": "hbm", "achieved": sol_achieved,
                  "peak": hbm_peak, "unit": "GB/s", "frac": sol_achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                  "kernel_ms": sol_ms, "algorithmic_bytes_per_launch": sol_bytes, "share_of_step": sol_ms / (ms_dev / args.steps),
                  "note": "L2-resident and bound by grid-barrier / L2 latency, not by HBM (SURVEY 8d): frac is reported "
