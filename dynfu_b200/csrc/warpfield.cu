@@ -395,63 +395,77 @@ __global__ void grid_occ_kernel(const int* __restrict__ start, GridDesc* __restr
     if (c < n && start[c + 1] > start[c]) occ[atomicAdd(&gd->n_occ, 1)] = c;
 }
 
-// top-8 insertion by the explicit key (dist2, idx)
-DFU_DEV void top8_insert_lex(Top8& t, float dist, int idx) {
+// ---- exact 8-NN through the grid ------------------------------------------------------------------------------
+// The search key (dist2, idx) is packed into one 64-bit word, distance bits high: squared distances are >= 0, so their
+// IEEE bit patterns order like unsigned integers and ONE unsigned compare is the lexicographic compare.  The list is
+// kept ascending in registers; an insertion is 8 compare-selects.
+struct Keys8 {
+    unsigned long long k[DFU_KNN];
+};
+DFU_DEV unsigned long long knn_key(float d, int idx) { return ((unsigned long long) __float_as_uint(d) << 32) | (unsigned) idx; }
+DFU_DEV void keys8_insert(Keys8& t, unsigned long long key) {
 #pragma unroll
     for (int k = DFU_KNN - 1; k > 0; --k) {
-        const bool shift = lex_less(dist, idx, t.d[k - 1], t.i[k - 1]);
-        const bool here = !shift && lex_less(dist, idx, t.d[k], t.i[k]);
-        t.i[k] = shift ? t.i[k - 1] : (here ? idx : t.i[k]);
-        t.d[k] = shift ? t.d[k - 1] : (here ? dist : t.d[k]);
+        const bool shift = key < t.k[k - 1];
+        const bool here = !shift && key < t.k[k];
+        t.k[k] = shift ? t.k[k - 1] : (here ? key : t.k[k]);
     }
-    if (lex_less(dist, idx, t.d[0], t.i[0])) {
-        t.d[0] = dist;
-        t.i[0] = idx;
-    }
+    if (key < t.k[0]) t.k[0] = key;
 }
-
-DFU_DEV void grid_visit_cell(const int* __restrict__ start, const float4* __restrict__ sorted, int cell, float qx, float qy, float qz, Top8& t) {
-    const int lo = __ldg(&start[cell]), hi = __ldg(&start[cell + 1]);
+// all nodes of the cells [c0, c1] of one grid row: consecutive cells are consecutive in `sorted`
+DFU_DEV void grid_visit_range(const int* __restrict__ start, const float4* __restrict__ sorted, int c0, int c1, float qx, float qy,
+                              float qz, Keys8& t) {
+    const int lo = __ldg(&start[c0]), hi = __ldg(&start[c1 + 1]);
     for (int j = lo; j < hi; ++j) {
         const float4 p = __ldg(&sorted[j]);
-        const float d = dist2(qx, qy, qz, p.x, p.y, p.z);
-        if (d <= t.d[DFU_KNN - 1]) {
-            const int idx = __float_as_int(p.w);
-            if (lex_less(d, idx, t.d[DFU_KNN - 1], t.i[DFU_KNN - 1])) top8_insert_lex(t, d, idx);
-        }
+        const unsigned long long key = knn_key(dist2(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+        if (key < t.k[DFU_KNN - 1]) keys8_insert(t, key);
     }
 }
 
-// exact 8-NN of one query through the grid.  Shells of growing Chebyshev radius around the query's cell (a
-// query near the nodes is done after 1-2); once the next shell would cost more cell visits than there are
-// NON-EMPTY cells, a query that is still not settled sweeps the list of non-empty cells instead, pruning each
-// by its box distance, so the cost stays bounded however far the query is from the nodes.
+// Shells of growing Chebyshev radius around the query's cell (a query near the nodes is done after the first 3x3x3
+// block); once the next shell would cost more cell visits than there are NON-EMPTY cells, a query that is still not
+// settled sweeps the list of non-empty cells instead, pruning each by its box distance, so the cost stays bounded
+// however far the query is from the nodes.
 DFU_DEV void knn8_grid(const GridDesc& g, const int* __restrict__ start, const float4* __restrict__ sorted,
-                       const int* __restrict__ occ, float qx, float qy, float qz, Top8& t) {
+                       const int* __restrict__ occ, float qx, float qy, float qz, Top8& out) {
+    Keys8 t;
+    const unsigned long long none = knn_key(INFINITY, 0x7fffffff);  // "no node": loses every tie
 #pragma unroll
-    for (int k = 0; k < DFU_KNN; ++k) {
-        t.d[k] = INFINITY;
-        t.i[k] = 0x7fffffff;  // "no node": loses every tie
-    }
+    for (int k = 0; k < DFU_KNN; ++k) t.k[k] = none;
     const int cx = grid_coord(qx, g.ox, g.inv_h, g.nx), cy = grid_coord(qy, g.oy, g.inv_h, g.ny), cz = grid_coord(qz, g.oz, g.inv_h, g.nz);
     bool settled = false;
-    int r = 0, rd = -1;  // rd: every cell within this Chebyshev radius has been visited
-    for (; (2 * r + 1) * (2 * r + 1) * (2 * r + 1) <= 2 * g.n_occ + 27; ++r) {
-        rd = r;
-        const int z0 = max(0, cz - r), z1 = min(g.nz - 1, cz + r);
-        const int y0 = max(0, cy - r), y1 = min(g.ny - 1, cy + r);
-        const int x0 = max(0, cx - r), x1 = min(g.nx - 1, cx + r);
+    int r = 1, rd = -1;  // rd: every cell within this Chebyshev radius has been visited
+    // radius 0 and 1 in one pass: nine row segments
+    {
+        const int z0 = max(0, cz - 1), z1 = min(g.nz - 1, cz + 1);
+        const int y0 = max(0, cy - 1), y1 = min(g.ny - 1, cy + 1);
+        const int x0 = max(0, cx - 1), x1 = min(g.nx - 1, cx + 1);
         for (int z = z0; z <= z1; ++z)
             for (int y = y0; y <= y1; ++y) {
-                const bool face = (abs(z - cz) == r) || (abs(y - cy) == r);
                 const int row = g.nx * (y + g.ny * z);
-                if (face) {
-                    for (int x = x0; x <= x1; ++x) grid_visit_cell(start, sorted, row + x, qx, qy, qz, t);
-                } else {  // interior rows of the shell: only the two end cells
-                    if (cx - r >= 0) grid_visit_cell(start, sorted, row + cx - r, qx, qy, qz, t);
-                    if (cx + r < g.nx) grid_visit_cell(start, sorted, row + cx + r, qx, qy, qz, t);
-                }
+                grid_visit_range(start, sorted, row + x0, row + x1, qx, qy, qz, t);
             }
+    }
+    for (;; ++r) {
+        if (r > 1) {
+            if ((2 * r + 1) * (2 * r + 1) * (2 * r + 1) > 2 * g.n_occ + 27) break;
+            const int z0 = max(0, cz - r), z1 = min(g.nz - 1, cz + r);
+            const int y0 = max(0, cy - r), y1 = min(g.ny - 1, cy + r);
+            const int x0 = max(0, cx - r), x1 = min(g.nx - 1, cx + r);
+            for (int z = z0; z <= z1; ++z)
+                for (int y = y0; y <= y1; ++y) {
+                    const bool face = (abs(z - cz) == r) || (abs(y - cy) == r);
+                    const int row = g.nx * (y + g.ny * z);
+                    if (face) {
+                        grid_visit_range(start, sorted, row + x0, row + x1, qx, qy, qz, t);
+                    } else {  // interior rows of the shell: only the two end cells
+                        if (cx - r >= 0) grid_visit_range(start, sorted, row + cx - r, row + cx - r, qx, qy, qz, t);
+                        if (cx + r < g.nx) grid_visit_range(start, sorted, row + cx + r, row + cx + r, qx, qy, qz, t);
+                    }
+                }
+        }
+        rd = r;
         // distance from the query to everything not visited yet: the nearest face of the visited box that
         // still has cells beyond it
         float L = INFINITY;
@@ -463,7 +477,8 @@ DFU_DEV void knn8_grid(const GridDesc& g, const int* __restrict__ start, const f
         if (cz + r < g.nz - 1) L = fminf(L, (g.oz + (float) (cz + r + 1) * g.h) - qz);
         // margin: binning and face coordinates are rounded (coordinates are O(1) m: 1e-5 m is > 100 ulp)
         const float Ls = L - 1e-5f - 1e-5f * g.h;
-        if (L == INFINITY || (Ls > 0.f && t.d[DFU_KNN - 1] < Ls * Ls)) {
+        const float d8 = __uint_as_float((unsigned) (t.k[DFU_KNN - 1] >> 32));
+        if (L == INFINITY || (Ls > 0.f && d8 < Ls * Ls)) {
             settled = true;
             break;
         }
@@ -478,12 +493,15 @@ DFU_DEV void knn8_grid(const GridDesc& g, const int* __restrict__ start, const f
             const float ddx = fmaxf(0.f, fmaxf(lx - qx, qx - (lx + g.h))), ddy = fmaxf(0.f, fmaxf(ly - qy, qy - (ly + g.h))),
                         ddz = fmaxf(0.f, fmaxf(lz - qz, qz - (lz + g.h)));
             const float dl = fmaxf(0.f, sqrtf(ddx * ddx + ddy * ddy + ddz * ddz) - 1e-5f - 1e-5f * g.h);
-            if (dl * dl <= t.d[DFU_KNN - 1]) grid_visit_cell(start, sorted, c, qx, qy, qz, t);
+            if (dl * dl <= __uint_as_float((unsigned) (t.k[DFU_KNN - 1] >> 32))) grid_visit_range(start, sorted, c, c, qx, qy, qz, t);
         }
     }
 #pragma unroll
-    for (int k = 0; k < DFU_KNN; ++k)
-        if (t.i[k] == 0x7fffffff) t.i[k] = -1;
+    for (int k = 0; k < DFU_KNN; ++k) {
+        out.d[k] = __uint_as_float((unsigned) (t.k[k] >> 32));
+        const int idx = (int) (unsigned) (t.k[k] & 0xffffffffull);
+        out.i[k] = idx == 0x7fffffff ? -1 : idx;
+    }
 }
 
 template <int OP>
