@@ -124,6 +124,7 @@ struct FieldInfo {
     bool translation_only;
     bool all_near;
     float r_zero, r_eff, reff2;
+    float maxw, dmax;  // largest dg_w, largest |dual.xyz| component
 };
 // A brick must run the exact per-voxel warp ("near") unless every voxel of it is PROVABLY left where it is:
 //  (a) all 8 weights are exactly 0.f beyond sqrt(209)*dg_w of every node (dfu_math.cuh node_weight), or
@@ -131,11 +132,13 @@ struct FieldInfo {
 //      when that is below p_c * 2^-26 (less than half an ulp of p_c >= voxel size) the addition returns p_c
 //      bit for bit.  Bricks touching index 0 of an axis (p_c == 0) are excluded from (b).
 DFU_DEV FieldInfo field_info(const IntegrateArgs& a) {
-    FieldInfo f{false, false, 0.f, 0.f, 0.f};
+    FieldInfo f{false, false, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (!a.warped) return f;
     f.translation_only = a.flags[0] != 0;
     const float maxw = __int_as_float(a.flags[1]);
     const float dmax = __int_as_float(a.flags[2]);
+    f.maxw = maxw;
+    f.dmax = dmax;
     f.r_zero = 14.4569f * maxw * 1.001f + 1e-6f;  // rule (a); 1.001 covers rounding
     f.all_near = (a.blend_mode == DFU_BLEND_REF_COMPOSE) && !f.translation_only;
     f.r_eff = f.r_zero;
@@ -441,6 +444,52 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
     }
 }
 
+// True when NO voxel of the index box [x0,x0+nx-1] x [y0,y0+7] x [z0,z0+7], moved by at most `delta` metres (Euclidean) from
+// its grid position, can pass the per-voxel tests of voxel_tsdf: the box (inflated by delta) is behind the camera, projects
+// outside the image, projects only onto pixels without depth, or lies entirely more than trunc behind the farthest depth it
+// can see.  All bounds carry margins far above the rounding of the per-voxel arithmetic.
+DFU_DEV bool box_unreachable(const IntegrateArgs& a, int x0, int nx, int y0, int z0, float delta) {
+    float zmin = INFINITY, zmax = -INFINITY, umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
+    float cxs = 0.f, cys = 0.f, czs = 0.f, cor[8][3];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float px = (float) (x0 + ((c & 1) ? nx - 1 : 0)) * a.vsx, py = (float) (y0 + ((c & 2) ? 7 : 0)) * a.vsy,
+                    pz = (float) (z0 + ((c & 4) ? 7 : 0)) * a.vsz;
+        cor[c][0] = a.R[0] * px + a.R[1] * py + a.R[2] * pz + a.T[0];
+        cor[c][1] = a.R[3] * px + a.R[4] * py + a.R[5] * pz + a.T[1];
+        cor[c][2] = a.R[6] * px + a.R[7] * py + a.R[8] * pz + a.T[2];
+        cxs += cor[c][0]; cys += cor[c][1]; czs += cor[c][2];
+        zmin = fminf(zmin, cor[c][2]);
+        zmax = fmaxf(zmax, cor[c][2]);
+    }
+    if (zmax + delta <= -1e-4f) return true;  // every voxel has vc.z <= 0
+    if (!(zmin - delta > 1e-3f)) return false;
+    cxs *= 0.125f; cys *= 0.125f; czs *= 0.125f;
+    float rad = 0.f, slope = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float iz = 1.f / cor[c][2];
+        const float u = a.fx * cor[c][0] * iz + a.cx, v = a.fy * cor[c][1] * iz + a.cy;
+        umin = fminf(umin, u); umax = fmaxf(umax, u);
+        vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+        slope = fmaxf(slope, fmaxf(fabsf(cor[c][0]), fabsf(cor[c][1])) * iz);
+        const float ex = cor[c][0] - cxs, ey = cor[c][1] - cys, ez = cor[c][2] - czs;
+        rad = fmaxf(rad, sqrtf(ex * ex + ey * ey + ez * ez));
+    }
+    // a displacement e, |e| <= delta, moves the projection by at most f * delta * (1 + |x|/z) / (z - delta) pixels
+    const float mpx = delta > 0.f ? fmaxf(a.fx, a.fy) * delta * (1.f + slope) / (zmin - delta) * 1.01f : 0.f;
+    // pixel rectangle the box can project to, one pixel of margin
+    const int pu0 = max(0, (int) floorf(fmaxf(umin - mpx, -1e6f)) - 1), pu1 = min(a.cols - 1, (int) floorf(fminf(umax + mpx, 1e6f)) + 1);
+    const int pv0 = max(0, (int) floorf(fmaxf(vmin - mpx, -1e6f)) - 1), pv1 = min(a.rows - 1, (int) floorf(fminf(vmax + mpx, 1e6f)) + 1);
+    if (pu0 > pu1 || pv0 > pv1) return true;  // projects outside the image
+    float dfar = 0.f;
+    for (int ty = pv0 / DT; ty <= pv1 / DT; ++ty)
+        for (int tx = pu0 / DT; tx <= pu1 / DT; ++tx) dfar = fmaxf(dfar, __ldg(&a.dmax_tiles[ty * a.dtx + tx]));
+    const float near_dist = sqrtf(cxs * cxs + cys * cys + czs * czs) - rad - delta;  // <= |vc| of every (moved) voxel
+    // dfar == 0: no depth anywhere it projects to; else sdf = Dp - |vc| <= dfar - near_dist < -trunc
+    return dfar == 0.f || dfar - near_dist < -a.trunc - 1e-3f;
+}
+
 // Hierarchical cull of the RIGID part of every tile, one thread per tile.  The tile's un-warped voxels lie in the
 // convex hull of its 8 transformed corners.  If that hull is behind the camera, projects outside the image, projects
 // only onto pixels without depth, or lies entirely more than trunc behind the farthest depth it can see, no voxel of
@@ -456,48 +505,7 @@ __global__ void tile_classify_kernel(const __grid_constant__ IntegrateArgs a) {
     bid /= a.ntx;
     const int y0 = (bid % a.nty) * 8;
     const int zt = a.zt0 + (bid / a.nty) * 8;
-    bool rigid_skip = false;
-    float zmin = INFINITY, zmax = -INFINITY, umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
-    float cxs = 0.f, cys = 0.f, czs = 0.f, cor[8][3];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float px = (float) (x0 + ((c & 1) ? 31 : 0)) * a.vsx, py = (float) (y0 + ((c & 2) ? 7 : 0)) * a.vsy,
-                    pz = (float) (zt + ((c & 4) ? 7 : 0)) * a.vsz;
-        cor[c][0] = a.R[0] * px + a.R[1] * py + a.R[2] * pz + a.T[0];
-        cor[c][1] = a.R[3] * px + a.R[4] * py + a.R[5] * pz + a.T[1];
-        cor[c][2] = a.R[6] * px + a.R[7] * py + a.R[8] * pz + a.T[2];
-        cxs += cor[c][0]; cys += cor[c][1]; czs += cor[c][2];
-        zmin = fminf(zmin, cor[c][2]);
-        zmax = fmaxf(zmax, cor[c][2]);
-    }
-    if (zmax <= -1e-4f) {
-        rigid_skip = true;  // every voxel has vc.z <= 0
-    } else if (zmin > 1e-3f) {
-        cxs *= 0.125f; cys *= 0.125f; czs *= 0.125f;
-        float rad = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float iz = 1.f / cor[c][2];
-            const float u = a.fx * cor[c][0] * iz + a.cx, v = a.fy * cor[c][1] * iz + a.cy;
-            umin = fminf(umin, u); umax = fmaxf(umax, u);
-            vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
-            const float ex = cor[c][0] - cxs, ey = cor[c][1] - cys, ez = cor[c][2] - czs;
-            rad = fmaxf(rad, sqrtf(ex * ex + ey * ey + ez * ez));
-        }
-        // pixel rectangle the tile can project to, one pixel of margin
-        const int pu0 = max(0, (int) floorf(fmaxf(umin, -1e6f)) - 1), pu1 = min(a.cols - 1, (int) floorf(fminf(umax, 1e6f)) + 1);
-        const int pv0 = max(0, (int) floorf(fmaxf(vmin, -1e6f)) - 1), pv1 = min(a.rows - 1, (int) floorf(fminf(vmax, 1e6f)) + 1);
-        if (pu0 > pu1 || pv0 > pv1) {
-            rigid_skip = true;  // projects outside the image
-        } else {
-            float dfar = 0.f;
-            for (int ty = pv0 / DT; ty <= pv1 / DT; ++ty)
-                for (int tx = pu0 / DT; tx <= pu1 / DT; ++tx) dfar = fmaxf(dfar, __ldg(&a.dmax_tiles[ty * a.dtx + tx]));
-            const float near_dist = sqrtf(cxs * cxs + cys * cys + czs * czs) - rad;  // <= |vc| of every voxel
-            // dfar == 0: no depth anywhere it projects to; else sdf = Dp - |vc| <= dfar - near_dist < -trunc
-            if (dfar == 0.f || dfar - near_dist < -a.trunc - 1e-3f) rigid_skip = true;
-        }
-    }
+    const bool rigid_skip = box_unreachable(a, x0, 32, y0, zt, 0.f);
     int near_mask = 0, need_fill = 0;
     if (a.warped) {
         const FieldInfo f = field_info(a);
@@ -509,6 +517,14 @@ __global__ void tile_classify_kernel(const __grid_constant__ IntegrateArgs a) {
             const float dmin = sqrtf(b.y) - r_brick;  // lower bound of voxel-to-node distance in this brick
             const bool on_zero_plane = (x0 + sb * 8 == 0) || (y0 == 0) || (zt == 0);
             if (f.all_near || dmin <= (on_zero_plane ? f.r_zero : f.r_eff)) {
+                // translation-only field: a voxel moves by |2 acc_c| <= 16 dmax w per coordinate, w <= exp(-dmin^2 / (2 maxw^2));
+                // a brick none of whose moved voxels can be updated needs neither the cache nor the warp
+                if (f.translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
+                    const float dm = fmaxf(dmin, 0.f);
+                    const float wmax = fminf(1.f, expf(-dm * dm / (2.f * f.maxw * f.maxw)) * 1.001f);
+                    const float delta = 1.7321f * 16.f * f.dmax * wmax * 1.001f + 1e-6f;
+                    if (box_unreachable(a, x0 + sb * 8, 8, y0, zt, delta)) continue;
+                }
                 near_mask |= 1 << sb;
                 if (a.knn_pool && !a.built[brick0 + sb]) need_fill = 1;
             }
