@@ -275,6 +275,41 @@ DFU_DEV void node_gather_data(const Problem& pb, int n, int lane, bool with_diag
     }
 }
 
+// The same gather (without the diagonal) in 2^40 fixed point: every term is rounded to an integer and integers add
+// associatively, so the result does not depend on the ORDER of the transposed list -- the lists then need no sorting
+// (versions 3 / 3r).  Terms are |tw * theta * e| << 2^23, a node collects < 2^19 of them.  Returns the sums in every lane.
+DFU_DEV void warp_sum_ll(long long& v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+}
+DFU_DEV void node_gather_data_fixed(const Problem& pb, int n, int lane, float& ax, float& ay, float& az) {
+    long long sx = 0, sy = 0, sz = 0;
+    const int lo = pb.tptr[n], hi = pb.tptr[n + 1];
+    for (int j = lo + lane; j < hi; j += 128) {
+        float w[4];
+        int v[4];
+        float4 s[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jj = j + 32 * u;
+            const bool ok = jj < hi;
+            w[u] = ok ? pb.tw[jj] : 0.f;
+            v[u] = ok ? pb.tv[jj] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] = v[u] >= 0 ? pb.s4[v[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (v[u] < 0) continue;
+            sx += __float2ll_rn(w[u] * s[u].x * FIX_SCALE);
+            sy += __float2ll_rn(w[u] * s[u].y * FIX_SCALE);
+            sz += __float2ll_rn(w[u] * s[u].z * FIX_SCALE);
+        }
+    }
+    warp_sum_ll(sx); warp_sum_ll(sy); warp_sum_ll(sz);
+    ax = (float) ((double) sx * FIX_INV); ay = (float) ((double) sy * FIX_INV); az = (float) ((double) sz * FIX_INV);
+}
+
 // lane-parallel regularisation gather for node n on vector x: sum over out- and in-edges (m != n) of
 // (x[n] - x[m]) in (gx,gy,gz), the edge count in cnt and (out-edges only) the squared differences in e2
 DFU_DEV void node_gather_reg(const Problem& pb, int n, int lane, const float* x, float& gx, float& gy, float& gz, float& cnt,
@@ -1081,14 +1116,14 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
             {
                 double rz = 0.0, er = 0.0;
                 for (int n = gw; n < N; n += nw) {
-                    float ax, ay, az, ad, gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
-                    node_gather_data(pb, n, lane, false, ax, ay, az, ad);
+                    float ax, ay, az, gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
+                    node_gather_data_fixed(pb, n, lane, ax, ay, az);  // already summed over the warp
                     if (pb.wreg2 > 0.f) {
                         node_gather_reg(pb, n, lane, pb.t, gx, gy, gz, cnt, e2);
+                        gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
                         ax -= pb.wreg2 * gx; ay -= pb.wreg2 * gy; az -= pb.wreg2 * gz;
                         e2 = warp_sum(e2);
                     }
-                    ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
                     const int off = pt.rowptr[n], len = pt.rowlen[n];
                     PROF(3);
                     if (gn == 0) {  // theta changed: data part of the row, ACC_W columns per pass
@@ -1438,16 +1473,13 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
             for (int r = 0; r < P3_R; ++r) {
                 if (rn[r] < 0) continue;  // uniform over the warp
                 const int n = rn[r];
-                float ax, ay, az, ad, gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
-                node_gather_data(pb, n, lane, false, ax, ay, az, ad);
-                if (pb.wreg2 > 0.f) {
-                    node_gather_reg(pb, n, lane, pb.t, gx, gy, gz, cnt, e2);
-                    ax -= pb.wreg2 * gx; ay -= pb.wreg2 * gy; az -= pb.wreg2 * gz;
-                    e2 = warp_sum(e2);
-                }
-                ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+                float ax, ay, az, gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
+                // b_n = sum tw * theta e in 2^40 fixed point (independent of the order of the node's list) ...
+                node_gather_data_fixed(pb, n, lane, ax, ay, az);
                 PROF(3);
-                if (gn == 0) {  // theta changed: data part of the row, ACC_W columns per pass
+                // ... and, when theta changed, the data part of row n of A (fixed point in shared memory), ACC_W columns per pass
+                const bool assemble = gn == 0;
+                if (assemble) {
                     const int lo = pb.tptr[n], hi = pb.tptr[n + 1];
                     const bool wide = hi - lo > FIX_MAX_DEG;  // too many contributions for the split words: 64-bit atomics
                     unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(acc_lo);
@@ -1509,6 +1541,14 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                                                             (wide ? (float) ((double) acc64[j] * FIX_INV) : fix2f(acc_lo[j], acc_hi[j]));
                         __syncwarp();
                     }
+                }
+                if (pb.wreg2 > 0.f) {
+                    node_gather_reg(pb, n, lane, pb.t, gx, gy, gz, cnt, e2);
+                    gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
+                    ax -= pb.wreg2 * gx; ay -= pb.wreg2 * gy; az -= pb.wreg2 * gz;
+                    e2 = warp_sum(e2);
+                }
+                if (assemble) {
                     // the diagonal
                     float D;
                     if (rds[r] < 32 * P3_LE) {
@@ -1833,6 +1873,18 @@ __global__ void k_fill(const int32_t* __restrict__ key, long n, const int* __res
         out[ptr[m] + atomicAdd(&cursor[m], 1)] = (int32_t) (e >> shift);
     }
 }
+// the same, writing the final (point, weight) lists directly in arrival order: versions 3 / 3r of the solver only consume
+// them through order-independent (fixed-point) sums, so they skip the sort
+__global__ void k_fill_emit(const int32_t* __restrict__ key, long n, const int* __restrict__ ptr, int* __restrict__ cursor,
+                            const float* __restrict__ wts, int32_t* __restrict__ tv, float* __restrict__ tw) {
+    const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) {
+        const int m = key[e];
+        const int slot = ptr[m] + atomicAdd(&cursor[m], 1);
+        tv[slot] = (int32_t) (e >> 3);
+        tw[slot] = wts[e];
+    }
+}
 // in-edge lists of the regularisation graph are short: insertion sort, one thread per node
 __global__ void k_sort_small(const int* __restrict__ ptr, int N, int32_t* __restrict__ a) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1910,6 +1962,7 @@ struct dfu_solver {
     unsigned long long *xw = nullptr, *pw = nullptr;
     size_t cap_nnz = 0, cap_slots = 0, cap_rows = 0;
     bool pattern_ready = false;
+    bool lists_sorted = true;    // transposed lists ordered by point id (needed by the float-order-dependent paths)
     int gn_steps_host = 0;
 };
 
@@ -2122,14 +2175,19 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
 }
 
 // sparsity pattern of the explicit normal matrix for this frame's graphs (version 3 of the persistent kernel)
+// can this problem run version 3 of the persistent kernel (explicit normal matrix)?
+bool pattern_eligible(const dfu_solver* s) {
+    const char* force = getenv("DFU_SOLVER_PATH");
+    if (force && (force[0] == 'm' || (force[0] == 'p' && (force[1] == '1' || force[1] == '2')))) return false;  // another path was asked for
+    const bool forced3 = force && force[0] == 'p' && force[1] == '3';
+    if (!forced3 && s->prm.linear_iter > P3_MAX_LINEAR_ITER) return false;
+    return !(s->coop_blocks3 == 0 || s->allreduce != nullptr || s->N > 65535 || (long) s->P >= (1L << 19));
+}
+
 int build_pattern(dfu_solver* s, cudaStream_t st) {
     s->pattern_ready = false;
     const int N = s->N, P = s->P;
-    const char* force = getenv("DFU_SOLVER_PATH");
-    if (force && (force[0] == 'm' || (force[0] == 'p' && (force[1] == '1' || force[1] == '2')))) return DFU_OK;  // another path was asked for
-    const bool forced3 = force && force[0] == 'p' && force[1] == '3';
-    if (!forced3 && s->prm.linear_iter > P3_MAX_LINEAR_ITER) return DFU_OK;
-    if (s->coop_blocks3 == 0 || s->allreduce != nullptr || N > 65535 || (long) P >= (1L << 19)) return DFU_OK;
+    if (!pattern_eligible(s)) return DFU_OK;
     // hard upper bound of the non-zeros: every (node, point) pair contributes at most 8 columns, plus 16 edges + diagonal
     const size_t nnz_cap = std::min<size_t>((size_t) 64 * P + (size_t) 17 * N, (size_t) N * N);
     const size_t slots = (size_t) 8 * P;
@@ -2316,24 +2374,28 @@ int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* ca
         DFU_LAUNCH_OK();
         s->reg_epoch = wf->node_epoch;
     }
-    // data graph (opt_solver.cpp:56-72) with the per-edge weights, and its transpose
-    if (P > 0) {
-        rc = dfu_wf_build_data_graph(wf, canon_v, live_v, P, s->nbr, s->wts, s->dvec, st);
-        if (rc != DFU_OK) return rc;
-    }
+    // data graph (opt_solver.cpp:56-72) with the per-edge weights (the kNN kernel also counts the references per node),
+    // and its transpose: per node the (point, weight) pairs -- in arrival order when only order-independent consumers
+    // will read them (versions 3 / 3r), sorted by point otherwise
     const long ne = (long) P * 8;
     DFU_CUDA_OK(cudaMemsetAsync(s->tmp, 0, 2 * (size_t) N * sizeof(int), st));
     if (P > 0) {
-        k_count<<<div_up(ne, TPB), TPB, 0, st>>>(s->nbr, ne, s->tmp);
-        DFU_LAUNCH_OK();
+        rc = dfu_wf_build_data_graph(wf, canon_v, live_v, P, s->nbr, s->wts, s->dvec, s->tmp, st);
+        if (rc != DFU_OK) return rc;
     }
     k_scan<<<1, 1024, 0, st>>>(s->tmp, N, s->tptr);
     DFU_LAUNCH_OK();
+    s->lists_sorted = !pattern_eligible(s);
     if (P > 0) {
-        k_fill<<<div_up(ne, TPB), TPB, 0, st>>>(s->nbr, ne, s->tptr, s->tmp + N, s->tent, 0);
-        DFU_LAUNCH_OK();
-        k_sort_emit<<<min(div_up((long) N * 32, TPB), 65535), TPB, 0, st>>>(s->tptr, N, s->tent, s->wts, s->tv, s->tw);
-        DFU_LAUNCH_OK();
+        if (s->lists_sorted) {
+            k_fill<<<div_up(ne, TPB), TPB, 0, st>>>(s->nbr, ne, s->tptr, s->tmp + N, s->tent, 0);
+            DFU_LAUNCH_OK();
+            k_sort_emit<<<min(div_up((long) N * 32, TPB), 65535), TPB, 0, st>>>(s->tptr, N, s->tent, s->wts, s->tv, s->tw);
+            DFU_LAUNCH_OK();
+        } else {
+            k_fill_emit<<<div_up(ne, TPB), TPB, 0, st>>>(s->nbr, ne, s->tptr, s->tmp + N, s->wts, s->tv, s->tw);
+            DFU_LAUNCH_OK();
+        }
     }
     DFU_CUDA_OK(cudaMemsetAsync(s->vec, 0, 18 * (size_t) N * sizeof(float), st));  // unknowns := 0 (opt_solver.cpp:192-193)
     rc = build_pattern(s, st);
@@ -2354,6 +2416,17 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream) {
     // DFU_SOLVER_PATH=multi forces the one-kernel-per-phase path (used by the tests to cover both)
     const char* force = getenv("DFU_SOLVER_PATH");
     const bool multi = s->allreduce != nullptr || s->coop_blocks == 0 || (force && force[0] == 'm');
+    if (!s->lists_sorted && (multi || !pattern_eligible(s)) && s->P > 0) {
+        // the path changed after init_problem (hook set, environment): the float-order-dependent kernels want sorted lists
+        const long ne = (long) s->P * 8;
+        DFU_CUDA_OK(cudaMemsetAsync(s->tmp + s->N, 0, (size_t) s->N * sizeof(int), st));
+        k_fill<<<div_up(ne, TPB), TPB, 0, st>>>(s->nbr, ne, s->tptr, s->tmp + s->N, s->tent, 0);
+        DFU_LAUNCH_OK();
+        k_sort_emit<<<min(div_up((long) s->N * 32, TPB), 65535), TPB, 0, st>>>(s->tptr, s->N, s->tent, s->wts, s->tv, s->tw);
+        DFU_LAUNCH_OK();
+        s->lists_sorted = true;
+        s->pattern_ready = false;  // its per-entry slots referred to the old order
+    }
     int rc = multi ? solve_multi_kernel(s, st) : solve_persistent(s, st);
     if (rc != DFU_OK) return rc;
     // write back ONCE: dg_se3 := DQ(0,0,0,t) * dg_se3 (opt_solver.cpp:270-285, node.cpp:19-23)

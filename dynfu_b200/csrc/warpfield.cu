@@ -160,6 +160,7 @@ struct PointArgs {
     float* wts;
     const float* live;
     float* dvec;
+    int* deg;         // OP_GRAPH (may be null): per-node count of referencing points, incremented here
     // OP_BOUNDS: queries are the centres of the 8x8x8 bricks of a volume
     float2* bounds;
     int bdim[3];
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(256) points_kernel(const PointArgs a) {
         if (active) {
             a.idx[(size_t) q * DFU_KNN + sub] = my_i;
             a.wts[(size_t) q * DFU_KNN + sub] = my_w;
+            if (a.deg && my_i >= 0) atomicAdd(&a.deg[my_i], 1);
             if (sub < 3) a.dvec[3 * (size_t) q + sub] = a.live[3 * (size_t) q + sub] - (sub == 0 ? qx : (sub == 1 ? qy : qz));
         }
         return;
@@ -544,6 +546,11 @@ __global__ void __launch_bounds__(128) points_grid_kernel(const PointArgs a, con
         a.dvec[3 * (size_t) q] = a.live[3 * (size_t) q] - qx;
         a.dvec[3 * (size_t) q + 1] = a.live[3 * (size_t) q + 1] - qy;
         a.dvec[3 * (size_t) q + 2] = a.live[3 * (size_t) q + 2] - qz;
+        if (a.deg) {
+#pragma unroll
+            for (int k = 0; k < DFU_KNN; ++k)
+                if (t.i[k] >= 0) atomicAdd(&a.deg[t.i[k]], 1);
+        }
         return;
     }
     const DQ b = blend(a.blend_mode, t, w, a.real, a.dual);
@@ -736,7 +743,7 @@ int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float v
 
 // data graph + weights + (live - canon) for the solver; requires N >= 8
 int dfu_wf_build_data_graph(const dfu_warpfield* wf, const float* canon, const float* live, int P, int32_t* nbr,
-                            float* wts, float* dvec, cudaStream_t st) {
+                            float* wts, float* dvec, int* deg, cudaStream_t st) {
     PointArgs a{};
     a.q = canon;
     a.Q = P;
@@ -744,6 +751,7 @@ int dfu_wf_build_data_graph(const dfu_warpfield* wf, const float* canon, const f
     a.wts = wts;
     a.live = live;
     a.dvec = dvec;
+    a.deg = deg;
     return launch_points<OP_GRAPH>(wf, a, st);
 }
 // regularisation graph: 8-NN of every node among the nodes (includes itself; opt_solver.cpp:74-105)
