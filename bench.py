@@ -279,7 +279,7 @@ def main():
         """inputs already in HBM"""
         dfu.compute_dists(depth_dev[i % RING], kp.intr, out=df._dists)
         if timed:
-            df.canonicalWarpedToLive, _ = df.warpfield.warpToLive(df.canonicalVertices, None, prm.blend_mode)
+            df.canonicalWarpedToLive, _ = df.warpCanonical()
             df.solver.initializeProblemInstance(df.canonicalWarpedToLive, live_dev[i % RING])
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()

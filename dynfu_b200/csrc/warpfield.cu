@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) points_kernel(const PointArgs a) {
             a.idx[(size_t) q * DFU_KNN + sub] = my_i;
             a.wts[(size_t) q * DFU_KNN + sub] = my_w;
             if (a.deg && my_i >= 0) atomicAdd(&a.deg[my_i], 1);
-            if (sub < 3) a.dvec[3 * (size_t) q + sub] = a.live[3 * (size_t) q + sub] - (sub == 0 ? qx : (sub == 1 ? qy : qz));
+            if (sub < 3 && a.dvec) a.dvec[3 * (size_t) q + sub] = a.live[3 * (size_t) q + sub] - (sub == 0 ? qx : (sub == 1 ? qy : qz));
         }
         return;
     }
@@ -543,9 +543,11 @@ __global__ void __launch_bounds__(128) points_grid_kernel(const PointArgs a, con
         float4* ww = reinterpret_cast<float4*>(a.wts + (size_t) q * DFU_KNN);
         ww[0] = make_float4(w[0], w[1], w[2], w[3]);
         ww[1] = make_float4(w[4], w[5], w[6], w[7]);
-        a.dvec[3 * (size_t) q] = a.live[3 * (size_t) q] - qx;
-        a.dvec[3 * (size_t) q + 1] = a.live[3 * (size_t) q + 1] - qy;
-        a.dvec[3 * (size_t) q + 2] = a.live[3 * (size_t) q + 2] - qz;
+        if (a.dvec) {
+            a.dvec[3 * (size_t) q] = a.live[3 * (size_t) q] - qx;
+            a.dvec[3 * (size_t) q + 1] = a.live[3 * (size_t) q + 1] - qy;
+            a.dvec[3 * (size_t) q + 2] = a.live[3 * (size_t) q + 2] - qz;
+        }
         if (a.deg) {
 #pragma unroll
             for (int k = 0; k < DFU_KNN; ++k)
@@ -565,6 +567,30 @@ __global__ void __launch_bounds__(128) points_grid_kernel(const PointArgs a, con
             const V3 rn = a.normal_mode == DFU_NORMAL_REF ? dq_transform_vertex(b, nn) : dq_rotate(b, nn);
             a.n_out[3 * (size_t) q] = rn.x; a.n_out[3 * (size_t) q + 1] = rn.y; a.n_out[3 * (size_t) q + 2] = rn.z;
         }
+    }
+}
+
+// Warp of a point set whose 8 nearest nodes and weights are cached (dfu_warpfield_warp_cached): same blend and transform
+// arithmetic as points_*_kernel<OP_WARP>, fed from the cache instead of a search
+__global__ void __launch_bounds__(256) warp_cached_kernel(const PointArgs a, const int32_t* __restrict__ ids, const float* __restrict__ wts) {
+    const long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.Q) return;
+    const float qx = a.q[3 * (size_t) q], qy = a.q[3 * (size_t) q + 1], qz = a.q[3 * (size_t) q + 2];
+    V3 nn{0.f, 0.f, 0.f};
+    if (a.n_in) nn = V3{a.n_in[3 * (size_t) q], a.n_in[3 * (size_t) q + 1], a.n_in[3 * (size_t) q + 2]};
+    const int4 i0 = *(reinterpret_cast<const int4*>(ids) + 2 * (size_t) q), i1 = *(reinterpret_cast<const int4*>(ids) + 2 * (size_t) q + 1);
+    const float4 w0 = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) q), w1 = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) q + 1);
+    Top8 t;
+    t.i[0] = i0.x; t.i[1] = i0.y; t.i[2] = i0.z; t.i[3] = i0.w; t.i[4] = i1.x; t.i[5] = i1.y; t.i[6] = i1.z; t.i[7] = i1.w;
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) t.d[k] = 0.f;  // the blend only reads the ids
+    const float w[DFU_KNN] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const DQ b = blend(a.blend_mode, t, w, a.real, a.dual);
+    const V3 r = dq_transform_vertex(b, V3{qx, qy, qz});
+    a.v_out[3 * (size_t) q] = r.x; a.v_out[3 * (size_t) q + 1] = r.y; a.v_out[3 * (size_t) q + 2] = r.z;
+    if (a.n_in && a.n_out) {
+        const V3 rn = a.normal_mode == DFU_NORMAL_REF ? dq_transform_vertex(b, nn) : dq_rotate(b, nn);
+        a.n_out[3 * (size_t) q] = rn.x; a.n_out[3 * (size_t) q + 1] = rn.y; a.n_out[3 * (size_t) q + 2] = rn.z;
     }
 }
 
@@ -662,7 +688,7 @@ int ensure_staging(dfu_warpfield* wf, size_t floats) {
 }  // namespace
 
 int dfu_wf_refresh_flags(dfu_warpfield* wf, cudaStream_t st) {
-    node_flags_kernel<<<1, 256, 0, st>>>(wf->pos_w, wf->real, wf->dual, wf->N, wf->flags);
+    node_flags_kernel<<<1, 1024, 0, st>>>(wf->pos_w, wf->real, wf->dual, wf->N, wf->flags);
     DFU_LAUNCH_OK();
     return DFU_OK;
 }
@@ -953,6 +979,94 @@ int dfu_warpfield_warp(const dfu_warpfield* wf, const float* v_xyz, const float*
     a.blend_mode = blend_mode;
     a.normal_mode = normal_mode;
     return launch_points<OP_WARP>(wf, a, as_stream(stream));
+}
+
+struct dfu_pointcache {
+    int device = 0;
+    int32_t* ids = nullptr;
+    float* wts = nullptr;
+    size_t cap = 0;
+    // what the cache was filled for
+    const dfu_warpfield* wf = nullptr;
+    uint64_t node_epoch = 0;
+    unsigned long long version = 0;
+    const float* v = nullptr;
+    int P = -1;
+};
+
+int dfu_pointcache_create(dfu_pointcache** out, int device) {
+    DFU_REQUIRE(out != nullptr, DFU_ERR_INVALID, "out is NULL");
+    int rc = dfu_device_check(device);
+    if (rc != DFU_OK) return rc;
+    *out = new dfu_pointcache();
+    (*out)->device = device;
+    return DFU_OK;
+}
+
+int dfu_pointcache_destroy(dfu_pointcache* c) {
+    if (!c) return DFU_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    cudaFree(c->ids);
+    cudaFree(c->wts);
+    cudaSetDevice(prev);
+    delete c;
+    return DFU_OK;
+}
+
+int dfu_warpfield_warp_cached(const dfu_warpfield* wf, dfu_pointcache* cache, unsigned long long points_version, const float* v_xyz,
+                              const float* n_xyz, int P, float* v_out, float* n_out, int blend_mode, int normal_mode,
+                              dfu_stream stream) {
+    DFU_REQUIRE(wf && cache && (P == 0 || (v_xyz && v_out)), DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(P >= 0, DFU_ERR_INVALID, "negative P");
+    DFU_REQUIRE(blend_mode == DFU_BLEND_REF_COMPOSE || blend_mode == DFU_BLEND_DQB_SUM, DFU_ERR_INVALID, "bad blend_mode");
+    DFU_REQUIRE(normal_mode == DFU_NORMAL_REF || normal_mode == DFU_NORMAL_ROTATE_ONLY, DFU_ERR_INVALID, "bad normal_mode");
+    DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
+    DFU_REQUIRE(v_out != v_xyz, DFU_ERR_INVALID, "the cached warp cannot run in place: the cache is keyed on the input points");
+    if (P == 0) return DFU_OK;
+    DFU_GUARD(wf->device);
+    cudaStream_t st = as_stream(stream);
+    const bool hit = cache->wf == wf && cache->node_epoch == wf->node_epoch && cache->version == points_version &&
+                     cache->v == v_xyz && cache->P == P;
+    if (!hit) {
+        if ((size_t) P > cache->cap) {
+            cudaFree(cache->ids);
+            cudaFree(cache->wts);
+            cache->ids = nullptr;
+            cache->wts = nullptr;
+            cache->cap = 0;
+            DFU_CUDA_OK(cudaMalloc(&cache->ids, (size_t) P * DFU_KNN * sizeof(int32_t)));
+            DFU_CUDA_OK(cudaMalloc(&cache->wts, (size_t) P * DFU_KNN * sizeof(float)));
+            cache->cap = (size_t) P;
+        }
+        cache->P = -1;
+        PointArgs g{};  // neighbours + weights of every point: the solver's graph kernel without its extras
+        g.q = v_xyz;
+        g.Q = P;
+        g.idx = cache->ids;
+        g.wts = cache->wts;
+        int rc = launch_points<OP_GRAPH>(wf, g, st);
+        if (rc != DFU_OK) return rc;
+        cache->wf = wf;
+        cache->node_epoch = wf->node_epoch;
+        cache->version = points_version;
+        cache->v = v_xyz;
+        cache->P = P;
+    }
+    PointArgs a{};
+    a.q = v_xyz;
+    a.Q = P;
+    a.n_in = n_xyz;
+    a.v_out = v_out;
+    a.n_out = n_out;
+    a.blend_mode = blend_mode;
+    a.normal_mode = normal_mode;
+    a.real = wf->real;
+    a.dual = wf->dual;
+    warp_cached_kernel<<<div_up(P, 256), 256, 0, st>>>(a, cache->ids, cache->wts);
+    DFU_LAUNCH_OK();
+    return DFU_OK;
 }
 
 }  // extern "C"

@@ -80,6 +80,7 @@ class DynFusion:
     def init(self, canonicalVertices, canonicalNormals=None, nodes=None):
         cv = torch.as_tensor(canonicalVertices, dtype=torch.float32).to(self.device).reshape(-1, 3).contiguous()
         self.canonicalVertices = cv
+        self._canon_version = getattr(self, "_canon_version", 0) + 1  # the cached warp below is keyed on it
         self.canonicalNormals = None if canonicalNormals is None else torch.as_tensor(
             canonicalNormals, dtype=torch.float32).to(self.device).reshape(-1, 3).contiguous()
         if nodes is None:
@@ -111,14 +112,19 @@ class DynFusion:
         """paired=True: liveVertices[i] belongs to canonicalVertices[i] (the solver tests' convention).
         paired=False: the reference's flow -- warp the canonical frame, then pick for every live vertex the nearest
         warped canonical vertex (findCorrespondingFrame, :196-197) and solve on those pairs."""
-        self.canonicalWarpedToLive, warpedNormals = self.warpfield.warpToLive(self.canonicalVertices, self.canonicalNormals,
-                                                                              self.params.blend_mode)
+        self.canonicalWarpedToLive, warpedNormals = self.warpCanonical()
         if paired:
             self.solver.initializeProblemInstance(self.canonicalWarpedToLive, liveVertices)
         else:
             corr_v, _ = self.findCorrespondingFrame(self.canonicalWarpedToLive, warpedNormals, liveVertices)
             self.solver.initializeProblemInstance(corr_v, liveVertices)
         self.solver.solveAll()
+
+    # warpfield->warpToLive(canonicalFrame) (dyn_fusion.cpp:196): the canonical frame is fixed between init() calls, so its
+    # nearest nodes and weights are cached on the device (bit-identical to the uncached warp)
+    def warpCanonical(self):
+        return self.warpfield.warpToLiveCached(self.canonicalVertices, self.canonicalNormals, self._canon_version,
+                                               self.params.blend_mode)
 
     # DynFusion::findCorrespondingFrame (src/dynfu/dyn_fusion.cpp:212-242)
     def findCorrespondingFrame(self, canonicalVertices, canonicalNormals, liveVertices):

@@ -31,7 +31,13 @@ class Warpfield:
         self._h = h
         self.epsilon = None
 
+    def _free_pcache(self):
+        if getattr(self, "_pcache", None) is not None and lib is not None:
+            lib.dfu_pointcache_destroy(self._pcache)
+            self._pcache = None
+
     def __del__(self):
+        self._free_pcache()
         h = getattr(self, "_h", None)
         if h:
             lib.dfu_warpfield_destroy(h)
@@ -87,6 +93,22 @@ class Warpfield:
         nu, nn = C.c_int(), C.c_int()
         check(lib.dfu_warpfield_update(self._h, dptr(v), v.shape[0], blend_mode, C.byref(nu), C.byref(nn), stream_ptr()))
         return nu.value, nn.value
+
+    # warpToLive for a fixed point set (the canonical frame): neighbours + weights cached across calls
+    def warpToLiveCached(self, vertices, normals=None, version=0, blend_mode=BLEND_REF_COMPOSE, normal_mode=NORMAL_REF):
+        """`vertices` must be the same tensor (same storage) from call to call; bump `version` when its contents change."""
+        v = _f32(vertices, (-1, 3), self.device)
+        if getattr(self, "_pcache", None) is None:
+            self._pcache = C.c_void_p()
+            check(lib.dfu_pointcache_create(C.byref(self._pcache), self.device.index or 0))
+        vo = torch.empty_like(v)
+        n = no = None
+        if normals is not None:
+            n = _f32(normals, (-1, 3), self.device)
+            no = torch.empty_like(n)
+        check(lib.dfu_warpfield_warp_cached(self._h, self._pcache, int(version), dptr(v), dptr(n), v.shape[0], dptr(vo), dptr(no),
+                                            blend_mode, normal_mode, stream_ptr()))
+        return vo, no
 
     def cacheStats(self):
         """(bricks the per-voxel neighbour cache holds, bricks currently valid) -- diagnostics"""

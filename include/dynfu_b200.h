@@ -116,6 +116,19 @@ int dfu_warpfield_blend(const dfu_warpfield* wf, const float* p_xyz, int Q, floa
 int dfu_warpfield_warp(const dfu_warpfield* wf, const float* v_xyz, const float* n_xyz, int P, float* v_out,
                        float* n_out, int blend_mode, int normal_mode, dfu_stream stream);
 
+/* Warpfield::warpToLive for a point set that does not change between calls -- the canonical frame, which DynFusion
+ * warps again every frame (src/dynfu/dyn_fusion.cpp:196).  The 8 nearest nodes of a point and their weights depend
+ * only on the point and the node POSITIONS (never on the node transforms), so they are computed on the first call
+ * and kept in `cache` until the points or the node positions change: `points_version` is the caller's change
+ * counter for v_xyz (same pointer + same version + same P = same points); node positions are tracked by the
+ * library.  Results are bit-identical to dfu_warpfield_warp.  Not in place (v_out != v_xyz). */
+typedef struct dfu_pointcache dfu_pointcache;
+int dfu_pointcache_create(dfu_pointcache** out, int device);
+int dfu_pointcache_destroy(dfu_pointcache* cache);
+int dfu_warpfield_warp_cached(const dfu_warpfield* wf, dfu_pointcache* cache, unsigned long long points_version,
+                              const float* v_xyz, const float* n_xyz, int P, float* v_out, float* n_out,
+                              int blend_mode, int normal_mode, dfu_stream stream);
+
 /* ------------------------------------------------------------------------------------------------
  * TSDF volume  (layout of kfusion::cuda::TsdfVolume: ushort2 {half tsdf bits, u16 weight} per voxel,
  * idx = x + y*dims.x + z*dims.x*dims.y, include/kfusion/cuda/device.hpp:20-35,59-67)

@@ -49,6 +49,33 @@ def test_knn_bit_exact(dfu, oracle, n_nodes, n_q):
     assert np.array_equal(d_g.cpu().numpy(), d_o)
 
 
+def test_cached_warp_is_bit_identical_and_tracks_changes(dfu, oracle):
+    """dfu_warpfield_warp_cached: neighbours + weights of a fixed point set are kept across calls; transforms may change
+    freely, a new node set or a new points version refills the cache"""
+    rng = np.random.default_rng(21)
+    pos, dq, dg_w, t_true = synth.sphere_nodes(2000, 0.0125, rotations=True)
+    v = dev((pos[rng.integers(0, 2000, 30000)] + rng.normal(0, 0.02, (30000, 3))).astype(np.float32))
+    n = dev(rng.normal(size=(30000, 3)).astype(np.float32))
+    wf = make_wf(dfu, pos, dq, dg_w)
+    for mode in (dfu.BLEND_REF_COMPOSE, dfu.BLEND_DQB_SUM):
+        a_v, a_n = wf.warpToLive(v, n, mode)
+        b_v, b_n = wf.warpToLiveCached(v, n, 1, mode)
+        c_v, c_n = wf.warpToLiveCached(v, n, 1, mode)  # served from the cache
+        assert torch.equal(a_v, b_v) and torch.equal(a_n, b_n) and torch.equal(a_v, c_v) and torch.equal(a_n, c_n)
+    wf.setTransformations(dev(synth.translations_to_dq(0.3 * t_true)))  # transforms only: cache stays valid
+    assert torch.equal(wf.warpToLive(v, None)[0], wf.warpToLiveCached(v, None, 1)[0])
+    v.add_(0.004)  # same storage, new contents: the caller bumps the version
+    assert torch.equal(wf.warpToLive(v, None)[0], wf.warpToLiveCached(v, None, 2)[0])
+    wf.init(0.0125, dev(pos[:1500] + np.float32(0.001)), dev(dq[:1500]), dev(dg_w[:1500]))  # new node positions
+    assert torch.equal(wf.warpToLive(v, None)[0], wf.warpToLiveCached(v, None, 2)[0])
+    with pytest.raises(dfu.DfuError):
+        lib = dfu.lib
+        import ctypes as C
+        lib.dfu_warpfield_warp_cached.restype = C.c_int
+        from dynfu_b200._lib import check, dptr, stream_ptr
+        check(lib.dfu_warpfield_warp_cached(wf.handle, wf._pcache, 2, dptr(v), None, 30000, dptr(v), None, 0, 0, stream_ptr()))
+
+
 def test_knn_matches_reference_nanoflann(dfu, oracle_nf):
     """straight against the reference's own KD-tree code (oracle/_ref, prebuilt from the reference header)"""
     rng = np.random.default_rng(5)

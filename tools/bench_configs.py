@@ -64,7 +64,7 @@ def run(name, dim, n_theta, n_y, eps, gn, pcg, rows=480, cols=640, z0=0, z1=None
     t = {}
 
     def solve(i):
-        df.canonicalWarpedToLive, _ = df.warpfield.warpToLive(df.canonicalVertices, None, prm.blend_mode)
+        df.canonicalWarpedToLive, _ = df.warpCanonical()
         df.solver.initializeProblemInstance(df.canonicalWarpedToLive, live_dev[i % 2])
         df.solver.solveAll()
 
