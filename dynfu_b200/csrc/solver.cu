@@ -1080,6 +1080,10 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, gw = tid >> 5, nw = nthreads >> 5;
     const int nb = gridDim.x, N = pb.N;
+    // every warp owns a contiguous block of rows (at most 32: N <= 65535 and >= 2368 resident warps): warp-per-row for the
+    // row products, lane-per-row (coalesced float4 accesses) for the vector updates
+    const int R = (N + nw - 1) / nw;
+    const int row0 = min(N, gw * R), row1 = min(N, row0 + R);
     unsigned bar_target = 0;
     unsigned long long* acc = acc_sm + (threadIdx.x >> 5) * ACC_W;
     float4 *S_r = pt.st, *S_w = pt.st + N, *S_z = pt.st + 2 * (size_t) N, *S_s = pt.st + 3 * (size_t) N,
@@ -1099,6 +1103,57 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
     for (int i = tid; i < 3 * N; i += nthreads) pb.t[i] = 0.f;  // unknowns := 0 (opt_solver.cpp:192-193)
     GRID_SYNC();
 
+    // y = A x for all rows of this warp, four rows in flight (their index / value / gather loads are issued together);
+    // the lane that owns row n (lane == n - row0) receives the result
+    auto spmv_block = [&](const float4* __restrict__ x, float& rx, float& ry, float& rz_) {
+        rx = ry = rz_ = 0.f;
+        for (int n0 = row0; n0 < row1; n0 += 4) {
+            int off[4], len[4], c[4][2];
+            float v[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool ok = n0 + q < row1;
+                off[q] = ok ? pt.rowptr[n0 + q] : 0;
+                len[q] = ok ? pt.rowlen[n0 + q] : 0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = lane + 32 * u;
+                    c[q][u] = j < len[q] ? pt.col[off[q] + j] : -1;
+                    v[q][u] = j < len[q] ? pt.vals[off[q] + j] : 0.f;
+                }
+            float ax[4], ay[4], az[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ax[q] = ay[q] = az[q] = 0.f;
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (c[q][u] >= 0) {
+                        const float4 m = __ldcg(x + c[q][u]);
+                        ax[q] = __fmaf_rn(v[q][u], m.x, ax[q]);
+                        ay[q] = __fmaf_rn(v[q][u], m.y, ay[q]);
+                        az[q] = __fmaf_rn(v[q][u], m.z, az[q]);
+                    }
+                for (int j = 64 + lane; j < len[q]; j += 32) {  // rows longer than 64 entries: the rest
+                    const float vv = pt.vals[off[q] + j];
+                    const float4 m = __ldcg(x + pt.col[off[q] + j]);
+                    ax[q] = __fmaf_rn(vv, m.x, ax[q]);
+                    ay[q] = __fmaf_rn(vv, m.y, ay[q]);
+                    az[q] = __fmaf_rn(vv, m.z, az[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ax[q] = warp_sum(ax[q]); ay[q] = warp_sum(ay[q]); az[q] = warp_sum(az[q]);
+                if (lane == n0 + q - row0) {
+                    rx = ax[q]; ry = ay[q]; rz_ = az[q];
+                }
+            }
+        }
+    };
+
     double rz_ref = -1.0, E = 0.0, E0 = 0.0;
     int pcg_total = 0, gn_total = 0;
     bool first = true, stop_all = false;
@@ -1115,7 +1170,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
             // ---- per row: b = -J^T r (+ regularisation), the row of A, D = A_nn, PCG start r = b, u = M^-1 b, x = 0 ----
             {
                 double rz = 0.0, er = 0.0;
-                for (int n = gw; n < N; n += nw) {
+                for (int n = row0; n < row1; ++n) {
                     float ax, ay, az, gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
                     node_gather_data_fixed(pb, n, lane, ax, ay, az);  // already summed over the warp
                     if (pb.wreg2 > 0.f) {
@@ -1197,10 +1252,11 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
             PROF(7);
             if (!conv0) {
                 // w0 = A u0; z = s = p = 0
-                for (int n = gw; n < N; n += nw) {
+                {
                     float wx, wy, wz;
-                    spmv_row(pt, pt.rowptr[n], pt.rowlen[n], lane, pt.exch, wx, wy, wz);
-                    if (lane == 0) {
+                    spmv_block(pt.exch, wx, wy, wz);
+                    const int n = row0 + lane;
+                    if (n < row1) {
                         S_w[n] = make_float4(wx, wy, wz, 0.f);
                         S_z[n] = zero4; S_s[n] = zero4; S_p[n] = zero4;
                     }
@@ -1212,8 +1268,9 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                     float4* ex = pt.exch + (size_t) buf * N;
                     // (r,u), (w,u) with u = M^-1 r; m = M^-1 w goes to the exchange buffer
                     double g = 0.0, d = 0.0;
-                    if (lane == 0)
-                        for (int n = gw; n < N; n += nw) {
+                    {
+                        const int n = row0 + lane;  // one row per lane
+                        if (n < row1) {
                             const float D = pb.nbuf[3 * (size_t) N + n];
                             const float inv = D > 0.f ? 1.f / D : 0.f;
                             const double invd = D > 0.f ? 1.0 / (double) D : 0.0;
@@ -1222,6 +1279,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                             d += ((double) w.x * r.x + (double) w.y * r.y + (double) w.z * r.z) * invd;
                             ex[n] = make_float4(w.x * inv, w.y * inv, w.z * inv, 0.f);
                         }
+                    }
                     {
                         const D4 s = block_sum4(D4{g, d, 0.0, 0.0}, sh4);
                         if (threadIdx.x == 0) {
@@ -1243,10 +1301,11 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                     const float af = (float) alpha, bf = (float) beta;
                     const bool last = it + 1 >= ctl.linear_iter;
                     PROF(11);
-                    for (int n = gw; n < N; n += nw) {
+                    {
                         float nx = 0.f, ny = 0.f, nz = 0.f;
-                        if (!last) spmv_row(pt, pt.rowptr[n], pt.rowlen[n], lane, ex, nx, ny, nz);  // n = A m
-                        if (lane == 0) {
+                        if (!last) spmv_block(ex, nx, ny, nz);  // n = A m
+                        const int n = row0 + lane;
+                        if (n < row1) {
                             const float D = pb.nbuf[3 * (size_t) N + n];
                             const float inv = D > 0.f ? 1.f / D : 0.f;
                             float4 r = S_r[n], w = S_w[n], z = S_z[n], sv = S_s[n], p = S_p[n], x = S_x[n];
@@ -1266,11 +1325,13 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                 }
             }
             // t += x (row-local), then everybody needs the new t
-            if (lane == 0)
-                for (int n = gw; n < N; n += nw) {
+            {
+                const int n = row0 + lane;
+                if (n < row1) {
                     const float4 x = S_x[n];
                     pb.t[3 * (size_t) n] += x.x; pb.t[3 * (size_t) n + 1] += x.y; pb.t[3 * (size_t) n + 2] += x.z;
                 }
+            }
             ++gn_total;
             PROF(13);
             GRID_SYNC();
@@ -1282,7 +1343,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
         const double e2 = phase_point_residual(pb, first, tid, nthreads);  // no GN step ran: weights at t = 0
         double er = 0.0;
         if (pb.wreg2 > 0.f)
-            for (int n = gw; n < N; n += nw) {
+            for (int n = row0; n < row1; ++n) {
                 float gx, gy, gz, cnt, r2;
                 node_gather_reg(pb, n, lane, pb.t, gx, gy, gz, cnt, r2);
                 r2 = warp_sum(r2);
@@ -2133,7 +2194,7 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
     // take the textbook PCG of version 2 / 1.
     const int want = forced ? force[1] - '0' : (s->prm.linear_iter <= P3_MAX_LINEAR_ITER ? 3 : 2);
     int ver = want;
-    if (ver == 3 && !(s->pattern_ready && s->coop_blocks3 > 0)) ver = 2;
+    if (ver == 3 && !(s->pattern_ready && s->coop_blocks3 > 0 && s->N <= 32 * s->coop_blocks3 * (PTPB / 32))) ver = 2;  // (lane-per-row blocks)
     if (ver == 2 && (s->coop_blocks2 == 0 || s->N > P2_NPW * s->coop_blocks2 * (PTPB / 32))) ver = 1;
     if (ver == 3) {
         Pattern pt{s->rowptr, s->rowlen, s->dslot, s->col, s->areg, s->vals, s->tslot, s->exch, s->st, s->xw, s->pw};
