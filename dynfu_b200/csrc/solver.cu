@@ -1170,7 +1170,9 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
             // ---- per row: b = -J^T r (+ regularisation), the row of A, D = A_nn, PCG start r = b, u = M^-1 b, x = 0 ----
             {
                 double rz = 0.0, er = 0.0;
-                for (int n = row0; n < row1; ++n) {
+                // (strided, not the contiguous blocks: neighbouring rows are equally heavy, and this phase walks whole
+                //  (point, weight) lists -- any warp may prepare any row, its outputs all go to memory)
+                for (int n = gw; n < N; n += nw) {
                     float ax, ay, az, gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
                     node_gather_data_fixed(pb, n, lane, ax, ay, az);  // already summed over the warp
                     if (pb.wreg2 > 0.f) {

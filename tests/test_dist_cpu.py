@@ -83,3 +83,26 @@ def test_two_rank_gloo_partition_and_allreduce():
     port = 29500 + (os.getpid() % 400)
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_balanced_slabs_tile_the_volume_and_follow_the_nodes():
+    import numpy as np
+    from dynfu_b200 import dist as dd
+
+    rng = np.random.default_rng(0)
+    node_z = rng.normal(1.4, 0.1, 4096)  # a surface band around z = 1.4 m of a 3 m volume
+    for world in (1, 2, 3, 4, 8):
+        prev = 0
+        for r in range(world):
+            z0, z1 = dd.balanced_slab_range(r, world, 512, node_z, 3.0 / 512, 0.25)
+            assert z0 == prev and z1 > z0 and z0 % 8 == 0 and (z1 % 8 == 0 or z1 == 512)
+            prev = z1
+        assert prev == 512
+    # 2 ranks: the cut goes through the band, not through the middle of the volume (plane 256 = 1.5 m would leave
+    # most nodes on one side)
+    z0, z1 = dd.balanced_slab_range(0, 2, 512, node_z, 3.0 / 512, 0.25)
+    assert abs(z1 * 3.0 / 512 - 1.4) < 0.1
+    # degenerate inputs still tile
+    assert dd.balanced_slab_range(0, 1, 64, [], 0.05, 0.1) == (0, 64)
+    parts = [dd.balanced_slab_range(r, 8, 16, [0.1], 0.05, 0.1) for r in range(8)]
+    assert parts[0][0] == 0 and parts[-1][1] == 16 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
