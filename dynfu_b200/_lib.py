@@ -86,6 +86,8 @@ _SIGS = {
     "dfu_voxel_grid_filter": ([_vp, _i, _f, _vp, C.POINTER(_i), _vp], _i),
     "dfu_warpfield_update": ([_vp, _vp, _i, _i, C.POINTER(_i), C.POINTER(_i), _vp], _i),
     "dfu_warpfield_cache_stats": ([_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _vp], _i),
+    "dfu_tsdf_raycast": ([_vp, C.POINTER(_i), C.POINTER(_f), _f, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), _i, _i, _f, _f, _vp, _sz,
+                         _vp, _sz, _vp, _sz, _vp], _i),
     "dfu_pointcache_create": ([C.POINTER(_vp), _i], _i),
     "dfu_pointcache_destroy": ([_vp], _i),
     "dfu_warpfield_warp_cached": ([_vp, _vp, C.c_ulonglong, _vp, _vp, _i, _vp, _vp, _i, _i, _vp], _i),

@@ -414,6 +414,19 @@ public:
                                               wf ? wf->raw() : nullptr, DFU_BLEND_REF_COMPOSE, 0, dims[2], nullptr),
                            "dfu_tsdf_integrate");
     }
+    // :95-129 with camera pose = identity rotation: depth (u16 mm) + normals (float4) of the fused model, device images
+    void setRaycastStepFactor(float f) { raycast_step_factor_ = f; }
+    void setGradientDeltaFactor(float f) { gradient_delta_factor_ = f; }
+    void raycast(const float intr[4], int rows, int cols, uint16_t* depth_dev, size_t depth_pitch, float* normals4_dev, size_t normals_pitch) {
+        float vs[3];
+        voxelSize(vs);
+        // cam2vol = pose_.inv() * camera_pose = translate(-pose_t); its rotation (and inverse) is the identity
+        const float c2v[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, -pose_t[0], -pose_t[1], -pose_t[2]};
+        const float rinv[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        dfu_adapter::check(dfu_tsdf_raycast(data_.p, dims, vs, trunc_dist_, c2v, rinv, intr, rows, cols, raycast_step_factor_,
+                                            gradient_delta_factor_, nullptr, 0, depth_dev, depth_pitch, normals4_dev, normals_pitch, nullptr),
+                           "dfu_tsdf_raycast");
+    }
     uint32_t* data() { return data_.p; }
     int dims[3];
 
@@ -423,6 +436,7 @@ private:
     float pose_t[3] = {0.f, 0.f, 0.f};
     float trunc_dist_ = 0.03f;  // tsdf_volume.cpp:21-22
     int max_weight_ = 128;
+    float raycast_step_factor_ = 0.75f, gradient_delta_factor_ = 0.75f;  // tsdf_volume.cpp:25-26
 };
 }  // namespace cuda
 }  // namespace kfusion

@@ -87,3 +87,33 @@ class TsdfVolume:
                                      self.max_weight, farr(v2c), farr(intr), dptr(dists), dists.stride(0) * 2, rows, cols,
                                      warpfield.handle if warpfield is not None else None, blend_mode, self.z0, self.z1,
                                      stream_ptr()))
+
+    # TsdfVolume::raycast (tsdf_volume.cpp:95-129): points or depth + normals of the fused model seen from camera_pose
+    raycast_step_factor = 0.75    # tsdf_volume.cpp:26
+    gradient_delta_factor = 0.75  # tsdf_volume.cpp:25 (KinFuParams sets 0.5, kinfu.cpp:38)
+
+    def setRaycastStepFactor(self, f):
+        self.raycast_step_factor = float(f)
+
+    def setGradientDeltaFactor(self, f):
+        self.gradient_delta_factor = float(f)
+
+    def raycast(self, camera_pose, intr, rows, cols, want="points"):
+        """returns (points [rows, cols, 4] float32 | depth [rows, cols] int16 (uint16 bits), normals [rows, cols, 4])"""
+        if self.z0 != 0 or self.z1 != self.dims[2]:
+            raise _lib.DfuError(1, "raycast needs the whole volume, this object holds a z-slab")
+        cam = torch.as_tensor(camera_pose, dtype=torch.float64).reshape(4, 4)
+        cam2vol = torch.linalg.inv(self.pose) @ cam  # pose_.inv() * camera_pose
+        rinv = torch.linalg.inv(cam2vol[:3, :3])
+        c2v = [float(x) for x in cam2vol[:3, :3].reshape(-1)] + [float(x) for x in cam2vol[:3, 3]]
+        ri = [float(x) for x in rinv.reshape(-1)]
+        normals = torch.empty((rows, cols, 4), dtype=torch.float32, device=self.device)
+        points = depth = None
+        if want == "points":
+            points = torch.empty((rows, cols, 4), dtype=torch.float32, device=self.device)
+        else:
+            depth = torch.empty((rows, cols), dtype=torch.int16, device=self.device)
+        check(lib.dfu_tsdf_raycast(self._base_ptr(), iarr(self.dims), farr(self.getVoxelSize()), self.trunc_dist, farr(c2v), farr(ri),
+                                   farr(intr), rows, cols, self.raycast_step_factor, self.gradient_delta_factor,
+                                   dptr(points), cols * 16, dptr(depth), cols * 2, dptr(normals), cols * 16, stream_ptr()))
+        return (points if want == "points" else depth), normals

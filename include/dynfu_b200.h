@@ -155,6 +155,18 @@ int dfu_tsdf_integrate(void* volume, const int dims_host[3], const float voxel_s
                        const uint16_t* dists, size_t dists_pitch_bytes, int rows, int cols, dfu_warpfield* wf,
                        int blend_mode, int z0, int z1, dfu_stream stream);
 
+/* TsdfVolume::raycast (src/kfusion/tsdf_volume.cpp:95-129 -> device::raycast, include/kfusion/internal.hpp, src/kfusion/
+ * cuda/tsdf_volume.cu:126-386): first + -> - zero crossing of the TSDF along every pixel's ray, refined by trilinear
+ * interpolation, normal from central differences of the interpolated TSDF.  cam2vol_host = volume_pose.inv() *
+ * camera_pose as {R row-major, t}; rinv_host = the inverse of its rotation (the reference passes both, :98-102).
+ * Outputs in the CAMERA frame like the reference: points4 and/or depth (u16 mm), normals4; NaN / 0 where a ray finds
+ * no surface.  Needs the whole volume (not a z-slab).  Arithmetic: IEEE, one rounding per operation (see raycast.cu). */
+int dfu_tsdf_raycast(const void* volume, const int dims_host[3], const float voxel_size_host[3], float trunc_dist,
+                     const float cam2vol_host[12], const float rinv_host[9], const float intr_host[4], int rows, int cols,
+                     float raycast_step_factor, float gradient_delta_factor, float* points4, size_t points_pitch_bytes,
+                     uint16_t* depth, size_t depth_pitch_bytes, float* normals4, size_t normals_pitch_bytes,
+                     dfu_stream stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Solver  (replaces CombinedSolver + Opt + energy.t)
  * ---------------------------------------------------------------------------------------------- */

@@ -662,6 +662,116 @@ long orc_warpfield_update(const float* pos, const float* dq, const float* dg_w, 
     return N + M;
 }
 
+/* ---- TsdfVolume::raycast (src/kfusion/tsdf_volume.cpp:95-129 -> src/kfusion/cuda/tsdf_volume.cu:126-386) ---------
+ * Canonical arithmetic: every operation of the reference's expressions rounded once in the order written, IEEE division
+ * and sqrt, normalized(v) = v / sqrt(dot), dot = (ax bx + ay by) + az bz; fetch_tsdf clamps its index into the volume.
+ * vol: packed voxels (half bits | weight << 16), x fastest.  cam2vol = {R row-major, t}; rinv = inverse rotation.
+ * points4 / normals4: rows*cols float4 (NaN where the ray finds no surface); depth_or_null: u16 millimetres. */
+namespace {
+struct RayVol {
+    const uint32_t* vol;
+    int dx, dy, dz;
+    float ivx, ivy, ivz;
+    float at(int x, int y, int z) const { return half2float((uint16_t) (vol[(size_t) x + (size_t) y * dx + (size_t) z * dx * dy] & 0xffffu)); }
+    float fetch(float px, float py, float pz) const {
+        int x = (int) nearbyintf(px * ivx), y = (int) nearbyintf(py * ivy), z = (int) nearbyintf(pz * ivz);
+        x = std::min(std::max(x, 0), dx - 1); y = std::min(std::max(y, 0), dy - 1); z = std::min(std::max(z, 0), dz - 1);
+        return at(x, y, z);
+    }
+    float interp(float cx, float cy, float cz) const {
+        const int gx = (int) floorf(cx), gy = (int) floorf(cy), gz = (int) floorf(cz);
+        if (gx < 0 || gx >= dx - 1 || gy < 0 || gy >= dy - 1 || gz < 0 || gz >= dz - 1) return std::numeric_limits<float>::quiet_NaN();
+        const float a = cx - (float) gx, b = cy - (float) gy, c = cz - (float) gz;
+        const float na = 1.f - a, nb = 1.f - b, nc = 1.f - c;
+        float t = 0.f;
+        t += at(gx, gy, gz) * na * nb * nc;
+        t += at(gx, gy, gz + 1) * na * nb * c;
+        t += at(gx, gy + 1, gz) * na * b * nc;
+        t += at(gx, gy + 1, gz + 1) * na * b * c;
+        t += at(gx + 1, gy, gz) * a * nb * nc;
+        t += at(gx + 1, gy, gz + 1) * a * nb * c;
+        t += at(gx + 1, gy + 1, gz) * a * b * nc;
+        t += at(gx + 1, gy + 1, gz + 1) * a * b * c;
+        return t;
+    }
+    float interp_m(float px, float py, float pz) const { return interp(px * ivx, py * ivy, pz * ivz); }
+};
+inline float rdot3(float ax, float ay, float az, float bx, float by, float bz) { return (ax * bx + ay * by) + az * bz; }
+}  // namespace
+
+void orc_raycast(const uint32_t* vol, const int dims[3], const float voxel[3], float trunc, const float cam2vol[12],
+                 const float rinv[9], const float intr[4], int rows, int cols, float step_factor, float grad_factor,
+                 float* points4, float* normals4, uint16_t* depth_or_null) {
+    RayVol V{vol, dims[0], dims[1], dims[2], 1.f / voxel[0], 1.f / voxel[1], 1.f / voxel[2]};
+    const float bmx = voxel[0] * (float) dims[0] - voxel[0], bmy = voxel[1] * (float) dims[1] - voxel[1],
+                bmz = voxel[2] * (float) dims[2] - voxel[2];
+    const float time_step = trunc * step_factor;
+    const float gdx = voxel[0] * grad_factor, gdy = voxel[1] * grad_factor, gdz = voxel[2] * grad_factor;
+    const float* R = cam2vol;
+    const float ox = cam2vol[9], oy = cam2vol[10], oz = cam2vol[11];
+    const float finvx = 1.f / intr[0], finvy = 1.f / intr[1], cx = intr[2], cy = intr[3];
+    const float qnan = std::numeric_limits<float>::quiet_NaN();
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            float* P = points4 + 4 * ((size_t) y * cols + x);
+            float* Nn = normals4 + 4 * ((size_t) y * cols + x);
+            for (int c = 0; c < 4; ++c) P[c] = Nn[c] = qnan;
+            if (depth_or_null) depth_or_null[(size_t) y * cols + x] = 0;
+            const float ux = 1.f * ((float) x - cx) * finvx, uy = 1.f * ((float) y - cy) * finvy, uz = 1.f;
+            float rdx = rdot3(R[0], R[1], R[2], ux, uy, uz), rdy = rdot3(R[3], R[4], R[5], ux, uy, uz), rdz = rdot3(R[6], R[7], R[8], ux, uy, uz);
+            const float len = sqrtf(rdot3(rdx, rdy, rdz, rdx, rdy, rdz));
+            rdx = rdx / len; rdy = rdy / len; rdz = rdz / len;
+            const float ix = 1.f / rdx, iy = 1.f / rdy, iz = 1.f / rdz;
+            const float tbx = ix * (0.f - ox), tby = iy * (0.f - oy), tbz = iz * (0.f - oz);
+            const float ttx = ix * (bmx - ox), tty = iy * (bmy - oy), ttz = iz * (bmz - oz);
+            const float mnx = fminf(ttx, tbx), mny = fminf(tty, tby), mnz = fminf(ttz, tbz);
+            const float mxx = fmaxf(ttx, tbx), mxy = fmaxf(tty, tby), mxz = fmaxf(ttz, tbz);
+            float tmin = fmaxf(fmaxf(mnx, mny), fmaxf(mnx, mnz));
+            float tmax = fminf(fminf(mxx, mxy), fminf(mxx, mxz));
+            tmin = fmaxf(0.f, tmin);
+            if (tmin >= tmax) continue;
+            tmax = tmax - time_step;
+            const float vsx = rdx * time_step, vsy = rdy * time_step, vsz = rdz * time_step;
+            float nx = ox + rdx * tmin, ny = oy + rdy * tmin, nz = oz + rdz * tmin;
+            float tsdf_next = V.fetch(nx, ny, nz);
+            for (float tcurr = tmin; tcurr < tmax; tcurr += time_step) {
+                const float tsdf_curr = tsdf_next;
+                const float cxm = nx, cym = ny, czm = nz;
+                nx += vsx; ny += vsy; nz += vsz;
+                tsdf_next = V.fetch(nx, ny, nz);
+                if (tsdf_curr < 0.f && tsdf_next > 0.f) break;
+                if (tsdf_curr > 0.f && tsdf_next < 0.f) {
+                    const float Ft = V.interp_m(cxm, cym, czm), Ftdt = V.interp_m(nx, ny, nz);
+                    const float Ts = tcurr - (time_step * Ft) / (Ftdt - Ft);
+                    const float vx = ox + rdx * Ts, vy = oy + rdy * Ts, vz = oz + rdz * Ts;
+                    float gx = (V.interp_m(vx + gdx, vy, vz) - V.interp_m(vx - gdx, vy, vz)) / gdx;
+                    float gy = (V.interp_m(vx, vy + gdy, vz) - V.interp_m(vx, vy - gdy, vz)) / gdy;
+                    float gz = (V.interp_m(vx, vy, vz + gdz) - V.interp_m(vx, vy, vz - gdz)) / gdz;
+                    const float gl = sqrtf(rdot3(gx, gy, gz, gx, gy, gz));
+                    gx = gx / gl; gy = gy / gl; gz = gz / gl;
+                    const float prod = gx * gy * gz;
+                    if (prod == prod) {
+                        const float dxv = vx - ox, dyv = vy - oy, dzv = vz - oz;
+                        Nn[0] = rdot3(rinv[0], rinv[1], rinv[2], gx, gy, gz);
+                        Nn[1] = rdot3(rinv[3], rinv[4], rinv[5], gx, gy, gz);
+                        Nn[2] = rdot3(rinv[6], rinv[7], rinv[8], gx, gy, gz);
+                        Nn[3] = 0.f;
+                        P[0] = rdot3(rinv[0], rinv[1], rinv[2], dxv, dyv, dzv);
+                        P[1] = rdot3(rinv[3], rinv[4], rinv[5], dxv, dyv, dzv);
+                        P[2] = rdot3(rinv[6], rinv[7], rinv[8], dxv, dyv, dzv);
+                        P[3] = 0.f;
+                        if (depth_or_null) {
+                            const float mm = P[2] * 1000.f;
+                            depth_or_null[(size_t) y * cols + x] = (uint16_t) std::min(std::max((int) mm, 0), 65535);
+                        }
+                    }
+                    break;
+                }
+            }
+        }
+}
+
 uint16_t orc_float2half(float f) { return float2half(f); }
 float orc_half2float(uint16_t h) { return half2float(h); }
 

@@ -91,6 +91,10 @@ long orc_unsupported(const float* pos, const float* dg_w, int N, const float* ve
 long orc_voxel_grid(const float* pts, long U, const float leaf[3], float* out, int order_mode);
 long orc_warpfield_update(const float* pos, const float* dq, const float* dg_w, int N, float epsilon,
                           const float* verts, long P, int blend_mode, float* pos_out, float* dq_out, float* w_out);
+/* ---- TsdfVolume::raycast (src/kfusion/cuda/tsdf_volume.cu:126-386) ---- */
+void orc_raycast(const uint32_t* vol, const int dims[3], const float voxel[3], float trunc, const float cam2vol[12],
+                 const float rinv[9], const float intr[4], int rows, int cols, float step_factor, float grad_factor,
+                 float* points4, float* normals4, uint16_t* depth_or_null);
 uint16_t orc_float2half(float f);
 float    orc_half2float(uint16_t h);
 

@@ -108,6 +108,7 @@ class Oracle:
         L.orc_voxel_grid.restype = C.c_long
         L.orc_warpfield_update.argtypes = [_fp, _fp, _fp, C.c_int, C.c_float, _fp, C.c_long, C.c_int, _fp, _fp, _fp]
         L.orc_warpfield_update.restype = C.c_long
+        L.orc_raycast.argtypes = [_u32p, _ip, _fp, C.c_float, _fp, _fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, _fp, _fp, _u16p]
         L.orc_float2half.argtypes = [C.c_float]
         L.orc_float2half.restype = C.c_uint16
         L.orc_half2float.argtypes = [C.c_uint16]
@@ -324,6 +325,18 @@ class Oracle:
         n = self.lib.orc_warpfield_update(_f(pos), _f(dq), _f(dg_w), N, epsilon, _f(verts), P, blend_mode, _f(po), _f(qo),
                                           _f(wo))
         return po[:n].copy(), qo[:n].copy(), wo[:n].copy()
+
+    def raycast(self, vol, voxel, trunc, cam2vol, rinv, intr, rows, cols, step_factor=0.75, grad_factor=0.75, want_depth=False):
+        """TsdfVolume::raycast: (points [rows, cols, 4], normals [rows, cols, 4][, depth u16])."""
+        vol = np.ascontiguousarray(vol, np.uint32)
+        dims = np.array(vol.shape[::-1], np.int32)
+        pts = np.empty((rows, cols, 4), np.float32)
+        nrm = np.empty((rows, cols, 4), np.float32)
+        dep = np.zeros((rows, cols), np.uint16) if want_depth else None
+        self.lib.orc_raycast(vol.ctypes.data_as(_u32p), dims.ctypes.data_as(_ip), _f(_f32(voxel)), float(trunc), _f(_f32(cam2vol)),
+                             _f(_f32(rinv)), _f(_f32(intr)), rows, cols, float(step_factor), float(grad_factor), _f(pts), _f(nrm),
+                             dep.ctypes.data_as(_u16p) if dep is not None else None)
+        return (pts, nrm, dep) if want_depth else (pts, nrm)
 
     def float2half(self, f):
         return self.lib.orc_float2half(f)

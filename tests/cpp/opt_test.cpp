@@ -214,6 +214,22 @@ TEST_F(TsdfTest, IdentityWarpEqualsRigidIntegrate) {
     }
     ASSERT_NEAR((double) diff, 0.0, 0.0);
     ASSERT_NEAR(touched > 1000 ? 1.0 : 0.0, 1.0, 0.0);
+    // TsdfVolume::raycast of the fused slab gives back (about) the depth it was fused from
+    dfu_adapter::DevArray<uint16_t> d_ray((size_t) rows * cols);
+    dfu_adapter::DevArray<float> d_nrm((size_t) rows * cols * 4);
+    a.raycast(intr, rows, cols, d_ray.p, cols * 2, d_nrm.p, cols * 16);
+    std::vector<uint16_t> ray((size_t) rows * cols);
+    d_ray.download(ray.data(), ray.size());
+    long hits = 0, close = 0;
+    for (int y = 120; y < 360; ++y)
+        for (int x = 180; x < 460; ++x) {
+            const size_t i = (size_t) y * cols + x;
+            if (!ray[i]) continue;
+            ++hits;
+            close += std::abs((int) ray[i] - (int) depth[i]) <= 60;  // one 47 mm voxel at 64^3 + the ramp
+        }
+    ASSERT_NEAR(hits > 20000 ? 1.0 : 0.0, 1.0, 0.0);
+    ASSERT_NEAR((double) close / (double) hits > 0.9 ? 1.0 : 0.0, 1.0, 0.0);
 }
 
 // ---- the rows around the solver, through the same class interface ------------------------------------------------

@@ -358,3 +358,49 @@ def test_process_frame_against_oracle_chain(fe, oracle):
     assert pg.shape == po.shape
     assert same_bits(pg, po) and same_bits(wg, wo)
     assert np.max(np.abs(qg - qo)) <= 1e-4 * max(np.abs(t_o).max(), 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ f4: raycast
+def _integrated_sphere_volume(dim=128):
+    import dynfu_b200
+    intr = synth.intr_for(320, 240)
+    depth = synth.sphere_depth(240, 320, intr)
+    dists = dynfu_b200.compute_dists(dev(depth.view(np.int16), torch.int16), intr)
+    vol = dynfu_b200.TsdfVolume((dim, dim, dim))
+    pose = torch.eye(4, dtype=torch.float64)
+    pose[:3, 3] = torch.tensor([-1.5, -1.5, 0.5], dtype=torch.float64)
+    vol.setPose(pose)
+    vol.setTruncDist(0.06)
+    for _ in range(3):
+        vol.integrate(dists, torch.eye(4, dtype=torch.float64), intr)
+    return vol, depth, intr
+
+
+@pytest.mark.parametrize("yaw", [0.0, 0.2])
+def test_raycast_bit_exact(fe, oracle, yaw):
+    """TsdfVolume::raycast (tsdf_volume.cu:126-386) of a volume fused from a sphere: points / depth / normals bit-exact"""
+    vol, depth, intr = _integrated_sphere_volume()
+    cam = np.eye(4)
+    cam[:3, :3] = [[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]]
+    cam[:3, 3] = [0.4 * np.sin(yaw) * 2, 0.0, 0.05 * yaw]
+    pose = vol.getPose().numpy()
+    cam2vol = np.linalg.inv(pose) @ cam
+    rinv = np.linalg.inv(cam2vol[:3, :3])
+    c2v = np.concatenate([cam2vol[:3, :3].reshape(-1), cam2vol[:3, 3]]).astype(np.float32)
+    v_host = vol.data.cpu().numpy().view(np.uint32)
+    p_o, n_o, d_o = oracle.raycast(v_host, vol.getVoxelSize(), vol.getTruncDist(), c2v, rinv.astype(np.float32).reshape(-1), intr, 240, 320,
+                                   want_depth=True)
+    p_g, n_g = vol.raycast(torch.as_tensor(cam), intr, 240, 320, want="points")
+    d_g, n_g2 = vol.raycast(torch.as_tensor(cam), intr, 240, 320, want="depth")
+    p_g, n_g, n_g2 = p_g.cpu().numpy(), n_g.cpu().numpy(), n_g2.cpu().numpy()
+    hit = ~np.isnan(p_o[..., 0])
+    assert hit.sum() > 5000
+    assert np.array_equal(hit, ~np.isnan(p_g[..., 0])) and np.array_equal(hit, ~np.isnan(n_g[..., 0]))
+    assert same_bits(p_g[hit], p_o[hit]) and same_bits(n_g[hit], n_o[hit]) and same_bits(n_g2[hit], n_o[hit])
+    assert np.array_equal(d_g.cpu().numpy().view(np.uint16), d_o)
+    if yaw == 0.0:  # the fused model reproduces the depth image it was fused from to within a voxel (23 mm at 128^3),
+        m = hit & (depth > 0)  # except at grazing angles near the silhouette
+        err = np.abs(d_o[m].astype(np.int32) - depth[m].astype(np.int32))
+        assert np.median(err) <= 12 and np.percentile(err, 90) <= 40
+        nrm = n_o[hit][:, :3]
+        assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-5)
