@@ -605,6 +605,24 @@ int dfu_solver_get_translations(const dfu_solver* s, float* t_xyz, dfu_stream st
     return DFU_OK;
 }
 
+namespace {
+__global__ void k_export_stats(const Scalars* __restrict__ sc, int gn_steps_host, double* __restrict__ out) {
+    out[0] = sc->E0;
+    out[1] = sc->E;
+    out[2] = (double) sc->pcg_iters;
+    out[3] = (double) (gn_steps_host >= 0 ? gn_steps_host : sc->gn_steps);
+}
+}  // namespace
+
+int dfu_solver_get_stats(const dfu_solver* s, double* stats_dev, dfu_stream stream) {
+    DFU_REQUIRE(s && stats_dev, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(s->problem_ready, DFU_ERR_NOT_INIT, "no problem instance");
+    (void) cudaGetLastError();
+    k_export_stats<<<1, 1, 0, as_stream(stream)>>>(s->sc, s->gn_steps_host, stats_dev);
+    DFU_LAUNCH_OK();
+    return DFU_OK;
+}
+
 int dfu_solver_get_stats_host(const dfu_solver* s, double stats_host[4], dfu_stream stream) {
     DFU_REQUIRE(s && stats_host, DFU_ERR_INVALID, "NULL argument");
     DFU_REQUIRE(s->problem_ready, DFU_ERR_NOT_INIT, "no problem instance");

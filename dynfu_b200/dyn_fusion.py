@@ -158,6 +158,78 @@ class DynFusion:
         self.frame_counter += 1
         return True
 
+    # ---- pipelined frame loop for a steady stream of sensor frames -------------------------------------------------
+    # streamFrame(depth, live) uploads this frame's pinned host inputs on a copy stream, runs the frame on the current
+    # stream, brings {node transforms, solver statistics} back to pinned host memory on a second copy stream, and returns
+    # the result of the PREVIOUS frame: the transfers of frame i overlap the kernels of frames i-1 / i+1 (two staging
+    # slots), every frame still pays its own H2D and D2H.
+    def _stream_state(self, live_host):
+        st = getattr(self, "_ss", None)
+        if st is None or st["live"][0].shape != live_host.shape:
+            n = self.warpfield.numNodes()
+            st = dict(h2d=torch.cuda.Stream(self.device), d2h=torch.cuda.Stream(self.device), slot=0, pending=None,
+                      depth=[torch.empty_like(self._depth_dev) for _ in range(2)],
+                      live=[torch.empty(live_host.shape, dtype=torch.float32, device=self.device) for _ in range(2)],
+                      dq_dev=[torch.empty((n, 8), dtype=torch.float32, device=self.device) for _ in range(2)],
+                      stats_dev=[torch.empty(4, dtype=torch.float64, device=self.device) for _ in range(2)],
+                      dq_host=[torch.empty((n, 8), dtype=torch.float32).pin_memory() for _ in range(2)],
+                      stats_host=[torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)],
+                      up=[torch.cuda.Event() for _ in range(2)], free=[torch.cuda.Event() for _ in range(2)],
+                      done=[torch.cuda.Event() for _ in range(2)], down=[torch.cuda.Event() for _ in range(2)])
+            for e in st["free"] + st["down"]:
+                e.record(torch.cuda.current_stream(self.device))
+            self._ss = st
+        return st
+
+    def streamFrame(self, depth_host, live_host):
+        """depth_host: pinned uint16/int16 [rows, cols]; live_host: pinned float32 [P, 3] paired with the canonical vertices.
+        Returns None on the first call, afterwards (node transforms [N, 8], {energies, iterations}) of the previous frame;
+        the transforms are a pinned staging buffer that is overwritten two calls later."""
+        from ._lib import check, dptr, lib, stream_ptr
+        kp = self.params.kinfuParams
+        st = self._stream_state(live_host)
+        s = st["slot"]
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(st["h2d"]):
+            st["h2d"].wait_event(st["free"][s])  # the frame that last used this slot has consumed it
+            st["depth"][s].copy_(depth_host.view(torch.int16) if depth_host.dtype == torch.uint16 else depth_host, non_blocking=True)
+            st["live"][s].copy_(live_host, non_blocking=True)
+            st["up"][s].record(st["h2d"])
+        cur.wait_event(st["up"][s])
+        cur.wait_event(st["down"][s])  # the result buffers of this slot have been read back
+        compute_dists(st["depth"][s], kp.intr, out=self._dists)
+        self.warpCanonicalToLiveOpt(st["live"][s])
+        self.volume.integrate(self._dists, self.camera_pose, kp.intr, self.warpfield, self.params.blend_mode)
+        check(lib.dfu_warpfield_get_nodes(self.warpfield.handle, None, dptr(st["dq_dev"][s]), None, stream_ptr()))
+        self.solver.getStatsAsync(st["stats_dev"][s])
+        st["free"][s].record(cur)
+        st["done"][s].record(cur)
+        with torch.cuda.stream(st["d2h"]):
+            st["d2h"].wait_event(st["done"][s])
+            st["dq_host"][s].copy_(st["dq_dev"][s], non_blocking=True)
+            st["stats_host"][s].copy_(st["stats_dev"][s], non_blocking=True)
+            st["down"][s].record(st["d2h"])
+        self.frame_counter += 1
+        prev, st["pending"], st["slot"] = st["pending"], s, 1 - s
+        if prev is None:
+            return None
+        st["down"][prev].synchronize()
+        e = st["stats_host"][prev]
+        return st["dq_host"][prev], dict(initial_energy=float(e[0]), final_energy=float(e[1]), pcg_iterations=int(e[2]),
+                                         gn_steps=int(e[3]))
+
+    def streamFlush(self):
+        """result of the last streamFrame call (waits for it)"""
+        st = getattr(self, "_ss", None)
+        if st is None or st["pending"] is None:
+            return None
+        p = st["pending"]
+        st["pending"] = None
+        st["down"][p].synchronize()
+        e = st["stats_host"][p]
+        return st["dq_host"][p], dict(initial_energy=float(e[0]), final_energy=float(e[1]), pcg_iterations=int(e[2]),
+                                      gn_steps=int(e[3]))
+
     # DynFusion::operator() (src/dynfu/dyn_fusion.cpp:48-145), hot-path steps
     def __call__(self, depth_host, liveVertices=None):
         kp = self.params.kinfuParams

@@ -101,6 +101,13 @@ class CombinedSolver:
         check(lib.dfu_solver_get_translations(self._h, dptr(t), stream_ptr()))
         return t
 
+    def getStatsAsync(self, out=None):
+        """the same four numbers as a float64 CUDA tensor [E0, E, pcg iterations, gn steps]: stream-ordered, no host sync"""
+        if out is None:
+            out = torch.empty(4, dtype=torch.float64, device=self.warpfield.device)
+        check(lib.dfu_solver_get_stats(self._h, dptr(out), stream_ptr()))
+        return out
+
     def getStats(self):
         """{initial energy, final energy, PCG iterations, GN steps} of the last solveAll (synchronises)."""
         s = (C.c_double * 4)()

@@ -221,6 +221,9 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream);
  * stats_host[4] = {initial energy, final energy, PCG iterations, GN steps} (synchronises the stream) */
 int dfu_solver_get_translations(const dfu_solver* s, float* t_xyz, dfu_stream stream);
 int dfu_solver_get_stats_host(const dfu_solver* s, double stats_host[4], dfu_stream stream);
+/* the same four numbers written to DEVICE memory, stream-ordered and without a synchronisation (pipelined frame loops
+ * copy them to pinned host memory together with the node transforms) */
+int dfu_solver_get_stats(const dfu_solver* s, double* stats_dev, dfu_stream stream);
 
 /* CombinedSolver::updateHuberWeights (opt_solver.cpp:241-268): huber[N], the value the reference's loop leaves
  * behind (its last neighbour); computed but never read by the reference's energy.  tukey[P] are the

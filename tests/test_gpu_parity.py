@@ -562,3 +562,39 @@ def test_knn_far_queries_grid_fallback(dfu, oracle):
     wf = make_wf(dfu, pos, dq, dg_w)
     idx_g, d_g = wf.findNeighborsIndex(8, dev(q), return_dist=True)
     assert np.array_equal(idx_g.cpu().numpy(), idx_o) and np.array_equal(d_g.cpu().numpy(), d_o)
+
+
+def test_stream_frame_equals_the_synchronous_frame_operator(dfu, oracle):
+    """DynFusion.streamFrame (double-buffered H2D / D2H on copy streams) delivers, one call late, exactly what the
+    synchronous operator computes"""
+    dim = 64
+    kp = dfu.KinFuParams(volume_dims=(dim, dim, dim))
+    prm = dfu.DynFuParams(kinfuParams=kp, epsilon=0.03, lambda_=200.0,
+                          solver=dfu.CombinedSolverParameters(numIter=3, nonLinearIter=1, linearIter=8, earlyOut=False, pcgTolerance=0.0))
+    depth = synth.sphere_depth()
+    pos, _, dg_w, t_true = synth.sphere_nodes(512, 0.03)
+    canon = synth.backproject(depth, synth.INTR, stride=4)
+    lives = [oracle.warp(pos, synth.translations_to_dq(s * t_true), dg_w, canon) for s in (0.05, 0.1, 0.05, 0.0)]
+    dpin = torch.from_numpy(depth.view(np.int16)).pin_memory()
+    lpin = [torch.from_numpy(l).pin_memory() for l in lives]
+
+    def fresh():
+        df = dfu.DynFusion(prm)
+        df.init(dev(canon), None, nodes=(dev(pos), dev(synth.identity_dq(512)), dev(dg_w)))
+        df(dpin)  # frame 0
+        return df
+
+    a, b = fresh(), fresh()
+    sync_results = []
+    for l in lpin:
+        a(dpin, dev(l.numpy()))
+        sync_results.append((a.warpfield.getNodes()[1].cpu().numpy().copy(), a.solver.getStats()))
+    def keep(r):  # the returned transforms live in a pinned staging slot that is re-used two calls later
+        return None if r is None else (r[0].numpy().copy(), r[1])
+
+    got = [keep(b.streamFrame(dpin, l)) for l in lpin] + [keep(b.streamFlush())]
+    assert got[0] is None and b.streamFlush() is None
+    for (dq_s, st_s), (dq_p, st_p) in zip(sync_results, got[1:]):
+        assert np.array_equal(dq_s, dq_p)
+        assert st_s == st_p
+    assert torch.equal(a.volume.data, b.volume.data)
