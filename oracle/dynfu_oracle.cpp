@@ -1135,6 +1135,395 @@ double orc_energy(const float* pos, const float* dg_w, int N, const float* canon
     return energy(pb, t);
 }
 
+/* ======================================================================================================================
+ * North-star extension P2PLANE_SE3 (BASELINE.json north_star (4)): a point-to-plane
+ * data term with one rigid increment per node.  There is NO reference implementation (energy.t is translation-only,
+ * point-to-point) -- parity unpinned; this double-precision Gauss-Newton / block-Jacobi PCG is the yardstick for the GPU
+ * path and is itself cross-checked with scipy.optimize.least_squares in the tests.
+ *
+ *   X_k in SE(3) per node (starts at identity), ŵ_vk = w_vk / sum_j w_vj (the reference's Gaussian weights, normalised)
+ *   p_v(X) = sum_k ŵ_vk X_k c_v                                  (linear blend of the node increments)
+ *   E(X)   = sum_v theta_v (n_v . (p_v - l_v))^2  +  w_reg^2 sum_n sum_{m in nbr(n), m != n} | X_n g_m - X_m g_m |^2
+ *   GN step: X_k <- exp(xi_k) X_k, xi = (omega, tau); rows  sqrt(theta) ŵ_vk [ (X_k c_v) x n_v ; n_v ]  and
+ *            [ -[X_n g_m]x  I ] for node n, [ [X_m g_m]x  -I ] for node m of an edge.
+ *   theta_v = calcTukeyBiweight(| p_v - l_v |) re-evaluated once per outer iteration, like the reference does for its own term.
+ *   At the end the increments are composed onto the nodes ONCE: dg_se3_k := DQ(X_k) * dg_se3_k.
+ * ==================================================================================================================== */
+namespace {
+struct SE3d {
+    double R[9], t[3];
+};
+inline void se3_identity(SE3d& X) {
+    for (int i = 0; i < 9; ++i) X.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    X.t[0] = X.t[1] = X.t[2] = 0.0;
+}
+inline void se3_apply(const SE3d& X, const double c[3], double o[3]) {
+    for (int r = 0; r < 3; ++r) o[r] = X.R[3 * r] * c[0] + X.R[3 * r + 1] * c[1] + X.R[3 * r + 2] * c[2] + X.t[r];
+}
+inline void cross3(const double a[3], const double b[3], double o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+/* exp of a twist (omega, tau): R = exp([omega]x), t = V tau */
+inline void se3_exp(const double xi[6], SE3d& X) {
+    const double wx = xi[0], wy = xi[1], wz = xi[2];
+    const double th2 = wx * wx + wy * wy + wz * wz, th = std::sqrt(th2);
+    double A, B, C;  /* sin(th)/th, (1-cos th)/th^2, (th - sin th)/th^3 */
+    if (th < 1e-6) {
+        A = 1.0 - th2 / 6.0; B = 0.5 - th2 / 24.0; C = 1.0 / 6.0 - th2 / 120.0;
+    } else {
+        A = std::sin(th) / th; B = (1.0 - std::cos(th)) / th2; C = (th - std::sin(th)) / (th2 * th);
+    }
+    const double K[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    double K2[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) K2[3 * r + c] = K[3 * r] * K[c] + K[3 * r + 1] * K[3 + c] + K[3 * r + 2] * K[6 + c];
+    double V[9];
+    for (int i = 0; i < 9; ++i) {
+        const double I = (i % 4 == 0) ? 1.0 : 0.0;
+        X.R[i] = I + A * K[i] + B * K2[i];
+        V[i] = I + B * K[i] + C * K2[i];
+    }
+    for (int r = 0; r < 3; ++r) X.t[r] = V[3 * r] * xi[3] + V[3 * r + 1] * xi[4] + V[3 * r + 2] * xi[5];
+}
+inline SE3d se3_mul(const SE3d& A, const SE3d& B) { /* A o B */
+    SE3d C;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) C.R[3 * r + c] = A.R[3 * r] * B.R[c] + A.R[3 * r + 1] * B.R[3 + c] + A.R[3 * r + 2] * B.R[6 + c];
+        C.t[r] = A.R[3 * r] * B.t[0] + A.R[3 * r + 1] * B.t[1] + A.R[3 * r + 2] * B.t[2] + A.t[r];
+    }
+    return C;
+}
+/* rotation matrix -> unit quaternion (w,x,y,z), Shepperd's method */
+inline void rot_to_quat(const double R[9], double q[4]) {
+    const double tr = R[0] + R[4] + R[8];
+    if (tr > 0) {
+        double s = std::sqrt(tr + 1.0) * 2;
+        q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s;
+    } else if (R[0] > R[4] && R[0] > R[8]) {
+        double s = std::sqrt(1.0 + R[0] - R[4] - R[8]) * 2;
+        q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s;
+    } else if (R[4] > R[8]) {
+        double s = std::sqrt(1.0 + R[4] - R[0] - R[8]) * 2;
+        q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s;
+    } else {
+        double s = std::sqrt(1.0 + R[8] - R[0] - R[4]) * 2;
+        q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s;
+    }
+}
+/* solve the 6x6 SPD system M z = r by Cholesky; returns false (z = 0) if M is not positive definite */
+inline bool chol6_solve(const double M[36], const double r[6], double z[6]) {
+    double L[36] = {0};
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = M[6 * i + j];
+            for (int k = 0; k < j; ++k) s -= L[6 * i + k] * L[6 * j + k];
+            if (i == j) {
+                if (!(s > 0)) {
+                    for (int k = 0; k < 6; ++k) z[k] = 0;
+                    return false;
+                }
+                L[6 * i + i] = std::sqrt(s);
+            } else {
+                L[6 * i + j] = s / L[6 * j + j];
+            }
+        }
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+        double s = r[i];
+        for (int k = 0; k < i; ++k) s -= L[6 * i + k] * y[k];
+        y[i] = s / L[6 * i + i];
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+        for (int k = i + 1; k < 6; ++k) s -= L[6 * k + i] * z[k];
+        z[i] = s / L[6 * i + i];
+    }
+    return true;
+}
+
+struct P2P {
+    const Problem* pb;
+    const float *canon, *live, *nrm, *pos;
+    std::vector<double> wn;   /* P*8 normalised weights */
+    std::vector<SE3d> X;      /* N */
+    std::vector<double> jac;  /* P*8*6: ŵ [q x n ; n] */
+    std::vector<double> e;    /* P: n.(p - l) */
+    std::vector<double> G;    /* N*8*2*3: for edge (n,i): X_n g_m and X_m g_m */
+};
+void p2p_point(const P2P& S, long v, double p[3]) {
+    p[0] = p[1] = p[2] = 0;
+    const double c[3] = {S.canon[3 * v], S.canon[3 * v + 1], S.canon[3 * v + 2]};
+    for (int k = 0; k < KNN; ++k) {
+        const double w = S.wn[v * KNN + k];
+        if (w == 0) continue;
+        double q[3];
+        se3_apply(S.X[S.pb->nbr[v * KNN + k]], c, q);
+        for (int r = 0; r < 3; ++r) p[r] += w * q[r];
+    }
+}
+void p2p_update_tukey(P2P& S, Problem& pb) {
+#pragma omp parallel for schedule(static)
+    for (long v = 0; v < pb.P; ++v) {
+        double p[3];
+        p2p_point(S, v, p);
+        float ef[3] = {(float) (S.live[3 * v] - p[0]), (float) (S.live[3 * v + 1] - p[1]), (float) (S.live[3 * v + 2] - p[2])};
+        double sw = 0;
+        for (int k = 0; k < KNN; ++k) sw += S.wn[v * KNN + k];
+        pb.theta[v] = sw > 0 ? (double) tukey(pb.prm->tukey_offset, pb.prm->psi_data, ef) : 0.0;
+    }
+}
+void p2p_linearise(P2P& S) {
+    const Problem& pb = *S.pb;
+#pragma omp parallel for schedule(static)
+    for (long v = 0; v < pb.P; ++v) {
+        const double c[3] = {S.canon[3 * v], S.canon[3 * v + 1], S.canon[3 * v + 2]};
+        const double n[3] = {S.nrm[3 * v], S.nrm[3 * v + 1], S.nrm[3 * v + 2]};
+        double p[3] = {0, 0, 0};
+        for (int k = 0; k < KNN; ++k) {
+            const double w = S.wn[v * KNN + k];
+            double q[3], qxn[3];
+            se3_apply(S.X[pb.nbr[v * KNN + k]], c, q);
+            cross3(q, n, qxn);
+            double* a = &S.jac[(v * KNN + k) * 6];
+            for (int r = 0; r < 3; ++r) {
+                p[r] += w * q[r];
+                a[r] = w * qxn[r];
+                a[3 + r] = w * n[r];
+            }
+        }
+        S.e[v] = n[0] * (p[0] - S.live[3 * v]) + n[1] * (p[1] - S.live[3 * v + 1]) + n[2] * (p[2] - S.live[3 * v + 2]);
+    }
+#pragma omp parallel for schedule(static)
+    for (int a = 0; a < pb.N; ++a)
+        for (int i = 0; i < KNN; ++i) {
+            const int m = pb.nnbr[(size_t) a * KNN + i];
+            const double g[3] = {S.pos[3 * (size_t) m], S.pos[3 * (size_t) m + 1], S.pos[3 * (size_t) m + 2]};
+            se3_apply(S.X[a], g, &S.G[((size_t) a * KNN + i) * 6]);
+            se3_apply(S.X[m], g, &S.G[((size_t) a * KNN + i) * 6 + 3]);
+        }
+}
+double p2p_energy(const P2P& S) {
+    const Problem& pb = *S.pb;
+    double E = 0;
+#pragma omp parallel for schedule(static) reduction(+ : E)
+    for (long v = 0; v < pb.P; ++v) {
+        double p[3];
+        p2p_point(S, v, p);
+        const double e = S.nrm[3 * v] * (p[0] - S.live[3 * v]) + S.nrm[3 * v + 1] * (p[1] - S.live[3 * v + 1]) +
+                         S.nrm[3 * v + 2] * (p[2] - S.live[3 * v + 2]);
+        E += pb.theta[v] * e * e;
+    }
+    double Er = 0;
+    for (int a = 0; a < pb.N; ++a)
+        for (int i = 0; i < KNN; ++i) {
+            const int m = pb.nnbr[(size_t) a * KNN + i];
+            if (m == a) continue;
+            const double g[3] = {S.pos[3 * (size_t) m], S.pos[3 * (size_t) m + 1], S.pos[3 * (size_t) m + 2]};
+            double x[3], y[3];
+            se3_apply(S.X[a], g, x);
+            se3_apply(S.X[m], g, y);
+            Er += (x[0] - y[0]) * (x[0] - y[0]) + (x[1] - y[1]) * (x[1] - y[1]) + (x[2] - y[2]) * (x[2] - y[2]);
+        }
+    return E + pb.wreg2 * Er;
+}
+/* y = (J^T J) x for x in R^{6N}; with rhs != nullptr also rhs = -J^T r0 and the 6x6 diagonal blocks D */
+void p2p_apply(const P2P& S, const double* x, double* y, double* rhs, double* D) {
+    const Problem& pb = *S.pb;
+    std::vector<double> s((size_t) pb.P);
+#pragma omp parallel for schedule(static)
+    for (long v = 0; v < pb.P; ++v) {
+        double acc = 0;
+        for (int k = 0; k < KNN; ++k) {
+            const double* a = &S.jac[(v * KNN + k) * 6];
+            const double* xk = x + 6 * (size_t) pb.nbr[v * KNN + k];
+            for (int r = 0; r < 6; ++r) acc += a[r] * xk[r];
+        }
+        s[(size_t) v] = pb.theta[v] * acc;
+    }
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < pb.N; ++n) {
+        double acc[6] = {0}, b[6] = {0}, M[36] = {0};
+        for (long qq = pb.tptr[n]; qq < pb.tptr[n + 1]; ++qq) {
+            const long ent = pb.tent[qq], v = ent / KNN;
+            const double* a = &S.jac[ent * 6];
+            for (int r = 0; r < 6; ++r) acc[r] += a[r] * s[(size_t) v];
+            if (rhs) {
+                for (int r = 0; r < 6; ++r) {
+                    b[r] -= pb.theta[v] * S.e[v] * a[r];
+                    for (int c = 0; c < 6; ++c) M[6 * r + c] += pb.theta[v] * a[r] * a[c];
+                }
+            }
+        }
+        if (pb.wreg2 > 0) {
+            /* edges where n is the source (out) and where n is the target (in) */
+            auto edge = [&](int src, int i, bool as_source) {
+                const int m = pb.nnbr[(size_t) src * KNN + i];
+                if (m == src) return;
+                const double* Gs = &S.G[((size_t) src * KNN + i) * 6];      /* X_src g_m */
+                const double* Gm = Gs + 3;                                   /* X_m g_m   */
+                const double* xs = x + 6 * (size_t) src;
+                const double* xm = x + 6 * (size_t) m;
+                double c1[3], c2[3], rho[3];
+                cross3(xs, Gs, c1);
+                cross3(xm, Gm, c2);
+                for (int r = 0; r < 3; ++r) rho[r] = c1[r] + xs[3 + r] - c2[r] - xm[3 + r];
+                const double* Gk = as_source ? Gs : Gm;
+                const double sg = as_source ? 1.0 : -1.0;
+                double gxr[3];
+                cross3(Gk, rho, gxr);
+                for (int r = 0; r < 3; ++r) {
+                    acc[r] += pb.wreg2 * sg * gxr[r];
+                    acc[3 + r] += pb.wreg2 * sg * rho[r];
+                }
+                if (rhs) {
+                    double rho0[3] = {Gs[0] - Gm[0], Gs[1] - Gm[1], Gs[2] - Gm[2]}, gx0[3];
+                    cross3(Gk, rho0, gx0);
+                    for (int r = 0; r < 3; ++r) {
+                        b[r] -= pb.wreg2 * sg * gx0[r];
+                        b[3 + r] -= pb.wreg2 * sg * rho0[r];
+                    }
+                    /* J = sg * [ -[Gk]x  I ]  ->  J^T J = [ [Gk]x^T [Gk]x   [Gk]x ; -[Gk]x  I ]  (sign cancels) */
+                    const double K[9] = {0, -Gk[2], Gk[1], Gk[2], 0, -Gk[0], -Gk[1], Gk[0], 0};
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c) {
+                            double ktk = 0;
+                            for (int k = 0; k < 3; ++k) ktk += K[3 * k + r] * K[3 * k + c];
+                            M[6 * r + c] += pb.wreg2 * ktk;
+                            M[6 * r + 3 + c] += pb.wreg2 * K[3 * r + c];       /* (-K)^T = K */
+                            M[6 * (3 + r) + c] += pb.wreg2 * (-K[3 * r + c]);
+                            if (r == c) M[6 * (3 + r) + 3 + c] += pb.wreg2;
+                        }
+                }
+            };
+            for (int i = 0; i < KNN; ++i) edge(n, i, true);
+            for (long qq = pb.rptr[n]; qq < pb.rptr[n + 1]; ++qq) {
+                const int src = pb.rent[qq];
+                for (int i = 0; i < KNN; ++i)
+                    if (pb.nnbr[(size_t) src * KNN + i] == n && src != n) edge(src, i, false);
+            }
+        }
+        for (int r = 0; r < 6; ++r) y[6 * (size_t) n + r] = acc[r];
+        if (rhs) {
+            for (int r = 0; r < 6; ++r) rhs[6 * (size_t) n + r] = b[r];
+            for (int r = 0; r < 36; ++r) D[36 * (size_t) n + r] = M[r];
+        }
+    }
+}
+}  // namespace
+
+int orc_solve_p2plane(const float* pos, float* dq_inout, const float* dg_w, int N, const float* canon, const float* live,
+                      const float* live_n, long P, const orc_solver_params* prm, double* X_out, double* stats_out) {
+    if (N < KNN) return 1;
+    Problem pb;
+    build_problem(pb, pos, dg_w, N, canon, live, P, prm);
+    P2P S;
+    S.pb = &pb; S.canon = canon; S.live = live; S.nrm = live_n; S.pos = pos;
+    S.wn.assign((size_t) P * KNN, 0.0);
+    for (long v = 0; v < P; ++v) {
+        double sw = 0;
+        for (int k = 0; k < KNN; ++k) sw += pb.w[v * KNN + k];
+        for (int k = 0; k < KNN; ++k) S.wn[v * KNN + k] = sw > 0 ? pb.w[v * KNN + k] / sw : 0.0;
+    }
+    S.X.resize((size_t) N);
+    for (auto& X : S.X) se3_identity(X);
+    S.jac.assign((size_t) P * KNN * 6, 0.0);
+    S.e.assign((size_t) P, 0.0);
+    S.G.assign((size_t) N * KNN * 6, 0.0);
+    const size_t n6 = (size_t) N * 6;
+    std::vector<double> b(n6), r(n6), z(n6), p(n6), q(n6), x(n6), D((size_t) N * 36), zero(n6, 0.0);
+    p2p_update_tukey(S, pb);
+    const double E0 = p2p_energy(S);
+    double E = E0, rz_ref = -1;
+    long pcg_total = 0, gn_total = 0;
+    auto precond = [&](const std::vector<double>& rr, std::vector<double>& zz) {
+        for (int n = 0; n < N; ++n) chol6_solve(&D[36 * (size_t) n], &rr[6 * (size_t) n], &zz[6 * (size_t) n]);
+    };
+    for (int outer = 0; outer < prm->num_iter; ++outer) {
+        p2p_update_tukey(S, pb);
+        for (int gn = 0; gn < prm->nonlinear_iter; ++gn) {
+            p2p_linearise(S);
+            p2p_apply(S, zero.data(), q.data(), b.data(), D.data());
+            std::fill(x.begin(), x.end(), 0.0);
+            r = b;
+            precond(r, z);
+            p = z;
+            double rz = 0;
+            for (size_t i = 0; i < n6; ++i) rz += r[i] * z[i];
+            if (rz_ref < 0) rz_ref = rz;
+            const double rz_stop = prm->pcg_tol * prm->pcg_tol * rz_ref;
+            for (int it = 0; it < prm->linear_iter && rz > 0; ++it) {
+                if (rz <= rz_stop) break;
+                p2p_apply(S, p.data(), q.data(), nullptr, nullptr);
+                double pq = 0;
+                for (size_t i = 0; i < n6; ++i) pq += p[i] * q[i];
+                if (!(pq > 0)) break;
+                const double alpha = rz / pq;
+                for (size_t i = 0; i < n6; ++i) {
+                    x[i] += alpha * p[i];
+                    r[i] -= alpha * q[i];
+                }
+                precond(r, z);
+                double rzn = 0;
+                for (size_t i = 0; i < n6; ++i) rzn += r[i] * z[i];
+                const double beta = rzn / rz;
+                rz = rzn;
+                for (size_t i = 0; i < n6; ++i) p[i] = z[i] + beta * p[i];
+                ++pcg_total;
+            }
+            for (int n = 0; n < N; ++n) {
+                SE3d dX;
+                se3_exp(&x[6 * (size_t) n], dX);
+                S.X[(size_t) n] = se3_mul(dX, S.X[(size_t) n]);
+            }
+            ++gn_total;
+            E = p2p_energy(S);
+        }
+    }
+    /* compose once onto the nodes: dg_se3 := DQ(X) * dg_se3 */
+    for (int n = 0; n < N; ++n) {
+        double qd[4];
+        rot_to_quat(S.X[(size_t) n].R, qd);
+        const float tf[3] = {(float) S.X[(size_t) n].t[0], (float) S.X[(size_t) n].t[1], (float) S.X[(size_t) n].t[2]};
+        DQ inc = dq_from_rot_trans(Quat{(float) qd[0], (float) qd[1], (float) qd[2], (float) qd[3]}, tf);
+        store_dq(dq_mul(inc, load_dq(dq_inout + 8 * (size_t) n)), dq_inout + 8 * (size_t) n);
+        if (X_out) {
+            for (int i = 0; i < 9; ++i) X_out[12 * (size_t) n + i] = S.X[(size_t) n].R[i];
+            for (int i = 0; i < 3; ++i) X_out[12 * (size_t) n + 9 + i] = S.X[(size_t) n].t[i];
+        }
+    }
+    if (stats_out) {
+        stats_out[0] = E0; stats_out[1] = E; stats_out[2] = (double) pcg_total; stats_out[3] = (double) gn_total;
+    }
+    return 0;
+}
+
+/* the same energy for arbitrary increments X (N*12: R row-major, t), Tukey weights evaluated at X_tukey: what the tests hand
+ * to scipy.optimize.least_squares */
+double orc_energy_p2plane(const float* pos, const float* dg_w, int N, const float* canon, const float* live, const float* live_n,
+                          long P, const orc_solver_params* prm, const double* X, const double* X_tukey) {
+    Problem pb;
+    build_problem(pb, pos, dg_w, N, canon, live, P, prm);
+    P2P S;
+    S.pb = &pb; S.canon = canon; S.live = live; S.nrm = live_n; S.pos = pos;
+    S.wn.assign((size_t) P * KNN, 0.0);
+    for (long v = 0; v < P; ++v) {
+        double sw = 0;
+        for (int k = 0; k < KNN; ++k) sw += pb.w[v * KNN + k];
+        for (int k = 0; k < KNN; ++k) S.wn[v * KNN + k] = sw > 0 ? pb.w[v * KNN + k] / sw : 0.0;
+    }
+    auto load = [&](const double* src) {
+        S.X.resize((size_t) N);
+        for (int n = 0; n < N; ++n) {
+            for (int i = 0; i < 9; ++i) S.X[(size_t) n].R[i] = src[12 * (size_t) n + i];
+            for (int i = 0; i < 3; ++i) S.X[(size_t) n].t[i] = src[12 * (size_t) n + 9 + i];
+        }
+    };
+    load(X_tukey);
+    p2p_update_tukey(S, pb);
+    load(X);
+    return p2p_energy(S);
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

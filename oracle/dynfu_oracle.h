@@ -137,6 +137,13 @@ double orc_energy(const float* pos, const float* dg_w, int N, const float* canon
                   const float* live, long P, const orc_solver_params* prm,
                   const double* t, const double* t_tukey);
 
+/* North-star extension P2PLANE_SE3 (no reference implementation; see the .cpp): point-to-plane data term, one rigid
+ * increment X_k per node (X_out[N*12]: R row-major then t), composed onto dq_inout once at the end. */
+int orc_solve_p2plane(const float* pos, float* dq_inout, const float* dg_w, int N, const float* canon, const float* live,
+                      const float* live_n, long P, const orc_solver_params* prm, double* X_out, double* stats_out);
+double orc_energy_p2plane(const float* pos, const float* dg_w, int N, const float* canon, const float* live,
+                          const float* live_n, long P, const orc_solver_params* prm, const double* X, const double* X_tukey);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -109,6 +109,11 @@ class Oracle:
         L.orc_warpfield_update.argtypes = [_fp, _fp, _fp, C.c_int, C.c_float, _fp, C.c_long, C.c_int, _fp, _fp, _fp]
         L.orc_warpfield_update.restype = C.c_long
         L.orc_raycast.argtypes = [_u32p, _ip, _fp, C.c_float, _fp, _fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, _fp, _fp, _u16p]
+        _dp = C.POINTER(C.c_double)
+        L.orc_solve_p2plane.argtypes = [_fp, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_long, C.POINTER(SolverParams), _dp, _dp]
+        L.orc_solve_p2plane.restype = C.c_int
+        L.orc_energy_p2plane.argtypes = [_fp, _fp, C.c_int, _fp, _fp, _fp, C.c_long, C.POINTER(SolverParams), _dp, _dp]
+        L.orc_energy_p2plane.restype = C.c_double
         L.orc_float2half.argtypes = [C.c_float]
         L.orc_float2half.restype = C.c_uint16
         L.orc_half2float.argtypes = [C.c_uint16]
@@ -407,6 +412,30 @@ class Oracle:
         tt = t if t_tukey is None else np.ascontiguousarray(t_tukey, np.float64)
         return self.lib.orc_energy(_f(pos), _f(dg_w), pos.shape[0], _f(canon), _f(live), canon.shape[0],
                                    C.byref(params), t.ctypes.data_as(_dp), tt.ctypes.data_as(_dp))
+
+    # ---- north-star extension: point-to-plane data term, rigid increment per node (no reference implementation) ----
+    def solve_p2plane(self, pos, dq, dg_w, canon, live, live_n, params):
+        """returns (X [N, 12] increments (R row-major, t), dq_out [N, 8], stats [E0, E, pcg, gn])"""
+        pos, dq, dg_w = _f32(pos, (-1, 3)), _f32(dq, (-1, 8)).copy(), _f32(dg_w)
+        canon, live, live_n = _f32(canon, (-1, 3)), _f32(live, (-1, 3)), _f32(live_n, (-1, 3))
+        N, P = pos.shape[0], canon.shape[0]
+        X = np.zeros((N, 12), np.float64)
+        stats = np.zeros(4, np.float64)
+        _dp = C.POINTER(C.c_double)
+        rc = self.lib.orc_solve_p2plane(_f(pos), _f(dq), _f(dg_w), N, _f(canon), _f(live), _f(live_n), P, C.byref(params),
+                                        X.ctypes.data_as(_dp), stats.ctypes.data_as(_dp))
+        if rc != 0:
+            raise ValueError("orc_solve_p2plane failed: %d" % rc)
+        return X, dq, stats
+
+    def energy_p2plane(self, pos, dg_w, canon, live, live_n, params, X, X_tukey=None):
+        pos, dg_w = _f32(pos, (-1, 3)), _f32(dg_w)
+        canon, live, live_n = _f32(canon, (-1, 3)), _f32(live, (-1, 3)), _f32(live_n, (-1, 3))
+        X = np.ascontiguousarray(X, np.float64).reshape(-1, 12)
+        Xt = X if X_tukey is None else np.ascontiguousarray(X_tukey, np.float64).reshape(-1, 12)
+        _dp = C.POINTER(C.c_double)
+        return self.lib.orc_energy_p2plane(_f(pos), _f(dg_w), pos.shape[0], _f(canon), _f(live), _f(live_n), canon.shape[0],
+                                           C.byref(params), X.ctypes.data_as(_dp), Xt.ctypes.data_as(_dp))
 
     def num_threads(self):
         return self.lib.orc_num_threads()
