@@ -47,6 +47,7 @@ namespace {
 #include "solver_matfree.cuh"
 #include "solver_normal.cuh"
 #include "solver_graph.cuh"
+#include "solver_p2plane.cuh"
 
 }  // namespace
 
@@ -92,6 +93,11 @@ struct dfu_solver {
     unsigned long long *xw = nullptr, *pw = nullptr;
     size_t cap_nnz = 0, cap_slots = 0, cap_rows = 0;
     bool pattern_ready = false;
+    // north-star extension: point-to-plane SE(3) data term (solver_p2plane.cuh)
+    int energy_mode = DFU_ENERGY_REF_TRANSLATION;
+    const float *canon_v = nullptr, *live_v = nullptr, *live_n = nullptr;  // caller-owned, valid until solve_all returns
+    float *p2p_pt = nullptr, *p2p_node = nullptr;                          // per-point / per-node scratch
+    size_t p2p_cap_pt = 0, p2p_cap_node = 0;
     bool lists_sorted = true;    // transposed lists ordered by point id (needed by the float-order-dependent paths)
     int gn_steps_host = 0;
 };
@@ -307,6 +313,7 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
 // sparsity pattern of the explicit normal matrix for this frame's graphs (version 3 of the persistent kernel)
 // can this problem run version 3 of the persistent kernel (explicit normal matrix)?
 bool pattern_eligible(const dfu_solver* s) {
+    if (s->energy_mode != DFU_ENERGY_REF_TRANSLATION) return false;
     const char* force = getenv("DFU_SOLVER_PATH");
     if (force && (force[0] == 'm' || (force[0] == 'p' && (force[1] == '1' || force[1] == '2')))) return false;  // another path was asked for
     const bool forced3 = force && force[0] == 'p' && force[1] == '3';
@@ -378,6 +385,113 @@ int build_pattern(dfu_solver* s, cudaStream_t st) {
     return DFU_OK;
 }
 
+
+// north-star extension: Gauss-Newton on the point-to-plane SE(3) energy, one kernel per phase
+int solve_p2plane(dfu_solver* s, cudaStream_t st) {
+    const int N = s->N, P = s->P;
+    const dfu_solver_params& prm = s->prm;
+    DFU_REQUIRE(s->live_n != nullptr, DFU_ERR_INVALID, "the point-to-plane energy needs the live normals (initializeProblemInstance)");
+    DFU_REQUIRE(s->lists_sorted, DFU_ERR_NOT_INIT, "set the energy before initializeProblemInstance");
+    // scratch: per point wn 8 | jac 48 | e | theta' (shared with s->theta) | sv  -> 58 floats; per node X 12 | G 48 | 6 vectors 36 | L 21
+    const size_t need_pt = (size_t) std::max(P, 1) * 58, need_node = (size_t) N * (12 + 48 + 36 + 21);
+    if (need_pt > s->p2p_cap_pt) {
+        cudaFree(s->p2p_pt);
+        s->p2p_pt = nullptr; s->p2p_cap_pt = 0;
+        DFU_CUDA_OK(cudaMalloc(&s->p2p_pt, need_pt * sizeof(float)));
+        s->p2p_cap_pt = need_pt;
+    }
+    if (need_node > s->p2p_cap_node) {
+        cudaFree(s->p2p_node);
+        s->p2p_node = nullptr; s->p2p_cap_node = 0;
+        DFU_CUDA_OK(cudaMalloc(&s->p2p_node, need_node * sizeof(float)));
+        s->p2p_cap_node = need_node;
+    }
+    P2PProblem pb{};
+    pb.N = N; pb.P = P;
+    pb.nbr = s->nbr; pb.wts = s->wts; pb.canon = s->canon_v; pb.live = s->live_v; pb.nrm = s->live_n;
+    pb.tptr = s->tptr; pb.tv = s->tv; pb.nnbr = s->nnbr; pb.rin_ptr = s->rin_ptr; pb.rin = s->rin; pb.pos_w = s->wf->pos_w;
+    pb.wreg2 = prm.lambda / ((float) N * 8.f);
+    pb.tukey_offset = prm.tukey_offset; pb.psi_data = prm.psi_data;
+    float* pp = s->p2p_pt;
+    pb.wn = pp; pp += (size_t) P * 8;
+    pb.jac = pp; pp += (size_t) P * 48;
+    pb.e = pp; pp += P;
+    pb.sv = pp;
+    pb.theta = s->theta;
+    float* pn = s->p2p_node;
+    pb.X = pn; pn += (size_t) N * 12;
+    pb.G = pn; pn += (size_t) N * 48;
+    pb.b = pn; pb.x = pn + 6 * (size_t) N; pb.r = pn + 12 * (size_t) N; pb.z = pn + 18 * (size_t) N; pb.p = pn + 24 * (size_t) N;
+    pb.q = pn + 30 * (size_t) N; pn += (size_t) N * 36;
+    pb.L = pn;
+    pb.part = s->part;
+    const int nblk_n = div_up(N, TPB), nblk_p = std::max(1, std::min(div_up(P, TPB), MAX_PARTIALS)),
+              nblk_e = std::min(div_up((long) N * 8, TPB), MAX_PARTIALS), nblk_w = std::min(div_up((long) N * 32, TPB), MAX_PARTIALS);
+    DFU_REQUIRE(div_up(P, TPB) <= MAX_PARTIALS && div_up((long) N * 8, TPB) <= MAX_PARTIALS, DFU_ERR_UNSUPPORTED,
+                "point-to-plane mode: at most 262144 points / 32768 nodes");
+    const double tol2 = (double) prm.pcg_tol * (double) prm.pcg_tol;
+    Scalars init{};
+    init.rz_ref = -1.0;
+    init.first = 1;
+    init.done_it = INT_MAX;
+    *s->sc_host = init;
+    DFU_CUDA_OK(cudaMemcpyAsync(s->sc, s->sc_host, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+    DFU_CUDA_OK(cudaStreamSynchronize(st));  // sc_host is re-used for read-backs
+    kp_init<<<std::max(nblk_n, div_up(P, TPB)), TPB, 0, st>>>(pb);
+    DFU_LAUNCH_OK();
+    bool stop_all = false;
+    s->gn_steps_host = -1;
+    for (int outer = 0; outer < prm.num_iter && !stop_all; ++outer) {
+        for (int gn = 0; gn < prm.nonlinear_iter; ++gn) {
+            kp_linearise<<<nblk_p, TPB, 0, st>>>(pb, gn == 0 ? 1 : 0);
+            DFU_LAUNCH_OK();
+            kp_edges<<<nblk_e, TPB, 0, st>>>(pb);
+            DFU_LAUNCH_OK();
+            kp_assemble<<<nblk_w, TPB, 0, st>>>(pb);
+            DFU_LAUNCH_OK();
+            kp_init_scalars<<<1, 32, 0, st>>>(pb, s->sc, nblk_p, nblk_e, nblk_w, tol2);
+            DFU_LAUNCH_OK();
+            if (prm.early_out) {
+                int rc = read_scalars(s, st);
+                if (rc != DFU_OK) return rc;
+                if (s->sc_host->done_it == 0) {
+                    if (gn == 0 && outer > 0) stop_all = true;
+                    break;
+                }
+            }
+            for (int it = 0; it < prm.linear_iter; ++it) {
+                kp_point_apply<<<nblk_p, TPB, 0, st>>>(pb, s->sc, it);
+                DFU_LAUNCH_OK();
+                kp_node_apply<<<nblk_w, TPB, 0, st>>>(pb, s->sc, it);
+                DFU_LAUNCH_OK();
+                kp_update<<<nblk_n, TPB, 0, st>>>(pb, s->sc, it, nblk_w);
+                DFU_LAUNCH_OK();
+                kp_direction<<<nblk_n, TPB, 0, st>>>(pb, s->sc, it, nblk_n, nblk_w, tol2);
+                DFU_LAUNCH_OK();
+                if (prm.early_out && (it & 15) == 15) {
+                    int rc = read_scalars(s, st);
+                    if (rc != DFU_OK) return rc;
+                    if (s->sc_host->done_it <= it + 1) break;
+                }
+            }
+            kp_expmap<<<nblk_n, TPB, 0, st>>>(pb, s->sc);
+            DFU_LAUNCH_OK();
+        }
+    }
+    // energy at the solution (Tukey weights of the last outer iteration; at the identity if no step ran)
+    kp_linearise<<<nblk_p, TPB, 0, st>>>(pb, prm.num_iter * prm.nonlinear_iter == 0 ? 1 : 0);
+    DFU_LAUNCH_OK();
+    kp_edges<<<nblk_e, TPB, 0, st>>>(pb);
+    DFU_LAUNCH_OK();
+    kp_final_energy<<<1, 32, 0, st>>>(pb, s->sc, nblk_p, nblk_e);
+    DFU_LAUNCH_OK();
+    // compose the increments onto the nodes once, like the reference does with its translations (opt_solver.cpp:270-285)
+    kp_compose<<<nblk_n, TPB, 0, st>>>(pb, s->wf->real, s->wf->dual);
+    DFU_LAUNCH_OK();
+    s->last_kernel = 0;
+    return dfu_wf_refresh_flags(s->wf, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -427,6 +541,8 @@ int dfu_solver_destroy(dfu_solver* s) {
     free_point_arrays(s);
     free_node_arrays(s);
     free_pattern_arrays(s);
+    cudaFree(s->p2p_pt);
+    cudaFree(s->p2p_node);
     cudaFree(s->pat_cursor);
     cudaFree(s->sc);
     cudaFreeHost(s->sc_host);
@@ -434,6 +550,21 @@ int dfu_solver_destroy(dfu_solver* s) {
     cudaFree(s->bar);
     cudaSetDevice(prev);
     delete s;
+    return DFU_OK;
+}
+
+int dfu_solver_set_energy(dfu_solver* s, int energy_mode) {
+    DFU_REQUIRE(s, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(energy_mode == DFU_ENERGY_REF_TRANSLATION || energy_mode == DFU_ENERGY_P2PLANE_SE3, DFU_ERR_INVALID, "bad energy mode");
+    s->energy_mode = energy_mode;
+    s->problem_ready = false;  // the transposed lists depend on the mode
+    return DFU_OK;
+}
+
+int dfu_solver_get_increments(const dfu_solver* s, float* X12, dfu_stream stream) {
+    DFU_REQUIRE(s && X12, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(s->energy_mode == DFU_ENERGY_P2PLANE_SE3 && s->p2p_node, DFU_ERR_NOT_INIT, "no point-to-plane solve has run");
+    DFU_CUDA_OK(cudaMemcpyAsync(X12, s->p2p_node, 12 * (size_t) s->N * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
     return DFU_OK;
 }
 
@@ -446,7 +577,7 @@ int dfu_solver_set_allreduce(dfu_solver* s, dfu_allreduce_fn fn, void* ctx) {
 
 int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* canon_n, const float* live_v,
                             const float* live_n, int P, const float affine_host[12], dfu_stream stream) {
-    (void) canon_n; (void) live_n; (void) affine_host;  // uploaded but never read by the reference's energy
+    (void) canon_n; (void) affine_host;  // uploaded but never read by the reference's energy (live_n: point-to-plane mode only)
     DFU_REQUIRE(s, DFU_ERR_INVALID, "NULL argument");
     DFU_REQUIRE(P >= 0 && (P == 0 || (canon_v && live_v)), DFU_ERR_INVALID, "bad point arrays");
     dfu_warpfield* wf = s->wf;
@@ -486,6 +617,7 @@ int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* ca
     }
     s->N = N;
     s->P = P;
+    s->canon_v = canon_v; s->live_v = live_v; s->live_n = live_n;
     int rc = DFU_OK;
     // regularisation graph (opt_solver.cpp:74-105) and its transpose: depend on node POSITIONS only, so they are
     // rebuilt exactly when the reference would see a different KD-tree (Warpfield::init / update)
@@ -545,6 +677,11 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream) {
     cudaStream_t st = as_stream(stream);
     // DFU_SOLVER_PATH=multi forces the one-kernel-per-phase path (used by the tests to cover both)
     const char* force = getenv("DFU_SOLVER_PATH");
+    if (s->energy_mode == DFU_ENERGY_P2PLANE_SE3) {
+        int rc = solve_p2plane(s, st);
+        if (prev != s->wf->device) cudaSetDevice(prev);
+        return rc;
+    }
     const bool multi = s->allreduce != nullptr || s->coop_blocks == 0 || (force && force[0] == 'm');
     if (!s->lists_sorted && (multi || !pattern_eligible(s)) && s->P > 0) {
         // the path changed after init_problem (hook set, environment): the float-order-dependent kernels want sorted lists

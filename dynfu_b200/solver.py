@@ -76,8 +76,27 @@ class CombinedSolver:
         lv = torch.as_tensor(liveVertices, dtype=torch.float32).to(dev).reshape(-1, 3).contiguous()
         if cv.shape != lv.shape:
             raise _lib.DfuError(1, "canonical and live frames must pair up vertex by vertex")
-        self._keep = (cv, lv)
-        check(lib.dfu_solver_init_problem(self._h, dptr(cv), None, dptr(lv), None, cv.shape[0], None, stream_ptr()))
+        ln = None
+        if liveNormals is not None:
+            ln = torch.as_tensor(liveNormals, dtype=torch.float32).to(dev).reshape(-1, 3).contiguous()
+            if ln.shape != lv.shape:
+                raise _lib.DfuError(1, "live normals must pair up with the live vertices")
+        self._keep = (cv, lv, ln)  # the point-to-plane mode reads them during solveAll
+        check(lib.dfu_solver_init_problem(self._h, dptr(cv), None, dptr(lv), dptr(ln), cv.shape[0], None, stream_ptr()))
+
+    # north-star extension (no reference implementation): point-to-plane data term with a rigid increment per node
+    ENERGY_REF_TRANSLATION = 0
+    ENERGY_P2PLANE_SE3 = 1
+
+    def setEnergy(self, mode):
+        """call before initializeProblemInstance; ENERGY_P2PLANE_SE3 needs liveNormals there"""
+        check(lib.dfu_solver_set_energy(self._h, int(mode)))
+
+    def getIncrements(self):
+        """ENERGY_P2PLANE_SE3: [N, 12] rigid increments (R row-major, t) of the last solve"""
+        x = torch.empty((self.warpfield.numNodes(), 12), dtype=torch.float32, device=self.warpfield.device)
+        check(lib.dfu_solver_get_increments(self._h, dptr(x), stream_ptr()))
+        return x
 
     # CombinedSolverBase::solveAll [Opt]
     def solveAll(self):

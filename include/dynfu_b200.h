@@ -184,6 +184,15 @@ typedef struct {
 } dfu_solver_params;
 
 /* all-reduce hook for data-parallel solves: sums buf[count] floats over ranks, in place, on stream */
+/* Energy minimised by the solver.
+ *   DFU_ENERGY_REF_TRANSLATION  the reference's energy.t: point-to-point, translations only (default; parity with the oracle)
+ *   DFU_ENERGY_P2PLANE_SE3      north-star extension without a reference implementation: sum theta (n_live . (p - live))^2
+ *                               with p = sum_k w^_k X_k canon (normalised weights), one rigid increment X_k per node,
+ *                               as-rigid-as-possible regulariser w_reg^2 |X_n g_m - X_m g_m|^2; needs live_n in
+ *                               dfu_solver_init_problem, whose point arrays must then stay valid until solve_all returns.
+ *                               The increments are composed onto the node transforms once at the end. */
+enum { DFU_ENERGY_REF_TRANSLATION = 0, DFU_ENERGY_P2PLANE_SE3 = 1 };
+
 typedef int (*dfu_allreduce_fn)(float* buf, size_t count, void* ctx, dfu_stream stream);
 
 /* CombinedSolver::CombinedSolver(warpfield, params, tukeyOffset, psi_data, lambda, psi_reg)
@@ -220,6 +229,10 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream);
 /* results of the last solve_all: t_xyz[N*3] (device, may be NULL) and
  * stats_host[4] = {initial energy, final energy, PCG iterations, GN steps} (synchronises the stream) */
 int dfu_solver_get_translations(const dfu_solver* s, float* t_xyz, dfu_stream stream);
+/* call before dfu_solver_init_problem */
+int dfu_solver_set_energy(dfu_solver* s, int energy_mode);
+/* DFU_ENERGY_P2PLANE_SE3: the rigid increments of the last solve, N x 12 floats (R row-major, t) */
+int dfu_solver_get_increments(const dfu_solver* s, float* X12, dfu_stream stream);
 int dfu_solver_get_stats_host(const dfu_solver* s, double stats_host[4], dfu_stream stream);
 /* the same four numbers written to DEVICE memory, stream-ordered and without a synchronisation (pipelined frame loops
  * copy them to pinned host memory together with the node transforms) */

@@ -598,3 +598,53 @@ def test_stream_frame_equals_the_synchronous_frame_operator(dfu, oracle):
         assert np.array_equal(dq_s, dq_p)
         assert st_s == st_p
     assert torch.equal(a.volume.data, b.volume.data)
+
+
+# ------------------------------------------------ north-star extension: point-to-plane SE(3) data term (parity unpinned)
+def test_p2plane_se3_matches_the_double_precision_oracle(dfu, oracle):
+    """converged energy and node transforms within 1e-4 relative of the oracle (which tests/test_oracle_p2plane.py pins
+    against scipy.optimize.least_squares); the reference has no such term"""
+    from tests.test_oracle_p2plane import rigid_scene
+
+    pos, dg_w, canon, live, live_n, R, t = rigid_scene(n_nodes=64, n_pts=6000, seed=7)
+    live = (live + np.random.default_rng(1).normal(0, 0.002, live.shape)).astype(np.float32)  # a minimum with E > 0
+    N = len(pos)
+    prm_o = pyoracle.default_params(num_iter=4, nonlinear_iter=3, linear_iter=300, lambda_=200.0, psi_data=1.0, pcg_tol=1e-12)
+    X_o, dq_o, st_o = oracle.solve_p2plane(pos, synth.identity_dq(N), dg_w, canon, live, live_n, prm_o)
+    wf = make_wf(dfu, pos, synth.identity_dq(N), dg_w, 0.08)
+    prm = dfu.CombinedSolverParameters(numIter=4, nonLinearIter=3, linearIter=300, earlyOut=False, pcgTolerance=1e-7)
+    s = dfu.CombinedSolver(wf, prm, 4.652, 1.0, 200.0, 1e-4)
+    s.setEnergy(s.ENERGY_P2PLANE_SE3)
+    s.initializeProblemInstance(dev(canon), dev(live), liveNormals=dev(live_n))
+    s.solveAll()
+    st = s.getStats()
+    assert st["gn_steps"] == 12
+    assert abs(st["initial_energy"] - st_o[0]) <= 1e-4 * st_o[0]
+    assert abs(st["final_energy"] - st_o[1]) <= 1e-4 * st_o[1], (st, st_o)
+    assert st_o[1] < 0.05 * st_o[0]
+    X_g = s.getIncrements().cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(X_g - X_o)) <= 1e-4 * np.abs(X_o).max()
+    # the increments were composed onto the nodes once: warping the canonical points now lands on the live surface
+    dq_g = wf.getNodes()[1].cpu().numpy()
+    assert np.max(np.abs(dq_g - dq_o)) <= 1e-4
+    warped, _ = wf.warpToLive(dev(canon), None, dfu.BLEND_DQB_SUM)
+    d = np.einsum("pi,pi->p", warped.cpu().numpy() - live, live_n)
+    assert np.sqrt(np.mean(d * d)) < 0.0025  # down to the noise that was added (2 mm), from a 3 cm motion
+
+
+def test_p2plane_needs_normals_and_leaves_the_reference_energy_alone(dfu, oracle):
+    pos, dg_w, canon, t_true = _wellposed(seed=13, N=256, P=4000)
+    live = oracle.warp(pos, synth.translations_to_dq(0.2 * t_true), dg_w, canon)
+    wf = make_wf(dfu, pos, synth.identity_dq(256), dg_w, 0.025)
+    prm = dfu.CombinedSolverParameters(numIter=2, nonLinearIter=1, linearIter=10, earlyOut=False, pcgTolerance=0.0)
+    s = dfu.CombinedSolver(wf, prm, 4.652, 1e-2, 200.0, 1e-4)
+    s.setEnergy(s.ENERGY_P2PLANE_SE3)
+    s.initializeProblemInstance(dev(canon), dev(live))  # no normals
+    with pytest.raises(dfu.DfuError):
+        s.solveAll()
+    s.setEnergy(s.ENERGY_REF_TRANSLATION)
+    with pytest.raises(dfu.DfuError):  # the problem instance belongs to the other mode
+        s.solveAll()
+    s.initializeProblemInstance(dev(canon), dev(live))
+    s.solveAll()
+    assert s.getStats()["gn_steps"] == 2

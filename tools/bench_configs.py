@@ -50,10 +50,11 @@ def timed(fn, n=20, warm=3):
     return a.elapsed_time(b) / n
 
 
-def run(name, dim, n_theta, n_y, eps, gn, pcg, rows=480, cols=640, z0=0, z1=None, do_solve=True, do_integrate=True):
+def run(name, dim, n_theta, n_y, eps, gn, pcg, rows=480, cols=640, z0=0, z1=None, do_solve=True, do_integrate=True, p2plane=False):
     sc = scene(dim, n_theta, n_y, eps, rows, cols)
     kp = dfu.KinFuParams(cols=cols, rows=rows, intr=tuple(float(x) for x in sc["intr"]), volume_dims=(dim, dim, dim))
     prm = dfu.DynFuParams(kinfuParams=kp, epsilon=eps, lambda_=200.0,
+                          blend_mode=dfu.BLEND_DQB_SUM if p2plane else dfu.BLEND_REF_COMPOSE,  # rotations: true DQ blending
                           solver=dfu.CombinedSolverParameters(numIter=gn, nonLinearIter=1, linearIter=pcg, earlyOut=False,
                                                               pcgTolerance=0.0))
     df = dfu.DynFusion(prm, device=DEV, z0=z0, z1=z1)
@@ -62,10 +63,18 @@ def run(name, dim, n_theta, n_y, eps, gn, pcg, rows=480, cols=640, z0=0, z1=None
     live_dev = [dev(l) for l in sc["lives"]]
     df(torch.from_numpy(sc["depth0"].view(np.int16)).pin_memory())
     t = {}
+    live_n = None
+    if p2plane:  # north-star extension: point-to-plane SE(3) data term; normals of the (bent) cylinder ~ radial
+        c = np.array([1.5, 1.5, 1.5]) + np.array([0.0, 0.0, 0.0])
+        nn = sc["canon"].astype(np.float64) - np.array([1.5, 0.0, 1.5])
+        nn[:, 1] = 0.0
+        nn /= np.linalg.norm(nn, axis=1, keepdims=True)
+        live_n = dev(nn.astype(np.float32))
+        df.solver.setEnergy(df.solver.ENERGY_P2PLANE_SE3)
 
     def solve(i):
         df.canonicalWarpedToLive, _ = df.warpCanonical()
-        df.solver.initializeProblemInstance(df.canonicalWarpedToLive, live_dev[i % 2])
+        df.solver.initializeProblemInstance(df.canonicalWarpedToLive, live_dev[i % 2], liveNormals=live_n)
         df.solver.solveAll()
 
     def integrate(i):
@@ -106,6 +115,8 @@ if __name__ == "__main__":
         run("C1 full frame", 256, 32, 32, 0.025, 5, 10)
     if "C2" in which:
         run("C2 warped integration only", 512, 64, 64, 0.0125, 5, 10, do_solve=False)
+    if "C3p" in which:  # the headline frame with the point-to-plane SE(3) term instead of the reference's energy
+        run("C3 with the point-to-plane SE(3) data term (north-star extension)", 512, 64, 64, 0.0125, 5, 10, p2plane=True)
     if "C4" in which:  # the slab holding the surface's z range is the heaviest one: planes 384..512 of 1024 (z 1.125..1.5 m)
         run("C4 per-GPU share at 8 GPUs (128-plane slab + replicated solve)", 1024, 128, 128, 0.00625, 5, 10, z0=384, z1=512)
     if "C5" in which:
