@@ -165,8 +165,12 @@ class DynFusion:
     # slots), every frame still pays its own H2D and D2H.
     def _stream_state(self, live_host):
         st = getattr(self, "_ss", None)
-        if st is None or st["live"][0].shape != live_host.shape:
-            n = self.warpfield.numNodes()
+        n = self.warpfield.numNodes()
+        if st is not None and (st["live"][0].shape != live_host.shape or st["dq_dev"][0].shape[0] != n):
+            self.streamFlush()  # sizes changed (new frame size, or Warpfield::update added nodes): start over
+            torch.cuda.synchronize(self.device)
+            st = None
+        if st is None:
             st = dict(h2d=torch.cuda.Stream(self.device), d2h=torch.cuda.Stream(self.device), slot=0, pending=None,
                       depth=[torch.empty_like(self._depth_dev) for _ in range(2)],
                       live=[torch.empty(live_host.shape, dtype=torch.float32, device=self.device) for _ in range(2)],

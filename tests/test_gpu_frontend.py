@@ -404,3 +404,21 @@ def test_raycast_bit_exact(fe, oracle, yaw):
         assert np.median(err) <= 12 and np.percentile(err, 90) <= 40
         nrm = n_o[hit][:, :3]
         assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-5)
+
+
+def test_update_with_fewer_than_eight_nodes(fe, oracle):
+    """the reference's findNeighbors returns fewer than 8 nodes when the field is that small: same decisions"""
+    pos = np.float32([[1.5, 1.5, 1.5], [1.6, 1.5, 1.5], [1.5, 1.62, 1.5]])
+    dq = synth.translations_to_dq(np.float32([[0.01, 0, 0], [0, 0.01, 0], [0, 0, 0.01]]))
+    w = np.float32([0.08, 0.08, 0.08])
+    rng = np.random.default_rng(3)
+    v = (np.float32([1.55, 1.55, 1.5]) + rng.uniform(-0.3, 0.3, (500, 3))).astype(np.float32)
+    mask_o = oracle.unsupported(pos, w, v)
+    assert 0 < mask_o.sum() < 500
+    po, qo, wo = oracle.warpfield_update(pos, dq, w, 0.04, v)
+    wf = make_wf(pos, dq, w, 0.04)
+    assert np.array_equal(wf.getUnsupportedVertices(dev(v), return_mask=True).cpu().numpy(), mask_o)
+    nu, nn = wf.update(dev(v))
+    assert nu == int(mask_o.sum()) and nn == po.shape[0] - 3
+    pg, qg, wg = [t.cpu().numpy() for t in wf.getNodes()]
+    assert same_bits(pg, po) and same_bits(wg, wo) and np.allclose(qg, qo, atol=2e-6)
