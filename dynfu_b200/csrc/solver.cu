@@ -392,8 +392,8 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     const dfu_solver_params& prm = s->prm;
     DFU_REQUIRE(s->live_n != nullptr, DFU_ERR_INVALID, "the point-to-plane energy needs the live normals (initializeProblemInstance)");
     DFU_REQUIRE(s->lists_sorted, DFU_ERR_NOT_INIT, "set the energy before initializeProblemInstance");
-    // scratch: per point wn 8 | jac 48 | e | theta' (shared with s->theta) | sv  -> 58 floats; per node X 12 | G 48 | 6 vectors 36 | L 21
-    const size_t need_pt = (size_t) std::max(P, 1) * 58, need_node = (size_t) N * (12 + 48 + 36 + 21);
+    // scratch: per point wn 8 | jac 48 | e | sv | tk (8 bytes) -> 60 floats; per node X 12 | G 48 | 6 vectors 36 | L 21
+    const size_t need_pt = (size_t) std::max(P, 1) * 60, need_node = (size_t) N * (12 + 48 + 36 + 21);
     if (need_pt > s->p2p_cap_pt) {
         cudaFree(s->p2p_pt);
         s->p2p_pt = nullptr; s->p2p_cap_pt = 0;
@@ -416,7 +416,8 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     pb.wn = pp; pp += (size_t) P * 8;
     pb.jac = pp; pp += (size_t) P * 48;
     pb.e = pp; pp += P;
-    pb.sv = pp;
+    pb.sv = pp; pp += P;
+    pb.tk = reinterpret_cast<unsigned char*>(pp);  // 8P bytes
     pb.theta = s->theta;
     float* pn = s->p2p_node;
     pb.X = pn; pn += (size_t) N * 12;
@@ -430,14 +431,9 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     DFU_REQUIRE(div_up(P, TPB) <= MAX_PARTIALS && div_up((long) N * 8, TPB) <= MAX_PARTIALS, DFU_ERR_UNSUPPORTED,
                 "point-to-plane mode: at most 262144 points / 32768 nodes");
     const double tol2 = (double) prm.pcg_tol * (double) prm.pcg_tol;
-    Scalars init{};
-    init.rz_ref = -1.0;
-    init.first = 1;
-    init.done_it = INT_MAX;
-    *s->sc_host = init;
-    DFU_CUDA_OK(cudaMemcpyAsync(s->sc, s->sc_host, sizeof(Scalars), cudaMemcpyHostToDevice, st));
-    DFU_CUDA_OK(cudaStreamSynchronize(st));  // sc_host is re-used for read-backs
-    kp_init<<<std::max(nblk_n, div_up(P, TPB)), TPB, 0, st>>>(pb);
+    kp_init<<<std::max(nblk_n, div_up(P, TPB)), TPB, 0, st>>>(pb, s->sc);  // also resets the device scalars
+    DFU_LAUNCH_OK();
+    kp_slots<<<nblk_w, TPB, 0, st>>>(pb);
     DFU_LAUNCH_OK();
     bool stop_all = false;
     s->gn_steps_host = -1;
@@ -449,7 +445,7 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
             DFU_LAUNCH_OK();
             kp_assemble<<<nblk_w, TPB, 0, st>>>(pb);
             DFU_LAUNCH_OK();
-            kp_init_scalars<<<1, 32, 0, st>>>(pb, s->sc, nblk_p, nblk_e, nblk_w, tol2);
+            kp_init_scalars<<<1, TPB, 0, st>>>(pb, s->sc, nblk_p, nblk_e, nblk_w, tol2);
             DFU_LAUNCH_OK();
             if (prm.early_out) {
                 int rc = read_scalars(s, st);
@@ -483,7 +479,7 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     DFU_LAUNCH_OK();
     kp_edges<<<nblk_e, TPB, 0, st>>>(pb);
     DFU_LAUNCH_OK();
-    kp_final_energy<<<1, 32, 0, st>>>(pb, s->sc, nblk_p, nblk_e);
+    kp_final_energy<<<1, TPB, 0, st>>>(pb, s->sc, nblk_p, nblk_e);
     DFU_LAUNCH_OK();
     // compose the increments onto the nodes once, like the reference does with its translations (opt_solver.cpp:270-285)
     kp_compose<<<nblk_n, TPB, 0, st>>>(pb, s->wf->real, s->wf->dual);

@@ -19,6 +19,7 @@ struct P2PProblem {
     const float *canon, *live, *nrm;
     const int* tptr;        // transposed graph: node -> points (sorted by point)
     const int32_t* tv;
+    unsigned char* tk;      // per transposed entry: slot of the node in its point's neighbour list
     const int32_t* nnbr;    // N*8 regularisation out-edges
     const int* rin_ptr;     // in-edges (sources, ascending)
     const int32_t* rin;
@@ -44,8 +45,17 @@ DFU_DEV void p2p_apply(const float* X, float cx, float cy, float cz, float& ox, 
     oz = X[6] * cx + X[7] * cy + X[8] * cz + X[11];
 }
 
-__global__ void __launch_bounds__(TPB) kp_init(P2PProblem pb) {
+__global__ void __launch_bounds__(TPB) kp_init(P2PProblem pb, Scalars* sc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        sc->rz[0] = sc->rz[1] = 0.0;
+        sc->rz_ref = -1.0;
+        sc->E = sc->E0 = 0.0;
+        sc->done_it = INT_MAX;
+        sc->pcg_iters = sc->gn_steps = 0;
+        sc->first = 1;
+        sc->spin_fail = 0;
+    }
     if (i < pb.N) {
 #pragma unroll
         for (int k = 0; k < 12; ++k) pb.X[12 * (size_t) i + k] = (k == 0 || k == 4 || k == 8) ? 1.f : 0.f;
@@ -126,6 +136,13 @@ DFU_DEV int p2p_slot(const P2PProblem& pb, int v, int n) {
     return k;
 }
 
+__global__ void __launch_bounds__(TPB) kp_slots(P2PProblem pb) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int n = gw; n < pb.N; n += nw)
+        for (int j = pb.tptr[n] + lane; j < pb.tptr[n + 1]; j += 32) pb.tk[j] = (unsigned char) p2p_slot(pb, pb.tv[j], n);
+}
+
 // regularisation part of (J^T J x)_n for node n (lane-parallel over its out- and in-edges), reduced over the warp
 DFU_DEV void p2p_reg_apply(const P2PProblem& pb, int n, int lane, const float* x, float (&acc)[6]) {
     const int lo = pb.rin_ptr[n], hi = pb.rin_ptr[n + 1];
@@ -163,7 +180,7 @@ __global__ void __launch_bounds__(TPB) kp_assemble(P2PProblem pb) {
         for (int i = 0; i < 21; ++i) M[i] = 0.0;
         for (int j = pb.tptr[n] + lane; j < pb.tptr[n + 1]; j += 32) {
             const int v = pb.tv[j];
-            const float* a = pb.jac + ((size_t) v * 8 + p2p_slot(pb, v, n)) * 6;
+            const float* a = pb.jac + ((size_t) v * 8 + pb.tk[j]) * 6;
             const double th = pb.theta[v], te = th * (double) pb.e[v];
             int idx = 0;
 #pragma unroll
@@ -275,8 +292,8 @@ DFU_DEV void p2p_precond(const float* L, const float (&r)[6], float (&z)[6]) {
     }
 }
 
-__global__ void kp_init_scalars(P2PProblem pb, Scalars* sc, int nblk_p, int nblk_e, int nblk_w, double tol2) {
-    __shared__ double sh[1];
+__global__ void __launch_bounds__(TPB) kp_init_scalars(P2PProblem pb, Scalars* sc, int nblk_p, int nblk_e, int nblk_w, double tol2) {
+    __shared__ double sh[TPB / 32];
     if (blockIdx.x != 0) return;
     const double ed = sum_partials(pb.part, nblk_p, sh);
     const double er = sum_partials(pb.part + MAX_PARTIALS, nblk_e, sh);
@@ -293,8 +310,8 @@ __global__ void kp_init_scalars(P2PProblem pb, Scalars* sc, int nblk_p, int nblk
     }
 }
 // energy only (after the last update)
-__global__ void kp_final_energy(P2PProblem pb, Scalars* sc, int nblk_p, int nblk_e) {
-    __shared__ double sh[1];
+__global__ void __launch_bounds__(TPB) kp_final_energy(P2PProblem pb, Scalars* sc, int nblk_p, int nblk_e) {
+    __shared__ double sh[TPB / 32];
     if (blockIdx.x != 0) return;
     const double ed = sum_partials(pb.part, nblk_p, sh);
     const double er = sum_partials(pb.part + MAX_PARTIALS, nblk_e, sh);
@@ -314,12 +331,20 @@ __global__ void __launch_bounds__(TPB) kp_point_apply(P2PProblem pb, const Scala
     const float th = pb.theta[v];
     float acc = 0.f;
     if (th != 0.f) {
+        const float4* a4 = reinterpret_cast<const float4*>(pb.jac + (size_t) v * 48);  // 8 x 6 floats = 12 x float4
+        float a[48];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const float4 t = a4[i];
+            a[4 * i] = t.x; a[4 * i + 1] = t.y; a[4 * i + 2] = t.z; a[4 * i + 3] = t.w;
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float* a = pb.jac + ((size_t) v * 8 + k) * 6;
-            const float* xk = pb.p + 6 * (size_t) pb.nbr[8 * (size_t) v + k];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) acc = __fmaf_rn(a[r], xk[r], acc);
+            const float2* x2 = reinterpret_cast<const float2*>(pb.p + 6 * (size_t) pb.nbr[8 * (size_t) v + k]);
+            const float2 x01 = x2[0], x23 = x2[1], x45 = x2[2];
+            acc = __fmaf_rn(a[6 * k], x01.x, acc); acc = __fmaf_rn(a[6 * k + 1], x01.y, acc);
+            acc = __fmaf_rn(a[6 * k + 2], x23.x, acc); acc = __fmaf_rn(a[6 * k + 3], x23.y, acc);
+            acc = __fmaf_rn(a[6 * k + 4], x45.x, acc); acc = __fmaf_rn(a[6 * k + 5], x45.y, acc);
         }
     }
     pb.sv[v] = th * acc;
@@ -336,9 +361,11 @@ __global__ void __launch_bounds__(TPB) kp_node_apply(P2PProblem pb, const Scalar
         for (int j = pb.tptr[n] + lane; j < pb.tptr[n + 1]; j += 32) {
             const int v = pb.tv[j];
             const float s = pb.sv[v];
-            const float* a = pb.jac + ((size_t) v * 8 + p2p_slot(pb, v, n)) * 6;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) acc[r] = __fmaf_rn(a[r], s, acc[r]);
+            const float2* a2 = reinterpret_cast<const float2*>(pb.jac + ((size_t) v * 8 + pb.tk[j]) * 6);
+            const float2 a01 = a2[0], a23 = a2[1], a45 = a2[2];
+            acc[0] = __fmaf_rn(a01.x, s, acc[0]); acc[1] = __fmaf_rn(a01.y, s, acc[1]);
+            acc[2] = __fmaf_rn(a23.x, s, acc[2]); acc[3] = __fmaf_rn(a23.y, s, acc[3]);
+            acc[4] = __fmaf_rn(a45.x, s, acc[4]); acc[5] = __fmaf_rn(a45.y, s, acc[5]);
         }
         if (pb.wreg2 > 0.f) p2p_reg_apply(pb, n, lane, pb.p, acc);
 #pragma unroll
