@@ -648,3 +648,41 @@ def test_p2plane_needs_normals_and_leaves_the_reference_energy_alone(dfu, oracle
     s.initializeProblemInstance(dev(canon), dev(live))
     s.solveAll()
     assert s.getStats()["gn_steps"] == 2
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_tsdf_warped_random_cameras_and_fields(dfu, oracle, seed):
+    """the exact culls of the integrator (depth tiles, rules (a)/(b), the inflated-brick cull of near bricks) under
+    tilted / shifted cameras, depth images with holes and translation fields from 0.1 mm to 3 cm: packed voxels
+    bit-exact against the oracle, which warps every voxel"""
+    rng = np.random.default_rng(100 + seed)
+    dim = 64
+    depth = synth.sphere_depth(bump=0.02 * (seed % 3)).copy()
+    depth[rng.random(depth.shape) < 0.01] = 0
+    if seed % 2:
+        depth[:, : 200 + 40 * seed] = 0  # half of the image without depth
+    dists = oracle.compute_dists(depth, synth.INTR)
+    pos, _, dg_w, t_true = synth.sphere_nodes(400 + 50 * seed, 0.03)
+    scale = [0.0005, 0.005, 0.05, 0.15, 0.0, 0.02][seed - 1]
+    dq = synth.translations_to_dq(scale * t_true)
+    ang = rng.uniform(-0.25, 0.25, 3)
+    cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+    R = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @
+         np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+    cam = np.eye(4)
+    cam[:3, :3] = R
+    cam[:3, 3] = rng.uniform(-0.15, 0.15, 3)
+    vol = _volume(dfu, dim)
+    v2c = torch.linalg.inv(torch.as_tensor(cam, dtype=torch.float64)) @ vol.getPose()
+    vol2cam = np.array([float(x) for x in v2c[:3, :3].reshape(-1)] + [float(x) for x in v2c[:3, 3]], np.float32)
+    wf = make_wf(dfu, pos, dq, dg_w, 0.03)
+    ref = np.zeros((dim,) * 3, np.uint32)
+    vs = synth.voxel_size(dim)
+    d = dev(dists.view(np.int16), torch.int16)
+    for frame in range(2):
+        oracle.tsdf_integrate(ref, vs, oracle.trunc_dist(synth.TRUNC, vs), synth.MAX_WEIGHT, vol2cam, synth.INTR, dists,
+                              nodes=(pos, dq, dg_w))
+        vol.integrate(d, cam, synth.INTR, wf)
+        got = vol.data.cpu().numpy().view(np.uint32)
+        assert _mismatch(got, ref) == 0, "%d voxels differ" % _mismatch(got, ref)
+    assert np.count_nonzero(ref) > 100
