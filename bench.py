@@ -127,6 +127,8 @@ def cpu_frame(scene, budget_planes=64):
     except FileNotFoundError:
         o = pyoracle.Oracle("brute")
         knn = "brute-force kNN (oracle/_ref absent)"
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    o.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     pos, dq, dg_w, canon = scene["pos"], scene["dq"], scene["dg_w"], scene["canon"]
     live, depth = scene["lives"][0], scene["depths"][0]
     t0 = time.perf_counter()

@@ -1524,6 +1524,15 @@ double orc_energy_p2plane(const float* pos, const float* dg_w, int N, const floa
     return p2p_energy(S);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm of the bench asks for all host threads explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void) n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -144,6 +144,7 @@ int orc_solve_p2plane(const float* pos, float* dq_inout, const float* dg_w, int 
 double orc_energy_p2plane(const float* pos, const float* dg_w, int N, const float* canon, const float* live,
                           const float* live_n, long P, const orc_solver_params* prm, const double* X, const double* X_tukey);
 
+void orc_set_num_threads(int n);
 int orc_num_threads(void);
 
 #ifdef __cplusplus

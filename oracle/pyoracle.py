@@ -134,6 +134,7 @@ class Oracle:
         L.orc_energy.argtypes = [_fp, _fp, C.c_int, _fp, _fp, C.c_long, C.POINTER(SolverParams), _dp, _dp]
         L.orc_energy.restype = C.c_double
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
 
     # ---- dual quaternions ------------------------------------------------------------------
     def dq_from_euler(self, yaw, pitch, roll, x, y, z):
@@ -436,6 +437,9 @@ class Oracle:
         _dp = C.POINTER(C.c_double)
         return self.lib.orc_energy_p2plane(_f(pos), _f(dg_w), pos.shape[0], _f(canon), _f(live), _f(live_n), canon.shape[0],
                                            C.byref(params), X.ctypes.data_as(_dp), Xt.ctypes.data_as(_dp))
+
+    def set_num_threads(self, n):
+        self.lib.orc_set_num_threads(int(n))
 
     def num_threads(self):
         return self.lib.orc_num_threads()
