@@ -634,22 +634,34 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                             reinterpret_cast<float*>(ex + rn[r])[lane] = s_w[r] * rinv[r];  // m = M^-1 w
                         }
                     }
-                    g = warp_sum(g); d = warp_sum(d);
-                    __syncthreads();
-                    if (lane == 0) {
+                    // only lanes 0..2 hold terms: two xor steps bring their sum to lane 0
+                    g += __shfl_xor_sync(0xffffffffu, g, 1); d += __shfl_xor_sync(0xffffffffu, d, 1);
+                    g += __shfl_xor_sync(0xffffffffu, g, 2); d += __shfl_xor_sync(0xffffffffu, d, 2);
+                    if (lane == 0) {  // (shw was last read before the previous grid barrier)
                         shw[wib] = g; shw[NWARP + wib] = d;
                     }
-                    __syncthreads();
-                    if (threadIdx.x == 0) {
-                        double tg = 0.0, td = 0.0;
-#pragma unroll
-                        for (int w = 0; w < NWARP; ++w) {
-                            tg += shw[w]; td += shw[NWARP + w];
-                        }
-                        partf[blockIdx.x] = make_float2((float) tg, (float) td);
-                    }
+                    __syncthreads();  // the CTA's m and partial terms are written
                     PROF(9);
-                    GRID_SYNC();
+                    if (wib == 0) {
+                        // CTA total in a fixed order (xor tree over the 16 warps), published, then the grid barrier proper:
+                        // the release covers every store of the CTA made before the __syncthreads above
+                        double tg = lane < NWARP ? shw[lane] : 0.0, td = lane < NWARP ? shw[NWARP + lane] : 0.0;
+#pragma unroll
+                        for (int o = NWARP / 2; o > 0; o >>= 1) {
+                            tg += __shfl_xor_sync(0xffffffffu, tg, o);
+                            td += __shfl_xor_sync(0xffffffffu, td, o);
+                        }
+                        if (lane == 0) {
+                            partf[blockIdx.x] = make_float2((float) tg, (float) td);
+                            bar_target += (unsigned) nb;
+                            unsigned seen;
+                            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+                            do {
+                                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+                            } while (seen < bar_target);
+                        }
+                    }
+                    __syncthreads();
                     PROF(10);
                     // after the barrier: the partial sums (first warp, loads issued first) and the row products n = A m,
                     // which do not depend on this iteration's scalars, share one L2 round trip
