@@ -19,6 +19,13 @@
  *                               IEEE arithmetic (see DESIGN.md "canonical arithmetic")
  *   - solver                  : parity UNPINNED at the Opt boundary (Opt/Terra are not in the tree,
  *                               Ceres is never linked); pinned only by the 8 OptTest post-conditions
+ *   - 1-NN correspondences    : PINNED against the reference's vendored nanoflann (as kNN)
+ *   - points/normals, raycast : parity UNPINNED -- no reference test; restated in IEEE arithmetic (division and
+ *                               sqrt instead of the GPU's approximate intrinsics), checked against analytic scenes
+ *   - Warpfield::update       : parity UNPINNED -- PCL 1.8.1's VoxelGrid is not vendored; its published algorithm
+ *                               is restated, float additions inside a cell in ascending point index
+ *   - point-to-plane SE(3)    : parity UNPINNED -- no reference implementation (north-star extension); pinned
+ *                               against scipy.optimize.least_squares in tests/test_oracle_p2plane.py
  */
 #ifndef DYNFU_ORACLE_H
 #define DYNFU_ORACLE_H
