@@ -83,6 +83,7 @@ struct dfu_solver {
     int coop_blocks2 = 0;        // same for version 2 of the kernel
     int coop_blocks3 = 0;        // same for version 3
     int coop_blocks3r = 0;       // same for version 3 with the rows in registers
+    int coop_blocks_p2p = 0;     // same for the point-to-plane kernel (P2P_TPB threads, up to 2 CTAs per SM)
     int last_kernel = 0;         // which persistent kernel the last solve used (1 / 2 / 3; 0: multi-kernel path)
     // explicit normal matrix (version 3): pattern per frame, values per re-weighting
     int *rowptr = nullptr, *rowlen = nullptr, *dslot = nullptr, *pat_cursor = nullptr;
@@ -98,6 +99,7 @@ struct dfu_solver {
     const float *canon_v = nullptr, *live_v = nullptr, *live_n = nullptr;  // caller-owned, valid until solve_all returns
     float *p2p_pt = nullptr, *p2p_node = nullptr;                          // per-point / per-node scratch
     size_t p2p_cap_pt = 0, p2p_cap_node = 0;
+    float* p2p_X = nullptr;                                                // the increments X_n inside p2p_node
     bool lists_sorted = true;    // transposed lists ordered by point id (needed by the float-order-dependent paths)
     int gn_steps_host = 0;
 };
@@ -386,14 +388,16 @@ int build_pattern(dfu_solver* s, cudaStream_t st) {
 }
 
 
-// north-star extension: Gauss-Newton on the point-to-plane SE(3) energy, one kernel per phase
+// north-star extension: Gauss-Newton on the point-to-plane SE(3) energy; one cooperative launch (kp_persistent), or one
+// kernel per phase (no cooperative launch / DFU_SOLVER_PATH=multi)
 int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     const int N = s->N, P = s->P;
     const dfu_solver_params& prm = s->prm;
     DFU_REQUIRE(s->live_n != nullptr, DFU_ERR_INVALID, "the point-to-plane energy needs the live normals (initializeProblemInstance)");
     DFU_REQUIRE(s->lists_sorted, DFU_ERR_NOT_INIT, "set the energy before initializeProblemInstance");
-    // scratch: per point wn 8 | jac 48 | e | sv | tk (8 bytes) -> 60 floats; per node X 12 | G 48 | 6 vectors 36 | L 21
-    const size_t need_pt = (size_t) std::max(P, 1) * 60, need_node = (size_t) N * (12 + 48 + 36 + 21);
+    // scratch per point (floats): wn 8 | jac 48 | ent 64 | tpos 8 | svT 8 | e | sv | tk (8 bytes) -> 140
+    // scratch per node: 7 vectors of 8 | X 12 | G 48 | Minv 36 | Gd 24 | L 21 -> 197   (orders keep the vector-loaded arrays aligned)
+    const size_t need_pt = (size_t) std::max(P, 1) * 140, need_node = (size_t) N * 197;
     if (need_pt > s->p2p_cap_pt) {
         cudaFree(s->p2p_pt);
         s->p2p_pt = nullptr; s->p2p_cap_pt = 0;
@@ -415,15 +419,22 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     float* pp = s->p2p_pt;
     pb.wn = pp; pp += (size_t) P * 8;
     pb.jac = pp; pp += (size_t) P * 48;
+    pb.ent = reinterpret_cast<float4*>(pp); pp += (size_t) P * 64;
+    pb.tpos = reinterpret_cast<int*>(pp); pp += (size_t) P * 8;
+    pb.svT = pp; pp += (size_t) P * 8;
     pb.e = pp; pp += P;
     pb.sv = pp; pp += P;
     pb.tk = reinterpret_cast<unsigned char*>(pp);  // 8P bytes
     pb.theta = s->theta;
     float* pn = s->p2p_node;
+    const size_t vs = (size_t) N * P2P_VS;
+    pb.b = pn; pb.x = pn + vs; pb.r = pn + 2 * vs; pb.z = pn + 3 * vs; pb.p = pn + 4 * vs; pb.q = pn + 5 * vs; pb.p2 = pn + 6 * vs;
+    pn += 7 * vs;
     pb.X = pn; pn += (size_t) N * 12;
+    s->p2p_X = pb.X;
     pb.G = pn; pn += (size_t) N * 48;
-    pb.b = pn; pb.x = pn + 6 * (size_t) N; pb.r = pn + 12 * (size_t) N; pb.z = pn + 18 * (size_t) N; pb.p = pn + 24 * (size_t) N;
-    pb.q = pn + 30 * (size_t) N; pn += (size_t) N * 36;
+    pb.Minv = pn; pn += (size_t) N * 36;
+    pb.Gd = pn; pn += (size_t) N * 24;
     pb.L = pn;
     pb.part = s->part;
     const int nblk_n = div_up(N, TPB), nblk_p = std::max(1, std::min(div_up(P, TPB), MAX_PARTIALS)),
@@ -431,6 +442,41 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     DFU_REQUIRE(div_up(P, TPB) <= MAX_PARTIALS && div_up((long) N * 8, TPB) <= MAX_PARTIALS, DFU_ERR_UNSUPPORTED,
                 "point-to-plane mode: at most 262144 points / 32768 nodes");
     const double tol2 = (double) prm.pcg_tol * (double) prm.pcg_tol;
+    const char* force = getenv("DFU_SOLVER_PATH");
+    if (s->coop_blocks_p2p > 0 && !(force && force[0] == 'm')) {
+        P2PCtl ctl{prm.num_iter, prm.nonlinear_iter, prm.linear_iter, prm.early_out, tol2, 16, nullptr};
+        if (const char* e = getenv("DFU_P2P_REFRESH")) ctl.refresh = std::max(1, atoi(e));  // experiments
+        static long long* prof_dev = nullptr;
+        const bool profile = getenv("DFU_SOLVER_PROFILE") != nullptr;
+        if (profile) {
+            if (!prof_dev) DFU_CUDA_OK(cudaMalloc(&prof_dev, P2P_PROF_N * sizeof(long long)));
+            DFU_CUDA_OK(cudaMemsetAsync(prof_dev, 0, P2P_PROF_N * sizeof(long long), st));
+            ctl.prof = prof_dev;
+        }
+        Scalars* sc = s->sc;
+        unsigned* bar = s->bar;
+        float4 *real = s->wf->real, *dual = s->wf->dual;
+        int blocks = s->coop_blocks_p2p;
+        if (const char* e = getenv("DFU_P2P_CTAS")) blocks = std::max(1, std::min(blocks, atoi(e)));  // experiments: fewer CTAs
+        DFU_CUDA_OK(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+        void* args[] = {&pb, &ctl, &sc, &bar, &real, &dual};
+        DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) kp_persistent, dim3(blocks), dim3(P2P_TPB), args, 0, st));
+        ++g_dfu_launches;
+        s->last_kernel = 4;
+        s->gn_steps_host = -1;  // read from the device scalars
+        if (getenv("DFU_DEBUG")) fprintf(stderr, "[dfu] point-to-plane persistent kernel, %d CTAs\n", blocks);
+        if (profile) {  // debugging aid: synchronises
+            long long h[P2P_PROF_N];
+            DFU_CUDA_OK(cudaMemcpyAsync(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
+            DFU_CUDA_OK(cudaStreamSynchronize(st));
+            static const char* names[P2P_PROF_N] = {"init", "linearise", "bar", "assemble", "bar", "scalars", "point_apply", "bar", "node_apply",
+                                                    "bar", "sum+update", "bar", "sum", "expmap+bar", "final", "-"};
+            fprintf(stderr, "[dfu] p2p cycles of CTA 0 (%d CTAs):", blocks);
+            for (int i = 0; i < P2P_PROF_N - 1; ++i) fprintf(stderr, " %s=%lld", names[i], h[i]);
+            fprintf(stderr, "\n");
+        }
+        return dfu_wf_refresh_flags(s->wf, st);
+    }
     kp_init<<<std::max(nblk_n, div_up(P, TPB)), TPB, 0, st>>>(pb, s->sc);  // also resets the device scalars
     DFU_LAUNCH_OK();
     kp_slots<<<nblk_w, TPB, 0, st>>>(pb);
@@ -518,6 +564,8 @@ int dfu_solver_create(dfu_solver** out, dfu_warpfield* wf, const dfu_solver_para
         s->coop_blocks3 = min(sms, MAX_PARTIALS);
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent3r, PTPB, 0) == cudaSuccess && per_sm >= 1)
         s->coop_blocks3r = min(sms, MAX_PARTIALS);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kp_persistent, P2P_TPB, 0) == cudaSuccess && per_sm >= 1)
+        s->coop_blocks_p2p = min(sms * min(per_sm, 2), MAX_PARTIALS);
     (void) cudaGetLastError();
     cudaSetDevice(prev);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
@@ -559,8 +607,8 @@ int dfu_solver_set_energy(dfu_solver* s, int energy_mode) {
 
 int dfu_solver_get_increments(const dfu_solver* s, float* X12, dfu_stream stream) {
     DFU_REQUIRE(s && X12, DFU_ERR_INVALID, "NULL argument");
-    DFU_REQUIRE(s->energy_mode == DFU_ENERGY_P2PLANE_SE3 && s->p2p_node, DFU_ERR_NOT_INIT, "no point-to-plane solve has run");
-    DFU_CUDA_OK(cudaMemcpyAsync(X12, s->p2p_node, 12 * (size_t) s->N * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
+    DFU_REQUIRE(s->energy_mode == DFU_ENERGY_P2PLANE_SE3 && s->p2p_X, DFU_ERR_NOT_INIT, "no point-to-plane solve has run");
+    DFU_CUDA_OK(cudaMemcpyAsync(X12, s->p2p_X, 12 * (size_t) s->N * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
     return DFU_OK;
 }
 

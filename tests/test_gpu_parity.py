@@ -601,10 +601,14 @@ def test_stream_frame_equals_the_synchronous_frame_operator(dfu, oracle):
 
 
 # ------------------------------------------------ north-star extension: point-to-plane SE(3) data term (parity unpinned)
-def test_p2plane_se3_matches_the_double_precision_oracle(dfu, oracle):
+@pytest.mark.parametrize("path", ["persistent", "multi"])
+def test_p2plane_se3_matches_the_double_precision_oracle(dfu, oracle, monkeypatch, path):
     """converged energy and node transforms within 1e-4 relative of the oracle (which tests/test_oracle_p2plane.py pins
-    against scipy.optimize.least_squares); the reference has no such term"""
+    against scipy.optimize.least_squares); the reference has no such term.  Both execution paths: the whole solve in one
+    cooperative launch, and one kernel per phase"""
     from tests.test_oracle_p2plane import rigid_scene
+
+    monkeypatch.setenv("DFU_SOLVER_PATH", path)
 
     pos, dg_w, canon, live, live_n, R, t = rigid_scene(n_nodes=64, n_pts=6000, seed=7)
     live = (live + np.random.default_rng(1).normal(0, 0.002, live.shape)).astype(np.float32)  # a minimum with E > 0
@@ -630,6 +634,43 @@ def test_p2plane_se3_matches_the_double_precision_oracle(dfu, oracle):
     warped, _ = wf.warpToLive(dev(canon), None, dfu.BLEND_DQB_SUM)
     d = np.einsum("pi,pi->p", warped.cpu().numpy() - live, live_n)
     assert np.sqrt(np.mean(d * d)) < 0.0025  # down to the noise that was added (2 mm), from a 3 cm motion
+
+
+@pytest.mark.parametrize("early_out,n_pts", [(False, 6000), (True, 6000), (False, 90000)])
+def test_p2plane_persistent_agrees_with_kernel_per_phase(dfu, oracle, monkeypatch, early_out, n_pts):
+    """the one-launch solve and the kernel-per-phase solve minimise the same energy with differently ordered float sums
+    (lanes per node, explicit block inverse, folded direction update): run to convergence they meet at the same minimiser;
+    stopped by the tolerance they stop after the same number of Gauss-Newton steps and a similar number of PCG iterations.
+    The one-launch solve is reproducible bit for bit.  (90 000 points: more points than resident threads, so the
+    thread-per-point rounds of the point phases run as well as the lane-per-slot remainder.)"""
+    from tests.test_oracle_p2plane import rigid_scene
+
+    pos, dg_w, canon, live, live_n, R, t = rigid_scene(n_nodes=64, n_pts=n_pts, seed=7)
+    live = (live + np.random.default_rng(2).normal(0, 0.002, live.shape)).astype(np.float32)
+    N = len(pos)
+    out = {}
+    for path in ("persistent", "multi", "persistent"):
+        monkeypatch.setenv("DFU_SOLVER_PATH", path)
+        wf = make_wf(dfu, pos, synth.identity_dq(N), dg_w, 0.08)
+        prm = dfu.CombinedSolverParameters(numIter=4, nonLinearIter=3, linearIter=300, earlyOut=early_out,
+                                           pcgTolerance=1e-3 if early_out else 1e-7)
+        s = dfu.CombinedSolver(wf, prm, 4.652, 1.0, 200.0, 1e-4)
+        s.setEnergy(s.ENERGY_P2PLANE_SE3)
+        s.initializeProblemInstance(dev(canon), dev(live), liveNormals=dev(live_n))
+        s.solveAll()
+        res = (s.getStats(), s.getIncrements().cpu().numpy(), wf.getNodes()[1].cpu().numpy())
+        if path == "persistent" and path in out:
+            assert res[0] == out[path][0] and np.array_equal(res[1], out[path][1]) and np.array_equal(res[2], out[path][2])
+        out[path] = res
+    a, b = out["persistent"], out["multi"]
+    assert a[0]["gn_steps"] == b[0]["gn_steps"], (a[0], b[0])
+    assert abs(a[0]["pcg_iterations"] - b[0]["pcg_iterations"]) <= 0.1 * b[0]["pcg_iterations"], (a[0], b[0])
+    assert a[0]["pcg_iterations"] < 4 * 3 * 300  # the tolerance ended the PCG runs
+    assert abs(a[0]["initial_energy"] - b[0]["initial_energy"]) <= 1e-6 * b[0]["initial_energy"]
+    tol = 1e-2 if early_out else 1e-4
+    assert abs(a[0]["final_energy"] - b[0]["final_energy"]) <= tol * b[0]["final_energy"], (a[0], b[0])
+    assert np.max(np.abs(a[1] - b[1])) <= tol * np.abs(b[1]).max()
+    assert np.max(np.abs(a[2] - b[2])) <= tol
 
 
 def test_p2plane_needs_normals_and_leaves_the_reference_energy_alone(dfu, oracle):
