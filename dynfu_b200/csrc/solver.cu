@@ -396,8 +396,8 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     DFU_REQUIRE(s->live_n != nullptr, DFU_ERR_INVALID, "the point-to-plane energy needs the live normals (initializeProblemInstance)");
     DFU_REQUIRE(s->lists_sorted, DFU_ERR_NOT_INIT, "set the energy before initializeProblemInstance");
     // scratch per point (floats): wn 8 | jac 48 | ent 64 | tpos 8 | svT 8 | e | sv | tk (8 bytes) -> 140
-    // scratch per node: 7 vectors of 8 | X 12 | G 48 | Minv 36 | Gd 24 | L 21 -> 197   (orders keep the vector-loaded arrays aligned)
-    const size_t need_pt = (size_t) std::max(P, 1) * 140, need_node = (size_t) N * 197;
+    // scratch per node: 7 vectors of 8 | X 12 | G 48 | Minv 36 | Gd 24 | L 21 | rslot (8 bytes) 2 -> 199   (orders keep the vector-loaded arrays aligned)
+    const size_t need_pt = (size_t) std::max(P, 1) * 140, need_node = (size_t) N * 199;
     if (need_pt > s->p2p_cap_pt) {
         cudaFree(s->p2p_pt);
         s->p2p_pt = nullptr; s->p2p_cap_pt = 0;
@@ -435,7 +435,8 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     pb.G = pn; pn += (size_t) N * 48;
     pb.Minv = pn; pn += (size_t) N * 36;
     pb.Gd = pn; pn += (size_t) N * 24;
-    pb.L = pn;
+    pb.L = pn; pn += (size_t) N * 21;
+    pb.rslot = reinterpret_cast<unsigned char*>(pn);  // 8N bytes
     pb.part = s->part;
     const int nblk_n = div_up(N, TPB), nblk_p = std::max(1, std::min(div_up(P, TPB), MAX_PARTIALS)),
               nblk_e = std::min(div_up((long) N * 8, TPB), MAX_PARTIALS), nblk_w = std::min(div_up((long) N * 32, TPB), MAX_PARTIALS);
@@ -565,7 +566,7 @@ int dfu_solver_create(dfu_solver** out, dfu_warpfield* wf, const dfu_solver_para
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent3r, PTPB, 0) == cudaSuccess && per_sm >= 1)
         s->coop_blocks3r = min(sms, MAX_PARTIALS);
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kp_persistent, P2P_TPB, 0) == cudaSuccess && per_sm >= 1)
-        s->coop_blocks_p2p = min(sms * min(per_sm, 2), MAX_PARTIALS);
+        s->coop_blocks_p2p = min(sms * min(per_sm, P2P_CTAS_PER_SM), MAX_PARTIALS);
     (void) cudaGetLastError();
     cudaSetDevice(prev);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {

@@ -45,6 +45,7 @@ struct P2PProblem {
     float* svT;    // 8P: theta (J x) of the entry's point, scattered by the point phase
     int* tpos;     // P*8: position of (point, slot) in the transposed lists
     float* Minv;   // N*36: inverse of the diagonal block (all zero: singular block)
+    unsigned char* rslot;  // 8N: for in-edge entry rin[i] = src of node n, the slot of n in src's out-edge list
     float* L;      // N*21: Cholesky factor of the diagonal block (row-major lower, packed), L[0] <= 0: singular block
     double* part;  // 4 * MAX_PARTIALS
 };
@@ -95,7 +96,20 @@ DFU_DEV void p2p_apply_d(const float* X, float cx, float cy, float cz, double& o
     oz = (double) r1.z * cx + (double) r1.w * cy + (double) r2.x * cz + (double) r2.w;
 }
 
-// linearisation point of point v: p_v, e_v = n.(p - l), the 8 Jacobian 6-vectors; optional Tukey update; returns theta e^2
+// Persistent kernel: the point-major arrays it owns are stored "lane-contiguous" -- 12 arrays of float4 [P] for the Jacobians
+// (element f = 6 k + c of point v lives in array f / 4) and 2 arrays of int4 [P] for tpos -- so a warp's load of one
+// register's worth touches 4 cache lines instead of 32 (the point phase is bound by L1 wavefronts, not by bytes).
+DFU_DEV float4* jac_s4(const P2PProblem& pb, int i, int v) { return reinterpret_cast<float4*>(pb.jac) + (size_t) i * pb.P + v; }
+DFU_DEV float2* jac_s2(const P2PProblem& pb, int q, int v) {  // pair q = 3 k + c / 2 of point v
+    return reinterpret_cast<float2*>(jac_s4(pb, q >> 1, v)) + (q & 1);
+}
+DFU_DEV int4* tpos_s4(const P2PProblem& pb, int h, int v) { return reinterpret_cast<int4*>(pb.tpos) + (size_t) h * pb.P + v; }
+DFU_DEV int* tpos_s1(const P2PProblem& pb, int k, int v) { return reinterpret_cast<int*>(tpos_s4(pb, k >> 2, v)) + (k & 3); }
+
+// linearisation point of point v: p_v, e_v = n.(p - l), the 8 Jacobian 6-vectors; optional Tukey update; returns theta e^2.
+// SOA (persistent kernel): lane-contiguous Jacobians, and {a, theta, e} scattered to the point's 8 transposed entries (the
+// node phases then read their lists contiguously instead of chasing point indices)
+template <bool SOA>
 DFU_DEV double p2p_linearise_point(const P2PProblem& pb, int v, bool update_tukey) {
     const float cx = pb.canon[3 * (size_t) v], cy = pb.canon[3 * (size_t) v + 1], cz = pb.canon[3 * (size_t) v + 2];
     const float nx = pb.nrm[3 * (size_t) v], ny = pb.nrm[3 * (size_t) v + 1], nz = pb.nrm[3 * (size_t) v + 2];
@@ -117,9 +131,11 @@ DFU_DEV double p2p_linearise_point(const P2PProblem& pb, int v, bool update_tuke
         a[6 * k] = w * (qy * nz - qz * ny); a[6 * k + 1] = w * (qz * nx - qx * nz); a[6 * k + 2] = w * (qx * ny - qy * nx);
         a[6 * k + 3] = w * nx; a[6 * k + 4] = w * ny; a[6 * k + 5] = w * nz;
     }
-    float4* j4 = reinterpret_cast<float4*>(pb.jac + (size_t) v * 48);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) j4[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+    for (int i = 0; i < 12; ++i) {
+        float4* dst = SOA ? jac_s4(pb, i, v) : reinterpret_cast<float4*>(pb.jac + (size_t) v * 48) + i;
+        *dst = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+    }
     const double dx = px - pb.live[3 * (size_t) v], dy = py - pb.live[3 * (size_t) v + 1], dz = pz - pb.live[3 * (size_t) v + 2];
     const double ed = (double) nx * dx + (double) ny * dy + (double) nz * dz;
     const float e = (float) ed;
@@ -131,12 +147,22 @@ DFU_DEV double p2p_linearise_point(const P2PProblem& pb, int v, bool update_tuke
     } else {
         th = pb.theta[v];
     }
+    if (SOA) {
+        const int4 t0 = *tpos_s4(pb, 0, v), t1 = *tpos_s4(pb, 1, v);
+        const int tp[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float4* r = pb.ent + 2 * (size_t) tp[k];
+            r[0] = make_float4(a[6 * k], a[6 * k + 1], a[6 * k + 2], a[6 * k + 3]);
+            r[1] = make_float4(a[6 * k + 4], a[6 * k + 5], th, e);
+        }
+    }
     return (double) th * ed * ed;
 }
 __global__ void __launch_bounds__(TPB) kp_linearise(P2PProblem pb, int update_tukey) {
     __shared__ double sh[TPB / 32];
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    const double e2 = v < pb.P ? p2p_linearise_point(pb, v, update_tukey != 0) : 0.0;
+    const double e2 = v < pb.P ? p2p_linearise_point<false>(pb, v, update_tukey != 0) : 0.0;
     const double bs = block_sum(e2, sh);
     if (threadIdx.x == 0) pb.part[blockIdx.x] = bs;
 }
@@ -595,6 +621,7 @@ struct P2PCtl {
     long long* prof;  // DFU_SOLVER_PROFILE: SM cycles of CTA 0 per phase (P2P_PROF_N slots), else NULL
 };
 constexpr int P2P_TPB = 256;
+constexpr int P2P_CTAS_PER_SM = 2;  // resident CTAs per SM the kernel is compiled for (128 registers; 3 CTAs / 80 registers spill in the point phase: 1.60 vs 1.28 ms)
 constexpr int P2P_PROF_N = 16;
 // phase timer of CTA 0 (thread 0): adds the cycles since the previous mark to slot i
 #define P2P_MARK(i)                                        \
@@ -604,13 +631,22 @@ constexpr int P2P_PROF_N = 16;
         t_mark = t_now;                                    \
     }
 
-// sum over the g lanes serving one node (xor butterfly: every lane ends with the total; all 32 lanes execute)
+// sum over the g lanes serving one node (xor butterfly: every lane ends with the total).  All 32 lanes execute all five
+// steps -- the groups of one warp may have different sizes -- and a lane adds only the steps inside its own group.
 DFU_DEV double group_sum(double v, int g) {
-    for (int o = g >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_xor_sync(0xffffffffu, v, o);
+        if (o < g) v += t;
+    }
     return v;
 }
 DFU_DEV float group_sum(float v, int g) {
-    for (int o = g >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float t = __shfl_xor_sync(0xffffffffu, v, o);
+        if (o < g) v += t;
+    }
     return v;
 }
 DFU_DEV void load6(const float* s, float (&v)[6]) {  // 32-byte aligned slot
@@ -663,8 +699,68 @@ DFU_DEV void p2p_chol_solve(const double (&L)[21], const double (&dinv)[6], cons
     }
 }
 
-// node n by its g lanes: b = -J^T r0 and the 6x6 diagonal block from the node's entry list (contiguous), then lanes 0..5
-// each solve for one column of the inverse and lane 6 for the PCG start (x = 0, r = b, z = M^-1 b, p = z); returns r.z there
+// The edges touching node n, for the persistent kernel: its 8 out-edges and its in-edges, one candidate per edge (rslot
+// names the slot of n in the source's list; the launch-per-phase path scans all 8 slots of every in-neighbour instead).
+// Self edges carry no residual.
+struct P2PEdge {
+    bool live, out;
+    int src, m, i;
+};
+DFU_DEV P2PEdge p2p_edge_of(const P2PProblem& pb, int n, int lo, int j) {
+    P2PEdge e;
+    e.out = j < 8;
+    e.src = e.out ? n : pb.rin[lo + j - 8];
+    e.i = e.out ? j : pb.rslot[lo + j - 8];
+    e.m = e.out ? pb.nnbr[(size_t) n * 8 + j] : n;
+    e.live = e.m != e.src;
+    return e;
+}
+DFU_DEV void p2p_reg_apply_T(const P2PProblem& pb, int n, int lig, int g, const float* x, float (&acc)[6]) {
+    const int lo = pb.rin_ptr[n], cnt = 8 + pb.rin_ptr[n + 1] - lo;
+    for (int j = lig; j < cnt; j += g) {
+        const P2PEdge e = p2p_edge_of(pb, n, lo, j);
+        if (!e.live) continue;
+        const float2* G2 = reinterpret_cast<const float2*>(pb.G + 6 * ((size_t) e.src * 8 + e.i));
+        const float2 g01 = G2[0], g23 = G2[1], g45 = G2[2];
+        const float G[6] = {g01.x, g01.y, g23.x, g23.y, g45.x, g45.y};
+        float xs[6], xm[6];
+        load6(x + P2P_VS * (size_t) e.src, xs);
+        load6(x + P2P_VS * (size_t) e.m, xm);
+        const float r0 = (xs[1] * G[2] - xs[2] * G[1]) + xs[3] - (xm[1] * G[5] - xm[2] * G[4]) - xm[3];
+        const float r1 = (xs[2] * G[0] - xs[0] * G[2]) + xs[4] - (xm[2] * G[3] - xm[0] * G[5]) - xm[4];
+        const float r2 = (xs[0] * G[1] - xs[1] * G[0]) + xs[5] - (xm[0] * G[4] - xm[1] * G[3]) - xm[5];
+        const float* Gk = e.out ? G : G + 3;
+        const float sg = e.out ? pb.wreg2 : -pb.wreg2;
+        acc[0] += sg * (Gk[1] * r2 - Gk[2] * r1);
+        acc[1] += sg * (Gk[2] * r0 - Gk[0] * r2);
+        acc[2] += sg * (Gk[0] * r1 - Gk[1] * r0);
+        acc[3] += sg * r0; acc[4] += sg * r1; acc[5] += sg * r2;
+    }
+}
+DFU_DEV void p2p_assemble_reg_T(const P2PProblem& pb, int n, int lig, int g, double (&b)[6], double (&M)[21]) {
+    const int lo = pb.rin_ptr[n], cnt = 8 + pb.rin_ptr[n + 1] - lo;
+    for (int j = lig; j < cnt; j += g) {
+        const P2PEdge e = p2p_edge_of(pb, n, lo, j);
+        if (!e.live) continue;
+        const size_t ei = (size_t) e.src * 8 + e.i;
+        const float* Gk = pb.G + 6 * ei + (e.out ? 0 : 3);
+        const float* D = pb.Gd + 3 * ei;
+        const double r0 = D[0], r1 = D[1], r2 = D[2];
+        const double gx = Gk[0], gy = Gk[1], gz = Gk[2];
+        const double sg = e.out ? (double) pb.wreg2 : -(double) pb.wreg2, w2 = pb.wreg2;
+        b[0] -= sg * (gy * r2 - gz * r1); b[1] -= sg * (gz * r0 - gx * r2); b[2] -= sg * (gx * r1 - gy * r0);
+        b[3] -= sg * r0; b[4] -= sg * r1; b[5] -= sg * r2;
+        M[0] += w2 * (gy * gy + gz * gz);
+        M[1] += w2 * (-gx * gy); M[2] += w2 * (gx * gx + gz * gz);
+        M[3] += w2 * (-gx * gz); M[4] += w2 * (-gy * gz); M[5] += w2 * (gx * gx + gy * gy);
+        M[7] += w2 * gz;   M[8] += w2 * (-gy);  M[9] += w2;
+        M[10] += w2 * (-gz); M[12] += w2 * gx;    M[14] += w2;
+        M[15] += w2 * gy;   M[16] += w2 * (-gx); M[20] += w2;
+    }
+}
+
+// node n by its g lanes: b = -J^T r0 and the 6x6 diagonal block from the node's entry list (contiguous), then up to seven
+// lanes solve for the six columns of the inverse and for the PCG start (x = 0, r = b, z = M^-1 b, p = z); returns r.z there
 DFU_DEV double p2p_assemble_node_T(const P2PProblem& pb, int n, bool active, int lig, int g) {
     double b[6] = {0, 0, 0, 0, 0, 0}, M[21];
 #pragma unroll
@@ -682,7 +778,7 @@ DFU_DEV double p2p_assemble_node_T(const P2PProblem& pb, int n, bool active, int
                 for (int c = 0; c <= r; ++c) M[idx++] += th * (double) a[r] * (double) a[c];
             }
         }
-        if (pb.wreg2 > 0.f) p2p_assemble_reg(pb, n, lig, g, b, M);
+        if (pb.wreg2 > 0.f) p2p_assemble_reg_T(pb, n, lig, g, b, M);
     }
 #pragma unroll
     for (int r = 0; r < 6; ++r) b[r] = group_sum(b[r], g);
@@ -690,28 +786,32 @@ DFU_DEV double p2p_assemble_node_T(const P2PProblem& pb, int n, bool active, int
     for (int i = 0; i < 21; ++i) M[i] = group_sum(M[i], g);
     double rz = 0.0;
     if (active && lig < 7) {
-        double L[21], dinv[6], rhs[6], sol[6];
+        double L[21], dinv[6];
         const bool ok = p2p_cholesky(M, L, dinv);
+        // seven solves shared by the group's lanes: roles 0..5 = columns of the inverse, role 6 = the PCG start
+        for (int role = lig; role < 7; role += g) {
+            double rhs[6], sol[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) rhs[i] = lig < 6 ? (i == lig ? 1.0 : 0.0) : b[i];
-        p2p_chol_solve(L, dinv, rhs, sol);
-        float o[6];
+            for (int i = 0; i < 6; ++i) rhs[i] = role < 6 ? (i == role ? 1.0 : 0.0) : b[i];
+            p2p_chol_solve(L, dinv, rhs, sol);
+            float o[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) o[i] = ok ? (float) sol[i] : 0.f;
-        if (lig < 6) {  // column lig of the (symmetric) inverse
-            float* Mi = pb.Minv + 36 * (size_t) n + 6 * lig;
+            for (int i = 0; i < 6; ++i) o[i] = ok ? (float) sol[i] : 0.f;
+            if (role < 6) {  // column `role` of the (symmetric) inverse
+                float* Mi = pb.Minv + 36 * (size_t) n + 6 * role;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) Mi[i] = o[i];
-        } else {
-            float bf[6];
-            const float zero[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int i = 0; i < 6; ++i) Mi[i] = o[i];
+            } else {
+                float bf[6];
+                const float zero[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                bf[i] = (float) b[i];
-                rz += ok ? b[i] * sol[i] : 0.0;
+                for (int i = 0; i < 6; ++i) {
+                    bf[i] = (float) b[i];
+                    rz += ok ? b[i] * sol[i] : 0.0;
+                }
+                const size_t s = P2P_VS * (size_t) n;
+                store6(pb.b + s, bf); store6(pb.r + s, bf); store6(pb.x + s, zero); store6(pb.z + s, o); store6(pb.p + s, o);
             }
-            const size_t s = P2P_VS * (size_t) n;
-            store6(pb.b + s, bf); store6(pb.r + s, bf); store6(pb.x + s, zero); store6(pb.z + s, o); store6(pb.p + s, o);
         }
     }
     return rz;
@@ -724,11 +824,10 @@ DFU_DEV void p2p_point_phase(const P2PProblem& pb, int v, const float* x, const 
     const float th = pb.theta[v];
     float s = 0.f;
     if (th != 0.f) {
-        const float4* a4 = reinterpret_cast<const float4*>(pb.jac + (size_t) v * 48);  // 8 x 6 floats = 12 x float4
         float a[48];
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
-            const float4 t = a4[i];
+            const float4 t = *jac_s4(pb, i, v);
             a[4 * i] = t.x; a[4 * i + 1] = t.y; a[4 * i + 2] = t.z; a[4 * i + 3] = t.w;
         }
         const int4 n0 = *reinterpret_cast<const int4*>(pb.nbr + 8 * (size_t) v), n1 = *reinterpret_cast<const int4*>(pb.nbr + 8 * (size_t) v + 4);
@@ -751,7 +850,7 @@ DFU_DEV void p2p_point_phase(const P2PProblem& pb, int v, const float* x, const 
         if (MODE == 1) s = __fmaf_rn(beta, pb.sv[v], s);
     }
     pb.sv[v] = s;
-    const int4 t0 = *reinterpret_cast<const int4*>(pb.tpos + 8 * (size_t) v), t1 = *reinterpret_cast<const int4*>(pb.tpos + 8 * (size_t) v + 4);
+    const int4 t0 = *tpos_s4(pb, 0, v), t1 = *tpos_s4(pb, 1, v);
     pb.svT[t0.x] = s; pb.svT[t0.y] = s; pb.svT[t0.z] = s; pb.svT[t0.w] = s;
     pb.svT[t1.x] = s; pb.svT[t1.y] = s; pb.svT[t1.z] = s; pb.svT[t1.w] = s;
 }
@@ -780,8 +879,8 @@ DFU_DEV void p2p_point_phase_slot(const P2PProblem& pb, long e, bool valid, cons
     if (valid) {
         th = pb.theta[v];
         if (th != 0.f) {
-            const float2* a2 = reinterpret_cast<const float2*>(pb.jac + 6 * (size_t) e);
-            const float2 a01 = a2[0], a23 = a2[1], a45 = a2[2];
+            const int k3 = 3 * (int) (e & 7);
+            const float2 a01 = *jac_s2(pb, k3, v), a23 = *jac_s2(pb, k3 + 1, v), a45 = *jac_s2(pb, k3 + 2, v);
             const size_t o = P2P_VS * (size_t) pb.nbr[e];
             float xv[6];
             load6(x + o, xv);
@@ -804,7 +903,7 @@ DFU_DEV void p2p_point_phase_slot(const P2PProblem& pb, long e, bool valid, cons
         s = __shfl_sync(0xffffffffu, s, (threadIdx.x & 31) & ~7);
     }
     if (head) pb.sv[v] = s;
-    if (valid) pb.svT[pb.tpos[e]] = s;
+    if (valid) pb.svT[*tpos_s1(pb, (int) (e & 7), v)] = s;
 }
 
 template <int MODE>
@@ -833,7 +932,7 @@ DFU_DEV double p2p_node_apply_T(const P2PProblem& pb, int n, bool active, int li
             acc[2] = __fmaf_rn(A.z, s, acc[2]); acc[3] = __fmaf_rn(A.w, s, acc[3]);
             acc[4] = __fmaf_rn(B.x, s, acc[4]); acc[5] = __fmaf_rn(B.y, s, acc[5]);
         }
-        if (pb.wreg2 > 0.f) p2p_reg_apply(pb, n, lig, x, acc, g);
+        if (pb.wreg2 > 0.f) p2p_reg_apply_T(pb, n, lig, g, x, acc);
     }
 #pragma unroll
     for (int r = 0; r < 6; ++r) acc[r] = group_sum(acc[r], g);
@@ -877,29 +976,6 @@ DFU_DEV double p2p_update_node_T(const P2PProblem& pb, int n, float alpha, const
     return rzn;
 }
 
-// linearisation of point v by one thread, {a, theta, e} scattered to the point's 8 transposed entries (the node phases
-// then read their lists contiguously instead of chasing point indices)
-DFU_DEV double p2p_linearise_point_T(const P2PProblem& pb, int v, bool update_tukey) {
-    const double e2 = p2p_linearise_point(pb, v, update_tukey);
-    const float th = pb.theta[v], e = pb.e[v];  // (just written by this thread)
-    const float4* j4 = reinterpret_cast<const float4*>(pb.jac + (size_t) v * 48);
-    float a[48];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-        const float4 t = j4[i];
-        a[4 * i] = t.x; a[4 * i + 1] = t.y; a[4 * i + 2] = t.z; a[4 * i + 3] = t.w;
-    }
-    const int4 t0 = *reinterpret_cast<const int4*>(pb.tpos + 8 * (size_t) v), t1 = *reinterpret_cast<const int4*>(pb.tpos + 8 * (size_t) v + 4);
-    const int tp[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        float4* r = pb.ent + 2 * (size_t) tp[k];
-        r[0] = make_float4(a[6 * k], a[6 * k + 1], a[6 * k + 2], a[6 * k + 3]);
-        r[1] = make_float4(a[6 * k + 4], a[6 * k + 5], th, e);
-    }
-    return e2;
-}
-
 // linearisation, one lane per (point, slot): the lane's Jacobian 6-vector, the point's position / residual / Tukey weight
 // by a sum over its 8 lanes; {a, theta, e} goes to the transposed entry, a also to the point-major copy.  Returns theta e^2
 // on the point's first lane.
@@ -919,8 +995,9 @@ DFU_DEV double p2p_linearise_slot(const P2PProblem& pb, long e, bool valid, bool
         const float qx = (float) qxd, qy = (float) qyd, qz = (float) qzd;
         a[0] = w * (qy * nz - qz * ny); a[1] = w * (qz * nx - qx * nz); a[2] = w * (qx * ny - qy * nx);
         a[3] = w * nx; a[4] = w * ny; a[5] = w * nz;
-        float2* j2 = reinterpret_cast<float2*>(pb.jac + 6 * (size_t) e);
-        j2[0] = make_float2(a[0], a[1]); j2[1] = make_float2(a[2], a[3]); j2[2] = make_float2(a[4], a[5]);
+        const int k3 = 3 * (int) (e & 7);
+        *jac_s2(pb, k3, v) = make_float2(a[0], a[1]); *jac_s2(pb, k3 + 1, v) = make_float2(a[2], a[3]);
+        *jac_s2(pb, k3 + 2, v) = make_float2(a[4], a[5]);
     }
     px = slot_sum(px); py = slot_sum(py); pz = slot_sum(pz); sw = slot_sum(sw);
     float ev = 0.f, th = 0.f;
@@ -941,7 +1018,7 @@ DFU_DEV double p2p_linearise_slot(const P2PProblem& pb, long e, bool valid, bool
     ev = __shfl_sync(0xffffffffu, ev, lane & ~7);
     th = __shfl_sync(0xffffffffu, th, lane & ~7);
     if (valid) {
-        float4* r = pb.ent + 2 * (size_t) pb.tpos[e];
+        float4* r = pb.ent + 2 * (size_t) *tpos_s1(pb, (int) (e & 7), v);
         r[0] = make_float4(a[0], a[1], a[2], a[3]);
         r[1] = make_float4(a[4], a[5], th, ev);
     }
@@ -951,7 +1028,7 @@ DFU_DEV double p2p_linearise_slot(const P2PProblem& pb, long e, bool valid, bool
 DFU_DEV double p2p_phase_linearise(const P2PProblem& pb, bool update_tukey, int tid, int T, double& er) {
     double ed = 0.0;
     const int full = (pb.P / T) * T;
-    for (int v = tid; v < full; v += T) ed += p2p_linearise_point_T(pb, v, update_tukey);
+    for (int v = tid; v < full; v += T) ed += p2p_linearise_point<true>(pb, v, update_tukey);
     const long e0 = 8L * full, e1 = 8L * pb.P;
     for (long base = e0; base < e1; base += T) {
         const long e = base + (T - 1 - tid) / 8 * 8 + (tid & 7);
@@ -961,7 +1038,7 @@ DFU_DEV double p2p_phase_linearise(const P2PProblem& pb, bool update_tukey, int 
     return ed;
 }
 
-__global__ void __launch_bounds__(P2P_TPB, 2)
+__global__ void __launch_bounds__(P2P_TPB, P2P_CTAS_PER_SM)
 kp_persistent(P2PProblem pb, P2PCtl ctl, Scalars* sc, unsigned* bar, float4* __restrict__ real, float4* __restrict__ dual) {
     __shared__ double sh[4 * (P2P_TPB / 32)];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
@@ -994,11 +1071,19 @@ kp_persistent(P2PProblem pb, P2PCtl ctl, Scalars* sc, unsigned* bar, float4* __r
 #pragma unroll
         for (int k = 0; k < 8; ++k) pb.wn[8 * (size_t) v + k] = s > 0.f ? w[k] / s : 0.f;
     }
-    for (int n = grp; n < pb.N; n += ngrp)
-        for (int j = pb.tptr[n] + lig; j < pb.tptr[n + 1]; j += g) {
+    for (int n = tid >> 5; n < pb.N; n += T >> 5) {  // (one warp per node)
+        for (int j = pb.tptr[n] + (tid & 31); j < pb.tptr[n + 1]; j += 32) {
             const int v = pb.tv[j];
-            pb.tpos[8 * (size_t) v + p2p_slot(pb, v, n)] = j;
+            *tpos_s1(pb, p2p_slot(pb, v, n), v) = j;
         }
+        for (int j = pb.rin_ptr[n] + (tid & 31); j < pb.rin_ptr[n + 1]; j += 32) {
+            const int src = pb.rin[j];
+            int k = 0;
+#pragma unroll
+            for (int i = 1; i < 8; ++i) k = pb.nnbr[(size_t) src * 8 + i] == n ? i : k;
+            pb.rslot[j] = (unsigned char) k;
+        }
+    }
     grid_barrier(bar, nb, target);
     P2P_MARK(0);
 
