@@ -48,6 +48,7 @@ namespace {
 #include "solver_normal.cuh"
 #include "solver_graph.cuh"
 #include "solver_p2plane.cuh"
+#include "solver_p2plane_persistent.cuh"
 
 }  // namespace
 
