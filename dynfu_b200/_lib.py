@@ -82,6 +82,7 @@ _SIGS = {
     "dfu_solver_get_stats_host": ([_vp, C.POINTER(C.c_double), _vp], _i),
     "dfu_solver_get_stats": ([_vp, _vp, _vp], _i),
     "dfu_solver_set_energy": ([_vp, _i], _i),
+    "dfu_solver_set_regulariser": ([_vp, _i], _i),
     "dfu_solver_get_increments": ([_vp, _vp, _vp], _i),
     "dfu_compute_points_normals": ([_vp, _sz, _i, _i, C.POINTER(_f), _vp, _sz, _vp, _sz, _vp], _i),
     "dfu_compact_points": ([_vp, _sz, _vp, _sz, _i, _i, C.POINTER(_f), _vp, _vp, _i, _vp, _vp], _i),

@@ -97,6 +97,7 @@ struct dfu_solver {
     bool pattern_ready = false;
     // north-star extension: point-to-plane SE(3) data term (solver_p2plane.cuh)
     int energy_mode = DFU_ENERGY_REF_TRANSLATION;
+    int reg_mode = DFU_REG_QUADRATIC;   // regulariser of the point-to-plane energy
     const float *canon_v = nullptr, *live_v = nullptr, *live_n = nullptr;  // caller-owned, valid until solve_all returns
     float *p2p_pt = nullptr, *p2p_node = nullptr;                          // per-point / per-node scratch
     size_t p2p_cap_pt = 0, p2p_cap_node = 0;
@@ -397,8 +398,8 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     DFU_REQUIRE(s->live_n != nullptr, DFU_ERR_INVALID, "the point-to-plane energy needs the live normals (initializeProblemInstance)");
     DFU_REQUIRE(s->lists_sorted, DFU_ERR_NOT_INIT, "set the energy before initializeProblemInstance");
     // scratch per point (floats): wn 8 | jac 48 | ent 64 | tpos 8 | svT 8 | e | sv | tk (8 bytes) -> 140
-    // scratch per node: 7 vectors of 8 | X 12 | G 48 | Minv 36 | Gd 24 | L 21 | rslot (8 bytes) 2 -> 199   (orders keep the vector-loaded arrays aligned)
-    const size_t need_pt = (size_t) std::max(P, 1) * 140, need_node = (size_t) N * 199;
+    // scratch per node: 7 vectors of 8 | X 12 | G 48 | Minv 36 | Gd 24 | ew 8 | L 21 | rslot (8 bytes) 2 -> 207   (orders keep the vector-loaded arrays aligned)
+    const size_t need_pt = (size_t) std::max(P, 1) * 140, need_node = (size_t) N * 207;
     if (need_pt > s->p2p_cap_pt) {
         cudaFree(s->p2p_pt);
         s->p2p_pt = nullptr; s->p2p_cap_pt = 0;
@@ -436,6 +437,8 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     pb.G = pn; pn += (size_t) N * 48;
     pb.Minv = pn; pn += (size_t) N * 36;
     pb.Gd = pn; pn += (size_t) N * 24;
+    pb.ew = pn; pn += (size_t) N * 8;
+    pb.reg_mode = s->reg_mode; pb.psi_reg = prm.psi_reg;
     pb.L = pn; pn += (size_t) N * 21;
     pb.rslot = reinterpret_cast<unsigned char*>(pn);  // 8N bytes
     pb.part = s->part;
@@ -489,7 +492,7 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
         for (int gn = 0; gn < prm.nonlinear_iter; ++gn) {
             kp_linearise<<<nblk_p, TPB, 0, st>>>(pb, gn == 0 ? 1 : 0);
             DFU_LAUNCH_OK();
-            kp_edges<<<nblk_e, TPB, 0, st>>>(pb);
+            kp_edges<<<nblk_e, TPB, 0, st>>>(pb, gn == 0 ? 1 : 0);
             DFU_LAUNCH_OK();
             kp_assemble<<<nblk_w, TPB, 0, st>>>(pb);
             DFU_LAUNCH_OK();
@@ -525,7 +528,7 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
     // energy at the solution (Tukey weights of the last outer iteration; at the identity if no step ran)
     kp_linearise<<<nblk_p, TPB, 0, st>>>(pb, prm.num_iter * prm.nonlinear_iter == 0 ? 1 : 0);
     DFU_LAUNCH_OK();
-    kp_edges<<<nblk_e, TPB, 0, st>>>(pb);
+    kp_edges<<<nblk_e, TPB, 0, st>>>(pb, prm.num_iter * prm.nonlinear_iter == 0 ? 1 : 0);
     DFU_LAUNCH_OK();
     kp_final_energy<<<1, TPB, 0, st>>>(pb, s->sc, nblk_p, nblk_e);
     DFU_LAUNCH_OK();
@@ -604,6 +607,13 @@ int dfu_solver_set_energy(dfu_solver* s, int energy_mode) {
     DFU_REQUIRE(energy_mode == DFU_ENERGY_REF_TRANSLATION || energy_mode == DFU_ENERGY_P2PLANE_SE3, DFU_ERR_INVALID, "bad energy mode");
     s->energy_mode = energy_mode;
     s->problem_ready = false;  // the transposed lists depend on the mode
+    return DFU_OK;
+}
+
+int dfu_solver_set_regulariser(dfu_solver* s, int reg_mode) {
+    DFU_REQUIRE(s, DFU_ERR_INVALID, "NULL argument");
+    DFU_REQUIRE(reg_mode == DFU_REG_QUADRATIC || reg_mode == DFU_REG_HUBER_ALPHA, DFU_ERR_INVALID, "bad regulariser");
+    s->reg_mode = reg_mode;
     return DFU_OK;
 }
 

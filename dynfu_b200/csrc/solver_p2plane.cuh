@@ -38,6 +38,9 @@ struct P2PProblem {
     float* X;      // N*12 (R row-major, t)
     float* G;      // N*8*6: X_n g_m | X_m g_m for out-edge (n, i)
     float* Gd;     // N*8*3: their difference, formed in double
+    float* ew;     // N*8: weight of out-edge (n, i): w_reg^2, times alpha_ij h_ij with the robust regulariser; 0 for self edges
+    int reg_mode;  // DFU_REG_*
+    float psi_reg;
     float *b, *x, *r, *z, *p, *q;  // N*P2P_VS (32-byte slot per node: one sector per gather)
     float* p2;     // second direction buffer of the persistent kernel
     // persistent kernel only
@@ -167,8 +170,11 @@ __global__ void __launch_bounds__(TPB) kp_linearise(P2PProblem pb, int update_tu
     if (threadIdx.x == 0) pb.part[blockIdx.x] = bs;
 }
 
-// X_n g_m and X_m g_m of out-edge i = n * 8 + k and their difference (formed in double); returns its regularisation energy
-DFU_DEV double p2p_edge(const P2PProblem& pb, int i) {
+// X_n g_m and X_m g_m of out-edge i = n * 8 + k and their difference (formed in double); returns its regularisation energy.
+// update_w: re-evaluate the edge weight -- w_reg^2, or with DFU_REG_HUBER_ALPHA (DynamicFusion eq. 8 as IRLS)
+// w_reg^2 max(dg_w_n, dg_w_m) h with the Huber weight h = 1 (|d| <= psi_reg) or psi_reg / |d| (opt_solver.cpp:233-239) --
+// which then stays frozen until the next outer iteration, like the Tukey weights of the data term
+DFU_DEV double p2p_edge(const P2PProblem& pb, int i, bool update_w) {
     const int n = i >> 3, m = pb.nnbr[i];
     const float4 g = pb.pos_w[m];
     float* G = pb.G + 6 * (size_t) i;
@@ -182,14 +188,25 @@ DFU_DEV double p2p_edge(const P2PProblem& pb, int i) {
         G[3 + c] = (float) b[c];
         D[c] = m == n ? 0.f : (float) (a[c] - b[c]);
     }
-    if (m == n) return 0.0;
-    const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
-    return (double) pb.wreg2 * (dx * dx + dy * dy + dz * dz);
+    const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2], d2 = dx * dx + dy * dy + dz * dz;
+    float w;
+    if (update_w) {
+        double wd = m == n ? 0.0 : (double) pb.wreg2;
+        if (pb.reg_mode == DFU_REG_HUBER_ALPHA) {
+            const double r = sqrt(d2), psi = pb.psi_reg;
+            wd *= (double) fmaxf(pb.pos_w[n].w, g.w) * (r <= psi ? 1.0 : psi / r);
+        }
+        w = (float) wd;
+        pb.ew[i] = w;
+    } else {
+        w = pb.ew[i];
+    }
+    return m == n ? 0.0 : (double) w * d2;
 }
-__global__ void __launch_bounds__(TPB) kp_edges(P2PProblem pb) {
+__global__ void __launch_bounds__(TPB) kp_edges(P2PProblem pb, int update_w) {
     __shared__ double sh[TPB / 32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const double er = i < pb.N * 8 ? p2p_edge(pb, i) : 0.0;
+    const double er = i < pb.N * 8 ? p2p_edge(pb, i, update_w != 0) : 0.0;
     const double bs = block_sum(er, sh);
     if (threadIdx.x == 0) pb.part[MAX_PARTIALS + blockIdx.x] = bs;
 }
@@ -226,7 +243,8 @@ DFU_DEV void p2p_reg_apply(const P2PProblem& pb, int n, int lane, const float* x
         const float r1 = (xs[2] * G[0] - xs[0] * G[2]) + xs[4] - (xm[2] * G[3] - xm[0] * G[5]) - xm[4];
         const float r2 = (xs[0] * G[1] - xs[1] * G[0]) + xs[5] - (xm[0] * G[4] - xm[1] * G[3]) - xm[5];
         const float* Gk = out ? G : G + 3;
-        const float sg = out ? pb.wreg2 : -pb.wreg2;
+        const float we = pb.ew[(size_t) src * 8 + i];
+        const float sg = out ? we : -we;
         acc[0] += sg * (Gk[1] * r2 - Gk[2] * r1);
         acc[1] += sg * (Gk[2] * r0 - Gk[0] * r2);
         acc[2] += sg * (Gk[0] * r1 - Gk[1] * r0);
@@ -248,7 +266,7 @@ DFU_DEV void p2p_assemble_reg(const P2PProblem& pb, int n, int lane, int g, doub
         const double r0 = D[0], r1 = D[1], r2 = D[2];
         const float* Gk = out ? G : G + 3;
         const double gx = Gk[0], gy = Gk[1], gz = Gk[2];
-        const double sg = out ? (double) pb.wreg2 : -(double) pb.wreg2, w2 = pb.wreg2;
+        const double w2 = pb.ew[(size_t) src * 8 + i], sg = out ? w2 : -w2;
         b[0] -= sg * (gy * r2 - gz * r1); b[1] -= sg * (gz * r0 - gx * r2); b[2] -= sg * (gx * r1 - gy * r0);
         b[3] -= sg * r0; b[4] -= sg * r1; b[5] -= sg * r2;
         // J^T J = [ K^T K  K ; -K  I ],  K = [Gk]x; lower triangle, row-major packed (r, c <= r)

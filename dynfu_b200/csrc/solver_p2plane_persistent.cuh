@@ -134,7 +134,8 @@ DFU_DEV void p2p_reg_apply_T(const P2PProblem& pb, int n, int lig, int g, const 
         const float r1 = (xs[2] * G[0] - xs[0] * G[2]) + xs[4] - (xm[2] * G[3] - xm[0] * G[5]) - xm[4];
         const float r2 = (xs[0] * G[1] - xs[1] * G[0]) + xs[5] - (xm[0] * G[4] - xm[1] * G[3]) - xm[5];
         const float* Gk = e.out ? G : G + 3;
-        const float sg = e.out ? pb.wreg2 : -pb.wreg2;
+        const float we = pb.ew[(size_t) e.src * 8 + e.i];
+        const float sg = e.out ? we : -we;
         acc[0] += sg * (Gk[1] * r2 - Gk[2] * r1);
         acc[1] += sg * (Gk[2] * r0 - Gk[0] * r2);
         acc[2] += sg * (Gk[0] * r1 - Gk[1] * r0);
@@ -151,7 +152,7 @@ DFU_DEV void p2p_assemble_reg_T(const P2PProblem& pb, int n, int lig, int g, dou
         const float* D = pb.Gd + 3 * ei;
         const double r0 = D[0], r1 = D[1], r2 = D[2];
         const double gx = Gk[0], gy = Gk[1], gz = Gk[2];
-        const double sg = e.out ? (double) pb.wreg2 : -(double) pb.wreg2, w2 = pb.wreg2;
+        const double w2 = pb.ew[ei], sg = e.out ? w2 : -w2;
         b[0] -= sg * (gy * r2 - gz * r1); b[1] -= sg * (gz * r0 - gx * r2); b[2] -= sg * (gx * r1 - gy * r0);
         b[3] -= sg * r0; b[4] -= sg * r1; b[5] -= sg * r2;
         M[0] += w2 * (gy * gy + gz * gz);
@@ -444,7 +445,7 @@ DFU_DEV double p2p_phase_linearise(const P2PProblem& pb, bool update_tukey, int 
         const long e = base + (T - 1 - tid) / 8 * 8 + (tid & 7);
         ed += p2p_linearise_slot(pb, e, e < e1, update_tukey);
     }
-    for (int i = tid; i < pb.N * 8; i += T) er += p2p_edge(pb, i);
+    for (int i = tid; i < pb.N * 8; i += T) er += p2p_edge(pb, i, update_tukey);
     return ed;
 }
 

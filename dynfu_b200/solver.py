@@ -92,6 +92,15 @@ class CombinedSolver:
         """call before initializeProblemInstance; ENERGY_P2PLANE_SE3 needs liveNormals there"""
         check(lib.dfu_solver_set_energy(self._h, int(mode)))
 
+    REG_QUADRATIC = 0
+    REG_HUBER_ALPHA = 1
+
+    def setRegulariser(self, mode):
+        """ENERGY_P2PLANE_SE3 only: REG_QUADRATIC (default) or REG_HUBER_ALPHA = DynamicFusion eq. 8, alpha_ij = max(dg_w)
+        times the Huber function with threshold psi_reg (the term the reference prepares and leaves out,
+        opt_solver.cpp:233-268, energy.t:76)"""
+        check(lib.dfu_solver_set_regulariser(self._h, int(mode)))
+
     def getIncrements(self):
         """ENERGY_P2PLANE_SE3: [N, 12] rigid increments (R row-major, t) of the last solve"""
         x = torch.empty((self.warpfield.numNodes(), 12), dtype=torch.float32, device=self.warpfield.device)

@@ -231,6 +231,16 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream);
 int dfu_solver_get_translations(const dfu_solver* s, float* t_xyz, dfu_stream stream);
 /* call before dfu_solver_init_problem */
 int dfu_solver_set_energy(dfu_solver* s, int energy_mode);
+/* Regulariser of DFU_ENERGY_P2PLANE_SE3 (the reference energy ignores it), effective from the next solve_all:
+ *   DFU_REG_QUADRATIC    w_reg^2 |X_i g_j - X_j g_j|^2 on every edge of the node graph -- the form energy.t:73-78 gives its
+ *                        translation-only regulariser (default);
+ *   DFU_REG_HUBER_ALPHA  the term the reference prepares and then leaves out (alpha: energy.t:76, Huber weights:
+ *                        opt_solver.cpp:233-268, TODO at energy.t:2), i.e. DynamicFusion eq. 8:
+ *                        w_reg^2 alpha_ij psi_reg(X_i g_j - X_j g_j), alpha_ij = max(dg_w_i, dg_w_j), psi_reg = Huber with
+ *                        threshold dfu_solver_params.psi_reg -- solved as IRLS, the Huber weight of an edge re-evaluated
+ *                        whenever the Tukey weights are (once per outer iteration). */
+enum { DFU_REG_QUADRATIC = 0, DFU_REG_HUBER_ALPHA = 1 };
+int dfu_solver_set_regulariser(dfu_solver* s, int reg_mode);
 /* DFU_ENERGY_P2PLANE_SE3: the rigid increments of the last solve, N x 12 floats (R row-major, t) */
 int dfu_solver_get_increments(const dfu_solver* s, float* X12, dfu_stream stream);
 int dfu_solver_get_stats_host(const dfu_solver* s, double stats_host[4], dfu_stream stream);

@@ -1249,7 +1249,30 @@ struct P2P {
     std::vector<double> jac;  /* P*8*6: ŵ [q x n ; n] */
     std::vector<double> e;    /* P: n.(p - l) */
     std::vector<double> G;    /* N*8*2*3: for edge (n,i): X_n g_m and X_m g_m */
+    const float* dg_w;
+    std::vector<double> ew;   /* N*8: weight of edge (n,i): w_reg^2, times alpha_ij h_ij with reg_mode 1; 0 for self edges */
 };
+/* edge weights at the current X (reg_mode 1: the Huber weight is frozen between outer iterations, like the Tukey weights) */
+void p2p_update_edge_weights(P2P& S) {
+    const Problem& pb = *S.pb;
+    S.ew.assign((size_t) pb.N * KNN, 0.0);
+    for (int a = 0; a < pb.N; ++a)
+        for (int i = 0; i < KNN; ++i) {
+            const int m = pb.nnbr[(size_t) a * KNN + i];
+            if (m == a) continue;
+            double w = pb.wreg2;
+            if (pb.prm->reg_mode == 1) {
+                const double g[3] = {S.pos[3 * (size_t) m], S.pos[3 * (size_t) m + 1], S.pos[3 * (size_t) m + 2]};
+                double x[3], y[3];
+                se3_apply(S.X[a], g, x);
+                se3_apply(S.X[m], g, y);
+                const double r = std::sqrt((x[0] - y[0]) * (x[0] - y[0]) + (x[1] - y[1]) * (x[1] - y[1]) + (x[2] - y[2]) * (x[2] - y[2]));
+                const double psi = pb.prm->psi_reg;
+                w *= std::max((double) S.dg_w[a], (double) S.dg_w[m]) * (r <= psi ? 1.0 : psi / r);
+            }
+            S.ew[(size_t) a * KNN + i] = w;
+        }
+}
 void p2p_point(const P2P& S, long v, double p[3]) {
     p[0] = p[1] = p[2] = 0;
     const double c[3] = {S.canon[3 * v], S.canon[3 * v + 1], S.canon[3 * v + 2]};
@@ -1322,9 +1345,9 @@ double p2p_energy(const P2P& S) {
             double x[3], y[3];
             se3_apply(S.X[a], g, x);
             se3_apply(S.X[m], g, y);
-            Er += (x[0] - y[0]) * (x[0] - y[0]) + (x[1] - y[1]) * (x[1] - y[1]) + (x[2] - y[2]) * (x[2] - y[2]);
+            Er += S.ew[(size_t) a * KNN + i] * ((x[0] - y[0]) * (x[0] - y[0]) + (x[1] - y[1]) * (x[1] - y[1]) + (x[2] - y[2]) * (x[2] - y[2]));
         }
-    return E + pb.wreg2 * Er;
+    return E + Er;
 }
 /* y = (J^T J) x for x in R^{6N}; with rhs != nullptr also rhs = -J^T r0 and the 6x6 diagonal blocks D */
 void p2p_apply(const P2P& S, const double* x, double* y, double* rhs, double* D) {
@@ -1359,6 +1382,7 @@ void p2p_apply(const P2P& S, const double* x, double* y, double* rhs, double* D)
             auto edge = [&](int src, int i, bool as_source) {
                 const int m = pb.nnbr[(size_t) src * KNN + i];
                 if (m == src) return;
+                const double we = S.ew[(size_t) src * KNN + i];
                 const double* Gs = &S.G[((size_t) src * KNN + i) * 6];      /* X_src g_m */
                 const double* Gm = Gs + 3;                                   /* X_m g_m   */
                 const double* xs = x + 6 * (size_t) src;
@@ -1372,15 +1396,15 @@ void p2p_apply(const P2P& S, const double* x, double* y, double* rhs, double* D)
                 double gxr[3];
                 cross3(Gk, rho, gxr);
                 for (int r = 0; r < 3; ++r) {
-                    acc[r] += pb.wreg2 * sg * gxr[r];
-                    acc[3 + r] += pb.wreg2 * sg * rho[r];
+                    acc[r] += we * sg * gxr[r];
+                    acc[3 + r] += we * sg * rho[r];
                 }
                 if (rhs) {
                     double rho0[3] = {Gs[0] - Gm[0], Gs[1] - Gm[1], Gs[2] - Gm[2]}, gx0[3];
                     cross3(Gk, rho0, gx0);
                     for (int r = 0; r < 3; ++r) {
-                        b[r] -= pb.wreg2 * sg * gx0[r];
-                        b[3 + r] -= pb.wreg2 * sg * rho0[r];
+                        b[r] -= we * sg * gx0[r];
+                        b[3 + r] -= we * sg * rho0[r];
                     }
                     /* J = sg * [ -[Gk]x  I ]  ->  J^T J = [ [Gk]x^T [Gk]x   [Gk]x ; -[Gk]x  I ]  (sign cancels) */
                     const double K[9] = {0, -Gk[2], Gk[1], Gk[2], 0, -Gk[0], -Gk[1], Gk[0], 0};
@@ -1388,10 +1412,10 @@ void p2p_apply(const P2P& S, const double* x, double* y, double* rhs, double* D)
                         for (int c = 0; c < 3; ++c) {
                             double ktk = 0;
                             for (int k = 0; k < 3; ++k) ktk += K[3 * k + r] * K[3 * k + c];
-                            M[6 * r + c] += pb.wreg2 * ktk;
-                            M[6 * r + 3 + c] += pb.wreg2 * K[3 * r + c];       /* (-K)^T = K */
-                            M[6 * (3 + r) + c] += pb.wreg2 * (-K[3 * r + c]);
-                            if (r == c) M[6 * (3 + r) + 3 + c] += pb.wreg2;
+                            M[6 * r + c] += we * ktk;
+                            M[6 * r + 3 + c] += we * K[3 * r + c];       /* (-K)^T = K */
+                            M[6 * (3 + r) + c] += we * (-K[3 * r + c]);
+                            if (r == c) M[6 * (3 + r) + 3 + c] += we;
                         }
                 }
             };
@@ -1417,7 +1441,7 @@ int orc_solve_p2plane(const float* pos, float* dq_inout, const float* dg_w, int 
     Problem pb;
     build_problem(pb, pos, dg_w, N, canon, live, P, prm);
     P2P S;
-    S.pb = &pb; S.canon = canon; S.live = live; S.nrm = live_n; S.pos = pos;
+    S.pb = &pb; S.canon = canon; S.live = live; S.nrm = live_n; S.pos = pos; S.dg_w = dg_w;
     S.wn.assign((size_t) P * KNN, 0.0);
     for (long v = 0; v < P; ++v) {
         double sw = 0;
@@ -1426,6 +1450,7 @@ int orc_solve_p2plane(const float* pos, float* dq_inout, const float* dg_w, int 
     }
     S.X.resize((size_t) N);
     for (auto& X : S.X) se3_identity(X);
+    p2p_update_edge_weights(S);
     S.jac.assign((size_t) P * KNN * 6, 0.0);
     S.e.assign((size_t) P, 0.0);
     S.G.assign((size_t) N * KNN * 6, 0.0);
@@ -1440,6 +1465,7 @@ int orc_solve_p2plane(const float* pos, float* dq_inout, const float* dg_w, int 
     };
     for (int outer = 0; outer < prm->num_iter; ++outer) {
         p2p_update_tukey(S, pb);
+        p2p_update_edge_weights(S);
         for (int gn = 0; gn < prm->nonlinear_iter; ++gn) {
             p2p_linearise(S);
             p2p_apply(S, zero.data(), q.data(), b.data(), D.data());
@@ -1504,7 +1530,7 @@ double orc_energy_p2plane(const float* pos, const float* dg_w, int N, const floa
     Problem pb;
     build_problem(pb, pos, dg_w, N, canon, live, P, prm);
     P2P S;
-    S.pb = &pb; S.canon = canon; S.live = live; S.nrm = live_n; S.pos = pos;
+    S.pb = &pb; S.canon = canon; S.live = live; S.nrm = live_n; S.pos = pos; S.dg_w = dg_w;
     S.wn.assign((size_t) P * KNN, 0.0);
     for (long v = 0; v < P; ++v) {
         double sw = 0;
@@ -1520,6 +1546,7 @@ double orc_energy_p2plane(const float* pos, const float* dg_w, int N, const floa
     };
     load(X_tukey);
     p2p_update_tukey(S, pb);
+    p2p_update_edge_weights(S);
     load(X);
     return p2p_energy(S);
 }

@@ -25,7 +25,9 @@
  *   - Warpfield::update       : parity UNPINNED -- PCL 1.8.1's VoxelGrid is not vendored; its published algorithm
  *                               is restated, float additions inside a cell in ascending point index
  *   - point-to-plane SE(3)    : parity UNPINNED -- no reference implementation (north-star extension); pinned
- *                               against scipy.optimize.least_squares in tests/test_oracle_p2plane.py
+ *                               against scipy.optimize.least_squares in tests/test_oracle_p2plane.py; its robust
+ *                               regulariser (reg_mode 1: alpha_ij * Huber, the term opt_solver.cpp:233-268 and
+ *                               energy.t:76 prepare and the reference leaves out) likewise
  */
 #ifndef DYNFU_ORACLE_H
 #define DYNFU_ORACLE_H
@@ -130,6 +132,9 @@ typedef struct {
     float tukey_offset, psi_data, lambda, psi_reg;
     double pcg_tol;        /* PCG stops when r.z <= tol^2 * (r.z of the first GN step); 0 = never */
     int   early_out;       /* stop outer loop when relative energy change < 1e-12 */
+    int   reg_mode;        /* P2PLANE only. 0: w_reg^2 |X_i g_j - X_j g_j|^2 on every edge; 1: DynamicFusion eq. 8,
+                              w_reg^2 alpha_ij psi_reg(.) with alpha_ij = max(dg_w_i, dg_w_j) and psi_reg = Huber, as IRLS:
+                              edge weight alpha_ij h_ij, h re-evaluated with the Tukey weights (opt_solver.cpp:233-268) */
 } orc_solver_params;
 
 /* Solves energy.t (translation-only point-to-point, un-normalised Gaussian weights) in double.

@@ -28,6 +28,7 @@ class SolverParams(C.Structure):
         ("psi_reg", C.c_float),
         ("pcg_tol", C.c_double),
         ("early_out", C.c_int),
+        ("reg_mode", C.c_int),
     ]
 
 
@@ -446,7 +447,7 @@ class Oracle:
 
 
 def default_params(num_iter=32, nonlinear_iter=16, linear_iter=256, tukey_offset=4.652, psi_data=1e-2, lambda_=0.0,
-                   psi_reg=1e-4, pcg_tol=1e-12, early_out=1):
+                   psi_reg=1e-4, pcg_tol=1e-12, early_out=1, reg_mode=0):
     """Defaults = test/opt_optimisation_test.cpp:38-44,115-122."""
     return SolverParams(num_iter, nonlinear_iter, linear_iter, tukey_offset, psi_data, lambda_, psi_reg, pcg_tol,
-                        early_out)
+                        early_out, reg_mode)

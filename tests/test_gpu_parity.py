@@ -676,6 +676,45 @@ def test_p2plane_persistent_agrees_with_kernel_per_phase(dfu, oracle, monkeypatc
     assert np.max(np.abs(a[2] - b[2])) <= tol
 
 
+@pytest.mark.parametrize("path", ["persistent", "multi"])
+def test_p2plane_robust_regulariser_matches_the_oracle(dfu, oracle, monkeypatch, path):
+    """REG_HUBER_ALPHA = DynamicFusion eq. 8 (alpha_ij = max(dg_w_i, dg_w_j), Huber with threshold psi_reg; the term the
+    reference prepares and leaves out, opt_solver.cpp:233-268 / energy.t:76) against the oracle's reg_mode 1, which
+    tests/test_oracle_p2plane.py pins against scipy; the motion is not rigid, so both Huber branches occur"""
+    from tests.test_oracle_p2plane import rigid_scene
+
+    monkeypatch.setenv("DFU_SOLVER_PATH", path)
+    pos, dg_w, canon, live, live_n, R, t = rigid_scene(n_nodes=64, n_pts=6000, seed=7)
+    rng = np.random.default_rng(4)
+    dg_w = (dg_w + rng.uniform(0.0, 0.08, dg_w.shape)).astype(np.float32)
+    live = (live + 0.004 * np.sin(9.0 * canon[:, :1]) * live_n + rng.normal(0, 0.001, live.shape)).astype(np.float32)
+    N = len(pos)
+    psi_reg = 1e-3
+    prm_o = pyoracle.default_params(num_iter=4, nonlinear_iter=3, linear_iter=300, lambda_=200.0, psi_data=1.0, pcg_tol=1e-12,
+                                    psi_reg=psi_reg, reg_mode=1)
+    X_o, dq_o, st_o = oracle.solve_p2plane(pos, synth.identity_dq(N), dg_w, canon, live, live_n, prm_o)
+    X_q, _, st_q = oracle.solve_p2plane(pos, synth.identity_dq(N), dg_w, canon, live, live_n,
+                                        pyoracle.default_params(num_iter=4, nonlinear_iter=3, linear_iter=300, lambda_=200.0,
+                                                                psi_data=1.0, pcg_tol=1e-12, psi_reg=psi_reg, reg_mode=0))
+    assert np.max(np.abs(X_q - X_o)) > 1e-3  # the robust weights change the answer well beyond the parity bound
+    wf = make_wf(dfu, pos, synth.identity_dq(N), dg_w, 0.08)
+    prm = dfu.CombinedSolverParameters(numIter=4, nonLinearIter=3, linearIter=300, earlyOut=False, pcgTolerance=1e-9)
+    s = dfu.CombinedSolver(wf, prm, 4.652, 1.0, 200.0, psi_reg)
+    s.setEnergy(s.ENERGY_P2PLANE_SE3)
+    s.setRegulariser(s.REG_HUBER_ALPHA)
+    s.initializeProblemInstance(dev(canon), dev(live), liveNormals=dev(live_n))
+    s.solveAll()
+    st = s.getStats()
+    assert st["gn_steps"] == 12
+    assert abs(st["initial_energy"] - st_o[0]) <= 1e-4 * st_o[0]
+    assert abs(st["final_energy"] - st_o[1]) <= 1e-4 * st_o[1], (st, st_o)
+    X_g = s.getIncrements().cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(X_g - X_o)) <= 1e-4 * np.abs(X_o).max()
+    assert np.max(np.abs(wf.getNodes()[1].cpu().numpy() - dq_o)) <= 1e-4
+    with pytest.raises(dfu.DfuError):
+        s.setRegulariser(7)
+
+
 def test_p2plane_needs_normals_and_leaves_the_reference_energy_alone(dfu, oracle):
     pos, dg_w, canon, t_true = _wellposed(seed=13, N=256, P=4000)
     live = oracle.warp(pos, synth.translations_to_dq(0.2 * t_true), dg_w, canon)

@@ -90,3 +90,67 @@ def test_p2plane_against_scipy_least_squares(oracle):
     E_oracle = oracle.energy_p2plane(pos, dg_w, canon, live, live_n, prm, X, ident)
     assert abs(E_oracle - st[1]) <= 1e-9 * max(st[1], 1e-30)
     assert E_oracle <= E_scipy * (1 + 1e-4) + 1e-15 and E_scipy <= E_oracle * (1 + 1e-4) + 1e-15, (E_oracle, E_scipy, st)
+
+
+def test_p2plane_robust_regularisation_against_scipy(oracle):
+    """reg_mode 1 (DynamicFusion eq. 8 as IRLS: edge weight w_reg^2 max(dg_w_i, dg_w_j) h_ij, h = Huber weight): with the
+    Tukey and Huber weights frozen at the result X1 of the first outer iteration, the second outer iteration of the oracle
+    must reach the minimum an independent LM finds for the same weighted residual vector"""
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    from scipy.spatial.transform import Rotation
+
+    pos, dg_w, canon, live, live_n, _, _ = rigid_scene(n_nodes=12, n_pts=150, angle=0.03, shift=(0.004, 0.0, -0.003))
+    rng = np.random.default_rng(3)
+    dg_w = (dg_w + rng.uniform(0.0, 0.08, dg_w.shape)).astype(np.float32)          # alpha_ij varies
+    live = (live + 0.004 * np.sin(9.0 * canon[:, :1]) * live_n).astype(np.float32)  # not a rigid motion: edges disagree
+    N = len(pos)
+    ident = np.tile(np.concatenate([np.eye(3).ravel(), np.zeros(3)]), (N, 1))
+    lam = 20.0
+    kw = dict(nonlinear_iter=10, linear_iter=300, lambda_=lam, psi_data=1.0, pcg_tol=1e-13, reg_mode=1)
+    X1, _, _ = oracle.solve_p2plane(pos, synth.identity_dq(N), dg_w, canon, live, live_n, pyoracle.default_params(num_iter=1, **kw))
+    nn_idx, _ = oracle.knn(pos, pos)
+    R1, t1 = X1[:, :9].reshape(N, 3, 3), X1[:, 9:]
+    edges = [(n, m) for n in range(N) for m in nn_idx[n] if m != n]
+    r1 = np.array([np.linalg.norm((R1[n] @ pos[m].astype(np.float64) + t1[n]) - (R1[m] @ pos[m].astype(np.float64) + t1[m]))
+                   for n, m in edges])
+    psi = float(np.median(r1))
+    assert r1.min() < psi < r1.max()  # both Huber branches occur
+    prm = pyoracle.default_params(num_iter=2, psi_reg=psi, **kw)
+    X2, _, st = oracle.solve_p2plane(pos, synth.identity_dq(N), dg_w, canon, live, live_n, prm)
+
+    idx, _ = oracle.knn(pos, canon)
+    w = np.array([[oracle.node_weight(pos[j], dg_w[j], canon[v]) for j in idx[v]] for v in range(len(canon))], np.float64)
+    wn = w / w.sum(1, keepdims=True)
+    q1 = np.einsum("pkij,pj->pki", R1[idx], canon.astype(np.float64)) + t1[idx]
+    p1 = (wn[..., None] * q1).sum(1)
+    theta = np.array([oracle.tukey(4.652, 1.0, (live[v] - p1[v]).astype(np.float32)) for v in range(len(canon))], np.float64)
+    h = np.where(r1 <= np.float32(psi), 1.0, np.float64(np.float32(psi)) / r1)
+    alpha = np.array([max(dg_w[n], dg_w[m]) for n, m in edges], np.float64)
+    we = np.sqrt(lam / (N * 8) * alpha * h)
+
+    def to_X(x):
+        x = x.reshape(N, 6)
+        return np.concatenate([Rotation.from_rotvec(x[:, :3]).as_matrix().reshape(N, 9), x[:, 3:]], 1)
+
+    def residuals(x):
+        Xm = to_X(x)
+        Rm, tm = Xm[:, :9].reshape(N, 3, 3), Xm[:, 9:]
+        q = np.einsum("pkij,pj->pki", Rm[idx], canon.astype(np.float64)) + tm[idx]
+        p = (wn[..., None] * q).sum(1)
+        r_data = np.sqrt(theta) * np.einsum("pi,pi->p", live_n.astype(np.float64), p - live)
+        r_reg = [we[i] * ((Rm[n] @ pos[m].astype(np.float64) + tm[n]) - (Rm[m] @ pos[m].astype(np.float64) + tm[m]))
+                 for i, (n, m) in enumerate(edges)]
+        return np.concatenate([r_data, np.concatenate(r_reg)])
+
+    x0 = np.zeros(6 * N)
+    E_id = oracle.energy_p2plane(pos, dg_w, canon, live, live_n, prm, ident, X1)
+    assert abs(np.sum(residuals(x0) ** 2) - E_id) < 1e-12 + 1e-7 * E_id  # same weights, same energy
+    sol = scipy_opt.least_squares(residuals, x0, method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15)
+    E_scipy = float(np.sum(sol.fun ** 2))
+    E_oracle = oracle.energy_p2plane(pos, dg_w, canon, live, live_n, prm, X2, X1)
+    assert abs(E_oracle - st[1]) <= 1e-9 * max(st[1], 1e-30)
+    assert E_oracle <= E_scipy * (1 + 1e-4) + 1e-15 and E_scipy <= E_oracle * (1 + 1e-4) + 1e-15, (E_oracle, E_scipy, st)
+    # and the robust weights matter: the plain quadratic regulariser ends somewhere else
+    X2q, _, _ = oracle.solve_p2plane(pos, synth.identity_dq(N), dg_w, canon, live, live_n,
+                                     pyoracle.default_params(num_iter=2, psi_reg=psi, **{**kw, "reg_mode": 0}))
+    assert np.max(np.abs(X2q - X2)) > 1e-5
