@@ -47,7 +47,7 @@ struct P2PProblem {
     float4* ent;   // 8P * 2: per transposed-graph entry (node <- point) {a0 a1 a2 a3 | a4 a5 theta e}: what the node gathers, in list order
     float* svT;    // 8P: theta (J x) of the entry's point, scattered by the point phase
     int* tpos;     // P*8: position of (point, slot) in the transposed lists
-    float* Minv;   // N*36: inverse of the diagonal block (all zero: singular block)
+    float* Minv;   // N*36 (28 used): persistent kernel's preconditioner, packed Cholesky factor + reciprocal diagonal (all zero: singular block)
     unsigned char* rslot;  // 8N: for in-edge entry rin[i] = src of node n, the slot of n in src's out-edge list
     float* L;      // N*21: Cholesky factor of the diagonal block (row-major lower, packed), L[0] <= 0: singular block
     double* part;  // 4 * MAX_PARTIALS

@@ -12,8 +12,8 @@
 //   * every (point, slot) knows its position in the transposed lists (tpos); the linearisation writes {a, theta, e} there
 //     (one 32-byte sector per entry) and the point phase scatters theta (J p) there, so a node reads its list contiguously;
 //   * a node is served by g = 32 / 16 / 8 lanes (the largest g with N g <= threads: every node in one pass when possible);
-//   * the block-Jacobi preconditioner is applied as an explicit 6x6 inverse (computed in double from the Cholesky factor by
-//     six lanes, one column each) -- no divisions in the PCG loop;
+//   * the block-Jacobi preconditioner is applied with the Cholesky factor and its reciprocal diagonal -- no divisions in the
+//     PCG loop;
 //   * the direction update is folded into the product: theta J (z + beta p_old) = theta J z + beta sv_old, so the point
 //     phase gathers z only (recomputed from z and p_old every 16th iteration to stop rounding drift).
 // Every CTA sums the per-CTA partials in the same fixed order, so all CTAs take the same decisions without a broadcast and
@@ -27,6 +27,7 @@ struct P2PCtl {
 constexpr int P2P_TPB = 256;
 constexpr int P2P_CTAS_PER_SM = 2;  // resident CTAs per SM the kernel is compiled for (128 registers; 3 CTAs / 80 registers spill in the point phase: 1.60 vs 1.28 ms)
 constexpr int P2P_PROF_N = 16;
+constexpr int P2P_FS = 28;  // floats per node of the stored preconditioner: 21 of the packed factor, 6 reciprocal diagonal entries, 1 pad
 // phase timer of CTA 0 (thread 0): adds the cycles since the previous mark to slot i
 #define P2P_MARK(i)                                        \
     if (ctl.prof != nullptr && tid == 0) {                 \
@@ -164,8 +165,8 @@ DFU_DEV void p2p_assemble_reg_T(const P2PProblem& pb, int n, int lig, int g, dou
     }
 }
 
-// node n by its g lanes: b = -J^T r0 and the 6x6 diagonal block from the node's entry list (contiguous), then up to seven
-// lanes solve for the six columns of the inverse and for the PCG start (x = 0, r = b, z = M^-1 b, p = z); returns r.z there
+// node n by its g lanes: b = -J^T r0 and the 6x6 diagonal block from the node's entry list (contiguous); lane 0 factors the
+// block (double), stores the factor for the PCG loop and the PCG start (x = 0, r = b, z = M^-1 b, p = z); returns r.z there
 DFU_DEV double p2p_assemble_node_T(const P2PProblem& pb, int n, bool active, int lig, int g) {
     double b[6] = {0, 0, 0, 0, 0, 0}, M[21];
 #pragma unroll
@@ -190,34 +191,31 @@ DFU_DEV double p2p_assemble_node_T(const P2PProblem& pb, int n, bool active, int
 #pragma unroll
     for (int i = 0; i < 21; ++i) M[i] = group_sum(M[i], g);
     double rz = 0.0;
-    if (active && lig < 7) {
-        double L[21], dinv[6];
+    if (active && lig == 0) {
+        double L[21], dinv[6], sol[6];
         const bool ok = p2p_cholesky(M, L, dinv);
-        // seven solves shared by the group's lanes: roles 0..5 = columns of the inverse, role 6 = the PCG start
-        for (int role = lig; role < 7; role += g) {
-            double rhs[6], sol[6];
+        p2p_chol_solve(L, dinv, b, sol);
+        // the preconditioner the PCG loop applies: the factor and its reciprocal diagonal in float (27 of the node's 28
+        // floats; dinv[0] = 0 marks a block that is not positive definite: z = 0 there)
+        float4* F = reinterpret_cast<float4*>(pb.Minv + P2P_FS * (size_t) n);
+        float f[28];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) rhs[i] = role < 6 ? (i == role ? 1.0 : 0.0) : b[i];
-            p2p_chol_solve(L, dinv, rhs, sol);
-            float o[6];
+        for (int i = 0; i < 21; ++i) f[i] = ok ? (float) L[i] : 0.f;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) o[i] = ok ? (float) sol[i] : 0.f;
-            if (role < 6) {  // column `role` of the (symmetric) inverse
-                float* Mi = pb.Minv + 36 * (size_t) n + 6 * role;
+        for (int i = 0; i < 6; ++i) f[21 + i] = ok ? (float) dinv[i] : 0.f;
+        f[27] = 0.f;
 #pragma unroll
-                for (int i = 0; i < 6; ++i) Mi[i] = o[i];
-            } else {
-                float bf[6];
-                const float zero[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < 7; ++i) F[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        float bf[6], o[6];
+        const float zero[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    bf[i] = (float) b[i];
-                    rz += ok ? b[i] * sol[i] : 0.0;
-                }
-                const size_t s = P2P_VS * (size_t) n;
-                store6(pb.b + s, bf); store6(pb.r + s, bf); store6(pb.x + s, zero); store6(pb.z + s, o); store6(pb.p + s, o);
-            }
+        for (int i = 0; i < 6; ++i) {
+            bf[i] = (float) b[i];
+            o[i] = ok ? (float) sol[i] : 0.f;
+            rz += ok ? b[i] * sol[i] : 0.0;
         }
+        const size_t s = P2P_VS * (size_t) n;
+        store6(pb.b + s, bf); store6(pb.r + s, bf); store6(pb.x + s, zero); store6(pb.z + s, o); store6(pb.p + s, o);
     }
     return rz;
 }
@@ -356,33 +354,45 @@ DFU_DEV double p2p_node_apply_T(const P2PProblem& pb, int n, bool active, int li
     return pq;
 }
 
-// x_n += alpha p_n, r_n -= alpha q_n, z_n = M_n^-1 r_n (explicit inverse); returns r_n . z_n
-// (loading the node's state before alpha is known, across the CTA-wide sum of the p.q partials, was tried: the 60 floats
-// spill and the phase gets slower)
+// x_n += alpha p_n, r_n -= alpha q_n, z_n = M_n^-1 r_n; returns r_n . z_n.  M_n^-1 is applied as two triangular solves with
+// the stored Cholesky factor and its reciprocal diagonal -- no divisions, ~40 dependent multiply-adds.  (An explicit 6x6
+// inverse in float is faster still but loses positive definiteness on the nearly singular blocks a locally planar patch
+// produces -- three of a node's six directions are held by the regulariser only -- and the iteration then depends on the
+// rounding of the inverse; (L L^T)^-1 is positive definite whatever the rounding of L.  Loading the node's state before
+// alpha is known, across the CTA-wide sum of the p.q partials, was tried as well: the floats spill, slower.)
 DFU_DEV double p2p_update_node_T(const P2PProblem& pb, int n, float alpha, const float* p) {
     const size_t s = P2P_VS * (size_t) n;
-    float xv[6], rv[6], qv[6], pv[6], zv[6], Mi[36];
+    float xv[6], rv[6], qv[6], pv[6], zv[6], f[28];
     load6(pb.x + s, xv); load6(pb.r + s, rv); load6(pb.q + s, qv); load6(p + s, pv);
-    const float4* M4 = reinterpret_cast<const float4*>(pb.Minv + 36 * (size_t) n);
+    const float4* F = reinterpret_cast<const float4*>(pb.Minv + P2P_FS * (size_t) n);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        const float4 t = M4[i];
-        Mi[4 * i] = t.x; Mi[4 * i + 1] = t.y; Mi[4 * i + 2] = t.z; Mi[4 * i + 3] = t.w;
+    for (int i = 0; i < 7; ++i) {
+        const float4 t = F[i];
+        f[4 * i] = t.x; f[4 * i + 1] = t.y; f[4 * i + 2] = t.z; f[4 * i + 3] = t.w;
     }
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
         xv[c] = __fmaf_rn(alpha, pv[c], xv[c]);
         rv[c] = __fmaf_rn(-alpha, qv[c], rv[c]);
     }
-    double rzn = 0.0;
+    float y[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        float t = 0.f;
+        float t = rv[i];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) t = __fmaf_rn(Mi[6 * i + j], rv[j], t);
-        zv[i] = t;
-        rzn += (double) rv[i] * t;
+        for (int k = 0; k < i; ++k) t = __fmaf_rn(-f[i * (i + 1) / 2 + k], y[k], t);
+        y[i] = t * f[21 + i];
     }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        float t = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) t = __fmaf_rn(-f[k * (k + 1) / 2 + i], zv[k], t);
+        zv[i] = t * f[21 + i];
+    }
+    double rzn = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rzn += (double) rv[i] * zv[i];
     store6(pb.x + s, xv); store6(pb.r + s, rv); store6(pb.z + s, zv);
     return rzn;
 }

@@ -667,7 +667,8 @@ def test_p2plane_persistent_agrees_with_kernel_per_phase(dfu, oracle, monkeypatc
         out[path] = res
     a, b = out["persistent"], out["multi"]
     assert a[0]["gn_steps"] == b[0]["gn_steps"], (a[0], b[0])
-    assert abs(a[0]["pcg_iterations"] - b[0]["pcg_iterations"]) <= 0.1 * b[0]["pcg_iterations"], (a[0], b[0])
+    if early_out:  # (at 1e-9 the later steps run into the float floor, where the count depends on the rounding)
+        assert abs(a[0]["pcg_iterations"] - b[0]["pcg_iterations"]) <= 0.1 * b[0]["pcg_iterations"], (a[0], b[0])
     assert a[0]["pcg_iterations"] < 4 * 3 * 300  # the tolerance ended the PCG runs
     assert abs(a[0]["initial_energy"] - b[0]["initial_energy"]) <= 1e-6 * b[0]["initial_energy"]
     tol = 1e-2 if early_out else 1e-4
@@ -713,6 +714,47 @@ def test_p2plane_robust_regulariser_matches_the_oracle(dfu, oracle, monkeypatch,
     assert np.max(np.abs(wf.getNodes()[1].cpu().numpy() - dq_o)) <= 1e-4
     with pytest.raises(dfu.DfuError):
         s.setRegulariser(7)
+
+
+def test_p2plane_persistent_at_scale_multi_pass_and_full_rounds(dfu, monkeypatch):
+    """the generic branches of the one-launch solve: 12 288 nodes (8 lanes per node, more nodes than lane groups: two passes),
+    229 k points (several thread-per-point rounds plus the lane-per-slot remainder), 1280x720 depth -- against the
+    kernel-per-phase path, which the oracle tests validate at small sizes.  First one PCG iteration per step, where the two
+    paths must agree to rounding in every increment; then a short fixed budget (2 GN x 8 PCG) compared through the energy"""
+    rows, cols = 720, 1280
+    intr = synth.intr_for(cols, rows)
+    canon = synth.backproject(synth.cylinder_depth(rows, cols, intr), intr)
+    eps = 0.006
+    pos, dq, w = synth.cylinder_nodes(128, 96, eps)
+    live = synth.bend(canon, 0.003)
+    nn = canon.astype(np.float64) - (np.array([0.0, 0.0, 2.0]) - synth.VOLUME_T)
+    nn[:, 1] = 0.0
+    nn /= np.linalg.norm(nn, axis=1, keepdims=True)
+    assert len(canon) > 200000 and len(pos) == 12288
+    out = {}
+    for path in ("persistent", "multi"):
+        for iters in (1, 8):
+            monkeypatch.setenv("DFU_SOLVER_PATH", path)
+            wf = make_wf(dfu, pos, dq, w, eps)
+            prm = dfu.CombinedSolverParameters(numIter=2, nonLinearIter=1, linearIter=iters, earlyOut=False, pcgTolerance=0.0)
+            s = dfu.CombinedSolver(wf, prm, 4.652, 1e-2, 200.0, 1e-4)
+            s.setEnergy(s.ENERGY_P2PLANE_SE3)
+            s.initializeProblemInstance(dev(canon), dev(live), liveNormals=dev(nn.astype(np.float32)))
+            s.solveAll()
+            out[path, iters] = (s.getStats(), s.getIncrements().cpu().numpy())
+    a, b = out["persistent", 1], out["multi", 1]
+    assert a[0]["pcg_iterations"] == b[0]["pcg_iterations"] == 2
+    assert abs(a[0]["final_energy"] - b[0]["final_energy"]) <= 1e-5 * b[0]["final_energy"], (a[0], b[0])
+    assert np.max(np.abs(a[1] - b[1])) <= 1e-6
+    a, b = out["persistent", 8], out["multi", 8]
+    assert a[0]["gn_steps"] == b[0]["gn_steps"] == 2 and a[0]["pcg_iterations"] == b[0]["pcg_iterations"] == 16
+    assert abs(a[0]["initial_energy"] - b[0]["initial_energy"]) <= 1e-6 * b[0]["initial_energy"]
+    assert b[0]["final_energy"] < 0.05 * b[0]["initial_energy"]
+    # The energy falls by five orders of magnitude: what is left is compared on the scale of what was there.  The raw
+    # increments are NOT compared: on a locally planar patch three of a node's six directions (sliding, spinning about the
+    # normal) are held by the weak regulariser only, a truncated PCG moves them by ~0.1 without changing the energy, and
+    # they differ between any two float implementations (1-iteration solves agree to 6e-8, see DESIGN.md 4.3).
+    assert abs(a[0]["final_energy"] - b[0]["final_energy"]) <= 1e-5 * b[0]["initial_energy"], (a[0], b[0])
 
 
 def test_p2plane_needs_normals_and_leaves_the_reference_energy_alone(dfu, oracle):
