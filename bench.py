@@ -236,6 +236,30 @@ def north_star_variant(scene, devs, steps=40, warmup=4):
 
 
 
+def cpu_variant_solve(scene):
+    """CPU baseline of the variant's solve: the double-precision oracle restatement of the point-to-plane SE(3) Gauss-Newton
+    / PCG (all host threads) on the first frame's problem -- the stand-in for the Ceres path the north star names, which
+    the reference never links."""
+    from oracle import pyoracle
+
+    try:
+        o = pyoracle.Oracle("nanoflann")
+    except FileNotFoundError:
+        o = pyoracle.Oracle("brute")
+    o.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    c_vol = np.asarray((0.0, 0.0, 2.0), np.float64) - synth.VOLUME_T
+    nn = scene["canon"].astype(np.float64) - c_vol
+    nn[:, 1] = 0.0
+    nn /= np.linalg.norm(nn, axis=1, keepdims=True)
+    prm = pyoracle.default_params(num_iter=GN_ITERS, nonlinear_iter=1, linear_iter=PCG_ITERS, lambda_=LAMBDA, pcg_tol=0.0, early_out=0)
+    t0 = time.perf_counter()
+    _, _, st = o.solve_p2plane(scene["pos"], scene["dq"], scene["dg_w"], scene["canon"], scene["lives"][0], nn.astype(np.float32), prm)
+    dt = time.perf_counter() - t0
+    return {"solve_ms": dt * 1e3, "cores": o.num_threads(), "kind": "port",
+            "sample": "the %dx%d point-to-plane solve of the first frame in full (graphs + weights + GN/PCG, double precision)" %
+                      (GN_ITERS, PCG_ITERS), "final_energy": float(st[1])}
+
+
 def config_dict(n_gpus, P):
     return {"workload": "C3 full per-frame loop at C2 size: compute_dists + warpToLive(8-NN+DQB) + %d GN x %d PCG + warped "
                         "TSDF integrate, %d^3 volume, %d nodes, %d surface points, 640x480 depth, bending cylinder" %
@@ -479,6 +503,11 @@ def main():
                 line["north_star_data_term"] = north_star_variant(scene, devs)
             except Exception as e:  # the headline line must not depend on the extension
                 line["north_star_data_term"] = {"error": repr(e)}
+            if not args.no_cpu_baseline and "error" not in line["north_star_data_term"]:
+                try:
+                    line["north_star_data_term"]["cpu_baseline"] = cpu_variant_solve(scene)
+                except Exception as e:
+                    line["north_star_data_term"]["cpu_baseline"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             c = cpu_frame(scene)
             line["cpu_baseline"] = {"value": c["frames_per_s"], "unit": "frames/s", "cores": c["cores"], "kind": "port",
