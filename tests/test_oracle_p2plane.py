@@ -154,3 +154,20 @@ def test_p2plane_robust_regularisation_against_scipy(oracle):
     X2q, _, _ = oracle.solve_p2plane(pos, synth.identity_dq(N), dg_w, canon, live, live_n,
                                      pyoracle.default_params(num_iter=2, psi_reg=psi, **{**kw, "reg_mode": 0}))
     assert np.max(np.abs(X2q - X2)) > 1e-5
+
+
+def test_p2plane_robust_regularisation_limits(oracle):
+    """reg_mode 1 with a threshold no edge exceeds and one common dg_w is the quadratic regulariser with lambda scaled by
+    alpha = dg_w (every Huber weight is 1); and the Huber weight itself is calcHuberWeight (opt_solver.cpp:233-239)"""
+    pos, dg_w, canon, live, live_n, _, _ = rigid_scene(n_nodes=16, n_pts=300, angle=0.04)
+    live = (live + 0.003 * np.sin(9.0 * canon[:, :1]) * live_n).astype(np.float32)
+    N = len(pos)
+    assert np.all(dg_w == dg_w[0])
+    kw = dict(num_iter=2, nonlinear_iter=4, linear_iter=200, psi_data=1.0, pcg_tol=1e-13)
+    Xr, _, str_ = oracle.solve_p2plane(pos, synth.identity_dq(N), dg_w, canon, live, live_n,
+                                       pyoracle.default_params(lambda_=40.0, psi_reg=1e3, reg_mode=1, **kw))
+    Xq, _, stq = oracle.solve_p2plane(pos, synth.identity_dq(N), dg_w, canon, live, live_n,
+                                      pyoracle.default_params(lambda_=40.0 * float(dg_w[0]), psi_reg=1e3, reg_mode=0, **kw))
+    assert np.max(np.abs(Xr - Xq)) <= 1e-9 and abs(str_[1] - stq[1]) <= 1e-9 * stq[1]
+    assert oracle.lib.orc_huber(np.float32(0.5), np.float32(0.25)) == 1.0
+    assert abs(oracle.lib.orc_huber(np.float32(0.5), np.float32(-2.0)) - 0.25) < 1e-7
