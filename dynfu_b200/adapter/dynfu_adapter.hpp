@@ -7,6 +7,7 @@
 //   Warpfield                    include/dynfu/warp_field.hpp:32-78
 //   CombinedSolver(+Parameters)  include/dynfu/utils/opt_solver.hpp:19-110 (+ Opt's CombinedSolverParameters)
 //   kfusion::cuda::TsdfVolume    include/kfusion/cuda/tsdf_volume.hpp:7-73 (create/clear/integrate/data)
+//   DynFusion (+DynFuParams)     include/dynfu/dyn_fusion.hpp, src/dynfu/dyn_fusion.cpp:48-210 (the frame operator, hot-path steps)
 //
 // PCL / OpenCV / Boost are not required: when their headers are absent the minimal stand-ins below
 // (pcl::PointXYZ, pcl::Normal, pcl::PointCloud, cv::Vec3f, cv::Affine3f) are used; define
@@ -477,3 +478,104 @@ inline std::shared_ptr<dynfu::Frame> findCorrespondingFrame(pcl::PointCloud<pcl:
     }
     return std::make_shared<dynfu::Frame>(0, rv, rn);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// DynFusion: the frame operator (src/dynfu/dyn_fusion.cpp:48-145) with its hot-path steps, and the members it calls
+// (init :147-168, initCanonicalFrame :170-175, addLiveFrame :177-180, warpCanonicalToLiveOpt :182-210).
+// DynFuParams carries the fields of DynFuParams::defaultParams (:6-31) plus the KinFuParams fields the path reads
+// (src/kfusion/kinfu.cpp:10-44).  Left to the caller, as rows outside the path: the bilateral
+// filter / depth truncation / ICP of :57-66,100-105 (ICP "not being done yet" in the reference either) and the
+// marching-cubes extraction of the live vertices (:117-134) -- the live frame is an argument instead (it can come
+// from dfu_compute_points_normals + dfu_compact_points).  Where the reference clears the volume and re-integrates
+// rigidly just to run marching cubes on it (:113-116, "FIXME ... shouldn't have to do this"), this operator does the
+// non-rigid surface fusion the reference's README lists as the next step: the live depth is integrated into the
+// canonical volume through the warp field.
+struct DynFuParams {
+    int rows = 480, cols = 640;                                   // kinfu.cpp:16-17
+    float intr[4] = {525.f, 525.f, 319.5f, 239.5f};               // :18 (fx, fy, cx, cy)
+    int volume_dims[3] = {128, 128, 128};                         // dyn_fusion.cpp:10
+    float volume_size[3] = {3.f, 3.f, 3.f};                       // kinfu.cpp:21
+    float volume_pose_t[3] = {-1.5f, -1.5f, 0.5f};                // :22 translate(-size/2, -size/2, 0.5)
+    float tsdf_trunc_dist = 0.04f;                                // :34
+    int tsdf_max_weight = 64;                                     // :35
+    float tukeyOffset = 4.652f, lambda = 200.f, psi_data = 0.01f, psi_reg = 1e-4f;  // dyn_fusion.cpp:13-20
+    float epsilon = 0.1f;                                         // :28
+    int node_step = 128;                                          // :150
+    CombinedSolverParameters solver;                              // :183-189 (numIter 24, nonLinearIter 16, linearIter 256, earlyOut)
+    static DynFuParams defaultParams() { return DynFuParams(); }
+};
+
+class DynFusion {
+public:
+    explicit DynFusion(const DynFuParams& p)
+        : dynfuParams(p), volume_(p.volume_dims[0], p.volume_dims[1], p.volume_dims[2]),
+          d_depth((size_t) p.rows * p.cols), d_dists((size_t) p.rows * p.cols) {
+        volume_.setSize(p.volume_size[0], p.volume_size[1], p.volume_size[2]);
+        volume_.setPose(p.volume_pose_t);
+        volume_.setTruncDist(p.tsdf_trunc_dist);
+        volume_.setMaxWeight(p.tsdf_max_weight);
+        volume_.clear();
+    }
+    DynFuParams& params() { return dynfuParams; }
+
+    // :48-145.  depth: HOST image, u16 millimetres, rows x cols.  Returns false for the first frame (the canonical one),
+    // true afterwards, like the reference.
+    bool operator()(const uint16_t* depth_mm, std::shared_ptr<dynfu::Frame> live = nullptr) {
+        const DynFuParams& p = dynfuParams;
+        d_depth.upload(depth_mm, (size_t) p.rows * p.cols);
+        dfu_adapter::check(dfu_compute_dists(d_depth.p, (size_t) p.cols * 2, d_dists.p, (size_t) p.cols * 2, p.rows, p.cols, p.intr, nullptr),
+                           "dfu_compute_dists");                                                         // :55
+        if (frame_counter_ == 0) {
+            volume_.integrate(d_dists.p, (size_t) p.cols * 2, p.rows, p.cols, p.intr, nullptr);          // :70
+            return ++frame_counter_, false;
+        }
+        if (live && warpfield) {
+            liveFrame = live;                                                                            // :137
+            warpCanonicalToLiveOpt(cv::Affine3f());                                                      // :140
+            warpfield->update(getCanonicalWarpedToLive());                                               // :142
+        }
+        volume_.integrate(d_dists.p, (size_t) p.cols * 2, p.rows, p.cols, p.intr, warpfield.get());      // (non-rigid fusion)
+        return ++frame_counter_, true;
+    }
+
+    // :147-168: canonical frame, one deformation node every node_step-th vertex, dg_w = 3 epsilon
+    void init(pcl::PointCloud<pcl::PointXYZ>& canonicalVertices, pcl::PointCloud<pcl::Normal>& canonicalNormals) {
+        initCanonicalFrame(canonicalVertices, canonicalNormals);
+        std::vector<std::shared_ptr<Node>> deformationNodes;
+        for (size_t i = 0; i < canonicalVertices.size(); i += (size_t) dynfuParams.node_step)
+            deformationNodes.push_back(std::make_shared<Node>(canonicalVertices[i],
+                                                              std::make_shared<DualQuaternion<float>>(0.f, 0.f, 0.f, 0.f, 0.f, 0.f),
+                                                              3 * dynfuParams.epsilon));
+        warpfield = std::make_shared<Warpfield>();
+        warpfield->init(dynfuParams.epsilon, deformationNodes);
+    }
+    void initCanonicalFrame(pcl::PointCloud<pcl::PointXYZ>& vertices, pcl::PointCloud<pcl::Normal>& normals) {  // :170-175
+        canonicalFrame = std::make_shared<dynfu::Frame>(0, vertices, normals);
+        canonicalFrameWarpedToLive = std::make_shared<dynfu::Frame>(0, vertices, normals);
+    }
+    void addLiveFrame(int frameID, pcl::PointCloud<pcl::PointXYZ>& vertices, pcl::PointCloud<pcl::Normal>& normals) {  // :177-180
+        liveFrame = std::make_shared<dynfu::Frame>(frameID, vertices, normals);
+    }
+    // :182-210 (the solver parameters come from DynFuParams::solver instead of being hard-coded)
+    void warpCanonicalToLiveOpt(cv::Affine3f affine) {
+        CombinedSolver combinedSolver(*warpfield, dynfuParams.solver, dynfuParams.tukeyOffset, dynfuParams.psi_data, dynfuParams.lambda,
+                                      dynfuParams.psi_reg);
+        canonicalFrameWarpedToLive = warpfield->warpToLive(canonicalFrame);
+        std::shared_ptr<dynfu::Frame> correspondingCanonicalFrame = findCorrespondingFrame(
+            canonicalFrameWarpedToLive->getVertices(), canonicalFrameWarpedToLive->getNormals(), liveFrame->getVertices());
+        combinedSolver.initializeProblemInstance(correspondingCanonicalFrame, liveFrame, affine);
+        combinedSolver.solveAll();
+    }
+    std::shared_ptr<dynfu::Frame> getCanonicalWarpedToLive() { return canonicalFrameWarpedToLive; }
+    std::shared_ptr<Warpfield> getWarpfield() { return warpfield; }
+    kfusion::cuda::TsdfVolume& tsdf() { return volume_; }
+    int frameCounter() const { return frame_counter_; }
+
+private:
+    DynFuParams dynfuParams;
+    kfusion::cuda::TsdfVolume volume_;
+    dfu_adapter::DevArray<uint16_t> d_depth, d_dists;
+    std::shared_ptr<Warpfield> warpfield;
+    std::shared_ptr<dynfu::Frame> canonicalFrame, canonicalFrameWarpedToLive, liveFrame;
+    int frame_counter_ = 0;
+};

@@ -54,19 +54,29 @@ def build(force=False, verbose=False):
     return OUT
 
 
-def build_cpp_tests(verbose=False):
-    """tests/cpp/opt_test: the reference's gtest cases compiled against the adapter header + the C-ABI library."""
+def _build_cpp(name):
     root = os.path.dirname(HERE)
-    src = os.path.join(root, "tests", "cpp", "opt_test.cpp")
-    out = os.path.join(root, "tests", "cpp", "opt_test")
+    src = os.path.join(root, "tests", "cpp", name + ".cpp")
+    out = os.path.join(root, "tests", "cpp", name)
     deps = [src, os.path.join(root, "tests", "cpp", "mini_gtest.h"), os.path.join(HERE, "adapter", "dynfu_adapter.hpp"), OUT]
     if _stale(out, deps):
         cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-I/usr/local/cuda/include", "-o", out, src, "-L" + HERE, "-ldynfu_b200",
                "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN/../../dynfu_b200", "-Wl,-rpath,/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError("building tests/cpp/opt_test failed:\n%s\n%s" % (r.stdout, r.stderr))
+            raise RuntimeError("building tests/cpp/%s failed:\n%s\n%s" % (name, r.stdout, r.stderr))
     return out
+
+
+def build_cpp_tests(verbose=False):
+    """tests/cpp/opt_test: the reference's gtest cases compiled against the adapter header + the C-ABI library
+    (and tests/cpp/frame_test: the frame operator through the same header)."""
+    _build_cpp("frame_test")
+    return _build_cpp("opt_test")
+
+
+def build_cpp_frame_test():
+    return _build_cpp("frame_test")
 
 
 if __name__ == "__main__":

@@ -534,6 +534,22 @@ def test_reference_gtest_cases_through_the_cpp_adapter(dfu):
     assert "11 tests, 0 failed" in r.stdout, r.stdout
 
 
+@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: compiled and predicted with the CPU "
+                                        "oracle (0.32 mm fit), not yet run on a GPU")
+def test_frame_operator_through_the_cpp_adapter(dfu):
+    """tests/cpp/frame_test.cpp: DynFusion::operator() (src/dynfu/dyn_fusion.cpp:48-145) as a C++ class over the C-ABI --
+    frame 0 fuses rigidly (bit-equal to TsdfVolume::integrate), frame 1 solves the warp field against a live frame
+    (findCorrespondingFrame + CombinedSolver + Warpfield::update) and fuses the live depth through it."""
+    import os
+    import subprocess
+    from dynfu_b200 import build as b
+
+    exe = b.build_cpp_frame_test()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(exe))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "1 tests, 0 failed" in r.stdout, r.stdout
+
+
 def test_two_gpus_equal_one_gpu(dfu):
     """z-slab + point-partition sharding over 2 GPUs == the single-GPU run (needs >= 2 GPUs on the box)"""
     import os
