@@ -451,3 +451,90 @@ def default_params(num_iter=32, nonlinear_iter=16, linear_iter=256, tukey_offset
     """Defaults = test/opt_optimisation_test.cpp:38-44,115-122."""
     return SolverParams(num_iter, nonlinear_iter, linear_iter, tukey_offset, psi_data, lambda_, psi_reg, pcg_tol,
                         early_out, reg_mode)
+
+
+class RefCuda:
+    """oracle/_ref/libdynfu_ref_cuda.so: the reference's OWN CUDA kernels (TSDF integrate / clear / raycast, compute_dists,
+    computePointNormals, marching cubes) compiled where they lie behind oracle/ref_shim (recipe: oracle/Makefile, target
+    refcuda).  Needs a GPU; arguments are torch CUDA tensors.  TEST INFRASTRUCTURE ONLY (`-m gpu` tests)."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libdynfu_ref_cuda.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path = path
+        L = self.lib = C.CDLL(path)
+        vp = C.c_void_p
+        L.ref_clear_volume.argtypes = [vp, _ip]
+        L.ref_integrate.argtypes = [vp, _ip, _fp, C.c_float, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, _fp, _fp]
+        L.ref_compute_dists.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_int, C.c_int, _fp]
+        L.ref_points_normals.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, _fp, vp, vp]
+        L.ref_raycast_points.argtypes = [vp, _ip, _fp, C.c_float, C.c_int, _fp, _fp, _fp, C.c_int, C.c_int, vp, vp, C.c_float,
+                                         C.c_float]
+        L.ref_mc_tables.argtypes = [_ip, _ip, _ip]
+        L.ref_mc_tables.restype = None
+        L.ref_marching_cubes.argtypes = [vp, _fp, C.c_float, C.c_int, _fp, vp, C.c_int, vp, C.c_int, _ip, _ip]
+
+    @staticmethod
+    def _dims(vol):
+        return np.array(vol.shape[::-1], np.int32)
+
+    @staticmethod
+    def _ok(rc, what):
+        if rc != 0:
+            raise RuntimeError("reference kernel %s failed" % what)
+
+    def clear_volume(self, vol):
+        """vol: int32 CUDA tensor [z][y][x] (packed ushort2)"""
+        d = self._dims(vol)
+        self._ok(self.lib.ref_clear_volume(vol.data_ptr(), d.ctypes.data_as(_ip)), "clear_volume")
+
+    def integrate(self, vol, voxel, trunc, max_weight, vol2cam, intr, dists):
+        """device::integrate on the int32 CUDA tensor vol [z][y][x]; dists: 16-bit CUDA tensor [rows][cols] of half bits"""
+        d = self._dims(vol)
+        voxel, vol2cam, intr = _f32(voxel), _f32(vol2cam), _f32(intr)
+        rows, cols = dists.shape
+        self._ok(self.lib.ref_integrate(vol.data_ptr(), d.ctypes.data_as(_ip), _f(voxel), float(trunc), int(max_weight),
+                                        dists.data_ptr(), dists.stride(0) * 2, rows, cols, _f(vol2cam), _f(intr)), "integrate")
+
+    def compute_dists(self, depth, dists_out, intr):
+        rows, cols = depth.shape
+        intr = _f32(intr)
+        self._ok(self.lib.ref_compute_dists(depth.data_ptr(), depth.stride(0) * 2, dists_out.data_ptr(), dists_out.stride(0) * 2,
+                                            rows, cols, _f(intr)), "compute_dists")
+
+    def points_normals(self, depth, points_out, normals_out, intr):
+        """points_out / normals_out: float32 CUDA tensors [rows][cols][4]"""
+        rows, cols = depth.shape
+        intr = _f32(intr)
+        self._ok(self.lib.ref_points_normals(depth.data_ptr(), depth.stride(0) * 2, rows, cols, _f(intr), points_out.data_ptr(),
+                                             normals_out.data_ptr()), "computePointNormals")
+
+    def raycast_points(self, vol, voxel, trunc, max_weight, cam2vol, rinv, intr, points_out, normals_out, step_factor,
+                       delta_factor):
+        d = self._dims(vol)
+        voxel, cam2vol, rinv, intr = _f32(voxel), _f32(cam2vol), _f32(rinv), _f32(intr)
+        rows, cols = points_out.shape[:2]
+        self._ok(self.lib.ref_raycast_points(vol.data_ptr(), d.ctypes.data_as(_ip), _f(voxel), float(trunc), int(max_weight),
+                                             _f(cam2vol), _f(rinv), _f(intr), rows, cols, points_out.data_ptr(),
+                                             normals_out.data_ptr(), float(step_factor), float(delta_factor)), "raycast")
+
+    def mc_tables(self):
+        """(edgeTable[256], triTable[256][16], numVertsTable[256]) of src/kfusion/marching_cubes.cpp:66-354"""
+        e = np.zeros(256, np.int32)
+        t = np.zeros(256 * 16, np.int32)
+        n = np.zeros(256, np.int32)
+        self.lib.ref_mc_tables(e.ctypes.data_as(_ip), t.ctypes.data_as(_ip), n.ctypes.data_as(_ip))
+        return e, t.reshape(256, 16), n
+
+    def marching_cubes(self, vol, voxel, trunc, max_weight, volume_size, occupied, triangles):
+        """the reference's marching cubes on a 128^3 volume; occupied: int32 CUDA [3][max_voxels] scratch, triangles: float32
+        CUDA [max_vertices][4].  Returns (n_voxels, n_vertices); voxel emission order is atomic-dependent."""
+        assert tuple(vol.shape) == (128, 128, 128)
+        voxel, volume_size = _f32(voxel), _f32(volume_size)
+        nv = np.zeros(1, np.int32)
+        nt = np.zeros(1, np.int32)
+        self._ok(self.lib.ref_marching_cubes(vol.data_ptr(), _f(voxel), float(trunc), int(max_weight), _f(volume_size),
+                                             occupied.data_ptr(), occupied.shape[1], triangles.data_ptr(), triangles.shape[0],
+                                             nv.ctypes.data_as(_ip), nt.ctypes.data_as(_ip)), "marching_cubes")
+        return int(nv[0]), int(nt[0])

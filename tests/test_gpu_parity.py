@@ -534,8 +534,6 @@ def test_reference_gtest_cases_through_the_cpp_adapter(dfu):
     assert "11 tests, 0 failed" in r.stdout, r.stdout
 
 
-@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: compiled and predicted with the CPU "
-                                        "oracle (0.32 mm fit), not yet run on a GPU")
 def test_frame_operator_through_the_cpp_adapter(dfu):
     """tests/cpp/frame_test.cpp: DynFusion::operator() (src/dynfu/dyn_fusion.cpp:48-145) as a C++ class over the C-ABI --
     frame 0 fuses rigidly (bit-equal to TsdfVolume::integrate), frame 1 solves the warp field against a live frame
