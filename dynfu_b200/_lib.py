@@ -48,6 +48,7 @@ _SIGS = {
     "dfu_last_error": ([], C.c_char_p),
     "dfu_launch_count": ([], C.c_ulonglong),
     "dfu_device_check": ([_i], _i),
+    "dfu_microbench_fp32": ([_i, C.POINTER(C.c_double), C.POINTER(C.c_double)], _i),
     "dfu_warpfield_create": ([C.POINTER(_vp), _i], _i),
     "dfu_warpfield_destroy": ([_vp], _i),
     "dfu_warpfield_init": ([_vp, _f, _vp, _vp, _vp, _i, _vp], _i),
@@ -66,6 +67,7 @@ _SIGS = {
     "dfu_tsdf_clear": ([_vp, C.POINTER(_i), _i, _i, _vp], _i),
     "dfu_tsdf_integrate": ([_vp, C.POINTER(_i), C.POINTER(_f), _f, _i, C.POINTER(_f), C.POINTER(_f), _vp, _sz, _i, _i,
                             _vp, _i, _i, _i, _vp], _i),
+    "dfu_tsdf_integrate_stats": ([C.POINTER(C.c_ulonglong), _vp], _i),
     "dfu_solver_create": ([C.POINTER(_vp), _vp, C.POINTER(SolverParams)], _i),
     "dfu_solver_destroy": ([_vp], _i),
     "dfu_solver_set_allreduce": ([_vp, ALLREDUCE_FN, _vp], _i),

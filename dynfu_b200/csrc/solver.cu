@@ -46,6 +46,7 @@ namespace {
 #include "solver_phases.cuh"
 #include "solver_matfree.cuh"
 #include "solver_normal.cuh"
+#include "solver_v4.cuh"
 #include "solver_graph.cuh"
 #include "solver_p2plane.cuh"
 #include "solver_p2plane_persistent.cuh"
@@ -84,8 +85,11 @@ struct dfu_solver {
     int coop_blocks2 = 0;        // same for version 2 of the kernel
     int coop_blocks3 = 0;        // same for version 3
     int coop_blocks3r = 0;       // same for version 3 with the rows in registers
+    int coop_blocks4 = 0;        // same for version 4 (tagged exchange, CTA-balanced assembly)
+    float4* t4 = nullptr;        // version 4: the unknowns as float4 per node
+    unsigned seq = 0;            // version 4: last sequence number handed out (tags of the exchanged words never repeat)
     int coop_blocks_p2p = 0;     // same for the point-to-plane kernel (P2P_TPB threads, up to 2 CTAs per SM)
-    int last_kernel = 0;         // which persistent kernel the last solve used (1 / 2 / 3; 0: multi-kernel path)
+    int last_kernel = 0;         // which persistent kernel the last solve used (1 / 2 / 3; 5 = version 4; 4 = point-to-plane; 0: multi-kernel path)
     // explicit normal matrix (version 3): pattern per frame, values per re-weighting
     int *rowptr = nullptr, *rowlen = nullptr, *dslot = nullptr, *pat_cursor = nullptr;
     int32_t* col = nullptr;
@@ -118,8 +122,9 @@ void free_point_arrays(dfu_solver* s) {
 }
 void free_pattern_arrays(dfu_solver* s) {
     cudaFree(s->rowptr); cudaFree(s->rowlen); cudaFree(s->dslot); cudaFree(s->col); cudaFree(s->areg); cudaFree(s->vals);
-    cudaFree(s->tslot); cudaFree(s->exch); cudaFree(s->st); cudaFree(s->xw); cudaFree(s->pw);
+    cudaFree(s->tslot); cudaFree(s->exch); cudaFree(s->st); cudaFree(s->xw); cudaFree(s->pw); cudaFree(s->t4);
     s->xw = s->pw = nullptr;
+    s->t4 = nullptr;
     s->rowptr = s->rowlen = s->dslot = nullptr;
     s->col = nullptr;
     s->areg = s->vals = nullptr;
@@ -273,22 +278,42 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
     // take the textbook PCG of version 2 / 1.
     const int want = forced ? force[1] - '0' : (s->prm.linear_iter <= P3_MAX_LINEAR_ITER ? 3 : 2);
     int ver = want;
+    bool ran_v4 = false;
     if (ver == 3 && !(s->pattern_ready && s->coop_blocks3 > 0 && s->N <= 32 * s->coop_blocks3 * (PTPB / 32))) ver = 2;  // (lane-per-row blocks)
     if (ver == 2 && (s->coop_blocks2 == 0 || s->N > P2_NPW * s->coop_blocks2 * (PTPB / 32))) ver = 1;
     if (ver == 3) {
         Pattern pt{s->rowptr, s->rowlen, s->dslot, s->col, s->areg, s->vals, s->tslot, s->exch, s->st, s->xw, s->pw};
         void* args[] = {&pb, &pt, &ctl, &sc, &bar};
-        // rows in registers when every node fits a register slot; DFU_SOLVER_PATH=p3g forces the generic kernel
+        // rows in registers when every node fits a register slot; DFU_SOLVER_PATH=p3g forces the generic kernel, p3 the
+        // barrier-per-iteration register kernel (3r), p4 / default: version 4 (tagged exchange, CTA-balanced assembly)
         const bool reg = s->coop_blocks3r > 0 && s->N <= P3_R * s->coop_blocks3r * (PTPB / 32) && !(force && force[1] == '3' && force[2] == 'g');
-        if (reg) {  // tags restart at 1 every launch: stale words of earlier launches must not look fresh
-            DFU_CUDA_OK(cudaMemsetAsync(s->xw, 0, 2 * 3 * (size_t) s->N * sizeof(unsigned long long), st));
-            DFU_CUDA_OK(cudaMemsetAsync(s->pw, 0, 2 * 2 * (size_t) MAX_PARTIALS * sizeof(unsigned long long), st));
+        // version 4 (barrier-free PCG exchange + CTA-balanced assembly) measures the same as 3r on B200 (profiles/r02_solver_experiments.md):
+        // opt-in with DFU_SOLVER_PATH=p4, covered by the same parity tests
+        const bool v4 = reg && s->coop_blocks4 > 0 && s->N <= P3_R * s->coop_blocks4 * (PTPB / 32) && s->N <= P4_MAX_N &&
+                        s->coop_blocks4 <= P4_MAX_CTAS && force && force[0] == 'p' && force[1] == '4';
+        if (v4) {
+            // sequence numbers of the tagged words: one per PCG iteration, never re-used (cleared buffers hold 0)
+            // (per Gauss-Newton step: one for u0 and one per PCG iteration)
+            const unsigned long long need = (unsigned long long) std::max(ctl.num_iter, 0) * std::max(ctl.nonlinear_iter, 0) *
+                                                ((unsigned long long) std::max(ctl.linear_iter, 0) + 1) + 2;
+            DFU_REQUIRE(need < 0x40000000ull, DFU_ERR_INVALID, "iteration budget too large for the tagged exchange");
+            if ((unsigned long long) s->seq + need >= 0xfffffff0ull) {  // wrap-around (after ~10^7 solves): start over on clean buffers
+                DFU_CUDA_OK(cudaMemsetAsync(s->xw, 0, 2 * 3 * (size_t) s->N * sizeof(unsigned long long), st));
+                DFU_CUDA_OK(cudaMemsetAsync(s->pw, 0, P4_PQ_BYTES, st));
+                s->seq = 0;
+            }
+            Exchange4 ex4{reinterpret_cast<float4*>(s->xw), reinterpret_cast<float4*>(s->pw), s->t4, s->seq};
+            s->seq += (unsigned) need;
+            void* args4[] = {&pb, &pt, &ex4, &ctl, &sc, &bar};
+            const size_t xs_bytes = (size_t) ((s->N + 15) / 16) * 16 * sizeof(float4);  // the fetched segments of the exchanged vector
+            DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent4, dim3(s->coop_blocks4), dim3(PTPB), args4, xs_bytes, st));
+            ran_v4 = true;
+        } else if (reg) {  // tags restart at 1 every launch: stale words of earlier launches must not look fresh
             DFU_CUDA_OK(cudaMemsetAsync(&s->sc->spin_fail, 0, sizeof(int), st));
-        }
-        if (reg)
             DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent3r, dim3(s->coop_blocks3r), dim3(PTPB), args, 0, st));
-        else
+        } else {
             DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent3, dim3(s->coop_blocks3), dim3(PTPB), args, 0, st));
+        }
         if (getenv("DFU_DEBUG")) fprintf(stderr, "[dfu] v3 %s\n", reg ? "rows in registers" : "generic");
     } else {
         void* args[] = {&pb, &ctl, &sc, &bar};
@@ -297,15 +322,18 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
         else
             DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent2, dim3(s->coop_blocks2), dim3(PTPB), args, 0, st));
     }
-    s->last_kernel = ver;
+    s->last_kernel = ran_v4 ? 5 : ver;
     ++g_dfu_launches;
     if (profile && ver == 3) {  // debugging aid: synchronises
         long long h[16];
         DFU_CUDA_OK(cudaMemcpyAsync(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
         DFU_CUDA_OK(cudaStreamSynchronize(st));
-        static const char* names[16] = {"misc", "residual", "bar", "gather_b", "assemble", "row_init", "bar", "sum_part", "spmv_w0",
-                                        "dots+m", "bar", "sum_part", "spmv+update", "t+=x", "bar", "final"};
-        fprintf(stderr, "[dfu] v3 cycles of CTA 0:");
+        static const char* names3[16] = {"misc", "residual", "bar", "gather_b", "assemble", "row_init", "bar", "sum_part", "spmv_w0",
+                                         "dots+m", "bar", "sum_part", "spmv+update", "t+=x", "bar", "final"};
+        static const char* names4[16] = {"misc", "residual", "bar", "assemble", "collect+reg", "publish", "bar+totals", "-", "spmv_w0",
+                                         "dots+m", "exchange+spmv", "cta_sync", "update", "t+=x", "bar", "final"};
+        const char** names = s->last_kernel == 5 ? names4 : names3;
+        fprintf(stderr, "[dfu] v%d cycles of CTA 0:", s->last_kernel == 5 ? 4 : 3);
         for (int i = 0; i < 16; ++i) fprintf(stderr, " %s=%lld", names[i], h[i]);
         fprintf(stderr, "\n");
     }
@@ -347,18 +375,24 @@ int build_pattern(dfu_solver* s, cudaStream_t st) {
         s->cap_slots = slots;
     }
     if ((size_t) N > s->cap_rows) {
-        cudaFree(s->rowptr); cudaFree(s->rowlen); cudaFree(s->dslot); cudaFree(s->exch); cudaFree(s->st); cudaFree(s->xw);
-        s->rowptr = s->rowlen = s->dslot = nullptr; s->exch = s->st = nullptr; s->xw = nullptr; s->cap_rows = 0;
+        cudaFree(s->rowptr); cudaFree(s->rowlen); cudaFree(s->dslot); cudaFree(s->exch); cudaFree(s->st); cudaFree(s->xw); cudaFree(s->t4);
+        s->rowptr = s->rowlen = s->dslot = nullptr; s->exch = s->st = nullptr; s->xw = nullptr; s->t4 = nullptr; s->cap_rows = 0;
         DFU_CUDA_OK(cudaMalloc(&s->rowptr, (size_t) N * sizeof(int)));
         DFU_CUDA_OK(cudaMalloc(&s->rowlen, (size_t) N * sizeof(int)));
         DFU_CUDA_OK(cudaMalloc(&s->dslot, (size_t) N * sizeof(int)));
         DFU_CUDA_OK(cudaMalloc(&s->exch, 2 * (size_t) N * sizeof(float4)));
         DFU_CUDA_OK(cudaMalloc(&s->st, 6 * (size_t) N * sizeof(float4)));
         DFU_CUDA_OK(cudaMalloc(&s->xw, 2 * 3 * (size_t) N * sizeof(unsigned long long)));
+        DFU_CUDA_OK(cudaMalloc(&s->t4, (size_t) N * sizeof(float4)));
+        // version 4 re-uses xw as its tagged exchange vector: cleared once, sequence numbers never repeat afterwards
+        DFU_CUDA_OK(cudaMemsetAsync(s->xw, 0, 2 * 3 * (size_t) N * sizeof(unsigned long long), st));
         s->cap_rows = (size_t) N;
     }
     if (!s->pat_cursor) DFU_CUDA_OK(cudaMalloc(&s->pat_cursor, sizeof(int)));
-    if (!s->pw) DFU_CUDA_OK(cudaMalloc(&s->pw, 2 * 2 * (size_t) MAX_PARTIALS * sizeof(unsigned long long)));
+    if (!s->pw) {  // version 4: per-CTA inboxes of the tagged partial sums, [2][P4_MAX_CTAS][P4_MAX_CTAS] float4
+        DFU_CUDA_OK(cudaMalloc(&s->pw, P4_PQ_BYTES));
+        DFU_CUDA_OK(cudaMemsetAsync(s->pw, 0, P4_PQ_BYTES, st));
+    }
     DFU_CUDA_OK(cudaMemsetAsync(s->pat_cursor, 0, sizeof(int), st));
     const int NW = (N + 31) / 32;
     const size_t smem = (size_t) 4 * 2 * NW * sizeof(unsigned);
@@ -569,6 +603,12 @@ int dfu_solver_create(dfu_solver** out, dfu_warpfield* wf, const dfu_solver_para
         s->coop_blocks3 = min(sms, MAX_PARTIALS);
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent3r, PTPB, 0) == cudaSuccess && per_sm >= 1)
         s->coop_blocks3r = min(sms, MAX_PARTIALS);
+    {
+        const int xs_max = (P4_MAX_N + 15) / 16 * 16 * (int) sizeof(float4);
+        if (coop && cudaFuncSetAttribute(k_solve_persistent4, cudaFuncAttributeMaxDynamicSharedMemorySize, xs_max) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent4, PTPB, xs_max) == cudaSuccess && per_sm >= 1)
+            s->coop_blocks4 = min(sms, MAX_PARTIALS);
+    }
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kp_persistent, P2P_TPB, 0) == cudaSuccess && per_sm >= 1)
         s->coop_blocks_p2p = min(sms * min(per_sm, P2P_CTAS_PER_SM), MAX_PARTIALS);
     (void) cudaGetLastError();
@@ -825,7 +865,7 @@ int dfu_solver_get_stats_host(const dfu_solver* s, double stats_host[4], dfu_str
     stats_host[1] = s->sc_host->E;
     stats_host[2] = (double) s->sc_host->pcg_iters;
     stats_host[3] = (double) (s->gn_steps_host >= 0 ? s->gn_steps_host : s->sc_host->gn_steps);
-    DFU_REQUIRE(!(s->last_kernel == 3 && s->sc_host->spin_fail), DFU_ERR_CUDA,
+    DFU_REQUIRE(!((s->last_kernel == 3 || s->last_kernel == 5) && s->sc_host->spin_fail), DFU_ERR_CUDA,
                 "persistent solver: an exchanged word never arrived (grid not co-resident?); result invalid");
     return DFU_OK;
 }

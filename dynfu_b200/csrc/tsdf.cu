@@ -51,6 +51,11 @@ struct IntegrateArgs {
     int ntiles;
     const float* dmax_tiles;  // max ray length per 16x16-pixel tile of the dists image (0: no depth in the tile)
     int dtx, dty;             // tiles per row / column
+    unsigned long long* stats;  // instrumentation of the last call on this device: [0] voxels updated, [1] quads (16 B) read + written,
+                                // [2] tiles with work, [3] bricks that ran the per-voxel warp (zeroed by tile_classify_kernel)
+};
+struct Tally {
+    unsigned vox = 0, quads = 0, bricks = 0;
 };
 
 constexpr int DT = 16;  // pixels per side of a depth tile
@@ -90,8 +95,10 @@ DFU_DEV uint32_t voxel_update(const IntegrateArgs& a, uint32_t packed, float tsd
     return pack_tsdf(tsdf_new, weight_new);
 }
 
-DFU_DEV void quad_commit(const IntegrateArgs& a, size_t lin, const bool (&hit)[4], const float (&ts)[4]) {
+DFU_DEV void quad_commit(const IntegrateArgs& a, size_t lin, const bool (&hit)[4], const float (&ts)[4], Tally& tally) {
     if (!(hit[0] | hit[1] | hit[2] | hit[3])) return;  // untouched quads cost no volume traffic
+    tally.vox += (unsigned) hit[0] + (unsigned) hit[1] + (unsigned) hit[2] + (unsigned) hit[3];
+    tally.quads += 1;
     uint4* p = reinterpret_cast<uint4*>(a.vol + lin);
     uint4 v = ld_stream(p);
     if (hit[0]) v.x = voxel_update(a, v.x, ts[0]);
@@ -172,7 +179,7 @@ DFU_DEV TileInfo tile_info(const IntegrateArgs& a, int tile, const FieldInfo& f)
 }
 
 // rigid pass over the quads of the bricks that are not near
-DFU_DEV void rigid_pass(const IntegrateArgs& a, const TileInfo& ti) {
+DFU_DEV void rigid_pass(const IntegrateArgs& a, const TileInfo& ti, Tally& tally) {
     const size_t plane = (size_t) a.dx * a.dy;
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {
@@ -187,7 +194,7 @@ DFU_DEV void rigid_pass(const IntegrateArgs& a, const TileInfo& ti) {
         float ts[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) hit[v] = voxel_tsdf(a, fmul((float) (x + v), a.vsx), py, pz, ts[v]);
-        quad_commit(a, (size_t) x + (size_t) y * a.dx + plane * (size_t) z, hit, ts);
+        quad_commit(a, (size_t) x + (size_t) y * a.dx + plane * (size_t) z, hit, ts, tally);
     }
 }
 
@@ -368,6 +375,7 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
     // persistent CTAs pull tiles from the compacted list of tiles that have work (tile_classify_kernel); a shared
     // ticket counter balances the very uneven tiles (rigid-only vs near bricks)
     __shared__ int s_ticket;
+    Tally tally;
 #pragma unroll 1
     for (;;) {
         if (tid == 0) s_ticket = atomicAdd(&a.work_count[MODE == MODE_FILL ? 3 : 2], 1);
@@ -377,7 +385,7 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
         if (wi >= n_work) break;
         const int tile = list[wi];
         const TileInfo ti = tile_info(a, tile, fi);
-        if (MODE != MODE_FILL && !(a.tile_flags[tile] & 16)) rigid_pass(a, ti);
+        if (MODE != MODE_FILL && !(a.tile_flags[tile] & 16)) rigid_pass(a, ti, tally);
         if (ti.near_mask == 0) continue;
         const int z = ti.zt + zz, y = ti.y0 + yy;
         const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
@@ -407,7 +415,8 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
                     const V3 p = warp_voxel_weights(a, ti, id, w, px[v], py, pz);
                     hit[v] = voxel_tsdf(a, p.x, p.y, p.z, ts[v]);
                 }
-                quad_commit(a, lin, hit, ts);
+                quad_commit(a, lin, hit, ts, tally);
+                if (tid == 0) tally.bricks += 1;
             } else {
                 __shared__ IntegrateSmem sm;
                 if (MODE == MODE_FILL && a.built[brick]) continue;  // uniform over the CTA
@@ -437,9 +446,24 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
                         const V3 w = warp_voxel(a, ti, t[v].i, px[v], py, pz, x + v > 0 && y > 0 && z > 0);
                         hit[v] = voxel_tsdf(a, w.x, w.y, w.z, ts[v]);
                     }
-                    quad_commit(a, lin, hit, ts);
+                    quad_commit(a, lin, hit, ts, tally);
+                    if (tid == 0) tally.bricks += 1;
                 }
             }
+        }
+    }
+    if (MODE != MODE_FILL && a.stats) {  // one atomic per warp and counter
+        unsigned v = tally.vox, q = tally.quads, b = tally.bricks;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if ((tid & 31) == 0) {
+            if (v) atomicAdd(&a.stats[0], (unsigned long long) v);
+            if (q) atomicAdd(&a.stats[1], (unsigned long long) q);
+            if (b) atomicAdd(&a.stats[3], (unsigned long long) b);
         }
     }
 }
@@ -500,6 +524,7 @@ DFU_DEV bool box_unreachable(const IntegrateArgs& a, int x0, int nx, int y0, int
 __global__ void tile_classify_kernel(const __grid_constant__ IntegrateArgs a) {
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= a.ntiles) return;
+    if (a.stats && tile < 4) a.stats[tile] = 0ull;  // (the integrate kernels of this call run after this kernel)
     int bid = tile;
     const int x0 = (bid % a.ntx) * 32;
     bid /= a.ntx;
@@ -531,7 +556,7 @@ __global__ void tile_classify_kernel(const __grid_constant__ IntegrateArgs a) {
         }
     }
     a.tile_flags[tile] = (unsigned char) (near_mask | (rigid_skip ? 16 : 0));
-    if (near_mask || !rigid_skip) a.work_tiles[atomicAdd(&a.work_count[0], 1)] = tile;
+    if (near_mask || !rigid_skip) a.work_tiles[atomicAdd(&a.work_count[0], 1)] = tile;  // (work_count[0] is copied to stats[2] by the host entry)
     if (need_fill) a.fill_tiles[atomicAdd(&a.work_count[1], 1)] = tile;
 }
 
@@ -597,7 +622,33 @@ cudaMemPool_t scratch_pool(int device) {
     return pools[device];
 }
 
+// instrumentation of the last dfu_tsdf_integrate call per device (see IntegrateArgs::stats)
+static unsigned long long* integrate_stats(int device) {
+    static unsigned long long* bufs[64] = {};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!bufs[device]) {
+        if (cudaMalloc(&bufs[device], 8 * sizeof(unsigned long long)) != cudaSuccess) {
+            (void) cudaGetLastError();
+            bufs[device] = nullptr;
+        } else {
+            cudaMemset(bufs[device], 0, 8 * sizeof(unsigned long long));
+        }
+    }
+    return bufs[device];
+}
+
 extern "C" {
+
+int dfu_tsdf_integrate_stats(unsigned long long stats_host[4], dfu_stream stream) {
+    DFU_REQUIRE(stats_host, DFU_ERR_INVALID, "NULL argument");
+    int device = 0;
+    DFU_CUDA_OK(cudaGetDevice(&device));
+    unsigned long long* d = integrate_stats(device);
+    DFU_REQUIRE(d != nullptr, DFU_ERR_CUDA, "no statistics buffer");
+    DFU_CUDA_OK(cudaMemcpyAsync(stats_host, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, as_stream(stream)));
+    DFU_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
+    return DFU_OK;
+}
 
 int dfu_compute_dists(const uint16_t* depth, size_t depth_pitch_bytes, uint16_t* dists, size_t dists_pitch_bytes,
                       int rows, int cols, const float intr_host[4], dfu_stream stream) {
@@ -706,6 +757,7 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
     a.work_tiles = reinterpret_cast<int*>(tiles + o_work);
     a.fill_tiles = reinterpret_cast<int*>(tiles + o_fill);
     DFU_CUDA_OK(cudaMemsetAsync(a.work_count, 0, 4 * sizeof(int), st));
+    a.stats = integrate_stats(device);
     depth_tiles_kernel<<<dim3(a.dtx, a.dty), DT * DT, 0, st>>>(dists, pitch, rows, cols, reinterpret_cast<float*>(tiles), a.dtx);
     DFU_LAUNCH_OK();
     tile_classify_kernel<<<div_up(nblocks, 128), 128, 0, st>>>(a);

@@ -70,6 +70,10 @@ const char* dfu_last_error(void);
 unsigned long long dfu_launch_count(void);
 /* 0 if a usable sm_100 device is visible, DFU_ERR_CUDA otherwise */
 int dfu_device_check(int device);
+/* Measurement aid (no reference counterpart; SURVEY.md section 6 asks for the FP32 SIMT peak as the denominator of the
+ * kNN roofline): times an FFMA-chain kernel on `device` (synchronous) and returns the achieved TFLOP/s and the SM clock
+ * that rate implies (MHz, may be NULL). */
+int dfu_microbench_fp32(int device, double* tflops_out, double* sm_mhz_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Warp field  (replaces Warpfield + Node + the nanoflann KD-tree + DualQuaternion on the hot path)
@@ -154,6 +158,11 @@ int dfu_tsdf_integrate(void* volume, const int dims_host[3], const float voxel_s
                        int max_weight, const float vol2cam_host[12], const float intr_host[4],
                        const uint16_t* dists, size_t dists_pitch_bytes, int rows, int cols, dfu_warpfield* wf,
                        int blend_mode, int z0, int z1, dfu_stream stream);
+/* Instrumentation (no reference counterpart): counters of the LAST dfu_tsdf_integrate call on the current device, read back
+ * synchronously: [0] voxels updated (tsdf_volume.cu:83-90 executed), [1] 16-byte quads read + written, [2] reserved,
+ * [3] 8^3 bricks that ran the per-voxel warp.  The algorithmic TSDF traffic of the call is 8 B x stats[0]. */
+int dfu_tsdf_integrate_stats(unsigned long long stats_host[4], dfu_stream stream);
+
 
 /* TsdfVolume::raycast (src/kfusion/tsdf_volume.cpp:95-129 -> device::raycast, include/kfusion/internal.hpp, src/kfusion/
  * cuda/tsdf_volume.cu:126-386): first + -> - zero crossing of the TSDF along every pixel's ray, refined by trilinear

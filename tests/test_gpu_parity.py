@@ -413,7 +413,7 @@ def test_solver_fixed_iteration_mode_is_async_and_matches_oracle(dfu, oracle):
     assert np.max(np.abs(t_g - t_o)) <= 1e-4 * np.abs(t_o).max()
 
 
-@pytest.mark.parametrize("path", ["p1", "p2", "p3", "p3g", "multi"])
+@pytest.mark.parametrize("path", ["p1", "p2", "p3", "p3g", "p4", "multi"])
 def test_solver_every_execution_path_matches_oracle(dfu, oracle, monkeypatch, path):
     """the persistent kernels (1: matrix-free from L2, 2: matrix-free with the graph in registers, 3: explicit normal matrix +
     pipelined PCG with the rows in registers, 3g: the same from L2) and the one-kernel-per-phase path solve the same problem"""
@@ -825,3 +825,31 @@ def test_tsdf_warped_random_cameras_and_fields(dfu, oracle, seed):
         got = vol.data.cpu().numpy().view(np.uint32)
         assert _mismatch(got, ref) == 0, "%d voxels differ" % _mismatch(got, ref)
     assert np.count_nonzero(ref) > 100
+
+
+def test_solver_repeated_solves_reuse_the_exchange_buffers(dfu, oracle, monkeypatch):
+    """version 4 of the persistent solver tags every exchanged word with a sequence number that must never repeat between
+    launches (nothing is cleared in between): 25 solves on the same solver object give the same bits every time and never
+    report a lost word"""
+    monkeypatch.setenv("DFU_SOLVER_PATH", "p4")
+    pos, dg_w, canon, t_true = _wellposed(seed=13, N=4096, P=60000)
+    N = len(pos)
+    live = oracle.warp(pos, synth.translations_to_dq(0.2 * t_true), dg_w, canon)
+    wf = make_wf(dfu, pos, synth.identity_dq(N), dg_w, 0.025)
+    prm = dfu.CombinedSolverParameters(numIter=5, nonLinearIter=1, linearIter=10, earlyOut=False, pcgTolerance=0.0)
+    s = dfu.CombinedSolver(wf, prm, 4.652, 1e-2, 200.0, 1e-4)
+    s.initializeProblemInstance(dev(canon), dev(live))
+    first = None
+    for rep in range(25):
+        wf.setTransformations(dev(synth.identity_dq(N)))
+        s.solveAll()
+        st = s.getStats()  # raises if a tagged word never arrived
+        t = s.getTranslations().cpu().numpy()
+        if first is None:
+            first = (st, t)
+            prm_o = pyoracle.default_params(num_iter=5, nonlinear_iter=1, linear_iter=10, lambda_=200.0, pcg_tol=0.0, early_out=0)
+            t_o, _, st_o = oracle.solve(pos, synth.identity_dq(N), dg_w, canon, live, prm_o)
+            assert abs(st["final_energy"] - st_o[1]) <= 1e-4 * st_o[1]
+            assert np.max(np.abs(t - t_o)) <= 1e-4 * np.abs(t_o).max()
+        else:
+            assert st == first[0] and np.array_equal(t, first[1]), "solve %d differs from the first" % rep
