@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from tests import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 DIM = 512
 N_THETA, N_Y = 64, 64
@@ -270,6 +270,7 @@ def config_dict(n_gpus, P):
 
 
 def run_reference(args):
+    """--impl reference: the restated reference path (oracle; kNN through the reference's own nanoflann) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -277,12 +278,16 @@ def run_reference(args):
     for _ in range(min(args.warmup, 1)):
         cpu_frame(scene, budget_planes=4)
     vals = []
-    for _ in range(max(1, min(args.steps, 3))):
+    t_start = time.time()
+    for _ in range(max(1, args.steps)):
         vals.append(cpu_frame(scene, budget_planes=64))
+        if time.time() - t_start > 150.0:  # keep the whole run within a few minutes whatever the host
+            break
     best = max(vals, key=lambda r: r["frames_per_s"])
-    fps = float(np.mean([r["frames_per_s"] for r in vals]))
+    fps = float(len(vals) / sum(1.0 / r["frames_per_s"] for r in vals))
     line = {"impl": "reference", "metric": "frames/sec (512^3 TSDF, 4096 nodes)", "value": fps, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / fps,
+            "n_gpus": args.gpus, "steps": len(vals), "steps_requested": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": 1000.0 / fps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args.gpus, len(scene["canon"])),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": best["cores"], "kind": "port",
@@ -294,14 +299,290 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------
+def parity_check(scene, devs):
+    """first frame of the bench scene solved on the GPU and by the CPU oracle: energies and node translations"""
+    import torch
+
+    import dynfu_b200 as dfu
+    from oracle import pyoracle
+
+    def dev(a):
+        return torch.as_tensor(np.ascontiguousarray(a)).to(devs, dtype=torch.float32)
+
+    try:
+        o = pyoracle.Oracle("nanoflann")
+    except FileNotFoundError:
+        o = pyoracle.Oracle("brute")
+    o.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    prm_o = pyoracle.default_params(num_iter=GN_ITERS, nonlinear_iter=1, linear_iter=PCG_ITERS, lambda_=LAMBDA, pcg_tol=0.0, early_out=0)
+    t_o, _, st_o = o.solve(scene["pos"], scene["dq"], scene["dg_w"], scene["canon"], scene["lives"][0], prm_o)
+    wf = dfu.Warpfield(devs)
+    wf.init(EPSILON, dev(scene["pos"]), dev(scene["dq"]), dev(scene["dg_w"]))
+    prm = dfu.CombinedSolverParameters(numIter=GN_ITERS, nonLinearIter=1, linearIter=PCG_ITERS, earlyOut=False, pcgTolerance=0.0)
+    s = dfu.CombinedSolver(wf, prm, 4.652, 1e-2, LAMBDA, 1e-4)
+    s.initializeProblemInstance(dev(scene["canon"]), dev(scene["lives"][0]))
+    s.solveAll()
+    st = s.getStats()
+    t_g = s.getTranslations().cpu().numpy().astype(np.float64)
+    rel_e = abs(st["final_energy"] - st_o[1]) / st_o[1]
+    rel_t = float(np.max(np.abs(t_g - t_o)) / np.abs(t_o).max())
+    return {"what": "first frame of this scene (identity field -> live frame 0, %d x %d): GPU solve vs the CPU oracle" % (GN_ITERS, PCG_ITERS),
+            "final_energy_gpu": st["final_energy"], "final_energy_cpu": float(st_o[1]), "rel_err": rel_e,
+            "max_translation_rel_err": rel_t, "tolerance": 1e-4, "ok": bool(rel_e <= 1e-4 and rel_t <= 1e-4)}
+
+
+def knn_rooflines(scene, devs, fp32_peak):
+    """kNN of the surface points among the nodes, timed alone: the grid-bucketed default and the TMA-staged brute force that
+    SURVEY 8(d) puts on the FP32 roofline (8 flop per (query, node) pair)"""
+    import torch
+
+    import dynfu_b200 as dfu
+
+    def dev(a):
+        return torch.as_tensor(np.ascontiguousarray(a)).to(devs, dtype=torch.float32)
+
+    q = dev(scene["canon"])
+    out = []
+    for kind in ("grid", "brute"):
+        if kind == "brute":
+            os.environ["DFU_POINT_KNN"] = "brute"
+        try:
+            wf = dfu.Warpfield(devs)
+            wf.init(EPSILON, dev(scene["pos"]), dev(scene["dq"]), dev(scene["dg_w"]))
+        finally:
+            os.environ.pop("DFU_POINT_KNN", None)
+        for _ in range(3):
+            wf.findNeighborsIndex(8, q)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(20):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            wf.findNeighborsIndex(8, q)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        flops = 8.0 * len(scene["pos"]) * len(scene["canon"])
+        ach = flops / (ms * 1e-3) / 1e12
+        out.append({"kernel": "knn8 of %d surface points among %d nodes, %s" %
+                              (len(scene["canon"]), len(scene["pos"]),
+                               "grid-bucketed exact search (points_grid_kernel, default)" if kind == "grid" else
+                               "brute force, node tiles staged by TMA bulk copies (points_kernel)"),
+                    "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak if fp32_peak else None,
+                    "traffic": None, "peak_source": "measured in this run (dfu_microbench_fp32: FFMA chains)", "kernel_ms": ms,
+                    "algorithmic_flops_per_launch": flops,
+                    "note": "algorithmic flops = 8 per (query, node) pair for ALL pairs (SURVEY 8d)" +
+                            ("; the grid search examines ~40 candidates per query instead of %d, so `achieved` is not a rate of "
+                             "executed flops" % len(scene["pos"]) if kind == "grid" else "")})
+    return out
+
+
+def dense_integration(scene, devs, hbm_peak, peak_src, steps=40, warmup=6):
+    """BASELINE configs[1] with a depth image that has a value at EVERY pixel (the cylinder in front of a wall at 3 m): warped
+    integration into the 512^3 volume through the solved warp field.  The whole frustum in front of the surfaces is updated,
+    so this is the streaming regime of the integrator; algorithmic bytes = 8 B x voxels actually updated."""
+    import ctypes as C
+
+    import torch
+
+    import dynfu_b200 as dfu
+    from dynfu_b200._lib import lib
+
+    def dev(a, dt=torch.float32):
+        return torch.as_tensor(np.ascontiguousarray(a)).to(devs, dtype=dt)
+
+    prm = dfu.DynFuParams(kinfuParams=dfu.KinFuParams(volume_dims=(DIM, DIM, DIM)), epsilon=EPSILON, lambda_=LAMBDA,
+                          solver=dfu.CombinedSolverParameters(numIter=GN_ITERS, nonLinearIter=1, linearIter=PCG_ITERS,
+                                                              earlyOut=False, pcgTolerance=0.0))
+    df = dfu.DynFusion(prm, device=devs)
+    df.init(dev(scene["canon"]), None, nodes=(dev(scene["pos"]), dev(scene["dq"]), dev(scene["dg_w"])))
+    df(torch.from_numpy(synth.with_wall(scene["depth0"]).view(np.int16)).pin_memory())
+    df.warpCanonicalToLiveOpt(dev(scene["lives"][0]))  # a solved (translation-only) field, like the headline frame
+    kp = prm.kinfuParams
+    dd = [dfu.compute_dists(dev(synth.with_wall(d).view(np.int16), torch.int16), kp.intr) for d in scene["depths"]]
+    for i in range(warmup):
+        df.volume.integrate(dd[i % RING], df.camera_pose, kp.intr, df.warpfield, prm.blend_mode)
+    torch.cuda.synchronize()
+    ev = []
+    for i in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        df.volume.integrate(dd[i % RING], df.camera_pose, kp.intr, df.warpfield, prm.blend_mode)
+        b.record()
+        ev.append((a, b))
+    torch.cuda.synchronize()
+    ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
+    st = (C.c_ulonglong * 4)()
+    lib.dfu_tsdf_integrate_stats(st, None)
+    touched, quads = int(st[0]), int(st[1])
+    ach = touched * ALGO_BYTES_PER_VOXEL / (ms * 1e-3) / 1e9
+    return {"kernel": "integrate, dense depth (cylinder in front of a wall at 3 m: every pixel has a depth), 512^3, 4096 nodes, warped",
+            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "peak_source": peak_src, "kernel_ms": ms, "voxels_updated": touched,
+            "algorithmic_bytes_per_launch": touched * ALGO_BYTES_PER_VOXEL,
+            "quad_bytes_per_launch": quads * 32, "quad_GBps": quads * 32 / (ms * 1e-3) / 1e9,
+            "full_sweep_GBps": DIM ** 3 * ALGO_BYTES_PER_VOXEL / (ms * 1e-3) / 1e9,
+            "bricks_warped": int(st[3]),
+            "note": "algorithmic bytes = 8 B per UPDATED voxel (4 B read + 4 B write; the reference also only touches updated "
+                    "voxels, tsdf_volume.cu:79-90); quad bytes = the 16-byte quads actually read and written (a quad with one updated "
+                    "voxel moves all four); full_sweep = 8 B x every voxel of the volume / time, for comparison with SURVEY 8(d)"}
+
+
+def multi_gpu_subrecords(rank, world, devs, comm, reps=5):
+    """N > 1: the two configurations of BASELINE.json that DO shard (the 0.5 ms headline frame cannot strong-scale: its
+    solve is latency-bound and replicated), each next to the same work on ONE GPU of the same run:
+      c5_partitioned  configs[4]: 300 k surface points / 32 768 nodes, 10 GN x 10 PCG -- points partitioned over the ranks,
+                      per-node normal-equation blocks all-reduced over NVLink by NCCL (one all-reduce per GN step + one per
+                      PCG iteration, issued by the library on the solver's stream);
+      c4_slab         configs[3]: warped integration into a 1024^3 volume with 16 384 nodes, one z-slab per rank (no
+                      collective on the data path).
+    Times are CUDA-event medians, max over ranks; `single_gpu_ms` is rank 0 doing ALL the work alone while the others wait."""
+    import torch
+    import torch.distributed as dist
+
+    import dynfu_b200 as dfu
+    from dynfu_b200 import dist as dfu_dist
+
+    def dev(a, dt=torch.float32):
+        return torch.as_tensor(np.ascontiguousarray(a)).to(devs, dtype=dt)
+
+    def median_ms(fn, reset=None, n=reps, warm=2):
+        ts = []
+        for i in range(warm + n):
+            if reset is not None:
+                reset()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= warm:
+                ts.append(a.elapsed_time(b))
+        return dfu_dist.max_over_ranks(float(np.median(ts)), devs)
+
+    out = {}
+    # ---- C5: partitioned data-term solve ------------------------------------------------------------------------
+    try:
+        eps = 0.004
+        pos, dq, dg_w = synth.cylinder_nodes(256, 128, eps)
+        rng = np.random.default_rng(synth.SEED + 8)
+        th = np.pi + rng.uniform(0.0, np.pi, 300000)
+        c_vol = np.array([0.0, 0.0, 2.0]) - synth.VOLUME_T
+        canon = np.stack([c_vol[0] + 0.3 * np.cos(th), c_vol[1] + rng.uniform(-0.8, 0.8, 300000), c_vol[2] + 0.3 * np.sin(th)],
+                         -1).astype(np.float32)
+        live = synth.bend(canon, 0.005 * eps / 0.0125)
+        prm = dfu.CombinedSolverParameters(numIter=10, nonLinearIter=1, linearIter=10, earlyOut=False, pcgTolerance=0.0)
+        ident = dev(dq)
+
+        def make(p0, p1, with_comm):
+            wf = dfu.Warpfield(devs)
+            wf.init(eps, dev(pos), ident, dev(dg_w))
+            sv = dfu.CombinedSolver(wf, prm, 4.652, 1e-2, LAMBDA, 1e-4)
+            if with_comm:
+                sv.setCommunicator(comm)
+            sv.initializeProblemInstance(dev(canon[p0:p1]), dev(live[p0:p1]))
+            return wf, sv
+
+        p0, p1 = dfu_dist.point_range(rank, world, len(canon))
+        wf, sv = make(p0, p1, True)
+        ms_n = median_ms(sv.solveAll, reset=lambda: wf.setTransformations(ident))
+        st_n = sv.getStats()
+        del sv, wf
+        ms_1, st_1 = None, None
+        if rank == 0:
+            wf, sv = make(0, len(canon), False)
+        # (every rank takes part in the barriers of median_ms; only rank 0 works)
+        ms_1 = median_ms((lambda: sv.solveAll()) if rank == 0 else (lambda: None),
+                         reset=(lambda: wf.setTransformations(ident)) if rank == 0 else None)
+        if rank == 0:
+            st_1 = sv.getStats()
+            del sv, wf
+        t1 = torch.tensor([ms_1 if rank == 0 else 0.0], device=devs)
+        dist.broadcast(t1, 0)
+        ms_1 = float(t1.item())
+        if rank == 0:
+            out["c5_partitioned"] = {
+                "workload": "configs[4]: 300000 surface points, 32768 nodes, 10 GN x 10 PCG, lambda %g; points partitioned over %d "
+                            "ranks" % (LAMBDA, world),
+                "collective": "ncclAllReduce(sum, f32) of [J^T r | diag J^T J | E] (4N+4 floats) per GN step and of A p (3N floats) per "
+                              "PCG iteration, on the solver's stream (comm.cu)",
+                "ms": ms_n, "single_gpu_ms": ms_1, "speedup": ms_1 / ms_n, "efficiency": ms_1 / ms_n / world,
+                "solves_per_s": 1e3 / ms_n, "final_energy": st_n["final_energy"], "final_energy_single_gpu": st_1["final_energy"],
+                "energy_rel_diff": abs(st_n["final_energy"] - st_1["final_energy"]) / st_1["final_energy"],
+                "note": "single_gpu_ms is the one-launch persistent kernel (no exchange); the partitioned path runs one kernel per "
+                        "phase between its all-reduces"}
+    except Exception as e:
+        if rank == 0:
+            out["c5_partitioned"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    # ---- C4: z-slab sharded warped integration ------------------------------------------------------------------
+    try:
+        dim, eps = 1024, 0.00625
+        depth0 = synth.cylinder_depth()
+        canon = synth.backproject(depth0, synth.INTR)
+        pos, dq, dg_w = synth.cylinder_nodes(128, 128, eps)
+        kappa = 0.005 * eps / 0.0125
+        depth1 = synth.cylinder_depth(kappa=kappa)
+        live = synth.bend(canon, kappa)
+        prm = dfu.DynFuParams(kinfuParams=dfu.KinFuParams(volume_dims=(dim, dim, dim)), epsilon=eps, lambda_=LAMBDA,
+                              solver=dfu.CombinedSolverParameters(numIter=GN_ITERS, nonLinearIter=1, linearIter=PCG_ITERS,
+                                                                  earlyOut=False, pcgTolerance=0.0))
+
+        def slab_run(z0, z1, active):
+            if not active:
+                return median_ms(lambda: None, n=reps, warm=3), 0
+            df = dfu.DynFusion(prm, device=devs, z0=z0, z1=z1)
+            df.init(dev(canon), None, nodes=(dev(pos), dev(dq), dev(dg_w)))
+            df(torch.from_numpy(depth0.view(np.int16)).pin_memory())
+            df.warpCanonicalToLiveOpt(dev(live))  # replicated solve: every rank holds the same field
+            d1 = dfu.compute_dists(dev(depth1.view(np.int16), torch.int16), prm.kinfuParams.intr)
+            ms = median_ms(lambda: df.volume.integrate(d1, df.camera_pose, prm.kinfuParams.intr, df.warpfield, prm.blend_mode),
+                           n=reps, warm=3)
+            import ctypes as C
+            from dynfu_b200._lib import lib
+            st = (C.c_ulonglong * 4)()
+            lib.dfu_tsdf_integrate_stats(st, None)
+            del df
+            torch.cuda.empty_cache()
+            return ms, int(st[0])
+
+        z0, z1 = dfu_dist.balanced_slab_range(rank, world, dim, pos[:, 2], 3.0 / dim, 0.25, behind=0.06)
+        ms_n, vox_n = slab_run(z0, z1, True)
+        tv = torch.tensor([float(vox_n)], device=devs, dtype=torch.float64)
+        dist.all_reduce(tv, op=dist.ReduceOp.SUM)
+        ms_1, vox_1 = slab_run(0, dim, rank == 0)
+        t1 = torch.tensor([ms_1 if rank == 0 else 0.0, float(vox_1)], device=devs, dtype=torch.float64)
+        dist.broadcast(t1, 0)
+        ms_1, vox_1 = float(t1[0].item()), int(t1[1].item())
+        if rank == 0:
+            out["c4_slab"] = {
+                "workload": "configs[3]: warped integration into a 1024^3 volume (4 GiB), 16384 nodes, 640x480 depth; %d z-slabs cut "
+                            "for equal work" % world,
+                "collective": "none on the data path (node transforms are replicated: every rank runs the same deterministic solve)",
+                "ms": ms_n, "single_gpu_ms": ms_1, "speedup": ms_1 / ms_n, "efficiency": ms_1 / ms_n / world,
+                "voxels_updated_all_ranks": int(tv.item()), "voxels_updated_single_gpu": vox_1,
+                "voxels_per_s": dim ** 3 / (ms_n * 1e-3)}
+    except Exception as e:
+        if rank == 0:
+            out["c4_slab"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--loops", type=int, default=0, help="repetitions of the timed K-step loop (0: as many as fit in ~1.5 s, 5..50)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-variant", action="store_true", help="skip the point-to-plane SE(3) variant of the frame (N = 1 only)")
+    ap.add_argument("--no-variant", action="store_true", help="skip the sub-records (point-to-plane variant, dense integration, kNN)")
+    ap.add_argument("--no-overlap", action="store_true", help="integrate on the same stream as the solve (sequential schedule)")
     ap.add_argument("--solver-parallel", default="auto", choices=["auto", "replicated", "partitioned"],
                     help="N > 1: every rank solves all points (no exchange) or the points are partitioned and the "
                          "normal-equation buffers all-reduced over NCCL; auto = partitioned from 100k points per rank")
@@ -309,6 +590,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+
+    import ctypes as C
 
     import torch
     import torch.distributed as dist
@@ -327,64 +610,56 @@ def main():
 
     scene = make_scene()
     P_all = len(scene["canon"])
-    # z-slab of this rank (multiples of 8 planes) and its contiguous point partition
     from dynfu_b200 import dist as dfu_dist
     # slabs of equal WORK: the near bricks cluster around the surface (a 0.6 m thick band of the 3 m volume)
     z0, z1 = dfu_dist.balanced_slab_range(rank, world, DIM, scene["pos"][:, 2], 3.0 / DIM, 0.25, behind=0.06) if world > 1 else (0, DIM)
     # the solve is latency-bound at this size (76k points, 4096 nodes): partitioning the points only adds one
     # all-reduce per PCG iteration, so by default every rank solves the whole (small) problem and only the volume
-    # is sharded; the partitioned + all-reduce mode is what larger problems (BASELINE configs[4]) use
+    # is sharded; the partitioned + all-reduce mode is what larger problems (BASELINE configs[4]) use -- see `c5_partitioned`
     mode = args.solver_parallel
     if mode == "auto":
         mode = "partitioned" if (world > 1 and P_all // world >= 100000) else "replicated"
     if world == 1:
         mode = "single"
     p0, p1 = dfu_dist.point_range(rank, world, P_all) if mode == "partitioned" else (0, P_all)
+    overlap = not args.no_overlap
 
     def dev(a, dt=torch.float32):
         return torch.as_tensor(np.ascontiguousarray(a)).to(devs, dtype=dt)
+
+    pc = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            pc = parity_check(scene, devs)
+        except Exception as e:  # the headline line must not depend on the checker
+            pc = {"error": repr(e)}
 
     prm = dfu.DynFuParams(kinfuParams=dfu.KinFuParams(volume_dims=(DIM, DIM, DIM)), epsilon=EPSILON, lambda_=LAMBDA,
                           solver=dfu.CombinedSolverParameters(numIter=GN_ITERS, nonLinearIter=1, linearIter=PCG_ITERS,
                                                               earlyOut=False, pcgTolerance=0.0))
     df = dfu.DynFusion(prm, device=devs, z0=z0, z1=z1)
+    df.stream_overlap = overlap
+    comm = None
+    if world > 1:
+        comm = dfu_dist.Communicator(devs)
     if mode == "partitioned":
-        df.comm = dfu_dist.Communicator(devs)
+        df.comm = comm
     df.init(dev(scene["canon"][p0:p1]), None, nodes=(dev(scene["pos"]), dev(scene["dq"]), dev(scene["dg_w"])))
 
     depth_host = [torch.from_numpy(d.view(np.int16)).pin_memory() for d in scene["depths"]]
     live_host = [torch.from_numpy(np.ascontiguousarray(l[p0:p1])).pin_memory() for l in scene["lives"]]
     depth_dev = [d.to(devs) for d in depth_host]
     live_dev = [l.to(devs) for l in live_host]
-    kp = prm.kinfuParams
 
     # frame 0 (untimed): the canonical volume, rigid integration of the undeformed surface
     df(torch.from_numpy(scene["depth0"].view(np.int16)).pin_memory())
     torch.cuda.synchronize()
 
-    ev_int = []
-    ev_sol = []
+    timers = {}
 
     def step_device(i, timed=False):
         """inputs already in HBM"""
-        dfu.compute_dists(depth_dev[i % RING], kp.intr, out=df._dists)
-        if timed:
-            df.canonicalWarpedToLive, _ = df.warpCanonical()
-            df.solver.initializeProblemInstance(df.canonicalWarpedToLive, live_dev[i % RING])
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            df.solver.solveAll()
-            s1.record()
-            ev_sol.append((s0, s1))
-        else:
-            df.warpCanonicalToLiveOpt(live_dev[i % RING])
-        if timed:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-        df.volume.integrate(df._dists, df.camera_pose, kp.intr, df.warpfield, prm.blend_mode)
-        if timed:
-            b.record()
-            ev_int.append((a, b))
+        df.frameDevice(depth_dev[i % RING], live_dev[i % RING], overlap=overlap, timers=timers if timed else None)
 
     def step_host(i):
         """public API with HOST buffers (DynFusion.streamFrame): depth + live points up from pinned memory, node transforms +
@@ -407,7 +682,7 @@ def main():
         for i in range(K):
             fn(i, **kw)
         if fin is not None:
-            fin()  # (the pipelined loop: wait for the last frame's results inside the timed region)
+            fin()  # (pipelined loops: the last frame's integration / results are inside the timed region)
         b.record()
         cpu_submit[fn.__name__] = (time.perf_counter() - t_cpu) * 1e3 / K  # host time to enqueue one step
         barrier()
@@ -418,33 +693,52 @@ def main():
 
     for i in range(args.warmup):
         step_device(i)
+    df.frameSync()
+    for i in range(args.warmup):
         step_host(i)
     df.streamFlush()
     barrier()
 
+    # EXACTLY K steps per loop, bracketed by barrier + synchronize, max over ranks; the loop is repeated and `value` is the
+    # median loop (a single 20-step loop is a 10 ms sample)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)  # let nvidia-smi start sampling
     launches0 = lib.dfu_launch_count()
     t_wall0 = time.time()
-    ms_dev = timed_loop(step_device, args.steps, timed=True)
+    first_ms = timed_loop(step_device, args.steps, fin=df.frameSync, timed=True)
     launches = lib.dfu_launch_count() - launches0
-    ms_e2e = timed_loop(step_host, args.steps, fin=df.streamFlush)
+    loops = args.loops if args.loops > 0 else int(min(50, max(5, 1500.0 / max(first_ms, 1e-3))))
+    if world > 1:  # every rank must run the same number of loops
+        t = torch.tensor([loops], device=devs)
+        dist.broadcast(t, 0)
+        loops = int(t.item())
+    dev_ms = [first_ms] + [timed_loop(step_device, args.steps, fin=df.frameSync, timed=True) for _ in range(loops - 1)]
+    e2e_ms = [timed_loop(step_host, args.steps, fin=df.streamFlush) for _ in range(loops)]
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     stats = df.solver.getStats()
+    ms_dev = float(np.median(dev_ms))
+    ms_e2e = float(np.median(e2e_ms))
 
-    # dominant kernel: integrate_kernel, timed with CUDA events on the launching stream inside the timed region
-    int_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_int]))
-    int_ms_t = torch.tensor([int_ms], device=devs)
+    def spread(v):
+        v = np.asarray(v) / args.steps
+        return {"loops": int(len(v)), "ms_per_step_median": float(np.median(v)), "min": float(v.min()), "max": float(v.max()),
+                "p10": float(np.quantile(v, 0.1)), "p90": float(np.quantile(v, 0.9)), "first_loop": float(v[0])}
+
+    # kernels, timed with CUDA events on the stream they are launched on, inside the timed loops
+    int_ms = dfu_dist.max_over_ranks(float(np.median([a.elapsed_time(b) for a, b in timers["integrate"]])), devs)
+    sol_ms = dfu_dist.max_over_ranks(float(np.median([a.elapsed_time(b) for a, b in timers["solve"]])), devs)
+    ist = (C.c_ulonglong * 4)()
+    lib.dfu_tsdf_integrate_stats(ist, None)
+    touched = torch.tensor([float(ist[0]), float(ist[1])], device=devs, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(int_ms_t, op=dist.ReduceOp.MAX)
-    int_ms = float(int_ms_t.item())
+        dist.all_reduce(touched, op=dist.ReduceOp.MAX)  # per-rank figures: the slowest rank's launch is what int_ms times
+    touched_vox, quads = int(touched[0].item()), int(touched[1].item())
     voxels_rank = DIM * DIM * (z1 - z0)
     hbm_peak, peak_src = peaks()
-    achieved = voxels_rank * ALGO_BYTES_PER_VOXEL / (int_ms * 1e-3) / 1e9
-    sol_ms = dfu_dist.max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev_sol])), devs)
+    achieved = touched_vox * ALGO_BYTES_PER_VOXEL / (int_ms * 1e-3) / 1e9
     # per GN iteration the assembly reads ~100 B/point, per PCG iteration ~100 B/point + N*(6+27)*4 B
     P_rank = p1 - p0
     sol_bytes = GN_ITERS * P_rank * 100 + GN_ITERS * PCG_ITERS * (P_rank * 100 + N_THETA * N_Y * 33 * 4)
@@ -453,61 +747,100 @@ def main():
     if rank == 0:
         fps = args.steps / (ms_dev * 1e-3)
         fps_e2e = args.steps / (ms_e2e * 1e-3)
+        step_ms = ms_dev / args.steps
+        traffic = {}
+        tf = os.path.join(ROOT, "profiles", "traffic_r02.json")
+        if world == 1 and os.path.exists(tf):  # one ncu --set full capture of THIS command at N = 1 (never re-used for slabs)
+            try:
+                traffic = json.load(open(tf))
+            except Exception:
+                traffic = {}
         line = {
             "metric": "frames/sec (512^3 TSDF, 4096 nodes)", "value": fps, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config_dict(world, P_all), solver_parallel=mode),
+            "config": dict(config_dict(world, P_all), solver_parallel=mode,
+                           schedule="integrate(i) on a second stream, overlapping the point pipeline of frame i+1" if overlap else
+                                    "sequential (one stream)",
+                           timing="K steps per loop (barrier + synchronize on both sides, CUDA events, max over ranks); "
+                                  "value = K / median over `timing.loops` loops"),
+            "timing": spread(dev_ms),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(depth_host[0].numel() * 2 + live_host[0].numel() * 4),
                     "d2h_bytes_per_step": int(N_THETA * N_Y * 8 * 4 + 32),
-                    "pipelined": "2 staging slots, H2D / D2H on copy streams; result of step i is consumed during step i+1"},
+                    "pipelined": "2 staging slots, H2D / D2H on copy streams; result of step i is consumed during step i+1",
+                    "timing": spread(e2e_ms)},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": cpu_submit.get("step_device"),
             "voxels_per_s": DIM ** 3 * fps,
             "roofline": None,
             "roofline_kernels": [
                 {"kernel": "integrate (depth_tiles + tile_classify + integrate_kernel<FILL> + integrate_kernel<CACHED>): "
                            "warped projective TSDF integration", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": int_ms,
-                 "algorithmic_bytes_per_launch": voxels_rank * ALGO_BYTES_PER_VOXEL, "share_of_step": int_ms / (ms_dev / args.steps),
-                 "note": "algorithmic bytes = 8 B for EVERY voxel of the volume (SURVEY 8d); the integrator only touches the voxels "
-                         "the depth image can update (exact culls), so achieved may exceed the copy peak -- `traffic` is what DRAM "
-                         "actually moved"},
+                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic.get("integrate_dram_bytes_per_launch"),
+                 "peak_source": peak_src, "kernel_ms": int_ms,
+                 "algorithmic_bytes_per_launch": touched_vox * ALGO_BYTES_PER_VOXEL, "voxels_updated": touched_vox,
+                 "quad_bytes_per_launch": quads * 32,
+                 "full_sweep": {"bytes": voxels_rank * ALGO_BYTES_PER_VOXEL,
+                                "GBps": voxels_rank * ALGO_BYTES_PER_VOXEL / (int_ms * 1e-3) / 1e9,
+                                "note": "8 B x EVERY voxel of the rank's slab / time (SURVEY 8d's sweep model); not a roofline "
+                                        "fraction -- the kernel proves most voxels untouched and never loads them"},
+                 "share_of_step": int_ms / step_ms,
+                 "note": "algorithmic bytes = 8 B x voxels UPDATED by this launch (counted in the kernel: 4 B read + 4 B write of "
+                         "the ushort2; the reference touches the same voxels, tsdf_volume.cu:79-90).  This scene has depth on a "
+                         "quarter of the image, so the launch is latency-bound (per-voxel neighbour cache), not streaming: see "
+                         "`integrate_dense` for the bandwidth regime"},
                 {"kernel": "k_solve_persistent3r: explicit normal matrix + pipelined PCG, 5 GN x 10 PCG in one cooperative launch"
                            if mode != "partitioned" else "solver phase kernels + NCCL all-reduces (5 GN x 10 PCG)", "bound": "hbm", "achieved": sol_achieved,
-                 "peak": hbm_peak, "unit": "GB/s", "frac": sol_achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                 "kernel_ms": sol_ms, "algorithmic_bytes_per_launch": sol_bytes, "share_of_step": sol_ms / (ms_dev / args.steps),
-                 "note": "L2-resident and bound by grid-barrier / L2 latency, not by HBM (SURVEY 8d): frac is reported "
-                         "for completeness"}],
+                 "peak": hbm_peak, "unit": "GB/s", "frac": sol_achieved / hbm_peak, "traffic": traffic.get("solver_dram_bytes_per_launch"),
+                 "peak_source": peak_src,
+                 "kernel_ms": sol_ms, "algorithmic_bytes_per_launch": sol_bytes, "share_of_step": sol_ms / step_ms,
+                 "note": "L2-resident and bound by inter-SM exchange latency (one L2 round trip pair per PCG iteration), not by HBM "
+                         "(SURVEY 8d); frac is reported for completeness -- profiles/r02_solver_experiments.md"}],
             "solver": {"final_energy": stats["final_energy"], "initial_energy": stats["initial_energy"],
                        "pcg_iterations": stats["pcg_iterations"], "gn_steps": stats["gn_steps"]},
+            "parity_check": pc,
             "clocks": clocks,
         }
-        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(traffic_file):
-            try:
-                tr = json.load(open(traffic_file))
-                line["roofline_kernels"][0]["traffic"] = tr.get("integrate_dram_bytes_per_launch")
-                line["roofline_kernels"][1]["traffic"] = tr.get("solver_dram_bytes_per_launch")
-                for rk in line["roofline_kernels"]:  # the same launch expressed in the DRAM bytes ncu measured
-                    if rk["traffic"]:
-                        rk["dram_achieved_GBps"] = rk["traffic"] / (rk["kernel_ms"] * 1e-3) / 1e9
-            except Exception:
-                pass
+        if traffic:
+            line["traffic_source"] = traffic.get("source")
+        for rk in line["roofline_kernels"]:
+            if rk["traffic"]:
+                rk["dram_achieved_GBps"] = rk["traffic"] / (rk["kernel_ms"] * 1e-3) / 1e9
+        if overlap:
+            line["roofline_kernels"][0]["note"] += ("; with the overlapped schedule the kernel shares the SMs with the next frame's point "
+                                                    "pipeline, so kernel_ms is its duration on its own stream, not its share of the step")
         # the contract's `roofline` object is the dominant kernel of the step
         line["roofline"] = max(line["roofline_kernels"], key=lambda r: r["kernel_ms"])
-        if world == 1 and not args.no_variant:
+    del df
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_variant and rank == 0:
+        try:
+            tf_, mhz = C.c_double(), C.c_double()
+            lib.dfu_microbench_fp32(local, C.byref(tf_), C.byref(mhz))
+            line["fp32_peak"] = {"tflops": tf_.value, "implied_sm_mhz": mhz.value, "how": "dfu_microbench_fp32: 16 FFMA chains per thread, "
+                                 "8 CTAs of 256 threads per SM, best of 4"}
+            line["roofline_kernels"] += knn_rooflines(scene, devs, tf_.value)
+        except Exception as e:
+            line["fp32_peak"] = {"error": repr(e)}
+        try:
+            line["integrate_dense"] = dense_integration(scene, devs, hbm_peak, peak_src)
+            line["roofline_kernels"].append(line["integrate_dense"])
+        except Exception as e:
+            line["integrate_dense"] = {"error": repr(e)}
+        try:
+            line["north_star_data_term"] = north_star_variant(scene, devs)
+        except Exception as e:  # the headline line must not depend on the extension
+            line["north_star_data_term"] = {"error": repr(e)}
+        if not args.no_cpu_baseline and "error" not in line["north_star_data_term"]:
             try:
-                del df
-                torch.cuda.empty_cache()
-                line["north_star_data_term"] = north_star_variant(scene, devs)
-            except Exception as e:  # the headline line must not depend on the extension
-                line["north_star_data_term"] = {"error": repr(e)}
-            if not args.no_cpu_baseline and "error" not in line["north_star_data_term"]:
-                try:
-                    line["north_star_data_term"]["cpu_baseline"] = cpu_variant_solve(scene)
-                except Exception as e:
-                    line["north_star_data_term"]["cpu_baseline"] = {"error": repr(e)}
+                line["north_star_data_term"]["cpu_baseline"] = cpu_variant_solve(scene)
+            except Exception as e:
+                line["north_star_data_term"]["cpu_baseline"] = {"error": repr(e)}
+    if world > 1 and not args.no_variant:
+        sub = multi_gpu_subrecords(rank, world, devs, comm)
+        if rank == 0:
+            line.update(sub)
+    if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             c = cpu_frame(scene)
             line["cpu_baseline"] = {"value": c["frames_per_s"], "unit": "frames/s", "cores": c["cores"], "kind": "port",

@@ -589,6 +589,7 @@ int dfu_solver_create(dfu_solver** out, dfu_warpfield* wf, const dfu_solver_para
     cudaGetDevice(&prev);
     cudaSetDevice(wf->device);
     cudaError_t e1 = cudaMalloc(&s->sc, sizeof(Scalars));
+    if (e1 == cudaSuccess) e1 = cudaMemset(s->sc, 0, sizeof(Scalars));  // (spin_fail is only written by the kernels that can set it)
     cudaError_t e2 = cudaMallocHost(&s->sc_host, sizeof(Scalars));
     cudaError_t e3 = cudaMalloc(&s->part, 4 * MAX_PARTIALS * sizeof(double));
     if (e3 == cudaSuccess) e3 = cudaMalloc(&s->bar, 64);

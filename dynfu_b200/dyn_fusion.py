@@ -73,6 +73,7 @@ class DynFusion:
         self._index = None     # frontend.PointIndex, built per frame like the reference's second KD-tree
         self.liveVertices = None
         self.liveNormals = None
+        self.stream_overlap = True  # streamFrame: integrate(i) on a second stream, overlapping the point pipeline of frame i+1
         self.allreduce = None  # python all-reduce hook (tests)
         self.comm = None       # dynfu_b200.dist.Communicator: NCCL issued from C++
 
@@ -158,6 +159,65 @@ class DynFusion:
         self.frame_counter += 1
         return True
 
+    # ---- one hot-path frame on device-resident inputs, integration overlapped with the next frame's point pipeline --
+    # The warped integration of frame i needs only the node transforms solve(i) wrote; the point pipeline of frame i+1
+    # (compute_dists, warp of the canonical frame, 8-NN graph, matrix pattern: ~0.1 ms of small kernels that leave most
+    # SMs idle) needs neither the volume nor anything the integrator writes.  So integrate(i) runs on a second stream and
+    # the only ordering added is: solve(i+1), which overwrites the transforms, waits for integrate(i).  Two dists buffers
+    # alternate.  Results are bit-identical to the sequential schedule (tests/test_gpu_frontend.py).
+    def _overlap_state(self):
+        st = getattr(self, "_ov", None)
+        if st is None:
+            st = dict(stream=torch.cuda.Stream(self.device), dists=[self._dists, torch.empty_like(self._dists)], slot=0,
+                      solved=torch.cuda.Event(), int_done=torch.cuda.Event(), pending=False)
+            self._ov = st
+        return st
+
+    def frameDevice(self, depth_dev, liveVertices, overlap=True, timers=None):
+        """compute_dists -> warpToLive(canonical) -> solve -> warped integration of `depth_dev` (int16/uint16 CUDA tensor).
+        timers: optional dict of lists; CUDA event pairs around the solve ('solve') and the integration ('integrate')."""
+        kp = self.params.kinfuParams
+        cur = torch.cuda.current_stream(self.device)
+        st = self._overlap_state()
+        d = st["dists"][st["slot"]] if overlap else self._dists
+        st["slot"] ^= 1 if overlap else 0
+        compute_dists(depth_dev, kp.intr, out=d)
+        self.canonicalWarpedToLive, _ = self.warpCanonical()
+        self.solver.initializeProblemInstance(self.canonicalWarpedToLive, liveVertices)
+        if st["pending"]:
+            cur.wait_event(st["int_done"])  # the integration of the previous frame still reads the transforms
+            st["pending"] = False
+        if timers is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(cur)
+        self.solver.solveAll()
+        if timers is not None:
+            b.record(cur)
+            timers.setdefault("solve", []).append((a, b))
+        istream = st["stream"] if overlap else cur
+        if overlap:
+            st["solved"].record(cur)
+            istream.wait_event(st["solved"])
+        with torch.cuda.stream(istream):
+            if timers is not None:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(istream)
+            self.volume.integrate(d, self.camera_pose, kp.intr, self.warpfield, self.params.blend_mode)
+            if timers is not None:
+                b.record(istream)
+                timers.setdefault("integrate", []).append((a, b))
+            if overlap:
+                st["int_done"].record(istream)
+                st["pending"] = True
+        self.frame_counter += 1
+
+    def frameSync(self):
+        """make the current stream wait for an integration still running on the overlap stream"""
+        st = getattr(self, "_ov", None)
+        if st is not None and st["pending"]:
+            torch.cuda.current_stream(self.device).wait_event(st["int_done"])
+            st["pending"] = False
+
     # ---- pipelined frame loop for a steady stream of sensor frames -------------------------------------------------
     # streamFrame(depth, live) uploads this frame's pinned host inputs on a copy stream, runs the frame on the current
     # stream, brings {node transforms, solver statistics} back to pinned host memory on a second copy stream, and returns
@@ -201,9 +261,8 @@ class DynFusion:
             st["up"][s].record(st["h2d"])
         cur.wait_event(st["up"][s])
         cur.wait_event(st["down"][s])  # the result buffers of this slot have been read back
-        compute_dists(st["depth"][s], kp.intr, out=self._dists)
-        self.warpCanonicalToLiveOpt(st["live"][s])
-        self.volume.integrate(self._dists, self.camera_pose, kp.intr, self.warpfield, self.params.blend_mode)
+        self.frameDevice(st["depth"][s], st["live"][s], overlap=self.stream_overlap)
+        self.frame_counter -= 1  # (counted below)
         check(lib.dfu_warpfield_get_nodes(self.warpfield.handle, None, dptr(st["dq_dev"][s]), None, stream_ptr()))
         self.solver.getStatsAsync(st["stats_dev"][s])
         st["free"][s].record(cur)
@@ -223,7 +282,8 @@ class DynFusion:
                                          gn_steps=int(e[3]))
 
     def streamFlush(self):
-        """result of the last streamFrame call (waits for it)"""
+        """result of the last streamFrame call (waits for it, and for an integration still running on the overlap stream)"""
+        self.frameSync()
         st = getattr(self, "_ss", None)
         if st is None or st["pending"] is None:
             return None

@@ -422,3 +422,35 @@ def test_update_with_fewer_than_eight_nodes(fe, oracle):
     assert nu == int(mask_o.sum()) and nn == po.shape[0] - 3
     pg, qg, wg = [t.cpu().numpy() for t in wf.getNodes()]
     assert same_bits(pg, po) and same_bits(wg, wo) and np.allclose(qg, qo, atol=2e-6)
+
+
+def test_overlapped_frame_schedule_is_bit_identical(fe):
+    """DynFusion.frameDevice(overlap=True) runs the integration of frame i on a second stream, concurrently with the point
+    pipeline of frame i+1: volume, node transforms and energies equal the sequential schedule bit for bit over six frames"""
+    import dynfu_b200 as dfu
+
+    dim = 128
+    pos, _, dg_w, t_true = synth.sphere_nodes(1024, 0.025)
+    depth0 = synth.sphere_depth()
+    canon = synth.backproject(depth0, synth.INTR)[::2]
+    depths = [dev(synth.sphere_depth(bump=0.002 * (1 + i % 3)).view(np.int16), torch.int16) for i in range(3)]
+    lives = [dev(canon + 0.002 * (1 + i % 3) * np.array([1.0, 0.5, -0.25], np.float32)) for i in range(3)]
+    out = {}
+    for overlap in (False, True):
+        prm = dfu.DynFuParams(kinfuParams=dfu.KinFuParams(volume_dims=(dim, dim, dim)), epsilon=0.025, lambda_=200.0,
+                              solver=dfu.CombinedSolverParameters(numIter=3, nonLinearIter=1, linearIter=8, earlyOut=False,
+                                                                  pcgTolerance=0.0))
+        df = dfu.DynFusion(prm)
+        df.init(dev(canon), None, nodes=(dev(pos), dev(synth.identity_dq(1024)), dev(dg_w)))
+        df(torch.from_numpy(depth0.view(np.int16)).pin_memory())
+        energies = []
+        for i in range(6):
+            df.frameDevice(depths[i % 3], lives[i % 3], overlap=overlap)
+            energies.append(df.solver.getStats()["final_energy"])
+        df.frameSync()
+        torch.cuda.synchronize()
+        out[overlap] = (df.volume.data.cpu().numpy().copy(), df.warpfield.getNodes()[1].cpu().numpy().copy(), energies)
+    assert np.array_equal(out[False][0], out[True][0])
+    assert same_bits(out[False][1], out[True][1])
+    assert out[False][2] == out[True][2]
+    assert (out[True][0] >> 16).max() == 7  # rigid frame 0 + six warped frames

@@ -15,7 +15,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import dynfu_b200 as dfu  # noqa: E402
-from tests import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 DEV = torch.device("cuda", 0)
 

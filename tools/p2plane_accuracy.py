@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import dynfu_b200 as dfu  # noqa: E402
 from oracle import pyoracle  # noqa: E402
-from tests import synth  # noqa: E402
+from tools import synth  # noqa: E402
 from tests.test_oracle_p2plane import rigid_scene  # noqa: E402
 
 
