@@ -43,24 +43,31 @@ struct IntegrateArgs {
     float4* w_pool;        // per-voxel weight cache (two float4 per voxel)
     unsigned char* built;
     // per-call scratch written by tile_classify_kernel
-    unsigned char* tile_flags;  // per 32x8x8 tile: bits 0-3 = near mask of its 4 bricks, bit 4 = rigid pass cannot touch a voxel
+    unsigned short* tile_flags; // per 32x8x8 tile: bits 0-3 = near mask of its 4 bricks, bit 4 = rigid pass cannot touch a voxel,
+                                // bits 8-11 = bricks all of whose voxels are PROVABLY updated with tsdf = 1 (free space in front of the surface)
     int* work_count;            // [0] tiles with any work, [1] tiles with a near brick missing from the 8-NN cache,
                                 // [2],[3] ticket counters of the two lists
     int* work_tiles;            // ids of the tiles with work
     int* fill_tiles;            // ids of the tiles to fill
     int ntiles;
-    const float* dmax_tiles;  // max ray length per 16x16-pixel tile of the dists image (0: no depth in the tile)
+    const float2* dmax_tiles;  // per 16x16-pixel tile of the dists image: .x = max ray length (0: no depth in the tile),
+                               // .y = min ray length (0: some pixel of the tile has no depth)
     int dtx, dty;             // tiles per row / column
     unsigned long long* stats;  // instrumentation of the last call on this device: [0] voxels updated, [1] quads (16 B) read + written,
-                                // [2] tiles with work, [3] bricks that ran the per-voxel warp (zeroed by tile_classify_kernel)
+                                // [2] voxels updated through the saturated-free-space path, [3] bricks that ran the per-voxel warp (zeroed by tile_classify_kernel)
 };
 struct Tally {
-    unsigned vox = 0, quads = 0, bricks = 0;
+    unsigned vox = 0, quads = 0, bricks = 0, sat = 0;
 };
 
 constexpr int DT = 16;  // pixels per side of a depth tile
 
 DFU_DEV uint4 ld_stream(const uint4* p) { return __ldcs(p); }
+// TMA bulk prefetch of a contiguous block into L2 (one instruction per block, no registers, no shared memory):
+// cp.async.bulk.prefetch.L2 -- bytes % 16 == 0, 16-byte aligned source
+DFU_DEV void tma_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 DFU_DEV void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
 
 // TsdfIntegrator::operator() body for one voxel whose (warped) volume-frame position is (px,py,pz)
@@ -121,6 +128,7 @@ struct TileInfo {
     int x0, y0, zt;
     size_t brick0;          // index of the tile's first brick in the brick table
     int near_mask;          // bit sb set: brick sb needs the exact per-voxel warp
+    int sat_mask;           // bit sb set: every voxel of brick sb is updated with tsdf = 1 (no per-voxel geometry needed)
     bool translation_only;  // every node is a pure translation
     float reff2;            // squared distance beyond which rule (b) below holds for a single voxel
     float r_brick;
@@ -171,6 +179,7 @@ DFU_DEV TileInfo tile_info(const IntegrateArgs& a, int tile, const FieldInfo& f)
     ti.y0 = tile_y * 8;
     ti.zt = a.zt0 + tile_z * 8;
     ti.near_mask = a.tile_flags[tile] & 15;
+    ti.sat_mask = (a.tile_flags[tile] >> 8) & 15;
     ti.translation_only = f.translation_only;
     ti.reff2 = f.reff2;
     ti.r_brick = 3.5f * sqrtf(a.vsx * a.vsx + a.vsy * a.vsy + a.vsz * a.vsz);  // brick half diagonal
@@ -178,23 +187,73 @@ DFU_DEV TileInfo tile_info(const IntegrateArgs& a, int tile, const FieldInfo& f)
     return ti;
 }
 
-// rigid pass over the quads of the bricks that are not near
-DFU_DEV void rigid_pass(const IntegrateArgs& a, const TileInfo& ti, Tally& tally) {
+// streaming update of a quad all of whose voxels receive tsdf = 1 (saturated free space): no projection, no depth fetch.
+// The store is elided when nothing changes (a voxel that already holds (1.0, max_weight) stays what it is).
+DFU_DEV void quad_saturate(const IntegrateArgs& a, size_t lin, Tally& tally) {
+    uint4* p = reinterpret_cast<uint4*>(a.vol + lin);
+    const uint4 v = ld_stream(p);
+    uint4 n;
+    n.x = voxel_update(a, v.x, 1.f);
+    n.y = voxel_update(a, v.y, 1.f);
+    n.z = voxel_update(a, v.z, 1.f);
+    n.w = voxel_update(a, v.w, 1.f);
+    tally.vox += 4;
+    tally.quads += 1;
+    tally.sat += 4;
+    if ((n.x ^ v.x) | (n.y ^ v.y) | (n.z ^ v.z) | (n.w ^ v.w)) st_stream(p, n);
+}
+
+// an entirely saturated tile (every voxel receives tsdf = 1): each thread its four quads with all four 128-bit loads in
+// flight; stores only where a voxel changes.  These tiles travel in the same ticket list as the others, so their streaming
+// overlaps the latency-bound near bricks of the neighbouring CTAs.
+DFU_DEV void saturate_tile(const IntegrateArgs& a, const TileInfo& ti, Tally& tally) {
+    const size_t plane = (size_t) a.dx * a.dy;
+    uint4* p[4];
+    uint4 v[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int lin = it * 128 + threadIdx.x;
+        const int qx = lin & 7, yy = (lin >> 3) & 7, zz = lin >> 6;
+        p[it] = reinterpret_cast<uint4*>(a.vol + (size_t) (ti.x0 + qx * 4) + (size_t) (ti.y0 + yy) * a.dx + plane * (size_t) (ti.zt + zz));
+        v[it] = ld_stream(p[it]);
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        uint4 nv;
+        nv.x = voxel_update(a, v[it].x, 1.f);
+        nv.y = voxel_update(a, v[it].y, 1.f);
+        nv.z = voxel_update(a, v[it].z, 1.f);
+        nv.w = voxel_update(a, v[it].w, 1.f);
+        if ((nv.x ^ v[it].x) | (nv.y ^ v[it].y) | (nv.z ^ v[it].z) | (nv.w ^ v[it].w)) st_stream(p[it], nv);
+    }
+    tally.vox += 16;
+    tally.quads += 4;
+    tally.sat += 16;
+}
+
+// rigid pass over the quads of the bricks that are not near (saturated bricks: streaming update)
+DFU_DEV void rigid_pass(const IntegrateArgs& a, const TileInfo& ti, bool skip_rigid, Tally& tally) {
     const size_t plane = (size_t) a.dx * a.dy;
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {
         const int lin = it * 128 + threadIdx.x;
         const int qx = lin & 7, yy = (lin >> 3) & 7, zz = lin >> 6;
         const int z = ti.zt + zz;
-        if ((ti.near_mask >> (qx >> 1)) & 1) continue;
+        const int sb = qx >> 1;
         if (z < a.z0 || z >= a.z1) continue;
         const int x = ti.x0 + qx * 4, y = ti.y0 + yy;
+        const size_t vlin = (size_t) x + (size_t) y * a.dx + plane * (size_t) z;
+        if ((ti.sat_mask >> sb) & 1) {
+            quad_saturate(a, vlin, tally);
+            continue;
+        }
+        if (skip_rigid || ((ti.near_mask >> sb) & 1)) continue;
         const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
         bool hit[4];
         float ts[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) hit[v] = voxel_tsdf(a, fmul((float) (x + v), a.vsx), py, pz, ts[v]);
-        quad_commit(a, (size_t) x + (size_t) y * a.dx + plane * (size_t) z, hit, ts, tally);
+        quad_commit(a, vlin, hit, ts, tally);
     }
 }
 
@@ -374,18 +433,49 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
     const int qx2 = tid & 1, yy = (tid >> 1) & 7, zz = tid >> 4;
     // persistent CTAs pull tiles from the compacted list of tiles that have work (tile_classify_kernel); a shared
     // ticket counter balances the very uneven tiles (rigid-only vs near bricks)
-    __shared__ int s_ticket;
+    __shared__ int s_ticket[2];
     Tally tally;
+    // the ticket of the NEXT tile is drawn while the current one is processed (an atomic round trip per tile otherwise)
+    if (tid == 0) s_ticket[0] = atomicAdd(&a.work_count[MODE == MODE_FILL ? 3 : 2], 1);
+    int par = 0;
 #pragma unroll 1
     for (;;) {
-        if (tid == 0) s_ticket = atomicAdd(&a.work_count[MODE == MODE_FILL ? 3 : 2], 1);
         __syncthreads();
-        const int wi = s_ticket;
-        __syncthreads();
+        const int wi = s_ticket[par];
         if (wi >= n_work) break;
+        int next_tile = -1;
+        if (tid == 0) {
+            const int nwi = atomicAdd(&a.work_count[MODE == MODE_FILL ? 3 : 2], 1);
+            s_ticket[par ^ 1] = nwi;
+            if (MODE == MODE_CACHED && nwi < n_work) next_tile = list[nwi];  // (consumed after the rigid pass: the load has time to land)
+        }
+        par ^= 1;
         const int tile = list[wi];
         const TileInfo ti = tile_info(a, tile, fi);
-        if (MODE != MODE_FILL && !(a.tile_flags[tile] & 16)) rigid_pass(a, ti, tally);
+        if (MODE != MODE_FILL && ti.sat_mask == 15 && ti.zt >= a.z0 && ti.zt + 8 <= a.z1) {
+            saturate_tile(a, ti, tally);
+            continue;
+        }
+        if (MODE != MODE_FILL && (!(a.tile_flags[tile] & 16) || ti.sat_mask)) rigid_pass(a, ti, (a.tile_flags[tile] & 16) != 0, tally);
+        if (MODE == MODE_CACHED && next_tile >= 0) {
+            // the neighbour-cache slabs (8 KB of ids + 16 KB of weights per brick, contiguous) of the NEXT tile's near bricks are
+            // pulled into L2 by the TMA engine while this tile's bricks are being processed: the per-voxel cache reads were the
+            // top stall of this kernel (dependent DRAM loads at 50 % occupancy)
+            const int nm = a.tile_flags[next_tile] & 15;
+            if (nm) {
+                int b = next_tile;
+                const int ntx_ = b % a.ntx;
+                b /= a.ntx;
+                const int nty_ = b % a.nty, ntz_ = b / a.nty;
+                const size_t nb0 = (size_t) (ntx_ * 4) + (size_t) a.bdx * ((size_t) nty_ + (size_t) a.bdy * (size_t) ((a.zt0 >> 3) + ntz_));
+#pragma unroll
+                for (int sb = 0; sb < 4; ++sb)
+                    if ((nm >> sb) & 1) {
+                        tma_prefetch_l2(a.knn_pool + (nb0 + sb) * 512, 512 * 16);
+                        tma_prefetch_l2(a.w_pool + (nb0 + sb) * 1024, 1024 * 16);
+                    }
+            }
+        }
         if (ti.near_mask == 0) continue;
         const int z = ti.zt + zz, y = ti.y0 + yy;
         const float py = fmul((float) y, a.vsy), pz = fmul((float) z, a.vsz);
@@ -453,26 +543,34 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
         }
     }
     if (MODE != MODE_FILL && a.stats) {  // one atomic per warp and counter
-        unsigned v = tally.vox, q = tally.quads, b = tally.bricks;
+        unsigned v = tally.vox, q = tally.quads, b = tally.bricks, sa = tally.sat;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             v += __shfl_xor_sync(0xffffffffu, v, o);
             q += __shfl_xor_sync(0xffffffffu, q, o);
             b += __shfl_xor_sync(0xffffffffu, b, o);
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
         }
         if ((tid & 31) == 0) {
             if (v) atomicAdd(&a.stats[0], (unsigned long long) v);
             if (q) atomicAdd(&a.stats[1], (unsigned long long) q);
             if (b) atomicAdd(&a.stats[3], (unsigned long long) b);
+            if (sa) atomicAdd(&a.stats[2], (unsigned long long) sa);
         }
     }
 }
 
-// True when NO voxel of the index box [x0,x0+nx-1] x [y0,y0+7] x [z0,z0+7], moved by at most `delta` metres (Euclidean) from
-// its grid position, can pass the per-voxel tests of voxel_tsdf: the box (inflated by delta) is behind the camera, projects
-// outside the image, projects only onto pixels without depth, or lies entirely more than trunc behind the farthest depth it
-// can see.  All bounds carry margins far above the rounding of the per-voxel arithmetic.
-DFU_DEV bool box_unreachable(const IntegrateArgs& a, int x0, int nx, int y0, int z0, float delta) {
+// Classification of the index box [x0,x0+nx-1] x [y0,y0+7] x [z0,z0+7] whose voxels are moved by at most `delta` metres
+// (Euclidean) from their grid positions.  Returns bit 0 (BOX_UNREACHABLE) when NO voxel can pass the per-voxel tests of
+// voxel_tsdf -- the box (inflated by delta) is behind the camera, projects outside the image, projects only onto pixels
+// without depth, or lies entirely more than trunc behind the farthest depth it can see -- and bit 1 (BOX_SATURATED) when EVERY
+// voxel passes them with tsdf == 1.0f exactly: the box is in front of the camera, projects inside the image onto pixels
+// that all carry a depth, and the nearest of those depths lies more than the truncation distance behind the farthest point of
+// the box (sdf >= trunc => fminf(1, sdf / trunc) == 1).  Free space between the camera and the surfaces -- most updated
+// voxels of a dense depth image -- then needs no projection at all.  All bounds carry margins far above the rounding of the
+// per-voxel arithmetic.
+enum { BOX_UNREACHABLE = 1, BOX_SATURATED = 2 };
+DFU_DEV int box_test(const IntegrateArgs& a, int x0, int nx, int y0, int z0, float delta) {
     float zmin = INFINITY, zmax = -INFINITY, umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
     float cxs = 0.f, cys = 0.f, czs = 0.f, cor[8][3];
 #pragma unroll
@@ -486,8 +584,8 @@ DFU_DEV bool box_unreachable(const IntegrateArgs& a, int x0, int nx, int y0, int
         zmin = fminf(zmin, cor[c][2]);
         zmax = fmaxf(zmax, cor[c][2]);
     }
-    if (zmax + delta <= -1e-4f) return true;  // every voxel has vc.z <= 0
-    if (!(zmin - delta > 1e-3f)) return false;
+    if (zmax + delta <= -1e-4f) return BOX_UNREACHABLE;  // every voxel has vc.z <= 0
+    if (!(zmin - delta > 1e-3f)) return 0;
     cxs *= 0.125f; cys *= 0.125f; czs *= 0.125f;
     float rad = 0.f, slope = 0.f;
 #pragma unroll
@@ -505,13 +603,22 @@ DFU_DEV bool box_unreachable(const IntegrateArgs& a, int x0, int nx, int y0, int
     // pixel rectangle the box can project to, one pixel of margin
     const int pu0 = max(0, (int) floorf(fmaxf(umin - mpx, -1e6f)) - 1), pu1 = min(a.cols - 1, (int) floorf(fminf(umax + mpx, 1e6f)) + 1);
     const int pv0 = max(0, (int) floorf(fmaxf(vmin - mpx, -1e6f)) - 1), pv1 = min(a.rows - 1, (int) floorf(fminf(vmax + mpx, 1e6f)) + 1);
-    if (pu0 > pu1 || pv0 > pv1) return true;  // projects outside the image
-    float dfar = 0.f;
+    if (pu0 > pu1 || pv0 > pv1) return BOX_UNREACHABLE;  // projects outside the image
+    float dfar = 0.f, dnear = INFINITY;
     for (int ty = pv0 / DT; ty <= pv1 / DT; ++ty)
-        for (int tx = pu0 / DT; tx <= pu1 / DT; ++tx) dfar = fmaxf(dfar, __ldg(&a.dmax_tiles[ty * a.dtx + tx]));
-    const float near_dist = sqrtf(cxs * cxs + cys * cys + czs * czs) - rad - delta;  // <= |vc| of every (moved) voxel
-    // dfar == 0: no depth anywhere it projects to; else sdf = Dp - |vc| <= dfar - near_dist < -trunc
-    return dfar == 0.f || dfar - near_dist < -a.trunc - 1e-3f;
+        for (int tx = pu0 / DT; tx <= pu1 / DT; ++tx) {
+            const float2 t = __ldg(&a.dmax_tiles[ty * a.dtx + tx]);
+            dfar = fmaxf(dfar, t.x);
+            dnear = fminf(dnear, t.y);
+        }
+    const float cdist = sqrtf(cxs * cxs + cys * cys + czs * czs);
+    // dfar == 0: no depth anywhere it projects to; else sdf = Dp - |vc| <= dfar - (|centre| - rad - delta) < -trunc
+    if (dfar == 0.f || dfar - (cdist - rad - delta) < -a.trunc - 1e-3f) return BOX_UNREACHABLE;
+    // saturated: inside the image by 0.01 pixel (far above the rounding of the per-voxel projection), every pixel valid,
+    // sdf >= dnear - (|centre| + rad + delta) >= trunc (1 + 1e-3)
+    const bool inside = umin - mpx >= 0.01f && vmin - mpx >= 0.01f && umax + mpx < (float) a.cols - 0.01f && vmax + mpx < (float) a.rows - 0.01f;
+    if (inside && dnear > 0.f && dnear < INFINITY && dnear - (cdist + rad + delta) >= a.trunc * 1.001f + 1e-4f) return BOX_SATURATED;
+    return 0;
 }
 
 // Hierarchical cull of the RIGID part of every tile, one thread per tile.  The tile's un-warped voxels lie in the
@@ -519,8 +626,8 @@ DFU_DEV bool box_unreachable(const IntegrateArgs& a, int x0, int nx, int y0, int
 // only onto pixels without depth, or lies entirely more than trunc behind the farthest depth it can see, no voxel of
 // it can pass the per-voxel tests (tsdf_volume.cu:70-79) and the rigid pass is skipped.  All bounds carry margins far
 // above the rounding of the per-voxel arithmetic, so the result is bit-identical.
-// The same thread classifies the tile's 4 bricks as near / not near (rules (a),(b) above) and appends the tile to the
-// work list (anything to do) and to the fill list (a near brick missing from the 8-NN cache).
+// The same thread classifies the tile's 4 bricks as near / not near (rules (a),(b) above) or saturated (box_test), and
+// appends the tile to the work list (anything to do) and to the fill list (a near brick missing from the 8-NN cache).
 __global__ void tile_classify_kernel(const __grid_constant__ IntegrateArgs a) {
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= a.ntiles) return;
@@ -530,8 +637,18 @@ __global__ void tile_classify_kernel(const __grid_constant__ IntegrateArgs a) {
     bid /= a.ntx;
     const int y0 = (bid % a.nty) * 8;
     const int zt = a.zt0 + (bid / a.nty) * 8;
-    const bool rigid_skip = box_unreachable(a, x0, 32, y0, zt, 0.f);
-    int near_mask = 0, need_fill = 0;
+    const int tt = box_test(a, x0, 32, y0, zt, 0.f);
+    const bool rigid_skip = (tt & BOX_UNREACHABLE) != 0;
+    int near_mask = 0, need_fill = 0, sat_mask = 0;
+    if (!a.warped) {
+        if (tt & BOX_SATURATED) {
+            sat_mask = 15;
+        } else if (!rigid_skip) {
+#pragma unroll
+            for (int sb = 0; sb < 4; ++sb)
+                if (box_test(a, x0 + sb * 8, 8, y0, zt, 0.f) & BOX_SATURATED) sat_mask |= 1 << sb;
+        }
+    }
     if (a.warped) {
         const FieldInfo f = field_info(a);
         const float r_brick = 3.5f * sqrtf(a.vsx * a.vsx + a.vsy * a.vsy + a.vsz * a.vsz);
@@ -543,40 +660,64 @@ __global__ void tile_classify_kernel(const __grid_constant__ IntegrateArgs a) {
             const bool on_zero_plane = (x0 + sb * 8 == 0) || (y0 == 0) || (zt == 0);
             if (f.all_near || dmin <= (on_zero_plane ? f.r_zero : f.r_eff)) {
                 // translation-only field: a voxel moves by |2 acc_c| <= 16 dmax w per coordinate, w <= exp(-dmin^2 / (2 maxw^2));
-                // a brick none of whose moved voxels can be updated needs neither the cache nor the warp
+                // a brick none of whose moved voxels can be updated needs neither the cache nor the warp, and neither does
+                // one all of whose moved voxels are saturated free space
                 if (f.translation_only && a.blend_mode == DFU_BLEND_REF_COMPOSE) {
                     const float dm = fmaxf(dmin, 0.f);
                     const float wmax = fminf(1.f, expf(-dm * dm / (2.f * f.maxw * f.maxw)) * 1.001f);
                     const float delta = 1.7321f * 16.f * f.dmax * wmax * 1.001f + 1e-6f;
-                    if (box_unreachable(a, x0 + sb * 8, 8, y0, zt, delta)) continue;
+                    const int bt = box_test(a, x0 + sb * 8, 8, y0, zt, delta);
+                    if (bt & BOX_UNREACHABLE) continue;
+                    if (bt & BOX_SATURATED) {
+                        sat_mask |= 1 << sb;
+                        continue;
+                    }
                 }
                 near_mask |= 1 << sb;
                 if (a.knn_pool && !a.built[brick0 + sb]) need_fill = 1;
+            } else if (tt & BOX_SATURATED) {
+                sat_mask |= 1 << sb;  // un-warped brick of a saturated tile
+            } else if (!rigid_skip && (box_test(a, x0 + sb * 8, 8, y0, zt, 0.f) & BOX_SATURATED)) {
+                sat_mask |= 1 << sb;  // un-warped brick in saturated free space
             }
         }
     }
-    a.tile_flags[tile] = (unsigned char) (near_mask | (rigid_skip ? 16 : 0));
-    if (near_mask || !rigid_skip) a.work_tiles[atomicAdd(&a.work_count[0], 1)] = tile;  // (work_count[0] is copied to stats[2] by the host entry)
+    a.tile_flags[tile] = (unsigned short) (near_mask | (rigid_skip ? 16 : 0) | (sat_mask << 8));
+    if (near_mask || sat_mask || !rigid_skip) a.work_tiles[atomicAdd(&a.work_count[0], 1)] = tile;  // (work_count[0] is copied to stats[2] by the host entry)
     if (need_fill) a.fill_tiles[atomicAdd(&a.work_count[1], 1)] = tile;
 }
 
-// max ray length per 16x16-pixel tile of the dists image (for the hierarchical cull of integrate_kernel)
+// max and min ray length per 16x16-pixel tile of the dists image (for the hierarchical cull / the saturation test)
 __global__ void __launch_bounds__(DT * DT) depth_tiles_kernel(const uint16_t* __restrict__ dists, size_t pitch, int rows, int cols,
-                                                              float* __restrict__ out, int dtx) {
-    __shared__ float sh[DT * DT / 32];
+                                                              float2* __restrict__ out, int dtx) {
+    __shared__ float sh[2][DT * DT / 32];
     const int x = blockIdx.x * DT + (threadIdx.x % DT), y = blockIdx.y * DT + (threadIdx.x / DT);
-    float d = 0.f;
-    if (x < cols && y < rows)
+    float d = 0.f, dn = INFINITY;  // pixels beyond the image border do not lower the minimum
+    if (x < cols && y < rows) {
         d = __half2float(__ushort_as_half(*reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(dists) + (size_t) y * pitch + 2 * (size_t) x)));
-    if (!(d == d)) d = INFINITY;  // NaN depth: never cull
+        dn = d;
+    }
+    if (!(d == d)) {  // NaN depth: never cull, never saturate
+        d = INFINITY;
+        dn = 0.f;
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = d;
+    for (int o = 16; o > 0; o >>= 1) {
+        d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+        dn = fminf(dn, __shfl_xor_sync(0xffffffffu, dn, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = d;
+        sh[1][threadIdx.x >> 5] = dn;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float m = 0.f;
-        for (int i = 0; i < DT * DT / 32; ++i) m = fmaxf(m, sh[i]);
-        out[blockIdx.y * dtx + blockIdx.x] = m;
+        float m = 0.f, mn = INFINITY;
+        for (int i = 0; i < DT * DT / 32; ++i) {
+            m = fmaxf(m, sh[0][i]);
+            mn = fminf(mn, sh[1][i]);
+        }
+        out[blockIdx.y * dtx + blockIdx.x] = make_float2(m, mn);
     }
 }
 
@@ -738,8 +879,8 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
     a.dty = div_up(rows, DT);
     a.ntiles = (int) nblocks;
     auto up = [](size_t b) { return (b + 255) / 256 * 256; };
-    const size_t o_flags = up((size_t) a.dtx * a.dty * sizeof(float));
-    const size_t o_count = o_flags + up((size_t) nblocks);
+    const size_t o_flags = up((size_t) a.dtx * a.dty * sizeof(float2));
+    const size_t o_count = o_flags + up((size_t) nblocks * sizeof(unsigned short));
     const size_t o_work = o_count + 256;
     const size_t o_fill = o_work + up((size_t) nblocks * sizeof(int));
     const size_t total = o_fill + up((size_t) nblocks * sizeof(int));
@@ -751,14 +892,14 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
         DFU_CUDA_OK(cudaMallocFromPoolAsync((void**) &tiles, total, pool, st));
     else
         DFU_CUDA_OK(cudaMallocAsync((void**) &tiles, total, st));
-    a.dmax_tiles = reinterpret_cast<float*>(tiles);
-    a.tile_flags = reinterpret_cast<unsigned char*>(tiles + o_flags);
+    a.dmax_tiles = reinterpret_cast<float2*>(tiles);
+    a.tile_flags = reinterpret_cast<unsigned short*>(tiles + o_flags);
     a.work_count = reinterpret_cast<int*>(tiles + o_count);
     a.work_tiles = reinterpret_cast<int*>(tiles + o_work);
     a.fill_tiles = reinterpret_cast<int*>(tiles + o_fill);
-    DFU_CUDA_OK(cudaMemsetAsync(a.work_count, 0, 4 * sizeof(int), st));
+    DFU_CUDA_OK(cudaMemsetAsync(a.work_count, 0, 8 * sizeof(int), st));
     a.stats = integrate_stats(device);
-    depth_tiles_kernel<<<dim3(a.dtx, a.dty), DT * DT, 0, st>>>(dists, pitch, rows, cols, reinterpret_cast<float*>(tiles), a.dtx);
+    depth_tiles_kernel<<<dim3(a.dtx, a.dty), DT * DT, 0, st>>>(dists, pitch, rows, cols, reinterpret_cast<float2*>(tiles), a.dtx);
     DFU_LAUNCH_OK();
     tile_classify_kernel<<<div_up(nblocks, 128), 128, 0, st>>>(a);
     DFU_LAUNCH_OK();

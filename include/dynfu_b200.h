@@ -159,7 +159,7 @@ int dfu_tsdf_integrate(void* volume, const int dims_host[3], const float voxel_s
                        const uint16_t* dists, size_t dists_pitch_bytes, int rows, int cols, dfu_warpfield* wf,
                        int blend_mode, int z0, int z1, dfu_stream stream);
 /* Instrumentation (no reference counterpart): counters of the LAST dfu_tsdf_integrate call on the current device, read back
- * synchronously: [0] voxels updated (tsdf_volume.cu:83-90 executed), [1] 16-byte quads read + written, [2] reserved,
+ * synchronously: [0] voxels updated (tsdf_volume.cu:83-90 executed), [1] 16-byte quads read + written, [2] voxels among [0] updated through the saturated-free-space path (tsdf == 1 proven per brick),
  * [3] 8^3 bricks that ran the per-voxel warp.  The algorithmic TSDF traffic of the call is 8 B x stats[0]. */
 int dfu_tsdf_integrate_stats(unsigned long long stats_host[4], dfu_stream stream);
 

@@ -853,3 +853,41 @@ def test_solver_repeated_solves_reuse_the_exchange_buffers(dfu, oracle, monkeypa
             assert np.max(np.abs(t - t_o)) <= 1e-4 * np.abs(t_o).max()
         else:
             assert st == first[0] and np.array_equal(t, first[1]), "solve %d differs from the first" % rep
+
+
+@pytest.mark.parametrize("warped", [False, True])
+def test_tsdf_dense_depth_saturated_free_space(dfu, oracle, warped):
+    """a depth image with a value at every pixel (sphere in front of a wall): most updated voxels are free space with
+    tsdf == 1, which the integrator proves per brick and updates without projecting (and without storing once the voxel
+    holds (1.0, max_weight)).  Packed voxels bit for bit against the oracle over five frames with max_weight = 3, and the
+    kernel's count of updated voxels equals the oracle's."""
+    import ctypes as C
+
+    from dynfu_b200._lib import lib
+
+    dim = 128
+    depth = synth.with_wall(synth.sphere_depth())
+    dists_np = oracle.compute_dists(depth, synth.INTR)
+    vs = synth.voxel_size(dim)
+    vol = dfu.TsdfVolume((dim, dim, dim))
+    vol.setTruncDist(synth.TRUNC)
+    vol.setMaxWeight(3)
+    pose = np.eye(4)
+    pose[:3, 3] = synth.VOLUME_T
+    vol.setPose(pose)
+    nodes, wf = None, None
+    if warped:
+        pos, dq, dg_w, _ = synth.sphere_nodes(1024, 0.025)
+        nodes = (pos, dq, dg_w)
+        wf = make_wf(dfu, pos, dq, dg_w, 0.025)
+    ref = np.zeros((dim,) * 3, np.uint32)
+    d = dev(dists_np.view(np.int16), torch.int16)
+    for frame in range(5):
+        touched = oracle.tsdf_integrate(ref, vs, vol.getTruncDist(), 3, synth.VOL2CAM, synth.INTR, dists_np, nodes=nodes)
+        vol.integrate(d, np.eye(4), synth.INTR, wf)
+        got = vol.data.cpu().numpy().view(np.uint32)
+        assert _mismatch(got, ref) == 0, "frame %d: %d voxels differ" % (frame, _mismatch(got, ref))
+        st = (C.c_ulonglong * 4)()
+        assert lib.dfu_tsdf_integrate_stats(st, None) == 0
+        assert int(st[0]) == touched, (frame, int(st[0]), touched)
+    assert touched > 0.2 * dim ** 3 and (ref >> 16).max() == 3
