@@ -67,6 +67,7 @@ _SIGS = {
     "dfu_tsdf_clear": ([_vp, C.POINTER(_i), _i, _i, _vp], _i),
     "dfu_tsdf_integrate": ([_vp, C.POINTER(_i), C.POINTER(_f), _f, _i, C.POINTER(_f), C.POINTER(_f), _vp, _sz, _i, _i,
                             _vp, _i, _i, _i, _vp], _i),
+    "dfu_marching_cubes": ([_vp, C.POINTER(_i), C.POINTER(_f), _vp, _vp, C.c_long, _vp, _vp], _i),
     "dfu_tsdf_integrate_stats": ([C.POINTER(C.c_ulonglong), _vp], _i),
     "dfu_solver_create": ([C.POINTER(_vp), _vp, C.POINTER(SolverParams)], _i),
     "dfu_solver_destroy": ([_vp], _i),

@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdynfu_b200.so")
-SOURCES = ["warpfield.cu", "tsdf.cu", "solver.cu", "comm.cu", "frontend.cu", "update.cu", "raycast.cu", "microbench.cu"]
+SOURCES = ["warpfield.cu", "tsdf.cu", "solver.cu", "comm.cu", "frontend.cu", "update.cu", "raycast.cu", "microbench.cu", "marching_cubes.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
@@ -28,7 +28,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inc"))]
     headers.append(os.path.join(HERE, "..", "include", "dynfu_b200.h"))
     headers.append(os.path.abspath(__file__))
     objs = []

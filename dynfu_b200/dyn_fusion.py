@@ -159,6 +159,31 @@ class DynFusion:
         self.frame_counter += 1
         return True
 
+    # DynFusion::operator() EXACTLY as the reference runs it (src/dynfu/dyn_fusion.cpp:48-145), for parity runs: the surface
+    # points are the marching-cubes vertices of the volume (:74-88, :120-134; "normals" = the positions, FIXME :80), frame 0
+    # seeds a node at every 128th vertex (:147-168), every later frame CLEARS the volume and integrates the live depth rigidly
+    # (:113-116 -- the reference never fuses non-rigidly), pairs live and warped canonical vertices by 1-NN (:212-242),
+    # solves, and grows the warp field (:142).  processFrame() above is the pipeline the north star asks for instead
+    # (warped fusion into the canonical volume, live points straight from the depth image).
+    def processFrameReference(self, depth_host):
+        kp = self.params.kinfuParams
+        depth = self.uploadDepth(depth_host)
+        compute_dists(depth, kp.intr, out=self._dists)  # :55
+        if self.frame_counter == 0 or self.warpfield is None:
+            self.volume.integrate(self._dists, self.camera_pose, kp.intr)  # :70
+            verts = self.volume.marchingCubes()[:, :3].contiguous()  # :74-85
+            self.init(verts, verts)  # :88-95
+            self.frame_counter += 1
+            return False
+        self.volume.clear()  # :114
+        self.volume.integrate(self._dists, self.camera_pose, kp.intr)  # :115
+        live = self.volume.marchingCubes()[:, :3].contiguous()  # :120-134
+        self.liveVertices, self.liveNormals = live, live
+        self.warpCanonicalToLiveOpt(live, paired=False)  # :140
+        self.warpfield.update(self.canonicalWarpedToLive, self.params.blend_mode)  # :142
+        self.frame_counter += 1
+        return True
+
     # ---- one hot-path frame on device-resident inputs, integration overlapped with the next frame's point pipeline --
     # The warped integration of frame i needs only the node transforms solve(i) wrote; the point pipeline of frame i+1
     # (compute_dists, warp of the canonical frame, 8-NN graph, matrix pattern: ~0.1 ms of small kernels that leave most

@@ -88,6 +88,24 @@ class TsdfVolume:
                                      warpfield.handle if warpfield is not None else None, blend_mode, self.z0, self.z1,
                                      stream_ptr()))
 
+    # kfusion::cuda::MarchingCubes::run (src/kfusion/marching_cubes.cpp:20-63) on this volume
+    def marchingCubes(self, capacity=None, with_cube_ids=False):
+        """triangle vertices of the zero level set, float32 [n, 4] = (x, y, z, 1) in volume-local metres (3 per triangle), in
+        the library's fixed order; n is read back from the device (one synchronisation, like the reference's download)."""
+        if self.z0 != 0 or self.z1 != self.dims[2]:
+            raise _lib.DfuError(1, "marching cubes needs the whole volume, this object holds a z-slab")
+        cap = int(capacity) if capacity is not None else 6 * 1000 * 1000  # DEFAULT_TRIANGLES_BUFFER_SIZE (marching_cubes.hpp:22)
+        verts = torch.empty((cap, 4), dtype=torch.float32, device=self.device)
+        ids = torch.empty(cap, dtype=torch.int32, device=self.device) if with_cube_ids else None
+        n = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(lib.dfu_marching_cubes(self._base_ptr(), iarr(self.dims), farr(self.size), dptr(verts), dptr(ids), cap, dptr(n),
+                                     stream_ptr()))
+        total = int(n.item())
+        m = min(total, cap)
+        if with_cube_ids:
+            return verts[:m], ids[:m], total
+        return verts[:m]
+
     # TsdfVolume::raycast (tsdf_volume.cpp:95-129): points or depth + normals of the fused model seen from camera_pose
     raycast_step_factor = 0.75    # tsdf_volume.cpp:26
     gradient_delta_factor = 0.75  # tsdf_volume.cpp:25 (KinFuParams sets 0.5, kinfu.cpp:38)

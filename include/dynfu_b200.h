@@ -158,6 +158,18 @@ int dfu_tsdf_integrate(void* volume, const int dims_host[3], const float voxel_s
                        int max_weight, const float vol2cam_host[12], const float intr_host[4],
                        const uint16_t* dists, size_t dists_pitch_bytes, int rows, int cols, dfu_warpfield* wf,
                        int blend_mode, int z0, int z1, dfu_stream stream);
+/* kfusion::cuda::MarchingCubes::run (include/kfusion/cuda/marching_cubes.hpp:35-36, src/kfusion/marching_cubes.cpp:20-63 ->
+ * device::getOccupiedVoxels / computeOffsetsAndTotalVertices / generateTriangles, src/kfusion/cuda/marching_cubes.cu:144-296):
+ * triangle vertices of the zero level set of the volume as (x, y, z, 1) in volume-local metres, three consecutive vertices
+ * per triangle -- what DynFusion::operator() downloads as the canonical / live surface points (dyn_fusion.cpp:74-88,120-134).
+ * Any dims with dims[0] % 4 == 0 (the reference hard-codes 128^3); volume_size_host = the volume's edge lengths in metres
+ * (cells are volume_size / dims, vertices carry the reference's half-cell shift); fixed output order (tiles of 32 x 8 x 8
+ * cubes ascending, cubes ascending inside a tile) instead of the reference's atomic order.  Writes at most `capacity`
+ * vertices (and, when cube_ids is non-NULL, the linear index x + dx (y + dy z) of each vertex's cube); *n_vertices_dev
+ * (device) receives the number of vertices that exist, which may exceed capacity.  Asynchronous. */
+int dfu_marching_cubes(const void* volume, const int dims[3], const float volume_size_host[3], void* vertices_xyz1,
+                       int32_t* cube_ids, long capacity, int* n_vertices_dev, dfu_stream stream);
+
 /* Instrumentation (no reference counterpart): counters of the LAST dfu_tsdf_integrate call on the current device, read back
  * synchronously: [0] voxels updated (tsdf_volume.cu:83-90 executed), [1] 16-byte quads read + written, [2] voxels among [0] updated through the saturated-free-space path (tsdf == 1 proven per brick),
  * [3] 8^3 bricks that ran the per-voxel warp.  The algorithmic TSDF traffic of the call is 8 B x stats[0]. */

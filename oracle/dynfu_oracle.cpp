@@ -1551,6 +1551,65 @@ double orc_energy_p2plane(const float* pos, const float* dg_w, int N, const floa
     return p2p_energy(S);
 }
 
+/* ---- marching cubes (src/kfusion/cuda/marching_cubes.cu:33-75 cube index, :77-140 occupied voxels, :181-199 cell
+ * centres + edge interpolation, :201-260 triangle emission; host flow src/kfusion/marching_cubes.cpp:20-63).
+ * Differences from the reference, all deliberate and stated in DESIGN.md: any volume size (the reference hard-codes 128^3,
+ * internal.hpp:74, marching_cubes.cu:151-152,283-285); cubes are emitted in a FIXED order -- tiles of 32 x 8 x 8 cubes in
+ * ascending (z, y, x) tile order, cubes in ascending (z, y, x) order inside a tile (the reference's order is decided by
+ * atomics, :108); IEEE arithmetic without contraction.  tri: the 256 x 16 triangle table.  Returns the number of vertices that
+ * exist; writes at most `capacity` of them as (x, y, z, 1) and, when cube_ids is non-NULL, the linear cube index of each. */
+long orc_marching_cubes(const uint32_t* vol, const int dims[3], const float volume_size[3], const signed char* tri, float* verts4,
+                        int32_t* cube_ids, long capacity) {
+    const int dx = dims[0], dy = dims[1], dz = dims[2];
+    const float cell[3] = {volume_size[0] / (float) dx, volume_size[1] / (float) dy, volume_size[2] / (float) dz};
+    auto vox = [&](int x, int y, int z, float& f, int& w) {
+        const uint32_t v = vol[(size_t) x + (size_t) dx * ((size_t) y + (size_t) dy * (size_t) z)];
+        f = half2float((uint16_t) (v & 0xffffu));
+        w = (int) (v >> 16);
+    };
+    static const int CX[8] = {0, 1, 1, 0, 0, 1, 1, 0}, CY[8] = {0, 0, 1, 1, 0, 0, 1, 1}, CZ[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    static const int EA[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, EB[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+    long n = 0;
+    const int ntx = (dx - 1 + 31) / 32, nty = (dy - 1 + 7) / 8, ntz = (dz - 1 + 7) / 8;
+    for (int tz = 0; tz < ntz; ++tz)
+        for (int ty = 0; ty < nty; ++ty)
+            for (int tx = 0; tx < ntx; ++tx)
+                for (int z = tz * 8; z < std::min(tz * 8 + 8, dz - 1); ++z)
+                    for (int y = ty * 8; y < std::min(ty * 8 + 8, dy - 1); ++y)
+                        for (int x = tx * 32; x < std::min(tx * 32 + 32, dx - 1); ++x) {
+                            float f[8];
+                            int cubeindex = 0;
+                            bool ok = true;
+                            for (int c = 0; c < 8 && ok; ++c) {  /* computeCubeIndex: 0 at the first corner without weight */
+                                int w;
+                                vox(x + CX[c], y + CY[c], z + CZ[c], f[c], w);
+                                if (w == 0) ok = false;
+                            }
+                            if (!ok) continue;
+                            for (int c = 0; c < 8; ++c) cubeindex += (f[c] < 0.f) ? (1 << c) : 0;
+                            const signed char* row = tri + 16 * cubeindex;
+                            if (row[0] < 0) continue;
+                            float p[8][3];
+                            for (int c = 0; c < 8; ++c) { /* getNodeCoo: (i + 0.5) * cell */
+                                p[c][0] = ((float) (x + CX[c]) + 0.5f) * cell[0];
+                                p[c][1] = ((float) (y + CY[c]) + 0.5f) * cell[1];
+                                p[c][2] = ((float) (z + CZ[c]) + 0.5f) * cell[2];
+                            }
+                            for (int i = 0; i < 16 && row[i] >= 0; ++i) {
+                                const int e = row[i], a = EA[e], b = EB[e];
+                                /* vertex_interp: t = (iso - f0) / (f1 - f0 + 1e-15f), p0 + t (p1 - p0) */
+                                const float t = (0.f - f[a]) / ((f[b] - f[a]) + 1e-15f);
+                                if (n < capacity) {
+                                    for (int k = 0; k < 3; ++k) verts4[4 * n + k] = p[a][k] + t * (p[b][k] - p[a][k]);
+                                    verts4[4 * n + 3] = 1.f;
+                                    if (cube_ids) cube_ids[n] = (int32_t) ((size_t) x + (size_t) dx * ((size_t) y + (size_t) dy * (size_t) z));
+                                }
+                                ++n;
+                            }
+                        }
+    return n;
+}
+
 /* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm of the bench asks for all host threads explicitly */
 void orc_set_num_threads(int n) {
 #ifdef _OPENMP

@@ -156,6 +156,10 @@ int orc_solve_p2plane(const float* pos, float* dq_inout, const float* dg_w, int 
 double orc_energy_p2plane(const float* pos, const float* dg_w, int N, const float* canon, const float* live,
                           const float* live_n, long P, const orc_solver_params* prm, const double* X, const double* X_tukey);
 
+/* ---- marching cubes (src/kfusion/cuda/marching_cubes.cu:33-260) : vertices of the zero level set, fixed tile order ---- */
+long orc_marching_cubes(const uint32_t* vol, const int dims[3], const float volume_size[3], const signed char* tri, float* verts4,
+                        int32_t* cube_ids, long capacity);
+
 void orc_set_num_threads(int n);
 int orc_num_threads(void);
 

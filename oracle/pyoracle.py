@@ -115,6 +115,8 @@ class Oracle:
         L.orc_solve_p2plane.restype = C.c_int
         L.orc_energy_p2plane.argtypes = [_fp, _fp, C.c_int, _fp, _fp, _fp, C.c_long, C.POINTER(SolverParams), _dp, _dp]
         L.orc_energy_p2plane.restype = C.c_double
+        L.orc_marching_cubes.argtypes = [_u32p, _ip, _fp, C.POINTER(C.c_int8), _fp, _ip, C.c_long]
+        L.orc_marching_cubes.restype = C.c_long
         L.orc_float2half.argtypes = [C.c_float]
         L.orc_float2half.restype = C.c_uint16
         L.orc_half2float.argtypes = [C.c_uint16]
@@ -344,6 +346,19 @@ class Oracle:
                              _f(_f32(rinv)), _f(_f32(intr)), rows, cols, float(step_factor), float(grad_factor), _f(pts), _f(nrm),
                              dep.ctypes.data_as(_u16p) if dep is not None else None)
         return (pts, nrm, dep) if want_depth else (pts, nrm)
+
+    def marching_cubes(self, vol, volume_size, tri_table, capacity=None):
+        """MarchingCubes::run: (vertices [n, 4], cube ids [n]) of the zero level set of vol (uint32 [z][y][x])."""
+        vol = np.ascontiguousarray(vol, np.uint32)
+        dims = np.array(vol.shape[::-1], np.int32)
+        tri = np.ascontiguousarray(tri_table, np.int8).reshape(256, 16)
+        cap = int(capacity) if capacity is not None else 15 * int(vol.size // 8 + 1024)
+        verts = np.empty((cap, 4), np.float32)
+        ids = np.empty(cap, np.int32)
+        n = self.lib.orc_marching_cubes(vol.ctypes.data_as(_u32p), dims.ctypes.data_as(_ip), _f(_f32(volume_size)),
+                                        tri.ctypes.data_as(C.POINTER(C.c_int8)), _f(verts), ids.ctypes.data_as(_ip), cap)
+        m = min(int(n), cap)
+        return verts[:m].copy(), ids[:m].copy(), int(n)
 
     def float2half(self, f):
         return self.lib.orc_float2half(f)
