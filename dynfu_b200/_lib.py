@@ -124,10 +124,12 @@ def iarr(vals):
     return (C.c_int * len(vals))(*[int(v) for v in vals])
 
 
-def stream_ptr(stream=None):
+def stream_ptr(stream=None, device=None):
+    """cudaStream_t of `stream`, or of torch's current stream ON `device` (the device that owns the object the call is made
+    for -- not the caller's current device)."""
     import torch
 
-    s = torch.cuda.current_stream() if stream is None else stream
+    s = torch.cuda.current_stream(device) if stream is None else stream
     return C.c_void_p(s.cuda_stream)
 
 

@@ -33,6 +33,40 @@ extern unsigned long long g_dfu_launches;
         DFU_CUDA_OK(cudaGetLastError());    \
     } while (0)
 
+// ---- device selection: every entry point runs on the device that owns its handle / buffers, whatever the caller's current
+// device is, and puts the caller's device back on every return path
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+// also drops any stale, non-sticky error another library left in the runtime, so that the launch checks
+// below report only this library's own failures
+#define DFU_GUARD(dev)                                                     \
+    DeviceGuard _guard(dev);                                               \
+    if (!_guard.ok) {                                                      \
+        dfu_set_error("%s: cannot select CUDA device %d", __func__, dev);  \
+        return DFU_ERR_CUDA;                                               \
+    }                                                                      \
+    (void) cudaGetLastError();
+// device that owns a device pointer (the current device when the runtime cannot tell)
+static inline int dfu_device_of(const void* p) {
+    cudaPointerAttributes at;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (p && cudaPointerGetAttributes(&at, p) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged))
+        return at.device;
+    (void) cudaGetLastError();
+    return cur;
+}
+
 static inline cudaStream_t as_stream(dfu_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int div_up(long a, long b) { return (int) ((a + b - 1) / b); }
 cudaMemPool_t scratch_pool(int device);  // tsdf.cu: private stream-ordered pool for per-call scratch

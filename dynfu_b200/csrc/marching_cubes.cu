@@ -272,7 +272,7 @@ extern "C" int dfu_marching_cubes(const void* volume, const int dims[3], const f
     DFU_REQUIRE(dims[0] > 0 && dims[0] % 4 == 0 && dims[1] > 0 && dims[2] > 0, DFU_ERR_INVALID, "dims.x must be a positive multiple of 4");
     DFU_REQUIRE(((uintptr_t) volume & 15) == 0, DFU_ERR_INVALID, "volume must be 16-byte aligned");
     DFU_REQUIRE(capacity >= 0, DFU_ERR_INVALID, "negative capacity");
-    (void) cudaGetLastError();
+    DFU_GUARD(dfu_device_of(volume));
     cudaStream_t st = as_stream(stream);
     int device = 0;
     DFU_CUDA_OK(cudaGetDevice(&device));

@@ -142,7 +142,7 @@ extern "C" int dfu_tsdf_raycast(const void* volume, const int dims_host[3], cons
     DFU_REQUIRE(points4 || depth, DFU_ERR_INVALID, "need a points image, a depth image, or both");
     DFU_REQUIRE(rows > 0 && cols > 0 && dims_host[0] > 1 && dims_host[1] > 1 && dims_host[2] > 1, DFU_ERR_INVALID, "bad size");
     DFU_REQUIRE(raycast_step_factor > 0.f && gradient_delta_factor > 0.f && trunc_dist > 0.f, DFU_ERR_INVALID, "bad step / delta / trunc");
-    (void) cudaGetLastError();
+    DFU_GUARD(dfu_device_of(volume));
     RayArgs a{};
     a.vol = static_cast<const uint32_t*>(volume);
     a.dx = dims_host[0]; a.dy = dims_host[1]; a.dz = dims_host[2];

@@ -681,10 +681,7 @@ int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* ca
     DFU_REQUIRE(wf->initialised, DFU_ERR_NOT_INIT, "warp field not initialised");
     DFU_REQUIRE(wf->N >= DFU_KNN, DFU_ERR_PRECONDITION, "the solver needs at least 8 nodes (reference UB, opt_solver.cpp:63-66)");
     DFU_REQUIRE((long) P * 8 < 0x7fffffffL, DFU_ERR_INVALID, "too many points");
-    int prev = 0;
-    cudaGetDevice(&prev);
-    if (prev != wf->device) DFU_CUDA_OK(cudaSetDevice(wf->device));
-    (void) cudaGetLastError();  // drop stale errors of other libraries
+    DFU_GUARD(wf->device);  // (restores the caller's device on every return path; drops stale errors of other libraries)
     cudaStream_t st = as_stream(stream);
     const int N = wf->N;
     if ((size_t) P > s->capP) {
@@ -760,24 +757,18 @@ int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* ca
     rc = build_pattern(s, st);
     if (rc != DFU_OK) return rc;
     s->problem_ready = true;
-    if (prev != wf->device) cudaSetDevice(prev);
     return DFU_OK;
 }
 
 int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream) {
     DFU_REQUIRE(s, DFU_ERR_INVALID, "NULL argument");
     DFU_REQUIRE(s->problem_ready, DFU_ERR_NOT_INIT, "initializeProblemInstance has not been called");
-    int prev = 0;
-    cudaGetDevice(&prev);
-    if (prev != s->wf->device) DFU_CUDA_OK(cudaSetDevice(s->wf->device));
-    (void) cudaGetLastError();
+    DFU_GUARD(s->wf->device);
     cudaStream_t st = as_stream(stream);
     // DFU_SOLVER_PATH=multi forces the one-kernel-per-phase path (used by the tests to cover both)
     const char* force = getenv("DFU_SOLVER_PATH");
     if (s->energy_mode == DFU_ENERGY_P2PLANE_SE3) {
-        int rc = solve_p2plane(s, st);
-        if (prev != s->wf->device) cudaSetDevice(prev);
-        return rc;
+        return solve_p2plane(s, st);
     }
     const bool multi = s->allreduce != nullptr || s->coop_blocks == 0 || (force && force[0] == 'm');
     if (!s->lists_sorted && (multi || !pattern_eligible(s)) && s->P > 0) {
@@ -794,9 +785,7 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream) {
     int rc = multi ? solve_multi_kernel(s, st) : solve_persistent(s, st);
     if (rc != DFU_OK) return rc;
     // write back ONCE: dg_se3 := DQ(0,0,0,t) * dg_se3 (opt_solver.cpp:270-285, node.cpp:19-23)
-    rc = dfu_warpfield_update_translations(s->wf, s->vec, stream);
-    if (prev != s->wf->device) cudaSetDevice(prev);
-    return rc;
+    return dfu_warpfield_update_translations(s->wf, s->vec, stream);
 }
 
 // CombinedSolver::updateHuberWeights (opt_solver.cpp:241-268): for node i the loop over its 8 neighbours overwrites

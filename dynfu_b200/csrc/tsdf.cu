@@ -795,6 +795,7 @@ int dfu_compute_dists(const uint16_t* depth, size_t depth_pitch_bytes, uint16_t*
                       int rows, int cols, const float intr_host[4], dfu_stream stream) {
     DFU_REQUIRE(depth && dists && intr_host, DFU_ERR_INVALID, "NULL argument");
     DFU_REQUIRE(rows > 0 && cols > 0, DFU_ERR_INVALID, "bad image size");
+    DFU_GUARD(dfu_device_of(depth));
     dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8));
     compute_dists_kernel<<<grid, block, 0, as_stream(stream)>>>(depth, depth_pitch_bytes, dists, dists_pitch_bytes, rows,
                                                                 cols, 1.f / intr_host[0], 1.f / intr_host[1],
@@ -811,6 +812,7 @@ float dfu_tsdf_trunc_dist(float requested, const float vs[3]) {
 int dfu_tsdf_clear(void* volume, const int dims[3], int z0, int z1, dfu_stream stream) {
     DFU_REQUIRE(volume && dims, DFU_ERR_INVALID, "NULL argument");
     DFU_REQUIRE(0 <= z0 && z0 <= z1 && z1 <= dims[2], DFU_ERR_INVALID, "bad z range");
+    DFU_GUARD(dfu_device_of(volume));
     const size_t plane = (size_t) dims[0] * dims[1];
     // pack_tsdf(0.f, 0) == 0x00000000 (tsdf_volume.cu:20)
     DFU_CUDA_OK(cudaMemsetAsync(reinterpret_cast<uint32_t*>(volume) + plane * (size_t) z0, 0,
@@ -829,7 +831,7 @@ int dfu_tsdf_integrate(void* volume, const int dims[3], const float vs[3], float
     DFU_REQUIRE(((uintptr_t) volume & 15) == 0, DFU_ERR_INVALID, "volume must be 16-byte aligned");
     DFU_REQUIRE(blend_mode == DFU_BLEND_REF_COMPOSE || blend_mode == DFU_BLEND_DQB_SUM, DFU_ERR_INVALID, "bad blend_mode");
     if (z0 == z1) return DFU_OK;
-    (void) cudaGetLastError();  // drop stale errors of other libraries
+    DFU_GUARD(wf ? wf->device : dfu_device_of(volume));  // (also drops stale errors of other libraries)
     cudaStream_t st = as_stream(stream);
     IntegrateArgs a{};
     a.vol = reinterpret_cast<uint32_t*>(volume);

@@ -472,10 +472,7 @@ int dfu_warpfield_update(dfu_warpfield* wf, const float* verts_xyz, int P, int b
     if (num_unsupported_host) *num_unsupported_host = 0;
     if (num_new_host) *num_new_host = 0;
     if (P == 0) return DFU_OK;
-    int prev = 0;
-    cudaGetDevice(&prev);
-    if (prev != wf->device) DFU_CUDA_OK(cudaSetDevice(wf->device));
-    (void) cudaGetLastError();
+    DFU_GUARD(wf->device);
     cudaStream_t st = as_stream(stream);
     const int sms = device_sms(wf->device);
     const int chunks = div_up(P, 32);
@@ -548,7 +545,6 @@ int dfu_warpfield_update(dfu_warpfield* wf, const float* verts_xyz, int P, int b
         if (rc == DFU_OK && num_new_host) *num_new_host = M;
     }
     cudaFreeAsync(mem, st);
-    if (prev != wf->device) cudaSetDevice(prev);
     if (rc == DFU_ERR_CUDA) dfu_set_error("dfu_warpfield_update: CUDA error %s", cudaGetErrorString(cudaGetLastError()));
     return rc;
 }

@@ -37,27 +37,6 @@ extern "C" int dfu_device_check(int device) {
 
 namespace {
 
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
-        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-    }
-    ~DeviceGuard() {
-        int cur = -1;
-        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-    }
-};
-// also drops any stale, non-sticky error another library left in the runtime, so that the launch checks
-// below report only this library's own failures
-#define DFU_GUARD(dev)                                                     \
-    DeviceGuard _guard(dev);                                               \
-    if (!_guard.ok) {                                                      \
-        dfu_set_error("%s: cannot select CUDA device %d", __func__, dev);  \
-        return DFU_ERR_CUDA;                                               \
-    }                                                                      \
-    (void) cudaGetLastError();
 
 // ---- node packing ------------------------------------------------------------------------------
 __global__ void pack_nodes_kernel(const float* __restrict__ pos, const float* __restrict__ dq,

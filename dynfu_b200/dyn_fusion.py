@@ -77,11 +77,25 @@ class DynFusion:
         self.allreduce = None  # python all-reduce hook (tests)
         self.comm = None       # dynfu_b200.dist.Communicator: NCCL issued from C++
 
+    # The canonical frame's nearest nodes and weights are cached on the device, keyed on (pointer, count, version): assigning a
+    # new tensor always bumps the version, so a tensor the allocator happens to place at the old address cannot alias the
+    # cache.  (Writing INTO the tensor in place is the one thing the key cannot see: call touchCanonical() after doing so.)
+    @property
+    def canonicalVertices(self):
+        return self._canonicalVertices
+
+    @canonicalVertices.setter
+    def canonicalVertices(self, value):
+        self._canonicalVertices = value
+        self._canon_version = getattr(self, "_canon_version", 0) + 1
+
+    def touchCanonical(self):
+        self._canon_version += 1
+
     # DynFusion::init (src/dynfu/dyn_fusion.cpp:147-168); explicit nodes may be given instead of the 128-stride pick
     def init(self, canonicalVertices, canonicalNormals=None, nodes=None):
         cv = torch.as_tensor(canonicalVertices, dtype=torch.float32).to(self.device).reshape(-1, 3).contiguous()
-        self.canonicalVertices = cv
-        self._canon_version = getattr(self, "_canon_version", 0) + 1  # the cached warp below is keyed on it
+        self.canonicalVertices = cv  # (the setter bumps the version the cached warp below is keyed on)
         self.canonicalNormals = None if canonicalNormals is None else torch.as_tensor(
             canonicalNormals, dtype=torch.float32).to(self.device).reshape(-1, 3).contiguous()
         if nodes is None:
@@ -288,7 +302,7 @@ class DynFusion:
         cur.wait_event(st["down"][s])  # the result buffers of this slot have been read back
         self.frameDevice(st["depth"][s], st["live"][s], overlap=self.stream_overlap)
         self.frame_counter -= 1  # (counted below)
-        check(lib.dfu_warpfield_get_nodes(self.warpfield.handle, None, dptr(st["dq_dev"][s]), None, stream_ptr()))
+        check(lib.dfu_warpfield_get_nodes(self.warpfield.handle, None, dptr(st["dq_dev"][s]), None, stream_ptr(device=self.device)))
         self.solver.getStatsAsync(st["stats_dev"][s])
         st["free"][s].record(cur)
         st["done"][s].record(cur)

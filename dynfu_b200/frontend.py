@@ -25,7 +25,7 @@ def compute_points_normals(depth, intr, points=None, normals=None):
     if normals is None:
         normals = torch.empty((rows, cols, 4), dtype=torch.float32, device=depth.device)
     check(lib.dfu_compute_points_normals(dptr2d(depth), depth.stride(0) * 2, rows, cols, farr(intr), dptr2d(points),
-                                         points.stride(0) * 4, dptr2d(normals), normals.stride(0) * 4, stream_ptr()))
+                                         points.stride(0) * 4, dptr2d(normals), normals.stride(0) * 4, stream_ptr(device=depth.device)))
     return points, normals
 
 
@@ -46,7 +46,7 @@ def compact_points(points, normals=None, xform=None, capacity=None, sync=True):
         xf = farr(list(m[:3, :3].reshape(-1)) + list(m[:3, 3]))
     check(lib.dfu_compact_points(dptr2d(points), points.stride(0) * 4, dptr2d(normals) if normals is not None else None,
                                  normals.stride(0) * 4 if normals is not None else 0, rows, cols, xf, dptr(out_v),
-                                 dptr(out_n) if out_n is not None else None, cap, dptr(count), stream_ptr()))
+                                 dptr(out_n) if out_n is not None else None, cap, dptr(count), stream_ptr(device=points.device)))
     if not sync:
         return out_v, out_n, count
     n = min(int(count.item()), cap)
@@ -58,7 +58,7 @@ def voxel_grid_filter(points, leaf=0.05):
     p = points.reshape(-1, 3).contiguous()
     out = torch.empty_like(p)
     m = C.c_int()
-    check(lib.dfu_voxel_grid_filter(dptr(p), p.shape[0], float(leaf), dptr(out), C.byref(m), stream_ptr()))
+    check(lib.dfu_voxel_grid_filter(dptr(p), p.shape[0], float(leaf), dptr(out), C.byref(m), stream_ptr(device=p.device)))
     return out[:m.value]
 
 
@@ -79,7 +79,7 @@ class PointIndex:
     def build(self, pts):
         pts = pts.reshape(-1, 3).contiguous()
         self._pts = pts
-        check(lib.dfu_pointindex_build(self._h, dptr(pts), pts.shape[0], stream_ptr()))
+        check(lib.dfu_pointindex_build(self._h, dptr(pts), pts.shape[0], stream_ptr(device=self.device)))
         return self
 
     def nearest(self, queries, return_dist=False):
@@ -87,7 +87,7 @@ class PointIndex:
         idx = torch.empty(q.shape[0], dtype=torch.int32, device=q.device)
         d2 = torch.empty(q.shape[0], dtype=torch.float32, device=q.device) if return_dist else None
         check(lib.dfu_pointindex_nearest(self._h, dptr(q), q.shape[0], dptr(idx), dptr(d2) if d2 is not None else None,
-                                         stream_ptr()))
+                                         stream_ptr(device=self.device)))
         return (idx, d2) if return_dist else idx
 
     def find_corresponding(self, canon_v, canon_n, live_v, return_index=False):
@@ -100,7 +100,7 @@ class PointIndex:
         self._pts = cv
         check(lib.dfu_find_corresponding(self._h, dptr(cv), dptr(cn) if cn is not None else None, cv.shape[0], dptr(lv),
                                          lv.shape[0], dptr(out_v), dptr(out_n) if out_n is not None else None,
-                                         dptr(idx) if idx is not None else None, stream_ptr()))
+                                         dptr(idx) if idx is not None else None, stream_ptr(device=self.device)))
         return (out_v, out_n, idx) if return_index else (out_v, out_n)
 
 

@@ -26,6 +26,7 @@ class CombinedSolver:
     # CombinedSolver::CombinedSolver (src/dynfu/utils/opt_solver.cpp:3-13)
     def __init__(self, warpfield, params, tukeyOffset, psi_data, lambda_, psi_reg):
         self.warpfield = warpfield  # shares the nodes, like the reference's by-value copy of shared_ptr<Node>s
+        self.device = warpfield.device
         self.params = params
         p = _lib.SolverParams(params.numIter, params.nonLinearIter, params.linearIter, tukeyOffset, psi_data, lambda_,
                               psi_reg, params.pcgTolerance, 1 if params.earlyOut else 0)
@@ -82,7 +83,7 @@ class CombinedSolver:
             if ln.shape != lv.shape:
                 raise _lib.DfuError(1, "live normals must pair up with the live vertices")
         self._keep = (cv, lv, ln)  # the point-to-plane mode reads them during solveAll
-        check(lib.dfu_solver_init_problem(self._h, dptr(cv), None, dptr(lv), dptr(ln), cv.shape[0], None, stream_ptr()))
+        check(lib.dfu_solver_init_problem(self._h, dptr(cv), None, dptr(lv), dptr(ln), cv.shape[0], None, stream_ptr(device=self.device)))
 
     # north-star extension (no reference implementation): point-to-plane data term with a rigid increment per node
     ENERGY_REF_TRANSLATION = 0
@@ -104,42 +105,42 @@ class CombinedSolver:
     def getIncrements(self):
         """ENERGY_P2PLANE_SE3: [N, 12] rigid increments (R row-major, t) of the last solve"""
         x = torch.empty((self.warpfield.numNodes(), 12), dtype=torch.float32, device=self.warpfield.device)
-        check(lib.dfu_solver_get_increments(self._h, dptr(x), stream_ptr()))
+        check(lib.dfu_solver_get_increments(self._h, dptr(x), stream_ptr(device=self.device)))
         return x
 
     # CombinedSolverBase::solveAll [Opt]
     def solveAll(self):
-        check(lib.dfu_solver_solve_all(self._h, stream_ptr()))
+        check(lib.dfu_solver_solve_all(self._h, stream_ptr(device=self.device)))
 
     # CombinedSolver::updateHuberWeights (src/dynfu/utils/opt_solver.cpp:241-268)
     def huberWeights(self):
         h = torch.empty((self.warpfield.numNodes(),), dtype=torch.float32, device=self.warpfield.device)
-        check(lib.dfu_solver_huber_weights(self._h, dptr(h), stream_ptr()))
+        check(lib.dfu_solver_huber_weights(self._h, dptr(h), stream_ptr(device=self.device)))
         return h
 
     # the tukey biweights (src/dynfu/utils/opt_solver.cpp:204-231) the last solve ended with
     def tukeyWeights(self):
         t = torch.empty((self._keep[0].shape[0],), dtype=torch.float32, device=self.warpfield.device)
-        check(lib.dfu_solver_tukey_weights(self._h, dptr(t), stream_ptr()))
+        check(lib.dfu_solver_tukey_weights(self._h, dptr(t), stream_ptr(device=self.device)))
         return t
 
     def getTranslations(self):
         n = self.warpfield.numNodes()
         t = torch.empty((n, 3), dtype=torch.float32, device=self.warpfield.device)
-        check(lib.dfu_solver_get_translations(self._h, dptr(t), stream_ptr()))
+        check(lib.dfu_solver_get_translations(self._h, dptr(t), stream_ptr(device=self.device)))
         return t
 
     def getStatsAsync(self, out=None):
         """the same four numbers as a float64 CUDA tensor [E0, E, pcg iterations, gn steps]: stream-ordered, no host sync"""
         if out is None:
             out = torch.empty(4, dtype=torch.float64, device=self.warpfield.device)
-        check(lib.dfu_solver_get_stats(self._h, dptr(out), stream_ptr()))
+        check(lib.dfu_solver_get_stats(self._h, dptr(out), stream_ptr(device=self.device)))
         return out
 
     def getStats(self):
         """{initial energy, final energy, PCG iterations, GN steps} of the last solveAll (synchronises)."""
         s = (C.c_double * 4)()
-        check(lib.dfu_solver_get_stats_host(self._h, s, stream_ptr()))
+        check(lib.dfu_solver_get_stats_host(self._h, s, stream_ptr(device=self.device)))
         return dict(initial_energy=s[0], final_energy=s[1], pcg_iterations=int(s[2]), gn_steps=int(s[3]))
 
 

@@ -13,7 +13,7 @@ def compute_dists(depth, intr, out=None):
     if out is None:
         out = torch.empty_like(depth)
     check(lib.dfu_compute_dists(dptr(depth), depth.stride(0) * 2, dptr(out), out.stride(0) * 2, rows, cols, farr(intr),
-                                stream_ptr()))
+                                stream_ptr(device=depth.device)))
     return out
 
 
@@ -75,7 +75,7 @@ class TsdfVolume:
 
     # TsdfVolume::clear (tsdf_volume.cpp:74-80)
     def clear(self):
-        check(lib.dfu_tsdf_clear(self._base_ptr(), iarr(self.dims), self.z0, self.z1, stream_ptr()))
+        check(lib.dfu_tsdf_clear(self._base_ptr(), iarr(self.dims), self.z0, self.z1, stream_ptr(device=self.device)))
 
     # TsdfVolume::integrate (tsdf_volume.cpp:82-93); warpfield=None is the reference's rigid integrator
     def integrate(self, dists, camera_pose, intr, warpfield=None, blend_mode=BLEND_REF_COMPOSE):
@@ -86,7 +86,7 @@ class TsdfVolume:
         check(lib.dfu_tsdf_integrate(self._base_ptr(), iarr(self.dims), farr(self.getVoxelSize()), self.trunc_dist,
                                      self.max_weight, farr(v2c), farr(intr), dptr(dists), dists.stride(0) * 2, rows, cols,
                                      warpfield.handle if warpfield is not None else None, blend_mode, self.z0, self.z1,
-                                     stream_ptr()))
+                                     stream_ptr(device=self.device)))
 
     # kfusion::cuda::MarchingCubes::run (src/kfusion/marching_cubes.cpp:20-63) on this volume
     def marchingCubes(self, capacity=None, with_cube_ids=False):
@@ -99,7 +99,7 @@ class TsdfVolume:
         ids = torch.empty(cap, dtype=torch.int32, device=self.device) if with_cube_ids else None
         n = torch.zeros(1, dtype=torch.int32, device=self.device)
         check(lib.dfu_marching_cubes(self._base_ptr(), iarr(self.dims), farr(self.size), dptr(verts), dptr(ids), cap, dptr(n),
-                                     stream_ptr()))
+                                     stream_ptr(device=self.device)))
         total = int(n.item())
         m = min(total, cap)
         if with_cube_ids:
@@ -133,5 +133,5 @@ class TsdfVolume:
             depth = torch.empty((rows, cols), dtype=torch.int16, device=self.device)
         check(lib.dfu_tsdf_raycast(self._base_ptr(), iarr(self.dims), farr(self.getVoxelSize()), self.trunc_dist, farr(c2v), farr(ri),
                                    farr(intr), rows, cols, self.raycast_step_factor, self.gradient_delta_factor,
-                                   dptr(points), cols * 16, dptr(depth), cols * 2, dptr(normals), cols * 16, stream_ptr()))
+                                   dptr(points), cols * 16, dptr(depth), cols * 2, dptr(normals), cols * 16, stream_ptr(device=self.device)))
         return (points if want == "points" else depth), normals

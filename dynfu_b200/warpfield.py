@@ -53,7 +53,7 @@ class Warpfield:
         pos = _f32(positions, (n, 3), self.device)
         dq = _f32(transformations, (n, 8), self.device)
         w = _f32(radial_basis_weights, (n,), self.device)
-        check(lib.dfu_warpfield_init(self._h, float(epsilon), dptr(pos), dptr(dq), dptr(w), n, stream_ptr()))
+        check(lib.dfu_warpfield_init(self._h, float(epsilon), dptr(pos), dptr(dq), dptr(w), n, stream_ptr(device=self.device)))
         self.epsilon = float(epsilon)
 
     def numNodes(self):
@@ -67,23 +67,23 @@ class Warpfield:
         pos = torch.empty((n, 3), dtype=torch.float32, device=self.device)
         dq = torch.empty((n, 8), dtype=torch.float32, device=self.device)
         w = torch.empty((n,), dtype=torch.float32, device=self.device)
-        check(lib.dfu_warpfield_get_nodes(self._h, dptr(pos), dptr(dq), dptr(w), stream_ptr()))
+        check(lib.dfu_warpfield_get_nodes(self._h, dptr(pos), dptr(dq), dptr(w), stream_ptr(device=self.device)))
         return pos, dq, w
 
     def setTransformations(self, transformations):
         dq = _f32(transformations, (self.numNodes(), 8), self.device)
-        check(lib.dfu_warpfield_set_transforms(self._h, dptr(dq), stream_ptr()))
+        check(lib.dfu_warpfield_set_transforms(self._h, dptr(dq), stream_ptr(device=self.device)))
 
     # Node::updateTransformation(DQ(0,0,0,t)) for every node (src/dynfu/utils/node.cpp:19-23)
     def updateTranslations(self, translations):
         t = _f32(translations, (self.numNodes(), 3), self.device)
-        check(lib.dfu_warpfield_update_translations(self._h, dptr(t), stream_ptr()))
+        check(lib.dfu_warpfield_update_translations(self._h, dptr(t), stream_ptr(device=self.device)))
 
     # Warpfield::getUnsupportedVertices (src/dynfu/warp_field.cpp:34-62): the unsupported vertices, in input order
     def getUnsupportedVertices(self, vertices, return_mask=False):
         v = _f32(vertices, (-1, 3), self.device)
         flags = torch.empty(v.shape[0], dtype=torch.uint8, device=self.device)
-        check(lib.dfu_warpfield_unsupported(self._h, dptr(v), v.shape[0], dptr(flags), stream_ptr()))
+        check(lib.dfu_warpfield_unsupported(self._h, dptr(v), v.shape[0], dptr(flags), stream_ptr(device=self.device)))
         mask = flags.bool()
         return mask if return_mask else v[mask]
 
@@ -91,7 +91,7 @@ class Warpfield:
     def update(self, vertices, blend_mode=BLEND_REF_COMPOSE):
         v = _f32(vertices, (-1, 3), self.device)
         nu, nn = C.c_int(), C.c_int()
-        check(lib.dfu_warpfield_update(self._h, dptr(v), v.shape[0], blend_mode, C.byref(nu), C.byref(nn), stream_ptr()))
+        check(lib.dfu_warpfield_update(self._h, dptr(v), v.shape[0], blend_mode, C.byref(nu), C.byref(nn), stream_ptr(device=self.device)))
         return nu.value, nn.value
 
     # warpToLive for a fixed point set (the canonical frame): neighbours + weights cached across calls
@@ -107,13 +107,13 @@ class Warpfield:
             n = _f32(normals, (-1, 3), self.device)
             no = torch.empty_like(n)
         check(lib.dfu_warpfield_warp_cached(self._h, self._pcache, int(version), dptr(v), dptr(n), v.shape[0], dptr(vo), dptr(no),
-                                            blend_mode, normal_mode, stream_ptr()))
+                                            blend_mode, normal_mode, stream_ptr(device=self.device)))
         return vo, no
 
     def cacheStats(self):
         """(bricks the per-voxel neighbour cache holds, bricks currently valid) -- diagnostics"""
         a, b = C.c_longlong(), C.c_longlong()
-        check(lib.dfu_warpfield_cache_stats(self._h, C.byref(a), C.byref(b), stream_ptr()))
+        check(lib.dfu_warpfield_cache_stats(self._h, C.byref(a), C.byref(b), stream_ptr(device=self.device)))
         return a.value, b.value
 
     # Warpfield::findNeighborsIndex (src/dynfu/warp_field.cpp:111-122), for [Q,3] vertices at once
@@ -123,14 +123,14 @@ class Warpfield:
         q = _f32(vertices, (-1, 3), self.device)
         idx = torch.empty((q.shape[0], KNN), dtype=torch.int32, device=self.device)
         d2 = torch.empty((q.shape[0], KNN), dtype=torch.float32, device=self.device) if return_dist else None
-        check(lib.dfu_warpfield_knn(self._h, dptr(q), q.shape[0], dptr(idx), dptr(d2), stream_ptr()))
+        check(lib.dfu_warpfield_knn(self._h, dptr(q), q.shape[0], dptr(idx), dptr(d2), stream_ptr(device=self.device)))
         return (idx, d2) if return_dist else idx
 
     # Warpfield::calcDQB (src/dynfu/warp_field.cpp:127-148)
     def calcDQB(self, points, blend_mode=BLEND_REF_COMPOSE):
         p = _f32(points, (-1, 3), self.device)
         out = torch.empty((p.shape[0], 8), dtype=torch.float32, device=self.device)
-        check(lib.dfu_warpfield_blend(self._h, dptr(p), p.shape[0], dptr(out), blend_mode, stream_ptr()))
+        check(lib.dfu_warpfield_blend(self._h, dptr(p), p.shape[0], dptr(out), blend_mode, stream_ptr(device=self.device)))
         return out
 
     # Warpfield::warpToLive (src/dynfu/warp_field.cpp:150-171): returns (vertices, normals)
@@ -142,5 +142,5 @@ class Warpfield:
             n = _f32(normals, (-1, 3), self.device)
             no = torch.empty_like(n)
         check(lib.dfu_warpfield_warp(self._h, dptr(v), dptr(n), v.shape[0], dptr(vo), dptr(no), blend_mode, normal_mode,
-                                     stream_ptr()))
+                                     stream_ptr(device=self.device)))
         return vo, no
