@@ -19,6 +19,13 @@ class DfuError(RuntimeError):
         self.code = code
 
 
+class FrameParams(C.Structure):
+    """dfu_frame_params (include/dynfu_b200.h)"""
+    _fields_ = [("volume", C.c_void_p), ("dims", C.c_int * 3), ("voxel_size", C.c_float * 3), ("trunc_dist", C.c_float),
+                ("max_weight", C.c_int), ("vol2cam", C.c_float * 12), ("intr", C.c_float * 4), ("rows", C.c_int), ("cols", C.c_int),
+                ("blend_mode", C.c_int), ("z0", C.c_int), ("z1", C.c_int)]
+
+
 class SolverParams(C.Structure):
     _fields_ = [
         ("num_iter", C.c_int),
@@ -67,6 +74,7 @@ _SIGS = {
     "dfu_tsdf_clear": ([_vp, C.POINTER(_i), _i, _i, _vp], _i),
     "dfu_tsdf_integrate": ([_vp, C.POINTER(_i), C.POINTER(_f), _f, _i, C.POINTER(_f), C.POINTER(_f), _vp, _sz, _i, _i,
                             _vp, _i, _i, _i, _vp], _i),
+    "dfu_frame": ([_vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, C.c_ulonglong, _vp, _vp, _i, _vp], _i),
     "dfu_marching_cubes": ([_vp, C.POINTER(_i), C.POINTER(_f), _vp, _vp, C.c_long, _vp, _vp], _i),
     "dfu_tsdf_integrate_stats": ([C.POINTER(C.c_ulonglong), _vp], _i),
     "dfu_solver_create": ([C.POINTER(_vp), _vp, C.POINTER(SolverParams)], _i),

@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdynfu_b200.so")
-SOURCES = ["warpfield.cu", "tsdf.cu", "solver.cu", "comm.cu", "frontend.cu", "update.cu", "raycast.cu", "microbench.cu", "marching_cubes.cu"]
+SOURCES = ["warpfield.cu", "tsdf.cu", "solver.cu", "comm.cu", "frontend.cu", "update.cu", "raycast.cu", "microbench.cu", "marching_cubes.cu", "frame.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",

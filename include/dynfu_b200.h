@@ -158,6 +158,32 @@ int dfu_tsdf_integrate(void* volume, const int dims_host[3], const float voxel_s
                        int max_weight, const float vol2cam_host[12], const float intr_host[4],
                        const uint16_t* dists, size_t dists_pitch_bytes, int rows, int cols, dfu_warpfield* wf,
                        int blend_mode, int z0, int z1, dfu_stream stream);
+/* The frame operator as one call: DynFusion::operator() (src/dynfu/dyn_fusion.cpp:48-145) -> warpCanonicalToLiveOpt
+ * (:182-210) on device-resident inputs.  computeDists (:55) -> warpToLive(canonical) (:196) -> initializeProblemInstance
+ * (:206) -> solveAll (:207; the node transforms are updated) -> integration of the live depth into the volume through the
+ * solved field.  wf == NULL or solver == NULL or P == 0: frame 0, rigid integration only (:70).
+ *   depth_mm      uint16 millimetres, row-pitched                 (cuda::Depth, include/kfusion/types.hpp)
+ *   dists         scratch of the same shape for the ray lengths   (KinFu::dists_, include/kfusion/kinfu.hpp:104)
+ *   canon_v       the canonical vertices [P][3]; canon_version = the caller's change counter for them (dfu_warpfield_warp_cached)
+ *   canon_warped  scratch [P][3]: the canonical vertices warped to the previous live frame (getCanonicalWarpedToLive)
+ *   live_v        the live vertices [P][3], paired with canon_v
+ * Asynchronous on `stream`. */
+typedef struct dfu_frame_params {
+    void* volume;          /* ushort2 voxels, borrowed */
+    int dims[3];
+    float voxel_size[3];
+    float trunc_dist;
+    int max_weight;
+    float vol2cam[12];     /* camera_pose.inv() * volume_pose: 9 floats row-major R, then t */
+    float intr[4];         /* fx, fy, cx, cy */
+    int rows, cols;
+    int blend_mode;        /* DFU_BLEND_* */
+    int z0, z1;            /* z-slab of this rank */
+} dfu_frame_params;
+int dfu_frame(dfu_warpfield* wf, dfu_solver* solver, dfu_pointcache* canon_cache, const dfu_frame_params* params,
+              const uint16_t* depth_mm, size_t depth_pitch_bytes, uint16_t* dists, size_t dists_pitch_bytes, const float* canon_v,
+              unsigned long long canon_version, float* canon_warped, const float* live_v, int P, dfu_stream stream);
+
 /* kfusion::cuda::MarchingCubes::run (include/kfusion/cuda/marching_cubes.hpp:35-36, src/kfusion/marching_cubes.cpp:20-63 ->
  * device::getOccupiedVoxels / computeOffsetsAndTotalVertices / generateTriangles, src/kfusion/cuda/marching_cubes.cu:144-296):
  * triangle vertices of the zero level set of the volume as (x, y, z, 1) in volume-local metres, three consecutive vertices

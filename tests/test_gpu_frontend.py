@@ -454,3 +454,58 @@ def test_overlapped_frame_schedule_is_bit_identical(fe):
     assert same_bits(out[False][1], out[True][1])
     assert out[False][2] == out[True][2]
     assert (out[True][0] >> 16).max() == 7  # rigid frame 0 + six warped frames
+
+
+def test_dfu_frame_single_call_equals_the_composed_frame(fe):
+    """dfu_frame (one C-ABI call per frame) == compute_dists + warpToLive + initializeProblemInstance + solveAll + integrate
+    issued one by one: volume and node transforms bit for bit over three frames"""
+    import ctypes as C
+
+    import dynfu_b200 as dfu
+    from dynfu_b200 import _lib
+    from dynfu_b200._lib import check, dptr, lib
+
+    dim = 128
+    pos, _, dg_w, _ = synth.sphere_nodes(1024, 0.025)
+    depth0 = synth.sphere_depth()
+    canon = synth.backproject(depth0, synth.INTR)[::2]
+    depths = [dev(synth.sphere_depth(bump=0.002 * (1 + i)).view(np.int16), torch.int16) for i in range(3)]
+    lives = [dev(canon + 0.002 * (1 + i) * np.array([1.0, 0.5, -0.25], np.float32)) for i in range(3)]
+    prm = dfu.DynFuParams(kinfuParams=dfu.KinFuParams(volume_dims=(dim, dim, dim)), epsilon=0.025, lambda_=200.0,
+                          solver=dfu.CombinedSolverParameters(numIter=3, nonLinearIter=1, linearIter=8, earlyOut=False,
+                                                              pcgTolerance=0.0))
+    out = {}
+    for single in (False, True):
+        df = dfu.DynFusion(prm)
+        df.init(dev(canon), None, nodes=(dev(pos), dev(synth.identity_dq(1024)), dev(dg_w)))
+        df(torch.from_numpy(depth0.view(np.int16)).pin_memory())
+        if not single:
+            for i in range(3):
+                df.frameDevice(depths[i], lives[i], overlap=False)
+        else:
+            kp = prm.kinfuParams
+            fp = _lib.FrameParams()
+            fp.volume = df.volume._base_ptr().value
+            fp.dims[:] = list(df.volume.dims)
+            fp.voxel_size[:] = list(df.volume.getVoxelSize())
+            fp.trunc_dist = df.volume.getTruncDist()
+            fp.max_weight = df.volume.getMaxWeight()
+            v2c = torch.linalg.inv(df.camera_pose) @ df.volume.pose
+            fp.vol2cam[:] = [float(x) for x in v2c[:3, :3].reshape(-1)] + [float(x) for x in v2c[:3, 3]]
+            fp.intr[:] = [float(x) for x in kp.intr]
+            fp.rows, fp.cols = kp.rows, kp.cols
+            fp.blend_mode = prm.blend_mode
+            fp.z0, fp.z1 = 0, dim
+            cache = C.c_void_p()
+            check(lib.dfu_pointcache_create(C.byref(cache), 0))
+            dists = torch.empty((kp.rows, kp.cols), dtype=torch.int16, device="cuda")
+            warped = torch.empty_like(df.canonicalVertices)
+            for i in range(3):
+                check(lib.dfu_frame(df.warpfield.handle, df.solver._h, cache, C.byref(fp), dptr(depths[i]), kp.cols * 2, dptr(dists),
+                                    kp.cols * 2, dptr(df.canonicalVertices), 1, dptr(warped), dptr(lives[i]),
+                                    df.canonicalVertices.shape[0], None))
+            torch.cuda.synchronize()
+            check(lib.dfu_pointcache_destroy(cache))
+        torch.cuda.synchronize()
+        out[single] = (df.volume.data.cpu().numpy().copy(), df.warpfield.getNodes()[1].cpu().numpy().copy())
+    assert np.array_equal(out[False][0], out[True][0]) and same_bits(out[False][1], out[True][1])
