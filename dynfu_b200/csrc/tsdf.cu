@@ -102,6 +102,16 @@ DFU_DEV uint32_t voxel_update(const IntegrateArgs& a, uint32_t packed, float tsd
     return pack_tsdf(tsdf_new, weight_new);
 }
 
+// the same update for tsdf == 1 (saturated free space).  Two cases need no arithmetic and give the same bits as the general
+// expression: a voxel that already holds 1.0 stays 1.0 (fma(1, W, 1) = W + 1 exactly, (W + 1) / (W + 1) = 1), and a voxel
+// without weight takes the new value ((0 * 0 + 1) / 1 = 1; a cleared voxel holds +0.0).  That is every free-space voxel after
+// its first frame.
+DFU_DEV uint32_t voxel_update_one(const IntegrateArgs& a, uint32_t packed) {
+    const uint32_t w = packed >> 16, h = packed & 0xffffu;
+    if (h == 0x3c00u || (w == 0u && h == 0u)) return 0x3c00u | ((uint32_t) min((int) w + 1, a.max_weight) << 16);
+    return voxel_update(a, packed, 1.f);
+}
+
 DFU_DEV void quad_commit(const IntegrateArgs& a, size_t lin, const bool (&hit)[4], const float (&ts)[4], Tally& tally) {
     if (!(hit[0] | hit[1] | hit[2] | hit[3])) return;  // untouched quads cost no volume traffic
     tally.vox += (unsigned) hit[0] + (unsigned) hit[1] + (unsigned) hit[2] + (unsigned) hit[3];
@@ -193,10 +203,10 @@ DFU_DEV void quad_saturate(const IntegrateArgs& a, size_t lin, Tally& tally) {
     uint4* p = reinterpret_cast<uint4*>(a.vol + lin);
     const uint4 v = ld_stream(p);
     uint4 n;
-    n.x = voxel_update(a, v.x, 1.f);
-    n.y = voxel_update(a, v.y, 1.f);
-    n.z = voxel_update(a, v.z, 1.f);
-    n.w = voxel_update(a, v.w, 1.f);
+    n.x = voxel_update_one(a, v.x);
+    n.y = voxel_update_one(a, v.y);
+    n.z = voxel_update_one(a, v.z);
+    n.w = voxel_update_one(a, v.w);
     tally.vox += 4;
     tally.quads += 1;
     tally.sat += 4;
@@ -220,10 +230,10 @@ DFU_DEV void saturate_tile(const IntegrateArgs& a, const TileInfo& ti, Tally& ta
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         uint4 nv;
-        nv.x = voxel_update(a, v[it].x, 1.f);
-        nv.y = voxel_update(a, v[it].y, 1.f);
-        nv.z = voxel_update(a, v[it].z, 1.f);
-        nv.w = voxel_update(a, v[it].w, 1.f);
+        nv.x = voxel_update_one(a, v[it].x);
+        nv.y = voxel_update_one(a, v[it].y);
+        nv.z = voxel_update_one(a, v[it].z);
+        nv.w = voxel_update_one(a, v[it].w);
         if ((nv.x ^ v[it].x) | (nv.y ^ v[it].y) | (nv.z ^ v[it].z) | (nv.w ^ v[it].w)) st_stream(p[it], nv);
     }
     tally.vox += 16;
