@@ -408,26 +408,24 @@ DFU_DEV void grid_visit_range(const int* __restrict__ start, const float4* __res
 // block); once the next shell would cost more cell visits than there are NON-EMPTY cells, a query that is still not
 // settled sweeps the list of non-empty cells instead, pruning each by its box distance, so the cost stays bounded
 // however far the query is from the nodes.
-DFU_DEV void knn8_grid(const GridDesc& g, const int* __restrict__ start, const float4* __restrict__ sorted,
-                       const int* __restrict__ occ, float qx, float qy, float qz, Top8& out) {
-    Keys8 t;
-    const unsigned long long none = knn_key(INFINITY, 0x7fffffff);  // "no node": loses every tie
-#pragma unroll
-    for (int k = 0; k < DFU_KNN; ++k) t.k[k] = none;
-    const int cx = grid_coord(qx, g.ox, g.inv_h, g.nx), cy = grid_coord(qy, g.oy, g.inv_h, g.ny), cz = grid_coord(qz, g.oz, g.inv_h, g.nz);
+// radius 0 and 1 around the query's cell: up to nine row segments (cells of one grid row are contiguous in `sorted`);
+// segment s of the block, s < grid_block_segments()
+DFU_DEV int grid_block_segments(const GridDesc& g, int cy, int cz) {
+    return (min(g.nz - 1, cz + 1) - max(0, cz - 1) + 1) * (min(g.ny - 1, cy + 1) - max(0, cy - 1) + 1);
+}
+DFU_DEV void grid_visit_block_segment(const GridDesc& g, const int* __restrict__ start, const float4* __restrict__ sorted, int cx,
+                                      int cy, int cz, int s, float qx, float qy, float qz, Keys8& t) {
+    const int y0 = max(0, cy - 1), ny = min(g.ny - 1, cy + 1) - y0 + 1;
+    const int z = max(0, cz - 1) + s / ny, y = y0 + s % ny;
+    const int row = g.nx * (y + g.ny * z);
+    grid_visit_range(start, sorted, row + max(0, cx - 1), row + min(g.nx - 1, cx + 1), qx, qy, qz, t);
+}
+
+// the rest of the search once the 3x3x3 block has been visited: settle test, further shells, sweep of the non-empty cells
+DFU_DEV void knn8_grid_continue(const GridDesc& g, const int* __restrict__ start, const float4* __restrict__ sorted,
+                                const int* __restrict__ occ, int cx, int cy, int cz, float qx, float qy, float qz, Keys8& t) {
     bool settled = false;
     int r = 1, rd = -1;  // rd: every cell within this Chebyshev radius has been visited
-    // radius 0 and 1 in one pass: nine row segments
-    {
-        const int z0 = max(0, cz - 1), z1 = min(g.nz - 1, cz + 1);
-        const int y0 = max(0, cy - 1), y1 = min(g.ny - 1, cy + 1);
-        const int x0 = max(0, cx - 1), x1 = min(g.nx - 1, cx + 1);
-        for (int z = z0; z <= z1; ++z)
-            for (int y = y0; y <= y1; ++y) {
-                const int row = g.nx * (y + g.ny * z);
-                grid_visit_range(start, sorted, row + x0, row + x1, qx, qy, qz, t);
-            }
-    }
     for (;; ++r) {
         if (r > 1) {
             if ((2 * r + 1) * (2 * r + 1) * (2 * r + 1) > 2 * g.n_occ + 27) break;
@@ -477,12 +475,96 @@ DFU_DEV void knn8_grid(const GridDesc& g, const int* __restrict__ start, const f
             if (dl * dl <= __uint_as_float((unsigned) (t.k[DFU_KNN - 1] >> 32))) grid_visit_range(start, sorted, c, c, qx, qy, qz, t);
         }
     }
+}
+DFU_DEV void keys8_to_top8(const Keys8& t, Top8& out) {
 #pragma unroll
     for (int k = 0; k < DFU_KNN; ++k) {
         out.d[k] = __uint_as_float((unsigned) (t.k[k] >> 32));
         const int idx = (int) (unsigned) (t.k[k] & 0xffffffffull);
         out.i[k] = idx == 0x7fffffff ? -1 : idx;
     }
+}
+
+// Shells of growing Chebyshev radius around the query's cell (a query near the nodes is done after the first 3x3x3
+// block); once the next shell would cost more cell visits than there are NON-EMPTY cells, a query that is still not
+// settled sweeps the list of non-empty cells instead, pruning each by its box distance, so the cost stays bounded
+// however far the query is from the nodes.
+DFU_DEV void knn8_grid(const GridDesc& g, const int* __restrict__ start, const float4* __restrict__ sorted,
+                       const int* __restrict__ occ, float qx, float qy, float qz, Top8& out) {
+    Keys8 t;
+    const unsigned long long none = knn_key(INFINITY, 0x7fffffff);  // "no node": loses every tie
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) t.k[k] = none;
+    const int cx = grid_coord(qx, g.ox, g.inv_h, g.nx), cy = grid_coord(qy, g.oy, g.inv_h, g.ny), cz = grid_coord(qz, g.oz, g.inv_h, g.nz);
+    const int nseg = grid_block_segments(g, cy, cz);
+    for (int s = 0; s < nseg; ++s) grid_visit_block_segment(g, start, sorted, cx, cy, cz, s, qx, qy, qz, t);
+    knn8_grid_continue(g, start, sorted, occ, cx, cy, cz, qx, qy, qz, t);
+    keys8_to_top8(t, out);
+}
+
+// The same search with EIGHT lanes per query (the data-graph build of the solver, once per frame over all surface points):
+// one thread per query is a chain of ~40 dependent candidate visits and 8 FP64 weight evaluations at 18 % occupancy.  The
+// lanes of a group take the row segments of the 3x3x3 block in turn, merge their sorted lists with a three-round shuffle
+// butterfly (the 8 smallest of two ascending lists form a bitonic sequence), run the settle test together (further shells
+// are rare and done redundantly), and each lane then evaluates ONE neighbour's weight.  Same keys, same result, bit for bit.
+DFU_DEV void keys8_merge_group8(Keys8& t) {
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+        unsigned long long o[DFU_KNN];
+#pragma unroll
+        for (int k = 0; k < DFU_KNN; ++k) o[k] = __shfl_xor_sync(0xffffffffu, t.k[DFU_KNN - 1 - k], off);  // partner's list, reversed
+#pragma unroll
+        for (int k = 0; k < DFU_KNN; ++k) t.k[k] = o[k] < t.k[k] ? o[k] : t.k[k];
+#pragma unroll
+        for (int st = DFU_KNN / 2; st > 0; st >>= 1)
+#pragma unroll
+            for (int k = 0; k < DFU_KNN; ++k)
+                if ((k & st) == 0 && t.k[k + st] < t.k[k]) {
+                    const unsigned long long tmp = t.k[k];
+                    t.k[k] = t.k[k + st];
+                    t.k[k + st] = tmp;
+                }
+    }
+}
+
+__global__ void __launch_bounds__(128) points_grid_graph8_kernel(const PointArgs a, const GridDesc* __restrict__ gd,
+                                                                 const int* __restrict__ start, const float4* __restrict__ sorted,
+                                                                 const int* __restrict__ occ) {
+    const int sub = threadIdx.x & 7;
+    const long qraw = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool active = qraw < a.Q;
+    const long q = active ? qraw : a.Q - 1;  // (inactive groups replay the last query: every lane takes part in the shuffles)
+    const GridDesc g = *gd;
+    const float qx = a.q[3 * (size_t) q], qy = a.q[3 * (size_t) q + 1], qz = a.q[3 * (size_t) q + 2];
+    Keys8 t;
+    const unsigned long long none = knn_key(INFINITY, 0x7fffffff);
+#pragma unroll
+    for (int k = 0; k < DFU_KNN; ++k) t.k[k] = none;
+    const int cx = grid_coord(qx, g.ox, g.inv_h, g.nx), cy = grid_coord(qy, g.oy, g.inv_h, g.ny), cz = grid_coord(qz, g.oz, g.inv_h, g.nz);
+    const int nseg = grid_block_segments(g, cy, cz);
+    for (int s = sub; s < nseg; s += 8) grid_visit_block_segment(g, start, sorted, cx, cy, cz, s, qx, qy, qz, t);
+    keys8_merge_group8(t);
+    knn8_grid_continue(g, start, sorted, occ, cx, cy, cz, qx, qy, qz, t);  // (uniform over the group)
+    // lane `sub` owns neighbour `sub`
+    unsigned long long mine = t.k[0];
+#pragma unroll
+    for (int k = 1; k < DFU_KNN; ++k) mine = sub == k ? t.k[k] : mine;
+    const float d = __uint_as_float((unsigned) (mine >> 32));
+    const int raw = (int) (unsigned) (mine & 0xffffffffull);
+    const int idx = raw == 0x7fffffff ? -1 : raw;
+    float w = 0.f;
+    if (idx >= 0) {
+        const float4 nd = __ldg(&a.pos_w[idx]);
+        w = node_weight(nd.x, nd.y, nd.z, nd.w, qx, qy, qz, d);
+    }
+    if (!active) return;
+    a.idx[(size_t) q * DFU_KNN + sub] = idx;
+    a.wts[(size_t) q * DFU_KNN + sub] = w;
+    if (a.dvec && sub < 3) {
+        const float qc = sub == 0 ? qx : (sub == 1 ? qy : qz);
+        a.dvec[3 * (size_t) q + sub] = a.live[3 * (size_t) q + sub] - qc;
+    }
+    if (a.deg && idx >= 0) atomicAdd(&a.deg[idx], 1);
 }
 
 template <int OP>
@@ -619,7 +701,10 @@ int launch_points(const dfu_warpfield* wf, PointArgs& a, cudaStream_t st) {
     if (OP != OP_BOUNDS && wf->N >= 64 && wf->grid.valid && wf->grid.node_epoch == wf->node_epoch &&
         ((reinterpret_cast<uintptr_t>(a.idx) | reinterpret_cast<uintptr_t>(a.dist2) | reinterpret_cast<uintptr_t>(a.wts) |
           reinterpret_cast<uintptr_t>(a.dq_out)) & 15) == 0) {
-        points_grid_kernel<OP><<<div_up(a.Q, 128), 128, 0, st>>>(a, wf->grid.desc, wf->grid.cell_start, wf->grid.sorted, wf->grid.occ);
+        if (OP == OP_GRAPH)  // eight lanes per query (bit-identical; DFU_POINT_KNN=grid1 keeps one thread per query)
+            points_grid_graph8_kernel<<<div_up((long) a.Q * 8, 128), 128, 0, st>>>(a, wf->grid.desc, wf->grid.cell_start, wf->grid.sorted, wf->grid.occ);
+        else
+            points_grid_kernel<OP><<<div_up(a.Q, 128), 128, 0, st>>>(a, wf->grid.desc, wf->grid.cell_start, wf->grid.sorted, wf->grid.occ);
         DFU_LAUNCH_OK();
         return DFU_OK;
     }
