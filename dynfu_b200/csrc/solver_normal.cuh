@@ -340,6 +340,76 @@ constexpr int P3_R = 2;
 constexpr int P3_LE = 2;
 constexpr int P3_MAX_LINEAR_ITER = 64;  // longer PCG runs use the textbook recurrences (versions 1 / 2)
 
+// Accumulators of one warp of version 3r: ACC_W low words + ACC_W high words (generic rows), or -- rows of at most 64 columns,
+// the usual case -- four bank-rotated copies of 64 low + 64 high words and the three 64-bit sums of b.
+constexpr int P3_FU = 2;  // entries per lane in flight in the fused sweep
+constexpr int P3_ACC_WORDS = 640, P3_ACC_COPY = 72, P3_ACC_HI = 320, P3_ACC_B = 616;
+
+// One sweep of node n's list (entries lo..hi of the transposed data graph) that accumulates BOTH b_n = sum tw * theta e (three
+// 64-bit fixed-point sums, left at acc + P3_ACC_B) and the data part of row n of A (2^40 fixed point as 20 + 20 bit halves in
+// 32-bit shared-memory atomics; slot s of the row is the sum of acc[s + 72 c] / acc[320 + s + 72 c] over the copies c).
+// Measured (profiles/r02_solver_experiments.md): the loop is bound by shared-memory atomic wavefronts -- the 32 points of a
+// batch share a handful of popular neighbours, 5.3 lanes per word per instruction on a single copy -- and by its two dependent
+// L2 round trips.  So: FOUR copies of the accumulators, 72 words apart so that one slot lies in four different banks (lane & 3
+// picks the copy; integer sums, any split gives the same bits); theta read from s4.w, the same 32-byte sector as theta e; and
+// the point ids of the NEXT 128 entries fetched a batch ahead.
+template <int FU>
+DFU_DEV void assemble_row_fused(const int32_t* __restrict__ tv, const float* __restrict__ tw,
+                                                const uint4* __restrict__ tslot, const float4* s4, const float* __restrict__ wts,
+                                                int lo, int hi, int lane, unsigned* acc) {
+    for (int j = lane; j < P3_ACC_WORDS; j += 32) acc[j] = 0u;
+    unsigned* my_lo = acc + P3_ACC_COPY * (lane & 3);
+    unsigned* my_hi = my_lo + P3_ACC_HI;
+    int vn[FU];
+    long long bx = 0, by = 0, bz = 0;
+#pragma unroll
+    for (int u = 0; u < FU; ++u) vn[u] = lo + lane + 32 * u < hi ? tv[lo + lane + 32 * u] : -1;
+    __syncwarp();
+    for (int e0 = lo + lane; e0 < hi; e0 += 32 * FU) {  // FU entries per lane in flight
+        int v[FU];
+        float c[FU];
+        uint4 sl[FU];
+        float4 w0[FU], w1[FU], se[FU];
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            v[u] = vn[u];
+            const int vv = v[u] >= 0 ? v[u] : 0;
+            const int ee = v[u] >= 0 ? e0 + 32 * u : lo;
+            c[u] = tw[ee];
+            sl[u] = tslot[ee];
+            se[u] = s4[vv];
+            w0[u] = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) vv);
+            w1[u] = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) vv + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < FU; ++u) vn[u] = e0 + 32 * FU + 32 * u < hi ? tv[e0 + 32 * FU + 32 * u] : -1;
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            if (v[u] < 0) continue;
+            bx += __float2ll_rn(c[u] * se[u].x * FIX_SCALE);
+            by += __float2ll_rn(c[u] * se[u].y * FIX_SCALE);
+            bz += __float2ll_rn(c[u] * se[u].z * FIX_SCALE);
+            const float cc = c[u] * se[u].w;
+            if (cc == 0.f) continue;
+            const float wk[8] = {w0[u].x, w0[u].y, w0[u].z, w0[u].w, w1[u].x, w1[u].y, w1[u].z, w1[u].w};
+            const unsigned sw[4] = {sl[u].x, sl[u].y, sl[u].z, sl[u].w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const unsigned long long f = (unsigned long long) __float2ll_rn(cc * wk[k] * FIX_SCALE);
+                const unsigned sidx = (k & 1) ? sw[k >> 1] >> 16 : sw[k >> 1] & 0xffffu;
+                atomicAdd(&my_lo[sidx], (unsigned) f & 0xfffffu);
+                atomicAdd(&my_hi[sidx], (unsigned) (f >> 20));
+            }
+        }
+    }
+    warp_sum_ll(bx); warp_sum_ll(by); warp_sum_ll(bz);
+    if (lane == 0) {
+        long long* out = reinterpret_cast<long long*>(acc + P3_ACC_B);
+        out[0] = bx; out[1] = by; out[2] = bz;
+    }
+    __syncwarp();
+}
+
 DFU_DEV void warp_total4(const double* part4, int nb, int lane, double& a, double& b, double& c) {
     a = b = c = 0.0;
     for (int i = lane; i < nb; i += 32) {
@@ -354,12 +424,13 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
     constexpr int NWARP = PTPB / 32;
     __shared__ double shw[3 * NWARP];
     __shared__ double tot_sm[3];
-    __shared__ unsigned acc_sm[NWARP * 2 * ACC_W];  // per warp: ACC_W low words, ACC_W high words
+    constexpr int ACC_WORDS = P3_ACC_WORDS, ACC_COPY = P3_ACC_COPY, ACC_HI = P3_ACC_HI;
+    __shared__ __align__(16) unsigned acc_sm[NWARP * ACC_WORDS];  // (layout: assemble_row_fused)
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gw = tid >> 5, nw = nthreads >> 5;
     const int nb = gridDim.x, N = pb.N;
     unsigned bar_target = 0;
-    unsigned* acc_lo = acc_sm + wib * 2 * ACC_W;
+    unsigned* acc_lo = acc_sm + wib * ACC_WORDS;
     unsigned* acc_hi = acc_lo + ACC_W;
 #define GRID_SYNC() grid_barrier(bar, (unsigned) nb, bar_target)
 #define PART(buf) (pb.part + (size_t) (buf) * 2 * MAX_PARTIALS)
@@ -416,7 +487,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
     // ---- my rows --------------------------------------------------------------------------------------------
     int rn[P3_R], roff[P3_R], rlen[P3_R], rds[P3_R];
     int rc[P3_R][P3_LE];
-    float ra[P3_R][P3_LE], rv[P3_R][P3_LE];
+    float rv[P3_R][P3_LE];  // (the regularisation values of the same entries are re-read from pt.areg when a row is assembled)
     float rD[P3_R], rinv[P3_R];
     double rinvd[P3_R];
     float s_r[P3_R], s_w[P3_R], s_z[P3_R], s_s[P3_R], s_p[P3_R], s_x[P3_R], s_t[P3_R];  // coordinate `lane` (lanes 0..2)
@@ -431,7 +502,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
 #pragma unroll
         for (int u = 0; u < P3_LE; ++u) {
             rc[r][u] = -1;
-            ra[r][u] = rv[r][u] = 0.f;
+            rv[r][u] = 0.f;
         }
         if (n < N) {
             roff[r] = pt.rowptr[n];
@@ -442,7 +513,6 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                 const int j = lane + 32 * u;
                 if (j < rlen[r]) {
                     rc[r][u] = pt.col[roff[r] + j];
-                    ra[r][u] = pt.areg[roff[r] + j];
                 }
             }
             if (lane < 3) pb.t[3 * (size_t) n + lane] = 0.f;  // unknowns := 0 (opt_solver.cpp:192-193)
@@ -490,15 +560,40 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                 if (rn[r] < 0) continue;  // uniform over the warp
                 const int n = rn[r];
                 float ax, ay, az, gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
-                // b_n = sum tw * theta e in 2^40 fixed point (independent of the order of the node's list) ...
-                node_gather_data_fixed(pb, n, lane, ax, ay, az);
-                PROF(3);
-                // ... and, when theta changed, the data part of row n of A (fixed point in shared memory), ACC_W columns per pass
+                // b_n = sum tw * theta e in 2^40 fixed point (independent of the order of the node's list) and, when theta
+                // changed, the data part of row n of A (fixed point in shared memory), ACC_W columns per pass.  The usual row
+                // does both in ONE sweep of the node's list: theta travels in s4.w, the same 32-byte sector as theta e.
                 const bool assemble = gn == 0;
+                const int lo = pb.tptr[n], hi = pb.tptr[n + 1];
+                const bool wide = hi - lo > FIX_MAX_DEG;  // too many contributions for the split words: 64-bit atomics
+                const bool fused = assemble && !wide && rlen[r] <= 32 * P3_LE;
+                if (!fused) node_gather_data_fixed(pb, n, lane, ax, ay, az);
+                PROF(3);
                 if (assemble) {
-                    const int lo = pb.tptr[n], hi = pb.tptr[n + 1];
-                    const bool wide = hi - lo > FIX_MAX_DEG;  // too many contributions for the split words: 64-bit atomics
                     unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(acc_lo);
+                    if (fused) {
+                        // the usual row (all of it in registers): one sweep, out of line so that its 80 registers of loads in flight
+                        // are not live across the PCG loop
+                        float areg_u[P3_LE];  // (fetched now: a dependent L2 round trip after the sweep otherwise)
+#pragma unroll
+                        for (int u = 0; u < P3_LE; ++u) areg_u[u] = rc[r][u] >= 0 ? pt.areg[roff[r] + lane + 32 * u] : 0.f;
+                        assemble_row_fused<P3_FU>(pb.tv, pb.tw, pt.tslot, pb.s4, pb.wts, lo, hi, lane, acc_lo);
+                        const long long bx = reinterpret_cast<const long long*>(acc_lo + P3_ACC_B)[0],
+                                        by = reinterpret_cast<const long long*>(acc_lo + P3_ACC_B)[1],
+                                        bz = reinterpret_cast<const long long*>(acc_lo + P3_ACC_B)[2];
+                        ax = (float) ((double) bx * FIX_INV); ay = (float) ((double) by * FIX_INV); az = (float) ((double) bz * FIX_INV);
+                        __syncwarp();
+#pragma unroll
+                        for (int u = 0; u < P3_LE; ++u)
+                            if (rc[r][u] >= 0) {
+                                const unsigned* a = acc_lo + lane + 32 * u;
+                                const unsigned long long sl4 = (unsigned long long) a[0] + a[ACC_COPY] + a[2 * ACC_COPY] + a[3 * ACC_COPY];
+                                const unsigned long long sh4 = (unsigned long long) a[ACC_HI] + a[ACC_HI + ACC_COPY] +
+                                                               a[ACC_HI + 2 * ACC_COPY] + a[ACC_HI + 3 * ACC_COPY];
+                                rv[r][u] = areg_u[u] + (float) ((double) ((sh4 << 20) + sl4) * FIX_INV);
+                            }
+                        __syncwarp();
+                    } else
                     for (int c0 = 0; c0 < rlen[r]; c0 += ACC_W) {
                         for (int j = lane; j < 2 * ACC_W; j += 32) acc_lo[j] = 0u;
                         __syncwarp();
@@ -548,7 +643,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
 #pragma unroll
                             for (int u = 0; u < P3_LE; ++u)
                                 if (rc[r][u] >= 0)
-                                    rv[r][u] = ra[r][u] + (wide ? (float) ((double) acc64[lane + 32 * u] * FIX_INV)
+                                    rv[r][u] = pt.areg[roff[r] + lane + 32 * u] + (wide ? (float) ((double) acc64[lane + 32 * u] * FIX_INV)
                                                                 : fix2f(acc_lo[lane + 32 * u], acc_hi[lane + 32 * u]));
                         }
                         for (int j = lane; j < ACC_W && c0 + j < rlen[r]; j += 32)

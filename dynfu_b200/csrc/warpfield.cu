@@ -502,14 +502,17 @@ DFU_DEV void knn8_grid(const GridDesc& g, const int* __restrict__ start, const f
     keys8_to_top8(t, out);
 }
 
-// The same search with EIGHT lanes per query (the data-graph build of the solver, once per frame over all surface points):
-// one thread per query is a chain of ~40 dependent candidate visits and 8 FP64 weight evaluations at 18 % occupancy.  The
-// lanes of a group take the row segments of the 3x3x3 block in turn, merge their sorted lists with a three-round shuffle
-// butterfly (the 8 smallest of two ascending lists form a bitonic sequence), run the settle test together (further shells
-// are rare and done redundantly), and each lane then evaluates ONE neighbour's weight.  Same keys, same result, bit for bit.
-DFU_DEV void keys8_merge_group8(Keys8& t) {
+// The same search with G lanes per query (the data-graph build of the solver, once per frame over all surface points): one
+// thread per query is a chain of ~40 dependent candidate visits and 8 FP64 weight evaluations, and 75 k queries fill a quarter
+// of the machine's thread slots.  The lanes of a group take the row segments of the 3x3x3 block in turn, merge their sorted
+// lists with a shuffle butterfly (the 8 smallest of two ascending lists form a bitonic sequence), run the settle test together
+// (further shells are rare and done redundantly), and share the 8 weight evaluations.  Same keys, same result, bit for bit.
+// Measured on the bench scene (initializeProblemInstance, B200): G = 1: 0.113-0.119 ms, 2: 0.105-0.115, 4: 0.110-0.118,
+// 8: 0.126-0.134 (the merge network outweighs the shorter chains) -- the default is 2; DFU_GRAPH_LANES=1|2|4 selects.
+template <int G>
+DFU_DEV void keys8_merge_group(Keys8& t) {
 #pragma unroll
-    for (int off = 1; off < 8; off <<= 1) {
+    for (int off = 1; off < G; off <<= 1) {
         unsigned long long o[DFU_KNN];
 #pragma unroll
         for (int k = 0; k < DFU_KNN; ++k) o[k] = __shfl_xor_sync(0xffffffffu, t.k[DFU_KNN - 1 - k], off);  // partner's list, reversed
@@ -527,11 +530,12 @@ DFU_DEV void keys8_merge_group8(Keys8& t) {
     }
 }
 
-__global__ void __launch_bounds__(128) points_grid_graph8_kernel(const PointArgs a, const GridDesc* __restrict__ gd,
-                                                                 const int* __restrict__ start, const float4* __restrict__ sorted,
-                                                                 const int* __restrict__ occ) {
-    const int sub = threadIdx.x & 7;
-    const long qraw = ((long) blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+template <int G>
+__global__ void __launch_bounds__(128) points_grid_graph_kernel(const PointArgs a, const GridDesc* __restrict__ gd,
+                                                                const int* __restrict__ start, const float4* __restrict__ sorted,
+                                                                const int* __restrict__ occ) {
+    const int sub = threadIdx.x & (G - 1);
+    const long qraw = ((long) blockIdx.x * blockDim.x + threadIdx.x) / G;
     const bool active = qraw < a.Q;
     const long q = active ? qraw : a.Q - 1;  // (inactive groups replay the last query: every lane takes part in the shuffles)
     const GridDesc g = *gd;
@@ -542,29 +546,36 @@ __global__ void __launch_bounds__(128) points_grid_graph8_kernel(const PointArgs
     for (int k = 0; k < DFU_KNN; ++k) t.k[k] = none;
     const int cx = grid_coord(qx, g.ox, g.inv_h, g.nx), cy = grid_coord(qy, g.oy, g.inv_h, g.ny), cz = grid_coord(qz, g.oz, g.inv_h, g.nz);
     const int nseg = grid_block_segments(g, cy, cz);
-    for (int s = sub; s < nseg; s += 8) grid_visit_block_segment(g, start, sorted, cx, cy, cz, s, qx, qy, qz, t);
-    keys8_merge_group8(t);
+    for (int s = sub; s < nseg; s += G) grid_visit_block_segment(g, start, sorted, cx, cy, cz, s, qx, qy, qz, t);
+    keys8_merge_group<G>(t);
     knn8_grid_continue(g, start, sorted, occ, cx, cy, cz, qx, qy, qz, t);  // (uniform over the group)
-    // lane `sub` owns neighbour `sub`
-    unsigned long long mine = t.k[0];
+    // lane `sub` owns neighbours sub, sub + G, ...
 #pragma unroll
-    for (int k = 1; k < DFU_KNN; ++k) mine = sub == k ? t.k[k] : mine;
-    const float d = __uint_as_float((unsigned) (mine >> 32));
-    const int raw = (int) (unsigned) (mine & 0xffffffffull);
-    const int idx = raw == 0x7fffffff ? -1 : raw;
-    float w = 0.f;
-    if (idx >= 0) {
-        const float4 nd = __ldg(&a.pos_w[idx]);
-        w = node_weight(nd.x, nd.y, nd.z, nd.w, qx, qy, qz, d);
+    for (int j = 0; j < DFU_KNN / G; ++j) {
+        unsigned long long mine = t.k[j * G];
+#pragma unroll
+        for (int k = 1; k < G; ++k) mine = sub == k ? t.k[j * G + k] : mine;
+        const float d = __uint_as_float((unsigned) (mine >> 32));
+        const int raw = (int) (unsigned) (mine & 0xffffffffull);
+        const int idx = raw == 0x7fffffff ? -1 : raw;
+        float w = 0.f;
+        if (idx >= 0) {
+            const float4 nd = __ldg(&a.pos_w[idx]);
+            w = node_weight(nd.x, nd.y, nd.z, nd.w, qx, qy, qz, d);
+        }
+        if (active) {
+            a.idx[(size_t) q * DFU_KNN + j * G + sub] = idx;
+            a.wts[(size_t) q * DFU_KNN + j * G + sub] = w;
+            if (a.deg && idx >= 0) atomicAdd(&a.deg[idx], 1);
+        }
     }
-    if (!active) return;
-    a.idx[(size_t) q * DFU_KNN + sub] = idx;
-    a.wts[(size_t) q * DFU_KNN + sub] = w;
-    if (a.dvec && sub < 3) {
-        const float qc = sub == 0 ? qx : (sub == 1 ? qy : qz);
-        a.dvec[3 * (size_t) q + sub] = a.live[3 * (size_t) q + sub] - qc;
+    if (active && a.dvec) {
+#pragma unroll
+        for (int c = sub; c < 3; c += G) {
+            const float qc = c == 0 ? qx : (c == 1 ? qy : qz);
+            a.dvec[3 * (size_t) q + c] = a.live[3 * (size_t) q + c] - qc;
+        }
     }
-    if (a.deg && idx >= 0) atomicAdd(&a.deg[idx], 1);
 }
 
 template <int OP>
@@ -701,8 +712,12 @@ int launch_points(const dfu_warpfield* wf, PointArgs& a, cudaStream_t st) {
     if (OP != OP_BOUNDS && wf->N >= 64 && wf->grid.valid && wf->grid.node_epoch == wf->node_epoch &&
         ((reinterpret_cast<uintptr_t>(a.idx) | reinterpret_cast<uintptr_t>(a.dist2) | reinterpret_cast<uintptr_t>(a.wts) |
           reinterpret_cast<uintptr_t>(a.dq_out)) & 15) == 0) {
-        if (OP == OP_GRAPH)  // eight lanes per query (bit-identical; DFU_POINT_KNN=grid1 keeps one thread per query)
-            points_grid_graph8_kernel<<<div_up((long) a.Q * 8, 128), 128, 0, st>>>(a, wf->grid.desc, wf->grid.cell_start, wf->grid.sorted, wf->grid.occ);
+        const char* env = OP == OP_GRAPH ? getenv("DFU_GRAPH_LANES") : nullptr;
+        const int lanes = OP == OP_GRAPH ? (env ? atoi(env) : 2) : 1;
+        if (lanes == 4)
+            points_grid_graph_kernel<4><<<div_up((long) a.Q * 4, 128), 128, 0, st>>>(a, wf->grid.desc, wf->grid.cell_start, wf->grid.sorted, wf->grid.occ);
+        else if (lanes == 2)
+            points_grid_graph_kernel<2><<<div_up((long) a.Q * 2, 128), 128, 0, st>>>(a, wf->grid.desc, wf->grid.cell_start, wf->grid.sorted, wf->grid.occ);
         else
             points_grid_kernel<OP><<<div_up(a.Q, 128), 128, 0, st>>>(a, wf->grid.desc, wf->grid.cell_start, wf->grid.sorted, wf->grid.occ);
         DFU_LAUNCH_OK();
