@@ -713,7 +713,9 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                     s_w[r] = lane < 3 ? w : 0.f;
                     s_z[r] = s_s[r] = s_p[r] = 0.f;
                 }
-                double gamma_prev = 0.0, alpha_prev = 0.0;
+                // (1 / gamma of the previous iteration is formed right after that iteration's update, off the critical path, and
+                //  gamma / alpha_prev = beta * denom_prev: one FP64 division between the totals and the update instead of three)
+                double gamma_prev = 0.0, inv_gamma_prev = 0.0, denom_prev = 0.0;
                 PROF(8);
                 for (int it = 0; it < ctl.linear_iter; ++it) {
                     const int buf = (it + 1) & 1;
@@ -791,8 +793,8 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                     const double gamma = tot_sm[0], delta = tot_sm[1];
                     PROF(11);
                     if (!(gamma > 0.0) || (it > 0 && gamma <= ctl.tol2 * rz_ref)) break;
-                    const double beta = it > 0 ? gamma / gamma_prev : 0.0;
-                    const double denom = it > 0 ? delta - beta * gamma / alpha_prev : delta;
+                    const double beta = it > 0 ? gamma * inv_gamma_prev : 0.0;
+                    const double denom = it > 0 ? delta - beta * beta * denom_prev : delta;
                     if (!(denom > 0.0)) break;
                     const double alpha = gamma / denom;
                     const float af = (float) alpha, bf = (float) beta;
@@ -811,7 +813,8 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                     PROF(12);
                     ++pcg_total;
                     gamma_prev = gamma;
-                    alpha_prev = alpha;
+                    inv_gamma_prev = 1.0 / gamma;
+                    denom_prev = denom;
                 }
             }
 #pragma unroll
