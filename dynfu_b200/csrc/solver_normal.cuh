@@ -342,6 +342,7 @@ constexpr int P3_MAX_LINEAR_ITER = 64;  // longer PCG runs use the textbook recu
 
 // Accumulators of one warp of version 3r: ACC_W low words + ACC_W high words (generic rows), or -- rows of at most 64 columns,
 // the usual case -- four bank-rotated copies of 64 low + 64 high words and the three 64-bit sums of b.
+constexpr int P3_XS_MAX = 1024;  // columns of the exchanged vector a CTA stages in shared memory (more: straight from L2)
 constexpr int P3_FU = 2;  // entries per lane in flight in the fused sweep
 constexpr int P3_ACC_WORDS = 640, P3_ACC_COPY = 72, P3_ACC_HI = 320, P3_ACC_B = 616;
 
@@ -426,6 +427,14 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
     __shared__ double tot_sm[3];
     constexpr int ACC_WORDS = P3_ACC_WORDS, ACC_COPY = P3_ACC_COPY, ACC_HI = P3_ACC_HI;
     __shared__ __align__(16) unsigned acc_sm[NWARP * ACC_WORDS];  // (layout: assemble_row_fused)
+    // The exchanged vector, staged: a CTA's rows reference a few hundred distinct columns (rows of neighbouring nodes share
+    // most of theirs), but every lane fetching its own column from L2 is 106 k sector requests per PCG iteration chip-wide
+    // on the 512 lines of one 64 KB vector -- measured 2.1 k cycles per iteration (profiles/r02_solver_experiments.md).  The
+    // CTA's column list is built once per launch; each iteration the CTA fetches those columns once, in ascending order,
+    // into shared memory (aliasing the assembly accumulators, idle during PCG) and the rows gather from there.
+    __shared__ unsigned short xlist[P3_XS_MAX];
+    __shared__ int xs_n;
+    float4* xs = reinterpret_cast<float4*>(acc_sm);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gw = tid >> 5, nw = nthreads >> 5;
     const int nb = gridDim.x, N = pb.N;
@@ -518,6 +527,64 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
             if (lane < 3) pb.t[3 * (size_t) n + lane] = 0.f;  // unknowns := 0 (opt_solver.cpp:192-193)
         }
     }
+    bool staged;
+    {
+        // bitmap of the columns the CTA's register entries reference -> ascending list, registers hold the position in it
+        unsigned* bm = acc_sm;
+        unsigned* bpre = acc_sm + 256;
+        const int nwb = (N + 31) >> 5;  // <= 148: N <= P3_R * 16 * gridDim.x
+        for (int w = threadIdx.x; w < nwb; w += blockDim.x) bm[w] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < P3_R; ++r)
+#pragma unroll
+            for (int u = 0; u < P3_LE; ++u)
+                if (rc[r][u] >= 0) atomicOr(&bm[rc[r][u] >> 5], 1u << (rc[r][u] & 31));
+        __syncthreads();
+        if (wib == 0) {
+            int base = 0;
+            for (int w0 = 0; w0 < nwb; w0 += 32) {
+                const int w = w0 + lane;
+                const int c = w < nwb ? __popc(bm[w]) : 0;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (w < nwb) bpre[w] = (unsigned) (base + inc - c);
+                base += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) xs_n = base;
+        }
+        __syncthreads();
+        staged = xs_n <= P3_XS_MAX && nwb <= 256;
+        if (staged) {
+            for (int w = threadIdx.x; w < nwb; w += blockDim.x) {
+                unsigned bits = bm[w];
+                int j = (int) bpre[w];
+                while (bits) {
+                    xlist[j++] = (unsigned short) (32 * w + __ffs(bits) - 1);
+                    bits &= bits - 1;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < P3_R; ++r)
+#pragma unroll
+                for (int u = 0; u < P3_LE; ++u)
+                    if (rc[r][u] >= 0)
+                        rc[r][u] = (int) bpre[rc[r][u] >> 5] + __popc(bm[rc[r][u] >> 5] & ((1u << (rc[r][u] & 31)) - 1u));
+        }
+        __syncthreads();
+    }
+    const int xs_count = staged ? xs_n : 0;
+    // the CTA's columns of x -> shared memory (every thread of the CTA calls this; ends with a CTA barrier)
+    auto stage_x = [&](const float4* x) {
+        if (staged) {
+            for (int i = threadIdx.x; i < xs_count; i += PTPB) xs[i] = __ldcg(x + xlist[i]);
+            __syncthreads();
+        }
+    };
     GRID_SYNC();
 
     // row product with the exchanged vector x (float4 per row): registers first, entries beyond 32 * P3_LE from L2
@@ -525,7 +592,8 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
         float ax = 0.f, ay = 0.f, az = 0.f;
         float4 m[P3_LE];
 #pragma unroll
-        for (int u = 0; u < P3_LE; ++u) m[u] = rc[r][u] >= 0 ? __ldcg(x + rc[r][u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < P3_LE; ++u)
+            m[u] = rc[r][u] >= 0 ? (staged ? xs[rc[r][u]] : __ldcg(x + rc[r][u])) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < P3_LE; ++u) {
             ax = __fmaf_rn(rv[r][u], m[u].x, ax);
@@ -706,6 +774,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
             }
             PROF(7);
             if (!conv0) {
+                stage_x(pt.exch);
 #pragma unroll
                 for (int r = 0; r < P3_R; ++r) {
                     if (rn[r] < 0) continue;
@@ -771,6 +840,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                         }
                     }
                     const bool last = it + 1 >= ctl.linear_iter;
+                    if (!last) stage_x(ex);
                     float nv[P3_R];
 #pragma unroll
                     for (int r = 0; r < P3_R; ++r) nv[r] = (rn[r] >= 0 && !last) ? spmv(r, ex) : 0.f;
