@@ -79,6 +79,8 @@ struct dfu_solver {
     Scalars* sc = nullptr;
     Scalars* sc_host = nullptr;  // pinned
     unsigned* bar = nullptr;     // grid-barrier counter of the persistent kernel
+    bool bar_clean = false;      // the last kernel on `bar` left it cleared (version 3r does)
+    bool writeback_fused = false;  // the last solve wrote the node transforms back itself (version 3r)
     uint64_t reg_epoch = 0;      // node-position epoch the regularisation graph was built for (0: never)
     bool problem_ready = false;
     int coop_blocks = 0;         // co-resident CTAs for the persistent kernel (0: not available)
@@ -259,7 +261,13 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
                  (double) s->prm.pcg_tol * (double) s->prm.pcg_tol, nullptr};
     Scalars* sc = s->sc;
     unsigned* bar = s->bar;
-    DFU_CUDA_OK(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+    // (version 3r leaves the barrier words cleared itself; anything else ran last: clear them here)
+    bool bar_cleared = false;
+    auto clear_bar = [&]() -> int {
+        if (!bar_cleared) DFU_CUDA_OK(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
+        bar_cleared = true;
+        return DFU_OK;
+    };
     static long long* prof_dev = nullptr;
     const bool profile = getenv("DFU_SOLVER_PROFILE") != nullptr;
     if (profile) {
@@ -278,11 +286,11 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
     // take the textbook PCG of version 2 / 1.
     const int want = forced ? force[1] - '0' : (s->prm.linear_iter <= P3_MAX_LINEAR_ITER ? 3 : 2);
     int ver = want;
-    bool ran_v4 = false;
+    bool ran_v4 = false, fused = false;
     if (ver == 3 && !(s->pattern_ready && s->coop_blocks3 > 0 && s->N <= 32 * s->coop_blocks3 * (PTPB / 32))) ver = 2;  // (lane-per-row blocks)
     if (ver == 2 && (s->coop_blocks2 == 0 || s->N > P2_NPW * s->coop_blocks2 * (PTPB / 32))) ver = 1;
     if (ver == 3) {
-        Pattern pt{s->rowptr, s->rowlen, s->dslot, s->col, s->areg, s->vals, s->tslot, s->exch, s->st, s->xw, s->pw};
+        Pattern pt{s->rowptr, s->rowlen, s->dslot, s->col, s->areg, s->vals, s->tslot, s->exch, s->st, s->xw, s->pw, nullptr, nullptr, nullptr, nullptr};
         void* args[] = {&pb, &pt, &ctl, &sc, &bar};
         // rows in registers when every node fits a register slot; DFU_SOLVER_PATH=p3g forces the generic kernel, p3 the
         // barrier-per-iteration register kernel (3r), p4 / default: version 4 (tagged exchange, CTA-balanced assembly)
@@ -305,24 +313,33 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
             Exchange4 ex4{reinterpret_cast<float4*>(s->xw), reinterpret_cast<float4*>(s->pw), s->t4, s->seq};
             s->seq += (unsigned) need;
             void* args4[] = {&pb, &pt, &ex4, &ctl, &sc, &bar};
+            if (clear_bar() != DFU_OK) return DFU_ERR_CUDA;
             const size_t xs_bytes = (size_t) ((s->N + 15) / 16) * 16 * sizeof(float4);  // the fetched segments of the exchanged vector
             DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent4, dim3(s->coop_blocks4), dim3(PTPB), args4, xs_bytes, st));
             ran_v4 = true;
-        } else if (reg) {  // tags restart at 1 every launch: stale words of earlier launches must not look fresh
-            DFU_CUDA_OK(cudaMemsetAsync(&s->sc->spin_fail, 0, sizeof(int), st));
+        } else if (reg) {
+            // one launch per solve and nothing around it: the kernel clears its own barrier words on the way out and writes the
+            // node transforms (and the warp field's flags) back itself
+            if (!s->bar_clean && clear_bar() != DFU_OK) return DFU_ERR_CUDA;
+            pt.wf_real = s->wf->real; pt.wf_dual = s->wf->dual; pt.wf_pos_w = s->wf->pos_w; pt.wf_flags = s->wf->flags;
             DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent3r, dim3(s->coop_blocks3r), dim3(PTPB), args, 0, st));
+            fused = true;
         } else {
+            if (clear_bar() != DFU_OK) return DFU_ERR_CUDA;
             DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent3, dim3(s->coop_blocks3), dim3(PTPB), args, 0, st));
         }
         if (getenv("DFU_DEBUG")) fprintf(stderr, "[dfu] v3 %s\n", reg ? "rows in registers" : "generic");
     } else {
         void* args[] = {&pb, &ctl, &sc, &bar};
+        if (clear_bar() != DFU_OK) return DFU_ERR_CUDA;
         if (ver == 1)
             DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent, dim3(s->coop_blocks), dim3(PTPB), args, 0, st));
         else
             DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent2, dim3(s->coop_blocks2), dim3(PTPB), args, 0, st));
     }
     s->last_kernel = ran_v4 ? 5 : ver;
+    s->bar_clean = fused;
+    s->writeback_fused = fused;
     ++g_dfu_launches;
     if (profile && ver == 3) {  // debugging aid: synchronises
         long long h[16];
@@ -497,7 +514,8 @@ int solve_p2plane(dfu_solver* s, cudaStream_t st) {
         float4 *real = s->wf->real, *dual = s->wf->dual;
         int blocks = s->coop_blocks_p2p;
         if (const char* e = getenv("DFU_P2P_CTAS")) blocks = std::max(1, std::min(blocks, atoi(e)));  // experiments: fewer CTAs
-        DFU_CUDA_OK(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+        DFU_CUDA_OK(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
+        s->bar_clean = false;
         void* args[] = {&pb, &ctl, &sc, &bar, &real, &dual};
         DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) kp_persistent, dim3(blocks), dim3(P2P_TPB), args, 0, st));
         ++g_dfu_launches;
@@ -782,9 +800,11 @@ int dfu_solver_solve_all(dfu_solver* s, dfu_stream stream) {
         s->lists_sorted = true;
         s->pattern_ready = false;  // its per-entry slots referred to the old order
     }
+    s->writeback_fused = false;
     int rc = multi ? solve_multi_kernel(s, st) : solve_persistent(s, st);
     if (rc != DFU_OK) return rc;
-    // write back ONCE: dg_se3 := DQ(0,0,0,t) * dg_se3 (opt_solver.cpp:270-285, node.cpp:19-23)
+    // write back ONCE: dg_se3 := DQ(0,0,0,t) * dg_se3 (opt_solver.cpp:270-285, node.cpp:19-23) -- version 3r has done it
+    if (s->writeback_fused) return DFU_OK;
     return dfu_warpfield_update_translations(s->wf, s->vec, stream);
 }
 
@@ -855,7 +875,7 @@ int dfu_solver_get_stats_host(const dfu_solver* s, double stats_host[4], dfu_str
     stats_host[1] = s->sc_host->E;
     stats_host[2] = (double) s->sc_host->pcg_iters;
     stats_host[3] = (double) (s->gn_steps_host >= 0 ? s->gn_steps_host : s->sc_host->gn_steps);
-    DFU_REQUIRE(!((s->last_kernel == 3 || s->last_kernel == 5) && s->sc_host->spin_fail), DFU_ERR_CUDA,
+    DFU_REQUIRE(!(s->last_kernel == 5 && s->sc_host->spin_fail), DFU_ERR_CUDA,
                 "persistent solver: an exchanged word never arrived (grid not co-resident?); result invalid");
     return DFU_OK;
 }

@@ -57,6 +57,11 @@ struct Pattern {
     float4* st;             // [6][N] row-local PCG state: r, w, z, s, p, x
     unsigned long long* xw; // register version: [2][N][3] exchanged vector as tagged words (float bits | tag << 32)
     unsigned long long* pw; // register version: [2][MAX_PARTIALS][2] tagged per-CTA partial sums
+    // version 3r writes the solution back itself (dg_se3 := DQ(0,0,0,t) * dg_se3 and the warp field's flags) when these are set
+    float4* wf_real;
+    float4* wf_dual;
+    const float4* wf_pos_w;
+    int* wf_flags;
 };
 constexpr int ACC_W = 256;                              // fixed-point accumulators per warp (columns per pass)
 constexpr float FIX_SCALE = 1099511627776.f;            // 2^40; contributions are <= 1

@@ -527,6 +527,9 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
             if (lane < 3) pb.t[3 * (size_t) n + lane] = 0.f;  // unknowns := 0 (opt_solver.cpp:192-193)
         }
     }
+    if (pt.wf_flags && tid == 0) {  // (recomputed with the write-back at the end)
+        pt.wf_flags[0] = 1; pt.wf_flags[1] = 0; pt.wf_flags[2] = 0;
+    }
     bool staged;
     {
         // bitmap of the columns the CTA's register entries reference -> ascending list, registers hold the position in it
@@ -913,6 +916,34 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                 if (lane == 0) er += (double) pb.wreg2 * r2;
             }
         }
+        // write back ONCE: dg_se3 := DQ(0,0,0,t) * dg_se3 (opt_solver.cpp:270-285, node.cpp:19-23), and the warp field's
+        // flags (see node_flags_kernel) -- every t is final and visible since the last grid barrier
+        if (pt.wf_real && tid < ((N + 31) & ~31)) {
+            int ok = 1;
+            float mw = 0.f, md = 0.f;
+            if (tid < N) {
+                const DQ inc = dq_from_translation(pb.t[3 * (size_t) tid], pb.t[3 * (size_t) tid + 1], pb.t[3 * (size_t) tid + 2]);
+                const DQ old{make_quat(pt.wf_real[tid]), make_quat(pt.wf_dual[tid])};
+                const DQ res = dq_mul(inc, old);
+                const float4 r = to_float4(res.real), d = to_float4(res.dual);
+                pt.wf_real[tid] = r;
+                pt.wf_dual[tid] = d;
+                ok = (r.x == 1.f && r.y == 0.f && r.z == 0.f && r.w == 0.f && d.x == 0.f);
+                mw = pt.wf_pos_w[tid].w;
+                md = fmaxf(fabsf(d.y), fmaxf(fabsf(d.z), fabsf(d.w)));
+            }
+            ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+                md = fmaxf(md, __shfl_xor_sync(0xffffffffu, md, o));
+            }
+            if (lane == 0) {
+                if (!ok) atomicAnd(&pt.wf_flags[0], 0);
+                atomicMax(reinterpret_cast<unsigned*>(&pt.wf_flags[1]), __float_as_uint(mw));  // non-negative floats
+                atomicMax(reinterpret_cast<unsigned*>(&pt.wf_flags[2]), __float_as_uint(md));
+            }
+        }
         publish(e2, er, 0.0, PART(0));
     }
     {
@@ -927,6 +958,14 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
         sc->pcg_iters = pcg_total;
         sc->gn_steps = gn_total;
         sc->first = 0;
+    }
+    // the last CTA out clears the barrier words for the next launch (everybody is past the final barrier when it leaves)
+    if (threadIdx.x == 0) {
+        const unsigned out = atomicAdd(bar + 1, 1u);
+        if (out == (unsigned) nb - 1u) {
+            bar[0] = 0u;
+            bar[1] = 0u;
+        }
     }
     PROF(15);
 #undef PROF
