@@ -145,5 +145,5 @@ struct dfu_warpfield {
 int dfu_wf_refresh_flags(dfu_warpfield* wf, cudaStream_t st);
 int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float voxel[3], int z0, int z1, cudaStream_t st);
 int dfu_wf_build_data_graph(const dfu_warpfield* wf, const float* canon, const float* live, int P, int32_t* nbr,
-                            float* wts, float* dvec, int* deg, cudaStream_t st);
+                            float* wts, float* dvec, int* deg, int32_t* rank, cudaStream_t st);
 int dfu_wf_build_node_graph(const dfu_warpfield* wf, int32_t* nnbr, cudaStream_t st);

@@ -753,13 +753,15 @@ int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* ca
     // will read them (versions 3 / 3r), sorted by point otherwise
     const long ne = (long) P * 8;
     DFU_CUDA_OK(cudaMemsetAsync(s->tmp, 0, 2 * (size_t) N * sizeof(int), st));
+    s->lists_sorted = !pattern_eligible(s);
     if (P > 0) {
-        rc = dfu_wf_build_data_graph(wf, canon_v, live_v, P, s->nbr, s->wts, s->dvec, s->tmp, st);
+        // (unsorted lists: the counting atomics of the kNN kernel hand every edge its position in its node's list -- s->tent is
+        //  free to hold them -- and the fill below is a plain scatter)
+        rc = dfu_wf_build_data_graph(wf, canon_v, live_v, P, s->nbr, s->wts, s->dvec, s->tmp, s->lists_sorted ? nullptr : s->tent, st);
         if (rc != DFU_OK) return rc;
     }
     k_scan<<<1, 1024, 0, st>>>(s->tmp, N, s->tptr);
     DFU_LAUNCH_OK();
-    s->lists_sorted = !pattern_eligible(s);
     if (P > 0) {
         if (s->lists_sorted) {
             k_fill<<<div_up(ne, TPB), TPB, 0, st>>>(s->nbr, ne, s->tptr, s->tmp + N, s->tent, 0);
@@ -767,7 +769,7 @@ int dfu_solver_init_problem(dfu_solver* s, const float* canon_v, const float* ca
             k_sort_emit<<<min(div_up((long) N * 32, TPB), 65535), TPB, 0, st>>>(s->tptr, N, s->tent, s->wts, s->tv, s->tw);
             DFU_LAUNCH_OK();
         } else {
-            k_fill_emit<<<div_up(ne, TPB), TPB, 0, st>>>(s->nbr, ne, s->tptr, s->tmp + N, s->wts, s->tv, s->tw);
+            k_fill_emit_ranked<<<div_up(ne, TPB), TPB, 0, st>>>(s->nbr, s->tent, ne, s->tptr, s->wts, s->tv, s->tw);
             DFU_LAUNCH_OK();
         }
     }

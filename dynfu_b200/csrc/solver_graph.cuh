@@ -50,6 +50,20 @@ __global__ void k_fill_emit(const int32_t* __restrict__ key, long n, const int* 
         tw[slot] = wts[e];
     }
 }
+// the same without atomics: the kNN kernel kept, per edge, the value its counting atomic returned (the edge's position in its
+// node's list, in arrival order)
+__global__ void k_fill_emit_ranked(const int32_t* __restrict__ key, const int32_t* __restrict__ rank, long n,
+                                   const int* __restrict__ ptr, const float* __restrict__ wts, int32_t* __restrict__ tv,
+                                   float* __restrict__ tw) {
+    const long e = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) {
+        const int m = key[e];
+        if (m < 0) return;
+        const int slot = ptr[m] + rank[e];
+        tv[slot] = (int32_t) (e >> 3);
+        tw[slot] = wts[e];
+    }
+}
 // in-edge lists of the regularisation graph are short: insertion sort, one thread per node
 __global__ void k_sort_small(const int* __restrict__ ptr, int N, int32_t* __restrict__ a) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;

@@ -140,6 +140,7 @@ struct PointArgs {
     const float* live;
     float* dvec;
     int* deg;         // OP_GRAPH (may be null): per-node count of referencing points, incremented here
+    int32_t* rank;    // OP_GRAPH (may be null, needs deg): per edge, how many references its node had before this one
     // OP_BOUNDS: queries are the centres of the 8x8x8 bricks of a volume
     float2* bounds;
     int bdim[3];
@@ -219,7 +220,10 @@ __global__ void __launch_bounds__(256) points_kernel(const PointArgs a) {
         if (active) {
             a.idx[(size_t) q * DFU_KNN + sub] = my_i;
             a.wts[(size_t) q * DFU_KNN + sub] = my_w;
-            if (a.deg && my_i >= 0) atomicAdd(&a.deg[my_i], 1);
+            if (a.deg && my_i >= 0) {
+                const int rk = atomicAdd(&a.deg[my_i], 1);
+                if (a.rank) a.rank[(size_t) q * DFU_KNN + sub] = rk;
+            }
             if (sub < 3 && a.dvec) a.dvec[3 * (size_t) q + sub] = a.live[3 * (size_t) q + sub] - (sub == 0 ? qx : (sub == 1 ? qy : qz));
         }
         return;
@@ -566,7 +570,10 @@ __global__ void __launch_bounds__(128) points_grid_graph_kernel(const PointArgs 
         if (active) {
             a.idx[(size_t) q * DFU_KNN + j * G + sub] = idx;
             a.wts[(size_t) q * DFU_KNN + j * G + sub] = w;
-            if (a.deg && idx >= 0) atomicAdd(&a.deg[idx], 1);
+            if (a.deg && idx >= 0) {
+                const int rk = atomicAdd(&a.deg[idx], 1);
+                if (a.rank) a.rank[(size_t) q * DFU_KNN + j * G + sub] = rk;
+            }
         }
     }
     if (active && a.dvec) {
@@ -623,7 +630,10 @@ __global__ void __launch_bounds__(128) points_grid_kernel(const PointArgs a, con
         if (a.deg) {
 #pragma unroll
             for (int k = 0; k < DFU_KNN; ++k)
-                if (t.i[k] >= 0) atomicAdd(&a.deg[t.i[k]], 1);
+                if (t.i[k] >= 0) {
+                    const int rk = atomicAdd(&a.deg[t.i[k]], 1);
+                    if (a.rank) a.rank[(size_t) q * DFU_KNN + k] = rk;
+                }
         }
         return;
     }
@@ -848,7 +858,7 @@ int dfu_wf_build_brick_table(dfu_warpfield* wf, const int dims[3], const float v
 
 // data graph + weights + (live - canon) for the solver; requires N >= 8
 int dfu_wf_build_data_graph(const dfu_warpfield* wf, const float* canon, const float* live, int P, int32_t* nbr,
-                            float* wts, float* dvec, int* deg, cudaStream_t st) {
+                            float* wts, float* dvec, int* deg, int32_t* rank, cudaStream_t st) {
     PointArgs a{};
     a.q = canon;
     a.Q = P;
@@ -857,6 +867,7 @@ int dfu_wf_build_data_graph(const dfu_warpfield* wf, const float* canon, const f
     a.live = live;
     a.dvec = dvec;
     a.deg = deg;
+    a.rank = rank;
     return launch_points<OP_GRAPH>(wf, a, st);
 }
 // regularisation graph: 8-NN of every node among the nodes (includes itself; opt_solver.cpp:74-105)
