@@ -2,7 +2,7 @@
 # Turns the captures of `bash profiles/profile_run_r02.sh` (gpurun_out/<tag>_*) into the tracked round-2 summaries.
 # usage: bash profiles/make_summaries_r02.sh r02f
 set -e
-tag=${1:-r02f}; out=r02
+tag=${1:-r02g}; out=r02
 cd "$(dirname "$0")/.."
 for k in integrate solver knn dense; do
   ncu -i gpurun_out/${tag}_$k.ncu-rep --page raw --csv > /tmp/${tag}_$k.csv 2>/dev/null
@@ -26,7 +26,7 @@ def per_launch(path, pattern):
 tr = {"integrate_dram_bytes_per_launch": per_launch("/tmp/%s_integrate.csv" % tag, "integrate_kernel<2>"),
       "solver_dram_bytes_per_launch": per_launch("/tmp/%s_solver.csv" % tag, "k_solve_persistent"),
       "dense_integrate_dram_bytes_per_launch": per_launch("/tmp/%s_dense.csv" % tag, "integrate_kernel<2>"),
-      "knn_dram_bytes_per_launch": per_launch("/tmp/%s_knn.csv" % tag, "points_grid_kernel"),
+      "knn_dram_bytes_per_launch": per_launch("/tmp/%s_knn.csv" % tag, "points_grid"),
       "source": "ncu --set full --clock-control none of `python bench.py` at N = 1 (sequential schedule), dram__bytes_read.sum + "
                 "dram__bytes_write.sum, mean over the captured steady-state launches (profiles/profile_run_r02.sh; summaries in "
                 "profiles/r02_*_ncu_full.txt)"}
