@@ -1001,12 +1001,26 @@ __global__ void __launch_bounds__(128) k_pattern(Problem pb, int NW, int* __rest
             const int m = pb.rin[j];
             atomicOr(&bm[m >> 5], 1u << (m & 31));
         }
-        for (int e = lo + lane; e < hi; e += 32) {
-            int nbk[8];
-            float wk[8];
-            load8(pb.nbr, pb.wts, pb.tv[e], nbk, wk);
+        // (both sweeps of the node's list keep four entries per lane in flight: the kernel is one wave of warps, each a chain of
+        //  dependent point-id -> neighbour-list loads; the second sweep finds the lists in L1)
+        for (int e0 = lo + lane; e0 < hi; e0 += 128) {
+            int v[4];
+            int4 na[4], nb4[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) atomicOr(&bm[nbk[k] >> 5], 1u << (nbk[k] & 31));
+            for (int u = 0; u < 4; ++u) v[u] = e0 + 32 * u < hi ? pb.tv[e0 + 32 * u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int vv = v[u] >= 0 ? v[u] : 0;
+                na[u] = *(reinterpret_cast<const int4*>(pb.nbr) + 2 * (size_t) vv);
+                nb4[u] = *(reinterpret_cast<const int4*>(pb.nbr) + 2 * (size_t) vv + 1);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (v[u] < 0) continue;
+                const int nbk[8] = {na[u].x, na[u].y, na[u].z, na[u].w, nb4[u].x, nb4[u].y, nb4[u].z, nb4[u].w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) atomicOr(&bm[nbk[k] >> 5], 1u << (nbk[k] & 31));
+            }
         }
         __syncwarp();
         // exclusive prefix of the word popcounts
@@ -1059,14 +1073,26 @@ __global__ void __launch_bounds__(128) k_pattern(Problem pb, int NW, int* __rest
             dslot[a] = ds;
             areg[off + ds] = pb.wreg2 * cnt;
         }
-        for (int e = lo + lane; e < hi; e += 32) {
-            int nbk[8];
-            float wk[8];
-            load8(pb.nbr, pb.wts, pb.tv[e], nbk, wk);
-            unsigned sk[8];
+        for (int e0 = lo + lane; e0 < hi; e0 += 128) {
+            int v[4];
+            int4 na[4], nb4[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sk[k] = slot_of(nbk[k]);
-            tslot[e] = make_uint4(sk[0] | (sk[1] << 16), sk[2] | (sk[3] << 16), sk[4] | (sk[5] << 16), sk[6] | (sk[7] << 16));
+            for (int u = 0; u < 4; ++u) v[u] = e0 + 32 * u < hi ? pb.tv[e0 + 32 * u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int vv = v[u] >= 0 ? v[u] : 0;
+                na[u] = *(reinterpret_cast<const int4*>(pb.nbr) + 2 * (size_t) vv);
+                nb4[u] = *(reinterpret_cast<const int4*>(pb.nbr) + 2 * (size_t) vv + 1);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (v[u] < 0) continue;
+                const int nbk[8] = {na[u].x, na[u].y, na[u].z, na[u].w, nb4[u].x, nb4[u].y, nb4[u].z, nb4[u].w};
+                unsigned sk[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sk[k] = slot_of(nbk[k]);
+                tslot[e0 + 32 * u] = make_uint4(sk[0] | (sk[1] << 16), sk[2] | (sk[3] << 16), sk[4] | (sk[5] << 16), sk[6] | (sk[7] << 16));
+            }
         }
         __syncwarp();
     }
