@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer over the round's kernels (small configurations; cooperative launches and clusters are supported by the tool)
 mkdir -p gpurun_out
-SEL1='solver_every_execution_path or solver_fixed_iteration or tsdf_dense_depth or tsdf_warped_bit_exact or p2plane_solver_matches'
+SEL1='solver_every_execution_path or solver_fixed_iteration or self_contained or lanes_per_query or tsdf_dense_depth or tsdf_warped_bit_exact or p2plane_solver_matches'
 SEL2='marching_cubes_bit_exact or dfu_frame or overlapped_frame'
 {
 echo "== memcheck: tests/test_gpu_parity.py -k \"$SEL1\""
