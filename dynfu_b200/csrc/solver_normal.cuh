@@ -27,9 +27,80 @@ DFU_DEV void spmv_row(const Pattern& pt, int off, int len, int lane, const float
     ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
 }
 
+// Accumulators of one warp of version 3r: ACC_W low words + ACC_W high words (generic rows), or -- rows of at most 64 columns,
+// the usual case -- four bank-rotated copies of 64 low + 64 high words and the three 64-bit sums of b.
+constexpr int P3_XS_MAX = 1024;  // columns of the exchanged vector a CTA stages in shared memory (more: straight from L2)
+constexpr int P3_FU = 2;  // entries per lane in flight in the fused sweep
+constexpr int P3_ACC_WORDS = 640, P3_ACC_COPY = 72, P3_ACC_HI = 320, P3_ACC_B = 616;
+
+// One sweep of node n's list (entries lo..hi of the transposed data graph) that accumulates BOTH b_n = sum tw * theta e (three
+// 64-bit fixed-point sums, left at acc + P3_ACC_B) and the data part of row n of A (2^40 fixed point as 20 + 20 bit halves in
+// 32-bit shared-memory atomics; slot s of the row is the sum of acc[s + 72 c] / acc[320 + s + 72 c] over the copies c).
+// Measured (profiles/r02_solver_experiments.md): the loop is bound by shared-memory atomic wavefronts -- the 32 points of a
+// batch share a handful of popular neighbours, 5.3 lanes per word per instruction on a single copy -- and by its two dependent
+// L2 round trips.  So: FOUR copies of the accumulators, 72 words apart so that one slot lies in four different banks (lane & 3
+// picks the copy; integer sums, any split gives the same bits); theta read from s4.w, the same 32-byte sector as theta e; and
+// the point ids of the NEXT 128 entries fetched a batch ahead.
+template <int FU>
+DFU_DEV void assemble_row_fused(const int32_t* __restrict__ tv, const float* __restrict__ tw,
+                                                const uint4* __restrict__ tslot, const float4* s4, const float* __restrict__ wts,
+                                                int lo, int hi, int lane, unsigned* acc) {
+    for (int j = lane; j < P3_ACC_WORDS; j += 32) acc[j] = 0u;
+    unsigned* my_lo = acc + P3_ACC_COPY * (lane & 3);
+    unsigned* my_hi = my_lo + P3_ACC_HI;
+    int vn[FU];
+    long long bx = 0, by = 0, bz = 0;
+#pragma unroll
+    for (int u = 0; u < FU; ++u) vn[u] = lo + lane + 32 * u < hi ? tv[lo + lane + 32 * u] : -1;
+    __syncwarp();
+    for (int e0 = lo + lane; e0 < hi; e0 += 32 * FU) {  // FU entries per lane in flight
+        int v[FU];
+        float c[FU];
+        uint4 sl[FU];
+        float4 w0[FU], w1[FU], se[FU];
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            v[u] = vn[u];
+            const int vv = v[u] >= 0 ? v[u] : 0;
+            const int ee = v[u] >= 0 ? e0 + 32 * u : lo;
+            c[u] = tw[ee];
+            sl[u] = tslot[ee];
+            se[u] = s4[vv];
+            w0[u] = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) vv);
+            w1[u] = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) vv + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < FU; ++u) vn[u] = e0 + 32 * FU + 32 * u < hi ? tv[e0 + 32 * FU + 32 * u] : -1;
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            if (v[u] < 0) continue;
+            bx += __float2ll_rn(c[u] * se[u].x * FIX_SCALE);
+            by += __float2ll_rn(c[u] * se[u].y * FIX_SCALE);
+            bz += __float2ll_rn(c[u] * se[u].z * FIX_SCALE);
+            const float cc = c[u] * se[u].w;
+            if (cc == 0.f) continue;
+            const float wk[8] = {w0[u].x, w0[u].y, w0[u].z, w0[u].w, w1[u].x, w1[u].y, w1[u].z, w1[u].w};
+            const unsigned sw[4] = {sl[u].x, sl[u].y, sl[u].z, sl[u].w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const unsigned long long f = (unsigned long long) __float2ll_rn(cc * wk[k] * FIX_SCALE);
+                const unsigned sidx = (k & 1) ? sw[k >> 1] >> 16 : sw[k >> 1] & 0xffffu;
+                atomicAdd(&my_lo[sidx], (unsigned) f & 0xfffffu);
+                atomicAdd(&my_hi[sidx], (unsigned) (f >> 20));
+            }
+        }
+    }
+    warp_sum_ll(bx); warp_sum_ll(by); warp_sum_ll(bz);
+    if (lane == 0) {
+        long long* out = reinterpret_cast<long long*>(acc + P3_ACC_B);
+        out[0] = bx; out[1] = by; out[2] = bz;
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Pattern pt, SolveCtl ctl, Scalars* sc, unsigned* bar) {
     __shared__ double sh4[4 * (PTPB / 32)];
-    __shared__ unsigned long long acc_sm[(PTPB / 32) * ACC_W];
+    __shared__ __align__(16) unsigned long long acc_sm[(PTPB / 32) * (P3_ACC_WORDS / 2)];  // per warp: ACC_W 64-bit words, or the layout of assemble_row_fused
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, gw = tid >> 5, nw = nthreads >> 5;
     const int nb = gridDim.x, N = pb.N;
@@ -38,7 +109,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
     const int R = (N + nw - 1) / nw;
     const int row0 = min(N, gw * R), row1 = min(N, row0 + R);
     unsigned bar_target = 0;
-    unsigned long long* acc = acc_sm + (threadIdx.x >> 5) * ACC_W;
+    unsigned long long* acc = acc_sm + (threadIdx.x >> 5) * (P3_ACC_WORDS / 2);
     float4 *S_r = pt.st, *S_w = pt.st + N, *S_z = pt.st + 2 * (size_t) N, *S_s = pt.st + 3 * (size_t) N,
            *S_p = pt.st + 4 * (size_t) N, *S_x = pt.st + 5 * (size_t) N;
 #define GRID_SYNC() grid_barrier(bar, (unsigned) nb, bar_target)
@@ -127,17 +198,33 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                 //  (point, weight) lists -- any warp may prepare any row, its outputs all go to memory)
                 for (int n = gw; n < N; n += nw) {
                     float ax, ay, az, gx = 0.f, gy = 0.f, gz = 0.f, cnt = 0.f, e2 = 0.f;
-                    node_gather_data_fixed(pb, n, lane, ax, ay, az);  // already summed over the warp
+                    const int off = pt.rowptr[n], len = pt.rowlen[n];
+                    const int lo = pb.tptr[n], hi = pb.tptr[n + 1];
+                    // the usual row (at most 64 columns, at most FIX_MAX_DEG points) when theta changed: b and the data part
+                    // of the row in ONE sweep of the node's list (assemble_row_fused: four bank-rotated accumulator copies,
+                    // native 32-bit shared-memory atomics, theta from s4.w); same integer sums as the general passes below
+                    const bool fused = gn == 0 && hi - lo <= FIX_MAX_DEG && len <= 64;
                     if (pb.wreg2 > 0.f) {
                         node_gather_reg(pb, n, lane, pb.t, gx, gy, gz, cnt, e2);
                         gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
-                        ax -= pb.wreg2 * gx; ay -= pb.wreg2 * gy; az -= pb.wreg2 * gz;
                         e2 = warp_sum(e2);
                     }
-                    const int off = pt.rowptr[n], len = pt.rowlen[n];
+                    if (!fused) node_gather_data_fixed(pb, n, lane, ax, ay, az);  // already summed over the warp
                     PROF(3);
-                    if (gn == 0) {  // theta changed: data part of the row, ACC_W columns per pass
-                        const int lo = pb.tptr[n], hi = pb.tptr[n + 1];
+                    if (fused) {
+                        unsigned* a32 = reinterpret_cast<unsigned*>(acc);
+                        assemble_row_fused<P3_FU>(pb.tv, pb.tw, pt.tslot, pb.s4, pb.wts, lo, hi, lane, a32);
+                        const long long* bsum = reinterpret_cast<const long long*>(a32 + P3_ACC_B);
+                        ax = (float) ((double) bsum[0] * FIX_INV); ay = (float) ((double) bsum[1] * FIX_INV); az = (float) ((double) bsum[2] * FIX_INV);
+                        for (int j = lane; j < len; j += 32) {
+                            const unsigned* q = a32 + j;
+                            const unsigned long long sl4 = (unsigned long long) q[0] + q[P3_ACC_COPY] + q[2 * P3_ACC_COPY] + q[3 * P3_ACC_COPY];
+                            const unsigned long long sh4s = (unsigned long long) q[P3_ACC_HI] + q[P3_ACC_HI + P3_ACC_COPY] +
+                                                            q[P3_ACC_HI + 2 * P3_ACC_COPY] + q[P3_ACC_HI + 3 * P3_ACC_COPY];
+                            pt.vals[off + j] = pt.areg[off + j] + (float) ((double) ((sh4s << 20) + sl4) * FIX_INV);
+                        }
+                        __syncwarp();
+                    } else if (gn == 0) {  // theta changed: data part of the row, ACC_W columns per pass
                         for (int c0 = 0; c0 < len; c0 += ACC_W) {
                             for (int j = lane; j < ACC_W; j += 32) acc[j] = 0ull;
                             __syncwarp();
@@ -164,6 +251,9 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                                 pt.vals[off + c0 + j] = pt.areg[off + c0 + j] + (float) ((double) (long long) acc[j] * FIX_INV);
                             __syncwarp();
                         }
+                    }
+                    if (pb.wreg2 > 0.f) {
+                        ax -= pb.wreg2 * gx; ay -= pb.wreg2 * gy; az -= pb.wreg2 * gz;
                     }
                     __syncwarp();
                     PROF(4);
@@ -216,7 +306,17 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                         S_z[n] = zero4; S_s[n] = zero4; S_p[n] = zero4;
                     }
                 }
-                double gamma_prev = 0.0, alpha_prev = 0.0;
+                // (one FP64 division between the totals and the update instead of three: 1 / gamma of the previous iteration is
+                //  formed right after that iteration's update, and gamma / alpha_prev = beta * denom_prev; the row's diagonal and
+                //  its reciprocals stay in registers across the iterations -- one row per lane)
+                double gamma_prev = 0.0, inv_gamma_prev = 0.0, denom_prev = 0.0;
+                float inv = 0.f;
+                double invd = 0.0;
+                if (row0 + lane < row1) {
+                    const float D = pb.nbuf[3 * (size_t) N + row0 + lane];
+                    inv = D > 0.f ? 1.f / D : 0.f;
+                    invd = D > 0.f ? 1.0 / (double) D : 0.0;
+                }
                 PROF(8);
                 for (int it = 0; it < ctl.linear_iter; ++it) {
                     const int buf = (it + 1) & 1;
@@ -226,9 +326,6 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                     {
                         const int n = row0 + lane;  // one row per lane
                         if (n < row1) {
-                            const float D = pb.nbuf[3 * (size_t) N + n];
-                            const float inv = D > 0.f ? 1.f / D : 0.f;
-                            const double invd = D > 0.f ? 1.0 / (double) D : 0.0;
                             const float4 r = S_r[n], w = S_w[n];
                             g += ((double) r.x * r.x + (double) r.y * r.y + (double) r.z * r.z) * invd;
                             d += ((double) w.x * r.x + (double) w.y * r.y + (double) w.z * r.z) * invd;
@@ -249,8 +346,8 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                     const D4 gd = sum_partials4(PART(buf), nb, sh4);
                     const double gamma = gd.a, delta = gd.b;
                     if (!(gamma > 0.0) || (it > 0 && gamma <= ctl.tol2 * rz_ref)) break;
-                    const double beta = it > 0 ? gamma / gamma_prev : 0.0;
-                    const double denom = it > 0 ? delta - beta * gamma / alpha_prev : delta;
+                    const double beta = it > 0 ? gamma * inv_gamma_prev : 0.0;
+                    const double denom = it > 0 ? delta - beta * beta * denom_prev : delta;
                     if (!(denom > 0.0)) break;
                     const double alpha = gamma / denom;
                     const float af = (float) alpha, bf = (float) beta;
@@ -261,8 +358,6 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                         if (!last) spmv_block(ex, nx, ny, nz);  // n = A m
                         const int n = row0 + lane;
                         if (n < row1) {
-                            const float D = pb.nbuf[3 * (size_t) N + n];
-                            const float inv = D > 0.f ? 1.f / D : 0.f;
                             float4 r = S_r[n], w = S_w[n], z = S_z[n], sv = S_s[n], p = S_p[n], x = S_x[n];
                             z.x = __fmaf_rn(bf, z.x, nx); z.y = __fmaf_rn(bf, z.y, ny); z.z = __fmaf_rn(bf, z.z, nz);
                             sv.x = __fmaf_rn(bf, sv.x, w.x); sv.y = __fmaf_rn(bf, sv.y, w.y); sv.z = __fmaf_rn(bf, sv.z, w.z);
@@ -276,7 +371,8 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                     PROF(12);
                     ++pcg_total;
                     gamma_prev = gamma;
-                    alpha_prev = alpha;
+                    inv_gamma_prev = 1.0 / gamma;
+                    denom_prev = denom;
                 }
             }
             // t += x (row-local), then everybody needs the new t
@@ -339,77 +435,6 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
 constexpr int P3_R = 2;
 constexpr int P3_LE = 2;
 constexpr int P3_MAX_LINEAR_ITER = 64;  // longer PCG runs use the textbook recurrences (versions 1 / 2)
-
-// Accumulators of one warp of version 3r: ACC_W low words + ACC_W high words (generic rows), or -- rows of at most 64 columns,
-// the usual case -- four bank-rotated copies of 64 low + 64 high words and the three 64-bit sums of b.
-constexpr int P3_XS_MAX = 1024;  // columns of the exchanged vector a CTA stages in shared memory (more: straight from L2)
-constexpr int P3_FU = 2;  // entries per lane in flight in the fused sweep
-constexpr int P3_ACC_WORDS = 640, P3_ACC_COPY = 72, P3_ACC_HI = 320, P3_ACC_B = 616;
-
-// One sweep of node n's list (entries lo..hi of the transposed data graph) that accumulates BOTH b_n = sum tw * theta e (three
-// 64-bit fixed-point sums, left at acc + P3_ACC_B) and the data part of row n of A (2^40 fixed point as 20 + 20 bit halves in
-// 32-bit shared-memory atomics; slot s of the row is the sum of acc[s + 72 c] / acc[320 + s + 72 c] over the copies c).
-// Measured (profiles/r02_solver_experiments.md): the loop is bound by shared-memory atomic wavefronts -- the 32 points of a
-// batch share a handful of popular neighbours, 5.3 lanes per word per instruction on a single copy -- and by its two dependent
-// L2 round trips.  So: FOUR copies of the accumulators, 72 words apart so that one slot lies in four different banks (lane & 3
-// picks the copy; integer sums, any split gives the same bits); theta read from s4.w, the same 32-byte sector as theta e; and
-// the point ids of the NEXT 128 entries fetched a batch ahead.
-template <int FU>
-DFU_DEV void assemble_row_fused(const int32_t* __restrict__ tv, const float* __restrict__ tw,
-                                                const uint4* __restrict__ tslot, const float4* s4, const float* __restrict__ wts,
-                                                int lo, int hi, int lane, unsigned* acc) {
-    for (int j = lane; j < P3_ACC_WORDS; j += 32) acc[j] = 0u;
-    unsigned* my_lo = acc + P3_ACC_COPY * (lane & 3);
-    unsigned* my_hi = my_lo + P3_ACC_HI;
-    int vn[FU];
-    long long bx = 0, by = 0, bz = 0;
-#pragma unroll
-    for (int u = 0; u < FU; ++u) vn[u] = lo + lane + 32 * u < hi ? tv[lo + lane + 32 * u] : -1;
-    __syncwarp();
-    for (int e0 = lo + lane; e0 < hi; e0 += 32 * FU) {  // FU entries per lane in flight
-        int v[FU];
-        float c[FU];
-        uint4 sl[FU];
-        float4 w0[FU], w1[FU], se[FU];
-#pragma unroll
-        for (int u = 0; u < FU; ++u) {
-            v[u] = vn[u];
-            const int vv = v[u] >= 0 ? v[u] : 0;
-            const int ee = v[u] >= 0 ? e0 + 32 * u : lo;
-            c[u] = tw[ee];
-            sl[u] = tslot[ee];
-            se[u] = s4[vv];
-            w0[u] = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) vv);
-            w1[u] = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) vv + 1);
-        }
-#pragma unroll
-        for (int u = 0; u < FU; ++u) vn[u] = e0 + 32 * FU + 32 * u < hi ? tv[e0 + 32 * FU + 32 * u] : -1;
-#pragma unroll
-        for (int u = 0; u < FU; ++u) {
-            if (v[u] < 0) continue;
-            bx += __float2ll_rn(c[u] * se[u].x * FIX_SCALE);
-            by += __float2ll_rn(c[u] * se[u].y * FIX_SCALE);
-            bz += __float2ll_rn(c[u] * se[u].z * FIX_SCALE);
-            const float cc = c[u] * se[u].w;
-            if (cc == 0.f) continue;
-            const float wk[8] = {w0[u].x, w0[u].y, w0[u].z, w0[u].w, w1[u].x, w1[u].y, w1[u].z, w1[u].w};
-            const unsigned sw[4] = {sl[u].x, sl[u].y, sl[u].z, sl[u].w};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const unsigned long long f = (unsigned long long) __float2ll_rn(cc * wk[k] * FIX_SCALE);
-                const unsigned sidx = (k & 1) ? sw[k >> 1] >> 16 : sw[k >> 1] & 0xffffu;
-                atomicAdd(&my_lo[sidx], (unsigned) f & 0xfffffu);
-                atomicAdd(&my_hi[sidx], (unsigned) (f >> 20));
-            }
-        }
-    }
-    warp_sum_ll(bx); warp_sum_ll(by); warp_sum_ll(bz);
-    if (lane == 0) {
-        long long* out = reinterpret_cast<long long*>(acc + P3_ACC_B);
-        out[0] = bx; out[1] = by; out[2] = bz;
-    }
-    __syncwarp();
-}
 
 DFU_DEV void warp_total4(const double* part4, int nb, int lane, double& a, double& b, double& c) {
     a = b = c = 0.0;
