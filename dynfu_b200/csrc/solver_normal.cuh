@@ -110,8 +110,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
     const int row0 = min(N, gw * R), row1 = min(N, row0 + R);
     unsigned bar_target = 0;
     unsigned long long* acc = acc_sm + (threadIdx.x >> 5) * (P3_ACC_WORDS / 2);
-    float4 *S_r = pt.st, *S_w = pt.st + N, *S_z = pt.st + 2 * (size_t) N, *S_s = pt.st + 3 * (size_t) N,
-           *S_p = pt.st + 4 * (size_t) N, *S_x = pt.st + 5 * (size_t) N;
+    float4* S_r = pt.st;  // b of every row, handed from the warp that prepared the row to the lane that owns it in the PCG loop
 #define GRID_SYNC() grid_barrier(bar, (unsigned) nb, bar_target)
 #define PART(buf) (pb.part + (size_t) (buf) * 2 * MAX_PARTIALS)
     long long t_prev = clock64();
@@ -127,30 +126,35 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
     for (int i = tid; i < 3 * N; i += nthreads) pb.t[i] = 0.f;  // unknowns := 0 (opt_solver.cpp:192-193)
     GRID_SYNC();
 
-    // y = A x for all rows of this warp, four rows in flight (their index / value / gather loads are issued together);
-    // the lane that owns row n (lane == n - row0) receives the result
+    // lane l owns row row0 + l in the vector updates: its offset / length (fixed for the launch) stay in registers
+    const int my_off = row0 + lane < row1 ? pt.rowptr[row0 + lane] : 0;
+    const int my_len = row0 + lane < row1 ? pt.rowlen[row0 + lane] : 0;
+    // y = A x for all rows of this warp, RQ rows in flight (their index / value loads are issued together, then their gathers:
+    // two dependent L2 round trips per batch -- the row bounds come from the owning lanes by shuffle); the lane that owns row n
+    // (lane == n - row0) receives the result
+    constexpr int RQ = 8;
     auto spmv_block = [&](const float4* __restrict__ x, float& rx, float& ry, float& rz_) {
         rx = ry = rz_ = 0.f;
-        for (int n0 = row0; n0 < row1; n0 += 4) {
-            int off[4], len[4], c[4][2];
-            float v[4][2];
+        for (int n0 = row0; n0 < row1; n0 += RQ) {
+            int off[RQ], len[RQ], c[RQ][2];
+            float v[RQ][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const bool ok = n0 + q < row1;
-                off[q] = ok ? pt.rowptr[n0 + q] : 0;
-                len[q] = ok ? pt.rowlen[n0 + q] : 0;
+            for (int q = 0; q < RQ; ++q) {
+                const int src = min(n0 + q - row0, 31);
+                off[q] = __shfl_sync(0xffffffffu, my_off, src);
+                len[q] = n0 + q < row1 ? __shfl_sync(0xffffffffu, my_len, src) : 0;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < RQ; ++q)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int j = lane + 32 * u;
                     c[q][u] = j < len[q] ? pt.col[off[q] + j] : -1;
                     v[q][u] = j < len[q] ? pt.vals[off[q] + j] : 0.f;
                 }
-            float ax[4], ay[4], az[4];
+            float ax[RQ], ay[RQ], az[RQ];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < RQ; ++q) {
                 ax[q] = ay[q] = az[q] = 0.f;
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < RQ; ++q) {
                 ax[q] = warp_sum(ax[q]); ay[q] = warp_sum(ay[q]); az[q] = warp_sum(az[q]);
                 if (lane == n0 + q - row0) {
                     rx = ax[q]; ry = ay[q]; rz_ = az[q];
@@ -264,7 +268,6 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                         pb.nbuf[3 * (size_t) N + n] = D;
                         pb.nbuf[3 * (size_t) n] = ax; pb.nbuf[3 * (size_t) n + 1] = ay; pb.nbuf[3 * (size_t) n + 2] = az;
                         S_r[n] = make_float4(ax, ay, az, 0.f);
-                        S_x[n] = zero4;
                         pt.exch[n] = make_float4(ax * inv, ay * inv, az * inv, 0.f);
                         rz += ((double) ax * ax + (double) ay * ay + (double) az * az) * invd;
                         er += (double) pb.wreg2 * e2;
@@ -297,13 +300,16 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
             PROF(7);
             if (!conv0) {
                 // w0 = A u0; z = s = p = 0
+                // (the PCG vectors of the lane's row live in registers for the whole loop: r was written by whichever warp
+                //  prepared the row, x is added to t at the end)
+                float4 r_ = zero4, w_ = zero4, z_ = zero4, s_ = zero4, p_ = zero4, x_ = zero4;
                 {
                     float wx, wy, wz;
                     spmv_block(pt.exch, wx, wy, wz);
                     const int n = row0 + lane;
                     if (n < row1) {
-                        S_w[n] = make_float4(wx, wy, wz, 0.f);
-                        S_z[n] = zero4; S_s[n] = zero4; S_p[n] = zero4;
+                        r_ = S_r[n];
+                        w_ = make_float4(wx, wy, wz, 0.f);
                     }
                 }
                 // (one FP64 division between the totals and the update instead of three: 1 / gamma of the previous iteration is
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                     {
                         const int n = row0 + lane;  // one row per lane
                         if (n < row1) {
-                            const float4 r = S_r[n], w = S_w[n];
+                            const float4 r = r_, w = w_;
                             g += ((double) r.x * r.x + (double) r.y * r.y + (double) r.z * r.z) * invd;
                             d += ((double) w.x * r.x + (double) w.y * r.y + (double) w.z * r.z) * invd;
                             ex[n] = make_float4(w.x * inv, w.y * inv, w.z * inv, 0.f);
@@ -358,14 +364,14 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                         if (!last) spmv_block(ex, nx, ny, nz);  // n = A m
                         const int n = row0 + lane;
                         if (n < row1) {
-                            float4 r = S_r[n], w = S_w[n], z = S_z[n], sv = S_s[n], p = S_p[n], x = S_x[n];
+                            float4 r = r_, w = w_, z = z_, sv = s_, p = p_, x = x_;
                             z.x = __fmaf_rn(bf, z.x, nx); z.y = __fmaf_rn(bf, z.y, ny); z.z = __fmaf_rn(bf, z.z, nz);
                             sv.x = __fmaf_rn(bf, sv.x, w.x); sv.y = __fmaf_rn(bf, sv.y, w.y); sv.z = __fmaf_rn(bf, sv.z, w.z);
                             p.x = __fmaf_rn(bf, p.x, r.x * inv); p.y = __fmaf_rn(bf, p.y, r.y * inv); p.z = __fmaf_rn(bf, p.z, r.z * inv);
                             x.x = __fmaf_rn(af, p.x, x.x); x.y = __fmaf_rn(af, p.y, x.y); x.z = __fmaf_rn(af, p.z, x.z);
                             r.x = __fmaf_rn(-af, sv.x, r.x); r.y = __fmaf_rn(-af, sv.y, r.y); r.z = __fmaf_rn(-af, sv.z, r.z);
                             w.x = __fmaf_rn(-af, z.x, w.x); w.y = __fmaf_rn(-af, z.y, w.y); w.z = __fmaf_rn(-af, z.z, w.z);
-                            S_r[n] = r; S_w[n] = w; S_z[n] = z; S_s[n] = sv; S_p[n] = p; S_x[n] = x;
+                            r_ = r; w_ = w; z_ = z; s_ = sv; p_ = p; x_ = x;
                         }
                     }
                     PROF(12);
@@ -374,13 +380,12 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3(Problem pb, Patte
                     inv_gamma_prev = 1.0 / gamma;
                     denom_prev = denom;
                 }
-            }
-            // t += x (row-local), then everybody needs the new t
-            {
-                const int n = row0 + lane;
-                if (n < row1) {
-                    const float4 x = S_x[n];
-                    pb.t[3 * (size_t) n] += x.x; pb.t[3 * (size_t) n + 1] += x.y; pb.t[3 * (size_t) n + 2] += x.z;
+                // t += x (row-local), then everybody needs the new t
+                {
+                    const int n = row0 + lane;
+                    if (n < row1) {
+                        pb.t[3 * (size_t) n] += x_.x; pb.t[3 * (size_t) n + 1] += x_.y; pb.t[3 * (size_t) n + 2] += x_.z;
+                    }
                 }
             }
             ++gn_total;
