@@ -438,6 +438,44 @@ def test_solver_every_execution_path_matches_oracle(dfu, oracle, monkeypatch, pa
     assert th.shape == (40000,) and th.min() >= 0.0 and th.max() <= 1.0 and th.mean() > 0.5
 
 
+@pytest.mark.parametrize("path", ["p3", "p3g"])
+def test_solver_long_rows_of_a_volumetric_node_cloud(dfu, oracle, monkeypatch, path, capfd):
+    """nodes on a strongly jittered 3-D lattice: some nodes share points with > 64 other nodes (8-NN in 3-D tops out near 70), so their rows of the normal matrix no longer fit
+    the 64 register slots / the one-sweep assembly -- the multi-pass assembly and the row tails from L2 of versions 3r and 3
+    (generic) against the oracle"""
+    monkeypatch.setenv("DFU_SOLVER_PATH", path)
+    monkeypatch.setenv("DFU_DEBUG", "1")
+    rng = np.random.default_rng(23)
+    g = 12
+    h = 0.03
+    lat = np.stack(np.meshgrid(np.arange(g), np.arange(g), np.arange(g), indexing="ij"), -1).reshape(-1, 3)
+    pos = (np.array([0.2, 0.2, 0.2]) + h * lat + rng.uniform(-0.45 * h, 0.45 * h, (g ** 3, 3))).astype(np.float32)
+    N = len(pos)
+    dg_w = np.full(N, 1.5 * h, np.float32)
+    canon = (np.array([0.2, 0.2, 0.2]) + rng.uniform(0.5 * h, (g - 1.5) * h, (40000, 3))).astype(np.float32)
+    _, ties = oracle.knn(pos, canon)
+    assert ties == 0
+    t_true = (0.004 * np.sin(8.0 * pos[:, [1, 2, 0]])).astype(np.float32)
+    live = oracle.warp(pos, synth.translations_to_dq(t_true), dg_w, canon)
+    prm_o = pyoracle.default_params(num_iter=3, nonlinear_iter=1, linear_iter=12, lambda_=50.0, pcg_tol=0.0, early_out=0)
+    t_o, _, st_o = oracle.solve(pos, synth.identity_dq(N), dg_w, canon, live, prm_o)
+    wf = make_wf(dfu, pos, synth.identity_dq(N), dg_w, h)
+    prm = dfu.CombinedSolverParameters(numIter=3, nonLinearIter=1, linearIter=12, earlyOut=False, pcgTolerance=0.0)
+    s = dfu.CombinedSolver(wf, prm, 4.652, 1e-2, 50.0, 1e-4)
+    s.initializeProblemInstance(dev(canon), dev(live))
+    s.solveAll()
+    st = s.getStats()
+    err = capfd.readouterr().err
+    import re
+    m = re.search(r"max row (\d+) rows>64 (\d+)", err)
+    assert m and int(m.group(1)) > 64 and int(m.group(2)) >= 10, m.group(0) if m else err[-400:]  # (8-NN in 3-D: rows top out near 70)
+    assert ("rows in registers" in err) == (path == "p3")
+    assert st["pcg_iterations"] == 36 and st["gn_steps"] == 3
+    assert abs(st["final_energy"] - st_o[1]) <= 1e-4 * st_o[1], (st, st_o)
+    t_g = s.getTranslations().cpu().numpy()
+    assert np.max(np.abs(t_g - t_o)) <= 1e-4 * np.abs(t_o).max()
+
+
 def test_solver_allreduce_hook_two_partitions(dfu, oracle):
     """data-parallel contract on one GPU: two solvers hold disjoint point partitions and exchange their
     normal-equation buffers through the all-reduce hook; the result equals the single-partition solve."""
