@@ -532,6 +532,10 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
     float s_r[P3_R], s_w[P3_R], s_z[P3_R], s_s[P3_R], s_p[P3_R], s_x[P3_R], s_t[P3_R];  // coordinate `lane` (lanes 0..2)
 #pragma unroll
     for (int r = 0; r < P3_R; ++r) {
+        // (row r of a warp is gw + r * nw: a node early in the order paired with one nw further on.  Measured alternatives, both
+        //  slower at N = 4096: second rows dealt round-robin over the CTAs for equal row counts per SM, 0.328 vs 0.302 ms -- the
+        //  L1 reuse of the points shared by neighbouring rows is lost; contiguous chunks of N / gridDim.x rows per CTA, 0.335 ms
+        //  -- list lengths vary smoothly along the node order, and the strided pairing is what balances them)
         const int n = gw + r * nw;
         rn[r] = n < N ? n : -1;
         roff[r] = rlen[r] = rds[r] = 0;
