@@ -51,7 +51,7 @@ DFU_DEV void assemble_row_fused(const int32_t* __restrict__ tv, const float* __r
     int vn[FU];
     long long bx = 0, by = 0, bz = 0;
 #pragma unroll
-    for (int u = 0; u < FU; ++u) vn[u] = lo + lane + 32 * u < hi ? tv[lo + lane + 32 * u] : -1;
+    for (int u = 0; u < FU; ++u) vn[u] = lo + lane + 32 * u < hi ? __ldcs(tv + lo + lane + 32 * u) : -1;
     __syncwarp();
     for (int e0 = lo + lane; e0 < hi; e0 += 32 * FU) {  // FU entries per lane in flight
         int v[FU];
@@ -63,14 +63,14 @@ DFU_DEV void assemble_row_fused(const int32_t* __restrict__ tv, const float* __r
             v[u] = vn[u];
             const int vv = v[u] >= 0 ? v[u] : 0;
             const int ee = v[u] >= 0 ? e0 + 32 * u : lo;
-            c[u] = tw[ee];
-            sl[u] = tslot[ee];
+            c[u] = __ldcs(tw + ee);  // (read once: streaming, the L1 is for the points' data shared by neighbouring rows)
+            sl[u] = __ldcs(tslot + ee);
             se[u] = s4[vv];
             w0[u] = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) vv);
             w1[u] = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) vv + 1);
         }
 #pragma unroll
-        for (int u = 0; u < FU; ++u) vn[u] = e0 + 32 * FU + 32 * u < hi ? tv[e0 + 32 * FU + 32 * u] : -1;
+        for (int u = 0; u < FU; ++u) vn[u] = e0 + 32 * FU + 32 * u < hi ? __ldcs(tv + e0 + 32 * FU + 32 * u) : -1;
 #pragma unroll
         for (int u = 0; u < FU; ++u) {
             if (v[u] < 0) continue;
