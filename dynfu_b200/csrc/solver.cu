@@ -290,7 +290,7 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
     if (ver == 3 && !(s->pattern_ready && s->coop_blocks3 > 0 && s->N <= 32 * s->coop_blocks3 * (PTPB / 32))) ver = 2;  // (lane-per-row blocks)
     if (ver == 2 && (s->coop_blocks2 == 0 || s->N > P2_NPW * s->coop_blocks2 * (PTPB / 32))) ver = 1;
     if (ver == 3) {
-        Pattern pt{s->rowptr, s->rowlen, s->dslot, s->col, s->areg, s->vals, s->tslot, s->exch, s->st, s->xw, s->pw, nullptr, nullptr, nullptr, nullptr};
+        Pattern pt{s->rowptr, s->rowlen, s->dslot, s->col, s->areg, s->vals, s->tslot, s->exch, s->st, s->xw, s->pw, nullptr, nullptr, nullptr, nullptr, nullptr};
         void* args[] = {&pb, &pt, &ctl, &sc, &bar};
         // rows in registers when every node fits a register slot; DFU_SOLVER_PATH=p3g forces the generic kernel, p3 the
         // barrier-per-iteration register kernel (3r), p4 / default: version 4 (tagged exchange, CTA-balanced assembly)
@@ -322,6 +322,7 @@ int solve_persistent(dfu_solver* s, cudaStream_t st) {
             // node transforms (and the warp field's flags) back itself
             if (!s->bar_clean && clear_bar() != DFU_OK) return DFU_ERR_CUDA;
             pt.wf_real = s->wf->real; pt.wf_dual = s->wf->dual; pt.wf_pos_w = s->wf->pos_w; pt.wf_flags = s->wf->flags;
+            pt.t4 = s->t4;
             DFU_CUDA_OK(cudaLaunchCooperativeKernel((void*) k_solve_persistent3r, dim3(s->coop_blocks3r), dim3(PTPB), args, 0, st));
             fused = true;
         } else {

@@ -62,6 +62,7 @@ struct Pattern {
     float4* wf_dual;
     const float4* wf_pos_w;
     int* wf_flags;
+    float4* t4;  // version 3r: the unknowns once more as one float4 per node (a point's 8 gathers are 8 loads instead of 24)
 };
 constexpr int ACC_W = 256;                              // fixed-point accumulators per warp (columns per pass)
 constexpr float FIX_SCALE = 1099511627776.f;            // 2^40; contributions are <= 1
@@ -188,6 +189,39 @@ DFU_DEV double phase_point_residual(const Problem& pb, bool update_tukey, int ti
     for (int v = tid; v < pb.P; v += nthreads) {
         float sx, sy, sz;
         point_gather(pb, v, pb.t, sx, sy, sz);
+        const float ex = pb.dvec[3 * (size_t) v] - sx, ey = pb.dvec[3 * (size_t) v + 1] - sy,
+                    ez = pb.dvec[3 * (size_t) v + 2] - sz;
+        float th;
+        if (update_tukey) {
+            th = tukey_biweight(pb.tukey_offset, pb.psi_data, ex, ey, ez);
+            pb.theta[v] = th;
+        } else {
+            th = pb.theta[v];
+        }
+        pb.s4[v] = make_float4(th * ex, th * ey, th * ez, th);
+        e2 += (double) th * ((double) ex * ex + (double) ey * ey + (double) ez * ez);
+    }
+    return e2;
+}
+
+// the same with the unknowns as one float4 per node: the residual pass is bound by the L1 requests of its gathers (24 scalar loads
+// per point from the float[3N] array), a float4 per neighbour is 8
+DFU_DEV double phase_point_residual_t4(const Problem& pb, const float4* __restrict__ t4, bool update_tukey, int tid, int nthreads) {
+    double e2 = 0.0;
+    for (int v = tid; v < pb.P; v += nthreads) {
+        int nb[8];
+        float w[8];
+        load8(pb.nbr, pb.wts, v, nb, w);
+        float4 xk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xk[k] = t4[nb[k]];
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sx = __fmaf_rn(w[k], xk[k].x, sx);
+            sy = __fmaf_rn(w[k], xk[k].y, sy);
+            sz = __fmaf_rn(w[k], xk[k].z, sz);
+        }
         const float ex = pb.dvec[3 * (size_t) v] - sx, ey = pb.dvec[3 * (size_t) v + 1] - sy,
                     ez = pb.dvec[3 * (size_t) v + 2] - sz;
         float th;

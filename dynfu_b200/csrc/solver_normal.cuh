@@ -559,6 +559,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                 }
             }
             if (lane < 3) pb.t[3 * (size_t) n + lane] = 0.f;  // unknowns := 0 (opt_solver.cpp:192-193)
+            if (lane == 0) pt.t4[n] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     if (pt.wf_flags && tid == 0) {  // (recomputed with the write-back at the end)
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
     for (int outer = 0; outer < ctl.num_iter && !stop_all; ++outer) {
         for (int gn = 0; gn < ctl.nonlinear_iter; ++gn) {
             PROF(0);
-            const double e2_local = phase_point_residual(pb, gn == 0, tid, nthreads);
+            const double e2_local = phase_point_residual_t4(pb, pt.t4, gn == 0, tid, nthreads);
             PROF(1);
             GRID_SYNC();
             PROF(2);
@@ -929,6 +930,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                 if (rn[r] >= 0 && lane < 3) {
                     s_t[r] += s_x[r];
                     pb.t[3 * (size_t) rn[r] + lane] = s_t[r];
+                    reinterpret_cast<float*>(pt.t4 + rn[r])[lane] = s_t[r];
                 }
             ++gn_total;
             PROF(13);
@@ -938,7 +940,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
     }
     // ---- final energy at the solution, Tukey weights of the last outer iteration -------------------------
     {
-        const double e2 = phase_point_residual(pb, first, tid, nthreads);  // no GN step ran: weights at t = 0
+        const double e2 = phase_point_residual_t4(pb, pt.t4, first, tid, nthreads);  // no GN step ran: weights at t = 0
         double er = 0.0;
         if (pb.wreg2 > 0.f) {
 #pragma unroll
