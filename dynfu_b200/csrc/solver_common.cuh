@@ -313,6 +313,23 @@ DFU_DEV void node_gather_data_fixed(const Problem& pb, int n, int lane, float& a
     ax = (float) ((double) sx * FIX_INV); ay = (float) ((double) sy * FIX_INV); az = (float) ((double) sz * FIX_INV);
 }
 
+// node_gather_reg on the float4 copy of the unknowns (one load per neighbour instead of three; same terms, same order)
+DFU_DEV void node_gather_reg_t4(const Problem& pb, int n, int lane, const float4* __restrict__ x4, float& gx, float& gy, float& gz,
+                                float& e2) {
+    gx = gy = gz = e2 = 0.f;
+    const float4 xn = x4[n];
+    const int lo = pb.rin_ptr[n], hi = pb.rin_ptr[n + 1];
+    for (int j = lane; j < 8 + (hi - lo); j += 32) {
+        const bool out = j < 8;
+        const int m = out ? pb.nnbr[(size_t) n * 8 + j] : pb.rin[lo + j - 8];
+        if (m == n) continue;
+        const float4 xm = x4[m];
+        const float d0 = xn.x - xm.x, d1 = xn.y - xm.y, d2 = xn.z - xm.z;
+        gx += d0; gy += d1; gz += d2;
+        if (out) e2 += d0 * d0 + d1 * d1 + d2 * d2;
+    }
+}
+
 // lane-parallel regularisation gather for node n on vector x: sum over out- and in-edges (m != n) of
 // (x[n] - x[m]) in (gx,gy,gz), the edge count in cnt and (out-edges only) the squared differences in e2
 DFU_DEV void node_gather_reg(const Problem& pb, int n, int lane, const float* x, float& gx, float& gy, float& gz, float& cnt,

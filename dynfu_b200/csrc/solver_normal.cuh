@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
                     }
                 }
                 if (pb.wreg2 > 0.f) {
-                    node_gather_reg(pb, n, lane, pb.t, gx, gy, gz, cnt, e2);
+                    node_gather_reg_t4(pb, n, lane, pt.t4, gx, gy, gz, e2);
                     gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
                     ax -= pb.wreg2 * gx; ay -= pb.wreg2 * gy; az -= pb.wreg2 * gz;
                     e2 = warp_sum(e2);
@@ -946,8 +946,8 @@ __global__ void __launch_bounds__(PTPB, 1) k_solve_persistent3r(Problem pb, Patt
 #pragma unroll
             for (int r = 0; r < P3_R; ++r) {
                 if (rn[r] < 0) continue;
-                float gx, gy, gz, cnt, r2;
-                node_gather_reg(pb, rn[r], lane, pb.t, gx, gy, gz, cnt, r2);
+                float gx, gy, gz, r2;
+                node_gather_reg_t4(pb, rn[r], lane, pt.t4, gx, gy, gz, r2);
                 r2 = warp_sum(r2);
                 if (lane == 0) er += (double) pb.wreg2 * r2;
             }
