@@ -158,12 +158,8 @@ DFU_DEV float tukey_biweight(float tukey_offset, float c, float ex, float ey, fl
 }
 
 DFU_DEV void load8(const int32_t* nbr, const float* wts, int v, int (&nb)[8], float (&w)[8]) {
-    const int4 a = *(reinterpret_cast<const int4*>(nbr) + 2 * (size_t) v);
-    const int4 b = *(reinterpret_cast<const int4*>(nbr) + 2 * (size_t) v + 1);
-    const float4 c = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) v);
-    const float4 d = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) v + 1);
-    nb[0] = a.x; nb[1] = a.y; nb[2] = a.z; nb[3] = a.w; nb[4] = b.x; nb[5] = b.y; nb[6] = b.z; nb[7] = b.w;
-    w[0] = c.x; w[1] = c.y; w[2] = c.z; w[3] = c.w; w[4] = d.x; w[5] = d.y; w[6] = d.z; w[7] = d.w;
+    ld256(nbr + 8 * (size_t) v, nb);  // (the graph of a frame is immutable while the solver kernels run)
+    ld256(wts + 8 * (size_t) v, w);
 }
 
 // sum_k w_k x[n_k] for one point

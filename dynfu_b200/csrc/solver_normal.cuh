@@ -57,7 +57,8 @@ DFU_DEV void assemble_row_fused(const int32_t* __restrict__ tv, const float* __r
         int v[FU];
         float c[FU];
         uint4 sl[FU];
-        float4 w0[FU], w1[FU], se[FU];
+        float4 se[FU];
+        float wq[FU][8];
 #pragma unroll
         for (int u = 0; u < FU; ++u) {
             v[u] = vn[u];
@@ -66,8 +67,7 @@ DFU_DEV void assemble_row_fused(const int32_t* __restrict__ tv, const float* __r
             c[u] = __ldcs(tw + ee);  // (read once: streaming, the L1 is for the points' data shared by neighbouring rows)
             sl[u] = __ldcs(tslot + ee);
             se[u] = s4[vv];
-            w0[u] = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) vv);
-            w1[u] = *(reinterpret_cast<const float4*>(wts) + 2 * (size_t) vv + 1);
+            ld256(wts + 8 * (size_t) vv, wq[u]);
         }
 #pragma unroll
         for (int u = 0; u < FU; ++u) vn[u] = e0 + 32 * FU + 32 * u < hi ? __ldcs(tv + e0 + 32 * FU + 32 * u) : -1;
@@ -79,11 +79,10 @@ DFU_DEV void assemble_row_fused(const int32_t* __restrict__ tv, const float* __r
             bz += __float2ll_rn(c[u] * se[u].z * FIX_SCALE);
             const float cc = c[u] * se[u].w;
             if (cc == 0.f) continue;
-            const float wk[8] = {w0[u].x, w0[u].y, w0[u].z, w0[u].w, w1[u].x, w1[u].y, w1[u].z, w1[u].w};
             const unsigned sw[4] = {sl[u].x, sl[u].y, sl[u].z, sl[u].w};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const unsigned long long f = (unsigned long long) __float2ll_rn(cc * wk[k] * FIX_SCALE);
+                const unsigned long long f = (unsigned long long) __float2ll_rn(cc * wq[u][k] * FIX_SCALE);
                 const unsigned sidx = (k & 1) ? sw[k >> 1] >> 16 : sw[k >> 1] & 0xffffu;
                 atomicAdd(&my_lo[sidx], (unsigned) f & 0xfffffu);
                 atomicAdd(&my_hi[sidx], (unsigned) (f >> 20));
