@@ -1040,19 +1040,15 @@ __global__ void __launch_bounds__(128) k_pattern(Problem pb, int NW, int* __rest
         //  dependent point-id -> neighbour-list loads; the second sweep finds the lists in L1)
         for (int e0 = lo + lane; e0 < hi; e0 += 128) {
             int v[4];
-            int4 na[4], nb4[4];
+            int nq[4][8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = e0 + 32 * u < hi ? pb.tv[e0 + 32 * u] : -1;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int vv = v[u] >= 0 ? v[u] : 0;
-                na[u] = *(reinterpret_cast<const int4*>(pb.nbr) + 2 * (size_t) vv);
-                nb4[u] = *(reinterpret_cast<const int4*>(pb.nbr) + 2 * (size_t) vv + 1);
-            }
+            for (int u = 0; u < 4; ++u) ld256(pb.nbr + 8 * (size_t) (v[u] >= 0 ? v[u] : 0), nq[u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (v[u] < 0) continue;
-                const int nbk[8] = {na[u].x, na[u].y, na[u].z, na[u].w, nb4[u].x, nb4[u].y, nb4[u].z, nb4[u].w};
+                const int (&nbk)[8] = nq[u];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) atomicOr(&bm[nbk[k] >> 5], 1u << (nbk[k] & 31));
             }
@@ -1110,19 +1106,15 @@ __global__ void __launch_bounds__(128) k_pattern(Problem pb, int NW, int* __rest
         }
         for (int e0 = lo + lane; e0 < hi; e0 += 128) {
             int v[4];
-            int4 na[4], nb4[4];
+            int nq[4][8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = e0 + 32 * u < hi ? pb.tv[e0 + 32 * u] : -1;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int vv = v[u] >= 0 ? v[u] : 0;
-                na[u] = *(reinterpret_cast<const int4*>(pb.nbr) + 2 * (size_t) vv);
-                nb4[u] = *(reinterpret_cast<const int4*>(pb.nbr) + 2 * (size_t) vv + 1);
-            }
+            for (int u = 0; u < 4; ++u) ld256(pb.nbr + 8 * (size_t) (v[u] >= 0 ? v[u] : 0), nq[u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (v[u] < 0) continue;
-                const int nbk[8] = {na[u].x, na[u].y, na[u].z, na[u].w, nb4[u].x, nb4[u].y, nb4[u].z, nb4[u].w};
+                const int (&nbk)[8] = nq[u];
                 unsigned sk[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) sk[k] = slot_of(nbk[k]);

@@ -512,8 +512,8 @@ __global__ void __launch_bounds__(128, MODE == MODE_CACHED ? 8 : 4) integrate_ke
                     // (48 bytes per voxel read exactly once: streamed past the L1, which keeps the nodes' dual parts and the
                     //  depth image that neighbouring voxels share)
                     unpack_ids(__ldcs(cache + v), id);
-                    const float4 w0 = __ldcs(wcache + 2 * v), w1 = __ldcs(wcache + 2 * v + 1);
-                    const float w[DFU_KNN] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    float w[DFU_KNN];
+                    ld256_cs(reinterpret_cast<const float*>(wcache + 2 * v), w);
                     const V3 p = warp_voxel_weights(a, ti, id, w, px[v], py, pz);
                     hit[v] = voxel_tsdf(a, p.x, p.y, p.z, ts[v]);
                 }
