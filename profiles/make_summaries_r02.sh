@@ -2,7 +2,7 @@
 # Turns the captures of `bash profiles/profile_run_r02.sh` (gpurun_out/<tag>_*) into the tracked round-2 summaries.
 # usage: bash profiles/make_summaries_r02.sh r02f
 set -e
-tag=${1:-r02i}; out=r02
+tag=${1:-r02j}; out=r02
 cd "$(dirname "$0")/.."
 for k in integrate solver knn dense; do
   ncu -i gpurun_out/${tag}_$k.ncu-rep --page raw --csv > /tmp/${tag}_$k.csv 2>/dev/null

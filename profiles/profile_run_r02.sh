@@ -3,7 +3,7 @@
 # (raw .ncu-rep files stay in gpurun_out/; profiles/make_summaries_r02.sh turns them into the tracked summaries)
 set -x
 mkdir -p gpurun_out
-T=r02i
+T=r02j
 timeout 600 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
 tail -c 400 gpurun_out/${T}_bench.err
 # steady state: 30 warm-up frame pairs first (the field needs a few bend cycles to become periodic), then the last frames
